@@ -1,0 +1,90 @@
+// Internal declarations shared by the CUDA kernels, the host quad stage and the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/aruco3_b200.h"
+
+namespace a3 {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const std::string &msg);
+a3_status fail(a3_status s, const std::string &msg);
+a3_status cuda_fail(cudaError_t e, const char *what);
+#define A3_CUDA(expr)                                                    \
+    do {                                                                 \
+        cudaError_t e__ = (expr);                                        \
+        if (e__ != cudaSuccess) return ::a3::cuda_fail(e__, #expr);      \
+    } while (0)
+
+// ---- K1: fused into_luma8 + adaptive_threshold (k1_threshold.cu) -------------------------------
+struct K1Params {
+    const uint8_t *src;   // device, n frames
+    int format;           // a3_format
+    uint32_t n, w, h;
+    size_t pitch, frame_stride;
+    uint8_t *grey;        // device n*h*w or null
+    uint8_t *mask;        // device n*h*w or null
+    uint32_t *bits;       // device n*h*ceil(w/32) or null
+    uint32_t radius;      // threshold_window
+};
+struct K1Tuning {
+    uint32_t strip_cols;  // core columns per strip (multiple of 32); 0 = auto
+    uint32_t seg_rows;    // output rows per CTA; 0 = auto
+    int force_no_tma;     // 1 = take the plain-load path even when the bulk-copy path is legal (tests)
+};
+struct K1LaunchInfo {
+    uint32_t grid, block, smem_bytes, strips, segs, strip_cols, seg_rows;
+    int tma, specialised_radius;
+};
+cudaError_t k1_gray_threshold(const K1Params &p, const K1Tuning *tuning, cudaStream_t stream, K1LaunchInfo *info);
+
+// ---- K2: per-candidate homography + warp + otsu + resize + bits + dictionary match (k2_decode.cu) ----
+struct K2Params {
+    const uint8_t *grey;        // device, n_frames*h*w
+    uint32_t w, h;
+    const uint32_t *quads;      // device n_quads*8
+    const uint32_t *quad_frame; // device n_quads or null (all frame 0)
+    uint32_t n_quads;
+    uint32_t patch_size;        // homography_sample_size
+    uint32_t mark_size;         // get_mark_size()
+    const uint64_t *codes;      // device dictionary
+    uint32_t n_codes;
+    uint32_t tau;
+    int filter_high_bit_errors;
+    const float *resize_w;      // device: resize tap weights (see ResizeTaps)
+    const int *resize_meta;     // device: per output index {left, count}, then for the 1x1 source
+    a3_decode *decodes;         // device n_quads
+    uint8_t *patches;           // device n_quads*ps*ps or null
+};
+cudaError_t k2_decode(const K2Params &p, cudaStream_t stream);
+size_t k2_smem_bytes(uint32_t patch_size, uint32_t mark_size, uint32_t n_codes);
+
+// image::imageops::resize(Triangle) tap table for n_in -> n_out, computed on the host in f32 with the
+// reference's expression order.  weights[o*max_taps + i], meta[2*o] = left, meta[2*o+1] = count.
+struct ResizeTaps {
+    uint32_t n_in, n_out, max_taps;
+    std::vector<float> weights;
+    std::vector<int> meta;
+};
+ResizeTaps make_resize_taps(uint32_t n_in, uint32_t n_out);
+
+// ---- host quad stage (host_quads.cpp) ---------------------------------------------------------------
+struct QuadStats {
+    uint64_t n_contours = 0, n_contour_points = 0, n_before_discard = 0;
+};
+// mask bits: h rows of `words_per_row` little-endian 32-bit words (bit x&31 of word x>>5), zero beyond w.
+// Appends 8 uint32 per surviving quad (x0,y0..x3,y3) to `quads`.
+void quads_from_bits(const uint32_t *bits, uint32_t words_per_row, uint32_t w, uint32_t h, const a3_config &cfg,
+                     std::vector<uint32_t> &quads, QuadStats *stats);
+void bits_from_mask(const uint8_t *mask, uint32_t w, uint32_t h, std::vector<uint32_t> &bits, uint32_t *words_per_row);
+
+// ---- dictionaries (a3_dictionary.cpp) ---------------------------------------------------------------
+uint8_t mark_size_of(uint8_t num_bits);
+
+}  // namespace a3

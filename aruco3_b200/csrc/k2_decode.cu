@@ -1,0 +1,371 @@
+// K2 — per-candidate decode (sm_100a). Compile this file with -fmad=false: the reference is Rust, which never
+// contracts a*b+c, and every float below is written in the reference's operation order.
+//
+// For each candidate quad this replaces, bit for bit (against oracle/a3ref.c):
+//   extract_homographies            /root/reference/src/aruco.rs:234-261  (imageproc Projection::from_control_points,
+//                                                                          warp_into Bilinear, default 0)
+//   homography_to_code_permutations /root/reference/src/aruco.rs:263-313  (otsu_level, threshold Binary,
+//                                                                          imageops::resize Triangle, >127, border test,
+//                                                                          4 rotations, rotate_bit_matrix :315-326)
+//   the match loop                  /root/reference/src/aruco.rs:75-96    (ARDictionary::find_nearest
+//                                                                          src/dictionaries.rs:160-196, hamming lib.rs:11-21)
+//
+// One persistent CTA of 256 threads loops over candidates; the dictionary is staged into shared memory once per
+// CTA and matched with __popcll over all four rotations; the winner is a packed-key block min so that both strict-<
+// tie rules of the reference hold (lowest rotation, then lowest index).  Latency/L2-bound and tiny next to K1.
+#include <math.h>
+
+#include "a3_internal.h"
+
+namespace a3 {
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Proj {
+    float inv[9];  // maps patch pixels back into the image (projection.invert())
+    int cls;       // 0 translation, 1 affine, 2 projection
+    int ok;
+};
+
+// f64 Gaussian elimination with partial pivoting — the very sequence of operations of oracle/a3ref.c:solve8.
+__device__ bool solve8(double a[8][9]) {
+    for (int col = 0; col < 8; col++) {
+        int piv = col;
+        double best = fabs(a[col][col]);
+        for (int r = col + 1; r < 8; r++) {
+            double v = fabs(a[r][col]);
+            if (v > best) { best = v; piv = r; }
+        }
+        if (best == 0.0) return false;
+        if (piv != col)
+            for (int k = 0; k < 9; k++) { double t = a[col][k]; a[col][k] = a[piv][k]; a[piv][k] = t; }
+        for (int r = col + 1; r < 8; r++) {
+            double f = a[r][col] / a[col][col];
+            for (int k = col; k < 9; k++) a[r][k] = a[r][k] - f * a[col][k];
+        }
+    }
+    for (int r = 7; r >= 0; r--) {
+        double s = a[r][8];
+        for (int k = r + 1; k < 8; k++) s = s - a[r][k] * a[k][8];
+        a[r][8] = s / a[r][r];
+    }
+    return true;
+}
+
+// Projection::from_control_points(quad, [(0,0),(h,0),(h,h),(0,h)]) followed by invert().
+__device__ void make_projection(const uint32_t *quad, float hs, Proj *out) {
+    const float to[8] = {0.0f, 0.0f, hs, 0.0f, hs, hs, 0.0f, hs};
+    double a[8][9];
+    for (int k = 0; k < 4; k++) {
+        double xf = (double)(float)quad[2 * k], yf = (double)(float)quad[2 * k + 1];
+        double x = (double)to[2 * k], y = (double)to[2 * k + 1];
+        double r0[9] = {0.0, 0.0, 0.0, -xf, -yf, -1.0, y * xf, y * yf, -y};
+        double r1[9] = {xf, yf, 1.0, 0.0, 0.0, 0.0, -x * xf, -x * yf, x};
+        for (int i = 0; i < 9; i++) { a[2 * k][i] = r0[i]; a[2 * k + 1][i] = r1[i]; }
+    }
+    out->ok = 0;
+    if (!solve8(a)) return;
+    float t[9];
+    for (int i = 0; i < 8; i++) t[i] = (float)a[i][8];
+    t[8] = 1.0f;
+    for (int i = 0; i < 8; i++)
+        if (!isfinite(t[i])) return;
+    int c = 2;
+    if (fabsf(t[6]) < 1e-10f && fabsf(t[7]) < 1e-10f && fabsf(t[8] - 1.0f) < 1e-10f) {
+        if (fabsf(t[0] - 1.0f) < 1e-10f && fabsf(t[1]) < 1e-10f && fabsf(t[3]) < 1e-10f && fabsf(t[4] - 1.0f) < 1e-10f) c = 0;
+        else c = 1;
+    }
+    out->cls = c;
+    // try_inverse (f32 adjugate) + normalize
+    float t00 = t[0], t01 = t[1], t02 = t[2], t10 = t[3], t11 = t[4], t12 = t[5], t20 = t[6], t21 = t[7], t22 = t[8];
+    float m00 = t11 * t22 - t12 * t21;
+    float m01 = t10 * t22 - t12 * t20;
+    float m02 = t10 * t21 - t11 * t20;
+    float det = t00 * m00 - t01 * m01 + t02 * m02;
+    if (fabsf(det) < 1e-10f) return;
+    float m10 = t01 * t22 - t02 * t21;
+    float m11 = t00 * t22 - t02 * t20;
+    float m12 = t00 * t21 - t01 * t20;
+    float m20 = t01 * t12 - t02 * t11;
+    float m21 = t00 * t12 - t02 * t10;
+    float m22 = t00 * t11 - t01 * t10;
+    float rr[9] = {m00 / det, -m10 / det, m20 / det, -m01 / det, m11 / det, -m21 / det, m02 / det, -m12 / det, m22 / det};
+    float s = rr[8];
+    for (int i = 0; i < 8; i++) out->inv[i] = rr[i] / s;
+    out->inv[8] = 1.0f;
+    out->ok = 1;
+}
+
+__device__ __forceinline__ uint8_t clamp_u8_trunc(float x) {  // <u8 as Clamp<f32>>::clamp
+    if (x < 255.0f) {
+        if (x > 0.0f) return (uint8_t)x;
+        return 0;
+    }
+    return 255;
+}
+
+// warp_into's per-pixel body: projective map + interpolate_bilinear with default 0.
+__device__ __forceinline__ uint8_t sample(const uint8_t *grey, uint32_t w, uint32_t h, const float *t, int cls, uint32_t ox,
+                                          uint32_t oy) {
+    float x = (float)ox, y = (float)oy, px, py;
+    if (cls == 2) {
+        float d = t[6] * x + t[7] * y + t[8];
+        px = (t[0] * x + t[1] * y + t[2]) / d;
+        py = (t[3] * x + t[4] * y + t[5]) / d;
+    } else if (cls == 1) {
+        px = t[0] * x + t[1] * y + t[2];
+        py = t[3] * x + t[4] * y + t[5];
+    } else {
+        px = x + t[2];
+        py = y + t[5];
+    }
+    float left = floorf(px), right = left + 1.0f, top = floorf(py), bottom = top + 1.0f;
+    float rw = px - left, bw = py - top;
+    if (left < 0.0f || right >= (float)w || top < 0.0f || bottom >= (float)h) return 0;
+    // NaN coordinates fall through every comparison (as in Rust) and `NaN as u32` is 0 there and here.
+    uint32_t l = isnan(left) ? 0u : (uint32_t)left, r = isnan(right) ? 0u : (uint32_t)right;
+    uint32_t tp = isnan(top) ? 0u : (uint32_t)top, b = isnan(bottom) ? 0u : (uint32_t)bottom;
+    float tl = (float)grey[(size_t)tp * w + l], tr = (float)grey[(size_t)tp * w + r];
+    float bl = (float)grey[(size_t)b * w + l], br = (float)grey[(size_t)b * w + r];
+    uint8_t topv = clamp_u8_trunc((1.0f - rw) * tl + rw * tr);
+    uint8_t botv = clamp_u8_trunc((1.0f - rw) * bl + rw * br);
+    return clamp_u8_trunc((1.0f - bw) * (float)topv + bw * (float)botv);
+}
+
+__global__ void __launch_bounds__(kThreads) k2_kernel(const K2Params p, const uint32_t max_taps) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t ps = p.patch_size, ms = p.mark_size, np = ps * ps;
+    // ---- carve ----
+    uint64_t *dict = reinterpret_cast<uint64_t *>(smem);                       // n_codes
+    float *tmp = reinterpret_cast<float *>(dict + p.n_codes);                 // ms * ps  (vertical pass, f32)
+    float *taps = tmp + ms * ps;                                              // ms * max_taps
+    int *meta = reinterpret_cast<int *>(taps + ms * max_taps);                // 2 * ms
+    uint32_t *hist = reinterpret_cast<uint32_t *>(meta + 2 * ms);             // 256
+    uint32_t *bwv = hist + 256;                                               // 256 background weights
+    uint32_t *bsv = bwv + 256;                                                // 256 background sums
+    double *var = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(bsv + 256) + 7) & ~(uintptr_t)7);  // 256
+    uint32_t *red = reinterpret_cast<uint32_t *>(var + 256);                  // 8 warp partials
+    uint8_t *reduced = reinterpret_cast<uint8_t *>(red + 8);                  // ms * ms (padded to x4)
+    uint8_t *patch = reduced + ((ms * ms + 3) & ~3u);                         // ps * ps
+    __shared__ Proj proj;
+    __shared__ uint64_t codes[4];
+    __shared__ int has_codes;
+    __shared__ uint32_t otsu_level;
+
+    const int t = threadIdx.x;
+    for (uint32_t i = t; i < p.n_codes; i += kThreads) dict[i] = p.codes[i];
+    for (uint32_t i = t; i < ms * max_taps; i += kThreads) taps[i] = p.resize_w[i];
+    for (uint32_t i = t; i < 2 * ms; i += kThreads) meta[i] = p.resize_meta[i];
+    __syncthreads();
+
+    for (uint32_t q = blockIdx.x; q < p.n_quads; q += gridDim.x) {
+        const uint32_t frame = p.quad_frame ? p.quad_frame[q] : 0;
+        const uint8_t *grey = p.grey + (size_t)frame * p.w * p.h;
+        if (t == 0) make_projection(p.quads + (size_t)q * 8, (float)ps, &proj);
+        hist[t] = 0;
+        __syncthreads();
+        const int ok = proj.ok;
+        a3_decode out;
+        out.homography_ok = (uint8_t)ok;
+        if (ok) {
+            // ---- warp: ps*ps bilinear samples, histogram on the fly ----
+            for (uint32_t i = t; i < np; i += kThreads) {
+                uint8_t v = sample(grey, p.w, p.h, proj.inv, proj.cls, i % ps, i / ps);
+                patch[i] = v;
+                atomicAdd(&hist[v], 1u);
+            }
+            __syncthreads();
+            // ---- otsu_level: integer prefix sums are exact, the f64 expression keeps the reference's order ----
+            if (t == 0) {
+                uint32_t bw = 0, bs = 0;
+                for (int i = 0; i < 256; i++) { bw += hist[i]; bs += (uint32_t)i * hist[i]; bwv[i] = bw; bsv[i] = bs; }
+            }
+            __syncthreads();
+            {
+                const uint32_t total = np;
+                const double total_sum = (double)bsv[255];
+                const uint32_t bw = bwv[t], fw = total - bw;
+                double v = -1.0;
+                if (bw != 0 && fw != 0) {
+                    double bsum = (double)bsv[t];
+                    double fsum = total_sum - bsum;
+                    double bm = bsum / (double)bw;
+                    double fm = fsum / (double)fw;
+                    double diff = bm - fm;
+                    double mds = diff * diff;
+                    v = (double)bw * (double)fw * mds;
+                }
+                var[t] = v;
+            }
+            __syncthreads();
+            if (t == 0) {
+                double largest = 0.0;
+                uint32_t best = 0;
+                for (int i = 0; i < 256; i++)
+                    if (var[i] > largest) { largest = var[i]; best = (uint32_t)i; }
+                otsu_level = best;
+            }
+            __syncthreads();
+            const uint32_t level = otsu_level;
+            // ---- threshold(Binary) + resize(Triangle): vertical pass into f32, then horizontal pass ----
+            for (uint32_t i = t; i < ms * ps; i += kThreads) {
+                const uint32_t oy = i / ps, x = i % ps;
+                const int left = meta[2 * oy], cnt = meta[2 * oy + 1];
+                const float *wv = taps + oy * max_taps;
+                float acc = 0.0f;
+                for (int k = 0; k < cnt; k++) {
+                    float s = patch[(size_t)(left + k) * ps + x] > level ? 255.0f : 0.0f;
+                    acc += s * wv[k];
+                }
+                tmp[i] = acc;
+            }
+            __syncthreads();
+            for (uint32_t i = t; i < ms * ms; i += kThreads) {
+                const uint32_t y = i / ms, ox = i % ms;
+                const int left = meta[2 * ox], cnt = meta[2 * ox + 1];
+                const float *wv = taps + ox * max_taps;
+                float acc = 0.0f;
+                for (int k = 0; k < cnt; k++) acc += tmp[y * ps + left + k] * wv[k];
+                float c = acc < 0.0f ? 0.0f : (acc > 255.0f ? 255.0f : acc);
+                reduced[i] = (uint8_t)roundf(c);
+            }
+            __syncthreads();
+        } else if (t == 0) {
+            // the reference decodes GrayImage::new(1,1): level 0, every cell 0 (src/aruco.rs:256)
+            otsu_level = 0;
+            for (uint32_t i = 0; i < ms * ms; i++) reduced[i] = 0;
+        }
+        if (p.patches) {
+            uint8_t *dst = p.patches + (size_t)q * np;
+            for (uint32_t i = t; i < np; i += kThreads) dst[i] = ok ? patch[i] : 0;
+        }
+        __syncthreads();
+        // ---- bits, border test, 4 rotations (src/aruco.rs:276-310) ----
+        if (t == 0) {
+            uint8_t bits[16 * 16], rot[16 * 16];
+            for (uint32_t i = 0; i < ms * ms; i++) bits[i] = reduced[i] > 127;
+            int good = 1;
+            const uint32_t end = ms ? ms - 1 : 0;
+            for (uint32_t i = 0; i < ms; i++)
+                if (bits[i * ms] || bits[i * ms + end] || bits[i] || bits[end * ms + i]) good = 0;
+            if (good) {
+                for (int r = 0; r < 4; r++) {
+                    uint64_t b = 0;
+                    for (uint32_t y = 1; y + 1 < ms; y++)
+                        for (uint32_t x = 1; x + 1 < ms; x++) {
+                            if (bits[y * ms + x]) b |= 1;
+                            b = (b << 1) | (b >> 63);
+                        }
+                    b = (b >> 1) | (b << 63);
+                    codes[r] = b;
+                    uint32_t rr = 0;  // rotate_bit_matrix: new[i][j] = old[j][W-1-i]
+                    for (int x = (int)ms - 1; x >= 0; x--, rr++)
+                        for (uint32_t y = 0; y < ms; y++) rot[rr * ms + y] = bits[y * ms + (uint32_t)x];
+                    for (uint32_t i = 0; i < ms * ms; i++) bits[i] = rot[i];
+                }
+            } else {
+                codes[0] = codes[1] = codes[2] = codes[3] = 0;
+            }
+            has_codes = good;
+        }
+        __syncthreads();
+        // ---- dictionary match: min over (dist, rotation, index) ----
+        uint32_t key = 0xffffffffu;
+        if (has_codes) {
+            const uint64_t c0 = codes[0], c1 = codes[1], c2 = codes[2], c3 = codes[3];
+            for (uint32_t i = t; i < p.n_codes; i += kThreads) {
+                const uint64_t d = dict[i];
+                uint32_t k0 = ((uint32_t)__popcll(d ^ c0) << 24) | (0u << 22) | i;
+                uint32_t k1 = ((uint32_t)__popcll(d ^ c1) << 24) | (1u << 22) | i;
+                uint32_t k2 = ((uint32_t)__popcll(d ^ c2) << 24) | (2u << 22) | i;
+                uint32_t k3 = ((uint32_t)__popcll(d ^ c3) << 24) | (3u << 22) | i;
+                key = min(key, min(min(k0, k1), min(k2, k3)));
+            }
+        }
+        key = __reduce_min_sync(0xffffffffu, key);
+        if ((t & 31) == 0) red[t >> 5] = key;
+        __syncthreads();
+        if (t == 0) {
+            uint32_t k = red[0];
+            for (int i = 1; i < kThreads / 32; i++) k = min(k, red[i]);
+            out.has_codes = (uint8_t)has_codes;
+            out.otsu = (uint8_t)otsu_level;
+            out.reserved[0] = out.reserved[1] = 0;
+            for (int r = 0; r < 4; r++) out.codes[r] = codes[r];
+            uint32_t dist = 255, rotation = 0, index = 0;  // find_nearest on an empty list returns (0, 255)
+            if (has_codes && p.n_codes) { dist = k >> 24; rotation = (k >> 22) & 3; index = k & 0x3fffffu; }
+            out.id = index;
+            out.rotation = (uint8_t)rotation;
+            out.hamming_distance = (uint8_t)dist;
+            out.accepted = (uint8_t)(has_codes && (!p.filter_high_bit_errors || dist < p.tau));
+            p.decodes[q] = out;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+size_t k2_smem_bytes(uint32_t ps, uint32_t ms, uint32_t n_codes) {
+    ResizeTaps tp = make_resize_taps(ps, ms);
+    size_t b = (size_t)n_codes * 8 + (size_t)ms * ps * 4 + (size_t)ms * tp.max_taps * 4 + (size_t)2 * ms * 4 + 3 * 256 * 4;
+    b = (b + 7) & ~(size_t)7;
+    b += 256 * 8 + 8 * 4 + ((ms * ms + 3) & ~3u) + (size_t)ps * ps;
+    return b + 16;
+}
+
+cudaError_t k2_decode(const K2Params &p, cudaStream_t stream) {
+    if (p.n_quads == 0) return cudaSuccess;
+    if (p.mark_size > 16 || p.mark_size < 3 || p.patch_size == 0 || p.n_codes >= (1u << 22)) return cudaErrorInvalidValue;
+    ResizeTaps tp = make_resize_taps(p.patch_size, p.mark_size);
+    // keep `var` 8-byte aligned: pad the float/int region to a multiple of 8 bytes by construction
+    size_t smem = k2_smem_bytes(p.patch_size, p.mark_size, p.n_codes);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint32_t grid = p.n_quads < (uint32_t)(2 * sms) ? p.n_quads : (uint32_t)(2 * sms);
+    k2_kernel<<<grid, kThreads, smem, stream>>>(p, tp.max_taps);
+    return cudaGetLastError();
+}
+
+// image::imageops::resize sampling taps for FilterType::Triangle (support 1.0), f32, reference expression order.
+ResizeTaps make_resize_taps(uint32_t n_in, uint32_t n_out) {
+    ResizeTaps t;
+    t.n_in = n_in; t.n_out = n_out; t.max_taps = 0;
+    std::vector<std::vector<float>> rows(n_out);
+    t.meta.resize(2 * (size_t)n_out);
+    const float ratio = (float)n_in / (float)n_out;
+    const float sratio = ratio < 1.0f ? 1.0f : ratio;
+    const float src_support = 1.0f * sratio;
+    for (uint32_t o = 0; o < n_out; o++) {
+        float input = ((float)o + 0.5f) * ratio;
+        long long left = (long long)floorf(input - src_support);
+        if (left < 0) left = 0;
+        if (left > (long long)n_in - 1) left = (long long)n_in - 1;
+        long long right = (long long)ceilf(input + src_support);
+        if (right < left + 1) right = left + 1;
+        if (right > (long long)n_in) right = (long long)n_in;
+        input = input - 0.5f;
+        float sum = 0.0f;
+        for (long long i = left; i < right; i++) {
+            float xx = ((float)i - input) / sratio;
+            float wv = fabsf(xx) < 1.0f ? 1.0f - fabsf(xx) : 0.0f;
+            rows[o].push_back(wv);
+            sum += wv;
+        }
+        for (float &wv : rows[o]) wv /= sum;
+        t.meta[2 * o] = (int)left;
+        t.meta[2 * o + 1] = (int)(right - left);
+        if (rows[o].size() > t.max_taps) t.max_taps = (uint32_t)rows[o].size();
+    }
+    t.weights.assign((size_t)n_out * t.max_taps, 0.0f);
+    for (uint32_t o = 0; o < n_out; o++)
+        for (size_t i = 0; i < rows[o].size(); i++) t.weights[(size_t)o * t.max_taps + i] = rows[o][i];
+    return t;
+}
+
+}  // namespace a3

@@ -1,0 +1,172 @@
+/*
+ * aruco3_b200 — C ABI of the B200-native detection path.
+ *
+ * This is the boundary a Rust `-sys` crate (or any FFI) binds to replace the reference's
+ * `Detector { config, dictionary }.detect(image) -> Detection`
+ * (/root/reference/src/aruco.rs:46-52, re-exported at /root/reference/src/lib.rs:6-7).
+ * The reference has no FFI of its own (pure Rust); every entry point below cites the Rust item it
+ * stands in for.  Plain pointers and sizes only; no C++ or torch types.  See INTEGRATION.md for the
+ * Rust-side binding.
+ *
+ * Conventions
+ *   - every function returns a3_status (0 = ok) unless stated; a3_last_error() gives the text of the
+ *     calling thread's last failure.  Nothing aborts or throws across this boundary (the reference
+ *     panics instead: unknown dictionary name src/dictionaries.rs:144, threshold_window == 0 and
+ *     epsilon <= 0 inside imageproc).
+ *   - there is NO CPU fallback: the pixel and decode stages run on the CUDA device or fail with
+ *     A3_ERR_CUDA.
+ *   - frames are tightly interleaved 8-bit pixels, row-major (`image::RgbImage` / `RgbaImage` /
+ *     `GrayImage` buffers); `pitch` = bytes per row, `frame_stride` = bytes between frames.
+ *   - a detector handle is thread-compatible, not thread-safe: one per (host thread, device).
+ */
+#ifndef ARUCO3_B200_H
+#define ARUCO3_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t a3_status;
+enum {
+    A3_OK = 0,
+    A3_ERR_INVALID_ARGUMENT = 1,   /* null pointer, zero size, threshold_window == 0, epsilon <= 0 ... */
+    A3_ERR_UNKNOWN_DICTIONARY = 2, /* the reference panics here (src/dictionaries.rs:144) */
+    A3_ERR_CUDA = 3,               /* no device / kernel or copy failed; text in a3_last_error() */
+    A3_ERR_CAPACITY = 4,           /* caller-provided output array too small; counts are still returned */
+    A3_ERR_UNSUPPORTED = 5,
+    A3_ERR_OUT_OF_MEMORY = 6
+};
+
+/* DynamicImage variants accepted at the boundary (callers pass RgbImage.into() / RgbaImage.into(),
+ * benches/detect_markers.rs:49, examples/webcam_kamera.rs:56); Luma8 passes through into_luma8. */
+typedef enum { A3_FMT_RGB8 = 0, A3_FMT_RGBA8 = 1, A3_FMT_LUMA8 = 2 } a3_format;
+typedef enum { A3_MEM_HOST = 0, A3_MEM_DEVICE = 1 } a3_mem_kind;
+
+/* DetectorConfig, field for field (src/aruco.rs:23-30); defaults src/aruco.rs:32-43. */
+typedef struct a3_config {
+    uint32_t threshold_window;              /* 7    */
+    double contour_simplification_epsilon;  /* 0.05 */
+    float min_side_length_factor;           /* 0.2  */
+    float min_corner_separation_factor;     /* 0.1  */
+    uint32_t homography_sample_size;        /* 49   */
+    uint8_t filter_high_bit_errors;         /* 1    */
+} a3_config;
+
+/* ARDictionary (src/dictionaries.rs:22-28). `tau` is the effective tau (dictionaries.rs:124). */
+typedef struct a3_dictionary {
+    uint8_t num_bits;
+    uint8_t tau;
+    uint32_t n_codes;
+    const uint64_t *codes; /* static storage inside the library */
+} a3_dictionary;
+
+/* Marker (src/aruco.rs:8-13) plus the frame / candidate it came from and the winning rotation.
+ * corners = x0,y0,...,x3,y3 after rotate_left(rotation) (src/aruco.rs:97-103). */
+typedef struct a3_marker {
+    uint64_t id;
+    uint64_t code;
+    uint32_t corners[8];
+    uint32_t frame;
+    uint32_t candidate;
+    uint8_t hamming_distance;
+    uint8_t rotation;
+    uint8_t reserved[6];
+} a3_marker;
+
+/* One decoded candidate (every quad, accepted or not): the intermediates of
+ * homography_to_code_permutations (src/aruco.rs:263-313) and of the match loop (src/aruco.rs:75-96). */
+typedef struct a3_decode {
+    uint64_t codes[4];     /* valid when has_codes */
+    uint64_t id;           /* index into code_list of the best match (valid when has_codes) */
+    uint8_t has_codes;     /* Some / None */
+    uint8_t homography_ok; /* 0: the reference pushed a 1x1 image (src/aruco.rs:256) */
+    uint8_t otsu;          /* otsu_level of the patch */
+    uint8_t rotation;
+    uint8_t hamming_distance;
+    uint8_t accepted;      /* passed `found_any && (!filter || dist < tau)` (src/aruco.rs:96) */
+    uint8_t reserved[2];
+} a3_decode;
+
+/* Counters + device-side stage times of the last call (CUDA events; host stage by steady_clock). */
+typedef struct a3_stats {
+    uint64_t n_frames, n_contours, n_contour_points, n_candidates_before_discard, n_candidates, n_markers;
+    double ms_h2d, ms_pixel_kernel, ms_mask_d2h, ms_host_quads, ms_decode_kernel, ms_d2h, ms_total;
+    uint32_t pixel_kernel_launches, decode_kernel_launches, host_threads, reserved;
+} a3_stats;
+
+/* Optional per-call outputs of a3_detect_batch (all may be NULL). Host pointers; tightly packed. */
+typedef struct a3_outputs {
+    uint8_t *grey;              /* n*h*w      Detection.grey                              */
+    uint8_t *mask;              /* n*h*w      the thresholded image (0/255)               */
+    uint32_t *candidates;       /* cand_capacity*8  Detection.candidates, frame-major     */
+    uint32_t *candidate_frame;  /* cand_capacity    frame index of each candidate         */
+    uint8_t *homographies;      /* cand_capacity*hs*hs  Detection.homographies (zeros when !homography_ok) */
+    a3_decode *decodes;         /* cand_capacity                                          */
+    uint32_t cand_capacity;
+    uint32_t n_candidates;      /* out */
+    uint32_t *frame_marker_offsets; /* n+1: markers of frame f are [off[f], off[f+1]) (may be NULL) */
+} a3_outputs;
+
+typedef struct a3_detector a3_detector;
+
+/* ---- library ---- */
+const char *a3_version(void);
+const char *a3_last_error(void);
+const char *a3_status_string(a3_status s);
+int32_t a3_device_count(void); /* 0 when no CUDA device is usable */
+
+/* ---- dictionaries (src/dictionaries.rs) ---- */
+int32_t a3_dictionary_count(void);
+const char *a3_dictionary_name(int32_t index);                                    /* get_dictionary_names :147-149 */
+a3_status a3_dictionary_by_name(const char *name, a3_dictionary *out);             /* new_from_named_dict :140-145  */
+uint8_t a3_dictionary_mark_size(const a3_dictionary *d);                           /* get_mark_size :154-156        */
+uint8_t a3_hamming_distance(uint64_t a, uint64_t b);                               /* src/lib.rs:11-21              */
+void a3_find_nearest(const a3_dictionary *d, uint64_t bits, uint64_t *index, uint8_t *dist); /* :160-196            */
+int32_t a3_try_find_nearest(const a3_dictionary *d, uint64_t bits, uint64_t *index, uint8_t *dist); /* :200-207      */
+uint8_t a3_make_binary_image(const a3_dictionary *d, uint64_t marker_id, uint8_t *bits, uint32_t capacity,
+                             uint32_t *n_bits);                                    /* make_binary_image :212-232    */
+
+/* ---- detector ---- */
+void a3_config_default(a3_config *cfg);                                            /* Default, src/aruco.rs:32-43   */
+a3_status a3_detector_create(const a3_config *cfg, const a3_dictionary *dict, int32_t device, a3_detector **out);
+void a3_detector_destroy(a3_detector *det);
+/* number of host threads used for the contour / quad stage (default: all cores, capped at 64) */
+a3_status a3_detector_set_host_threads(a3_detector *det, uint32_t threads);
+
+/* Detector::detect over a batch of n equally sized frames (src/aruco.rs:52-121 per frame).
+ * markers are written frame-major, in candidate order within a frame (the order of Detection.markers).
+ * Returns A3_ERR_CAPACITY (with *n_markers = the number found) when marker_capacity is too small. */
+a3_status a3_detect_batch(a3_detector *det, const void *frames, a3_format format, a3_mem_kind mem, uint32_t n,
+                          uint32_t width, uint32_t height, size_t pitch, size_t frame_stride, a3_marker *markers,
+                          uint32_t marker_capacity, uint32_t *n_markers, a3_outputs *outputs, a3_stats *stats);
+
+/* ---- stage entry points (parity probes; the same kernels a3_detect_batch launches) ---- */
+
+/* into_luma8 + adaptive_threshold (src/aruco.rs:60-61). All pointers are DEVICE pointers when
+ * mem == A3_MEM_DEVICE (no copies, launches on `cuda_stream`, a cudaStream_t or NULL, and returns
+ * without synchronising), HOST pointers otherwise (copies in and out, synchronous).
+ * grey / mask: n*h*w bytes each; mask_bits: n*h*ceil(w/32) little-endian words, bit (x&31) of word x>>5.
+ * Any of the three outputs may be NULL. */
+a3_status a3_gray_threshold_batch(a3_detector *det, const void *frames, a3_format format, a3_mem_kind mem,
+                                  uint32_t n, uint32_t width, uint32_t height, size_t pitch, size_t frame_stride,
+                                  uint8_t *grey, uint8_t *mask, uint32_t *mask_bits, void *cuda_stream);
+
+/* find_contours + contours_to_candidates + enforce_clockwise_corners + discard_too_near
+ * (src/aruco.rs:64-69) on one host mask (0 / non-zero bytes). Host stage of the product. */
+a3_status a3_quads_from_mask(const a3_config *cfg, const uint8_t *mask, uint32_t width, uint32_t height,
+                             uint32_t *quads, uint32_t quad_capacity, uint32_t *n_quads, a3_stats *stats);
+
+/* extract_homographies + homography_to_code_permutations + the match loop (src/aruco.rs:72-113) for
+ * n_quads candidates over grey frames. HOST pointers; quads n_quads*8, quad_frame n_quads (frame index of
+ * each quad; NULL = all frame 0); patches (optional) n_quads*hs*hs. */
+a3_status a3_decode_candidates(a3_detector *det, const uint8_t *grey, uint32_t n_frames, uint32_t width,
+                               uint32_t height, const uint32_t *quads, const uint32_t *quad_frame, uint32_t n_quads,
+                               a3_decode *decodes, uint8_t *patches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARUCO3_B200_H */

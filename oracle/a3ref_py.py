@@ -1,0 +1,237 @@
+"""ctypes view of oracle/liba3ref.so — TEST INFRASTRUCTURE ONLY (see oracle/a3ref.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+FMT_RGB8, FMT_RGBA8, FMT_LUMA8 = 0, 1, 2
+
+
+class Config(C.Structure):
+    _fields_ = [("threshold_window", C.c_uint32), ("contour_simplification_epsilon", C.c_double),
+                ("min_side_length_factor", C.c_float), ("min_corner_separation_factor", C.c_float),
+                ("homography_sample_size", C.c_uint32), ("filter_high_bit_errors", C.c_uint8)]
+
+
+class Dictionary(C.Structure):
+    _fields_ = [("num_bits", C.c_uint8), ("tau", C.c_uint8), ("n_codes", C.c_uint32),
+                ("codes", C.POINTER(C.c_uint64))]
+
+
+class Marker(C.Structure):
+    _fields_ = [("id", C.c_uint64), ("code", C.c_uint64), ("corners", C.c_uint32 * 8), ("candidate", C.c_uint32),
+                ("hamming_distance", C.c_uint8), ("rotation", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
+class Contours(C.Structure):
+    _fields_ = [("n_contours", C.c_uint32), ("n_points", C.c_uint32), ("offsets", C.POINTER(C.c_uint32)),
+                ("points", C.POINTER(C.c_uint32)), ("is_outer", C.POINTER(C.c_uint8))]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("n_contours", "n_contour_points", "reject_point_count", "reject_convexity",
+                                          "reject_edge_length", "n_candidates_before_discard", "n_candidates",
+                                          "n_border_pass", "n_markers")] + \
+               [(n, C.c_double) for n in ("ms_gray", "ms_threshold", "ms_contours", "ms_quads", "ms_warp", "ms_decode",
+                                          "ms_total")]
+
+
+class Detection(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("grey", C.POINTER(C.c_uint8)),
+                ("mask", C.POINTER(C.c_uint8)), ("n_candidates", C.c_uint32), ("candidates", C.POINTER(C.c_uint32)),
+                ("patch_size", C.c_uint32), ("homographies", C.POINTER(C.c_uint8)),
+                ("homography_ok", C.POINTER(C.c_uint8)), ("otsu", C.POINTER(C.c_uint8)),
+                ("has_codes", C.POINTER(C.c_uint8)), ("codes", C.POINTER(C.c_uint64)), ("n_markers", C.c_uint32),
+                ("markers", C.POINTER(Marker)), ("stats", Stats)]
+
+
+_lib = None
+
+
+def build() -> Path:
+    subprocess.run(["make", "-s", "-C", str(HERE)], check=True)
+    return HERE / "liba3ref.so"
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = HERE / "liba3ref.so"
+        if not so.exists():
+            build()
+        L = C.CDLL(str(so))
+        L.a3ref_dictionary_name.restype = C.c_char_p
+        L.a3ref_hamming_distance.restype = C.c_uint8
+        L.a3ref_hamming_distance.argtypes = [C.c_uint64, C.c_uint64]
+        L.a3ref_calculate_tau.restype = C.c_uint8
+        L.a3ref_mark_size.restype = C.c_uint8
+        L.a3ref_find_nearest.argtypes = [C.POINTER(Dictionary), C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
+        L.a3ref_try_find_nearest.argtypes = L.a3ref_find_nearest.argtypes
+        L.a3ref_make_binary_image.argtypes = [C.POINTER(Dictionary), C.c_uint64, C.c_void_p, C.c_uint32]
+        L.a3ref_make_binary_image.restype = C.c_uint32
+        L.a3ref_to_luma8.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p]
+        L.a3ref_adaptive_threshold.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.a3ref_find_contours.restype = C.POINTER(Contours)
+        L.a3ref_find_contours.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.a3ref_contours_free.argtypes = [C.POINTER(Contours)]
+        L.a3ref_approximate_polygon_dp.restype = C.c_size_t
+        L.a3ref_approximate_polygon_dp.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_void_p]
+        L.a3ref_convex_hull.restype = C.c_size_t
+        L.a3ref_convex_hull.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.a3ref_contours_to_candidates.restype = C.c_uint32
+        L.a3ref_contours_to_candidates.argtypes = [C.POINTER(Contours), C.c_uint32, C.c_double,
+                                                   C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(Stats)]
+        L.a3ref_enforce_clockwise_corners.argtypes = [C.c_void_p, C.c_uint32]
+        L.a3ref_discard_too_near.restype = C.c_uint32
+        L.a3ref_discard_too_near.argtypes = [C.c_void_p, C.c_uint32, C.c_float]
+        L.a3ref_perimeter.restype = C.c_float
+        L.a3ref_perimeter.argtypes = [C.c_void_p]
+        L.a3ref_projection_from_control_points.argtypes = [C.c_void_p] * 4 + [C.POINTER(C.c_int)]
+        L.a3ref_extract_homography.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.a3ref_otsu_level.restype = C.c_uint8
+        L.a3ref_otsu_level.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.a3ref_resize_triangle.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.a3ref_homography_to_code_permutations.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint8, C.c_void_p,
+                                                            C.c_void_p, C.c_void_p]
+        L.a3ref_rotate_bit_matrix.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.a3ref_default_config.argtypes = [C.POINTER(Config)]
+        L.a3ref_detect.restype = C.POINTER(Detection)
+        L.a3ref_detect.argtypes = [C.POINTER(Config), C.POINTER(Dictionary), C.c_void_p, C.c_int, C.c_uint32,
+                                   C.c_uint32, C.c_size_t]
+        L.a3ref_detection_free.argtypes = [C.POINTER(Detection)]
+        L.a3ref_detect_many.restype = C.c_uint64
+        L.a3ref_detect_many.argtypes = [C.POINTER(Config), C.POINTER(Dictionary), C.c_void_p, C.c_int, C.c_uint32,
+                                        C.c_uint32, C.c_uint32, C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(Stats)]
+        _lib = L
+    return _lib
+
+
+def default_config(**overrides) -> Config:
+    cfg = Config()
+    lib().a3ref_default_config(C.byref(cfg))
+    for k, v in overrides.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def dictionary(name: str) -> Dictionary:
+    d = Dictionary()
+    if lib().a3ref_dictionary_by_name(name.encode(), C.byref(d)) != 0:
+        raise KeyError(name)
+    return d
+
+
+def find_nearest(d: Dictionary, bits: int):
+    idx, dist = C.c_uint64(), C.c_uint8()
+    lib().a3ref_find_nearest(C.byref(d), bits, C.byref(idx), C.byref(dist))
+    return idx.value, dist.value
+
+
+def try_find_nearest(d: Dictionary, bits: int):
+    idx, dist = C.c_uint64(), C.c_uint8()
+    ok = lib().a3ref_try_find_nearest(C.byref(d), bits, C.byref(idx), C.byref(dist))
+    return (idx.value, dist.value) if ok else None
+
+
+def _fmt_of(img: np.ndarray) -> int:
+    if img.ndim == 2:
+        return FMT_LUMA8
+    return {3: FMT_RGB8, 4: FMT_RGBA8}[img.shape[2]]
+
+
+def to_luma8(img: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img)
+    h, w = img.shape[:2]
+    out = np.empty((h, w), np.uint8)
+    lib().a3ref_to_luma8(img.ctypes.data, _fmt_of(img), w, h, img.strides[0], out.ctypes.data)
+    return out
+
+
+def adaptive_threshold(grey: np.ndarray, radius: int = 7) -> np.ndarray:
+    grey = np.ascontiguousarray(grey)
+    out = np.empty_like(grey)
+    lib().a3ref_adaptive_threshold(grey.ctypes.data, grey.shape[1], grey.shape[0], radius, out.ctypes.data)
+    return out
+
+
+def find_contours(mask: np.ndarray):
+    """-> list of int arrays [n,2] (x,y), list of is_outer flags."""
+    mask = np.ascontiguousarray(mask)
+    c = lib().a3ref_find_contours(mask.ctypes.data, mask.shape[1], mask.shape[0])
+    cc = c.contents
+    offs = np.ctypeslib.as_array(cc.offsets, (cc.n_contours + 1,)).copy()
+    pts = np.ctypeslib.as_array(cc.points, (max(cc.n_points, 1), 2))[:cc.n_points].copy()
+    outer = np.ctypeslib.as_array(cc.is_outer, (max(cc.n_contours, 1),))[:cc.n_contours].copy() if cc.n_contours else np.zeros(0, np.uint8)
+    lib().a3ref_contours_free(c)
+    return [pts[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)], outer
+
+
+def candidates_from_mask(mask: np.ndarray, cfg: Config | None = None):
+    """find_contours -> contours_to_candidates -> enforce_clockwise -> discard_too_near; -> uint32 [n,8]."""
+    cfg = cfg or default_config()
+    mask = np.ascontiguousarray(mask)
+    h, w = mask.shape
+    mn = min(w, h)
+    min_edge = int(np.float32(mn) * np.float32(cfg.min_side_length_factor))
+    min_sep = float(np.float32(mn) * np.float32(cfg.min_corner_separation_factor))
+    c = lib().a3ref_find_contours(mask.ctypes.data, w, h)
+    quads = C.POINTER(C.c_uint32)()
+    st = Stats()
+    n = lib().a3ref_contours_to_candidates(c, min_edge, cfg.contour_simplification_epsilon, C.byref(quads), C.byref(st))
+    lib().a3ref_contours_free(c)
+    lib().a3ref_enforce_clockwise_corners(quads, n)
+    n = lib().a3ref_discard_too_near(quads, n, min_sep)
+    out = np.ctypeslib.as_array(quads, (max(n, 1), 8))[:n].copy()
+    C.CDLL(None).free(quads)
+    return out
+
+
+class Result:
+    """Python copy of a3ref_detection (all stages)."""
+
+    def __init__(self, det: Detection):
+        w, h, n, ps = det.width, det.height, det.n_candidates, det.patch_size
+        arr = np.ctypeslib.as_array
+        self.grey = arr(det.grey, (h, w)).copy()
+        self.mask = arr(det.mask, (h, w)).copy()
+        self.candidates = arr(det.candidates, (max(n, 1), 8))[:n].copy()
+        self.homographies = arr(det.homographies, (max(n, 1), ps, ps))[:n].copy()
+        self.homography_ok = arr(det.homography_ok, (max(n, 1),))[:n].copy()
+        self.otsu = arr(det.otsu, (max(n, 1),))[:n].copy()
+        self.has_codes = arr(det.has_codes, (max(n, 1),))[:n].copy()
+        self.codes = arr(det.codes, (max(n, 1), 4))[:n].copy()
+        self.markers = [dict(id=int(m.id), code=int(m.code), corners=[int(v) for v in m.corners],
+                             candidate=int(m.candidate), hamming_distance=int(m.hamming_distance),
+                             rotation=int(m.rotation)) for m in (det.markers[i] for i in range(det.n_markers))]
+        self.stats = {f: getattr(det.stats, f) for f, _ in Stats._fields_}
+
+
+def detect(img: np.ndarray, dict_name: str = "ARUCO", cfg: Config | None = None) -> Result:
+    cfg = cfg or default_config()
+    d = dictionary(dict_name)
+    img = np.ascontiguousarray(img)
+    h, w = img.shape[:2]
+    p = lib().a3ref_detect(C.byref(cfg), C.byref(d), img.ctypes.data, _fmt_of(img), w, h, img.strides[0])
+    res = Result(p.contents)
+    lib().a3ref_detection_free(p)
+    return res
+
+
+def detect_many(frames: np.ndarray, dict_name: str = "ARUCO", cfg: Config | None = None, threads: int = 1):
+    """Frame-parallel CPU baseline; -> (total markers, summed stats dict)."""
+    cfg = cfg or default_config()
+    d = dictionary(dict_name)
+    frames = np.ascontiguousarray(frames)
+    n, h, w = frames.shape[:3]
+    fmt = FMT_LUMA8 if frames.ndim == 3 else {3: FMT_RGB8, 4: FMT_RGBA8}[frames.shape[3]]
+    st = Stats()
+    total = lib().a3ref_detect_many(C.byref(cfg), C.byref(d), frames.ctypes.data, fmt, n, w, h, frames.strides[1],
+                                    frames.strides[0], threads, C.byref(st))
+    return int(total), {f: getattr(st, f) for f, _ in Stats._fields_}
