@@ -55,6 +55,11 @@ class A3Outputs(C.Structure):
                 ("n_candidates", C.c_uint32), ("frame_marker_offsets", C.c_void_p)]
 
 
+class A3K1Tuning(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("strip_cols", "seg_rows", "force_no_tma", "force_generic", "tma_rows", "tma_stages",
+                                          "chunk_frames", "reserved")]
+
+
 class A3Error(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"aruco3_b200 status {status}: {message}")
@@ -108,6 +113,7 @@ def lib():
     L.a3_detector_destroy.restype = None
     L.a3_detector_destroy.argtypes = [vp]
     L.a3_detector_set_host_threads.argtypes = [vp, u32]
+    L.a3_detector_set_k1_tuning.argtypes = [vp, C.POINTER(A3K1Tuning)]
     L.a3_detect_batch.argtypes = [vp, vp, C.c_int, C.c_int, u32, u32, u32, sz, sz, vp, u32, C.POINTER(u32),
                                   C.POINTER(A3Outputs), C.POINTER(A3Stats)]
     L.a3_gray_threshold_batch.argtypes = [vp, vp, C.c_int, C.c_int, u32, u32, u32, sz, sz, vp, vp, vp, vp]

@@ -80,6 +80,9 @@ struct a3_detector {
     uint32_t mark_size = 0;
     uint32_t max_taps = 0;
     a3::Slot slot[2];
+    a3::K1Tuning k1_tuning{};
+    bool has_tuning = false;
+    uint32_t chunk_override = 0;
     a3::DevBuf<uint64_t> d_codes;
     a3::DevBuf<float> d_taps;
     a3::DevBuf<int> d_meta;
@@ -233,6 +236,21 @@ a3_status a3_detector_set_host_threads(a3_detector *d, uint32_t threads) {
     return A3_OK;
 }
 
+a3_status a3_detector_set_k1_tuning(a3_detector *d, const a3_k1_tuning *t) {
+    if (!d) return fail(A3_ERR_INVALID_ARGUMENT, "a3_detector_set_k1_tuning: null detector");
+    d->has_tuning = t != nullptr;
+    d->k1_tuning = K1Tuning{};
+    d->chunk_override = 0;
+    if (t) {
+        if (t->tma_rows != 0 && t->tma_rows != 1 && t->tma_rows != 2 && t->tma_rows != 4) return fail(A3_ERR_INVALID_ARGUMENT, "tma_rows must be 0, 1, 2 or 4");
+        if (t->tma_stages > 8) return fail(A3_ERR_INVALID_ARGUMENT, "tma_stages must be <= 8");
+        d->k1_tuning.strip_cols = t->strip_cols; d->k1_tuning.seg_rows = t->seg_rows; d->k1_tuning.force_no_tma = (int)t->force_no_tma;
+        d->k1_tuning.force_generic = (int)t->force_generic; d->k1_tuning.tma_rows = t->tma_rows; d->k1_tuning.tma_stages = t->tma_stages;
+        d->chunk_override = t->chunk_frames;
+    }
+    return A3_OK;
+}
+
 a3_status a3_gray_threshold_batch(a3_detector *d, const void *frames, a3_format format, a3_mem_kind mem, uint32_t n,
                                   uint32_t w, uint32_t h, size_t pitch, size_t frame_stride, uint8_t *grey, uint8_t *mask,
                                   uint32_t *mask_bits, void *cuda_stream) {
@@ -246,7 +264,7 @@ a3_status a3_gray_threshold_batch(a3_detector *d, const void *frames, a3_format 
     p.format = format; p.n = n; p.w = w; p.h = h; p.pitch = pitch; p.frame_stride = frame_stride; p.radius = d->cfg.threshold_window;
     if (mem == A3_MEM_DEVICE) {
         p.src = static_cast<const uint8_t *>(frames); p.grey = grey; p.mask = mask; p.bits = mask_bits;
-        A3_CUDA(k1_gray_threshold(p, nullptr, static_cast<cudaStream_t>(cuda_stream), nullptr));
+        A3_CUDA(k1_gray_threshold(p, d->has_tuning ? &d->k1_tuning : nullptr, static_cast<cudaStream_t>(cuda_stream), nullptr));
         return A3_OK;
     }
     // host pointers: stage through slot 0, chunk by chunk, synchronously
@@ -263,7 +281,7 @@ a3_status a3_gray_threshold_batch(a3_detector *d, const void *frames, a3_format 
         if (mask_bits) A3_CUDA(s.d_bits.reserve(c * wpr * h));
         p.src = s.d_src.p; p.n = c;
         p.grey = grey ? s.d_grey.p : nullptr; p.mask = mask ? s.d_mask.p : nullptr; p.bits = mask_bits ? s.d_bits.p : nullptr;
-        A3_CUDA(k1_gray_threshold(p, nullptr, s.stream, nullptr));
+        A3_CUDA(k1_gray_threshold(p, d->has_tuning ? &d->k1_tuning : nullptr, s.stream, nullptr));
         if (grey) A3_CUDA(cudaMemcpyAsync(grey + f0 * px, s.d_grey.p, c * px, cudaMemcpyDeviceToHost, s.stream));
         if (mask) A3_CUDA(cudaMemcpyAsync(mask + f0 * px, s.d_mask.p, c * px, cudaMemcpyDeviceToHost, s.stream));
         if (mask_bits) A3_CUDA(cudaMemcpyAsync(mask_bits + f0 * wpr * h, s.d_bits.p, c * wpr * h * 4, cudaMemcpyDeviceToHost, s.stream));
@@ -339,7 +357,8 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
     A3_CUDA(cudaSetDevice(d->device));
     const double t_begin = now_ms();
     const size_t px = (size_t)w * h, wpr = (w + 31) / 32, np = (size_t)d->cfg.homography_sample_size * d->cfg.homography_sample_size;
-    const uint32_t chunk = chunk_frames(n, w, h, bpp);
+    uint32_t chunk = chunk_frames(n, w, h, bpp);
+    if (d->chunk_override) chunk = d->chunk_override < n ? d->chunk_override : n;
     const uint32_t nchunks = (n + chunk - 1) / chunk;
     const bool want_mask = outs && outs->mask, want_grey = outs && outs->grey, want_patches = outs && outs->homographies;
     a3_stats st;
@@ -365,7 +384,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         K1Params p;
         p.src = src; p.format = format; p.n = cn; p.w = w; p.h = h; p.pitch = pitch; p.frame_stride = frame_stride;
         p.grey = s.d_grey.p; p.mask = want_mask ? s.d_mask.p : nullptr; p.bits = s.d_bits.p; p.radius = d->cfg.threshold_window;
-        A3_CUDA(k1_gray_threshold(p, nullptr, s.stream, nullptr));
+        A3_CUDA(k1_gray_threshold(p, d->has_tuning ? &d->k1_tuning : nullptr, s.stream, nullptr));
         st.pixel_kernel_launches++;
         A3_CUDA(cudaEventRecord(s.ev_k1, s.stream));
         A3_CUDA(cudaMemcpyAsync(s.h_bits.p, s.d_bits.p, cn * wpr * h * 4, cudaMemcpyDeviceToHost, s.stream));

@@ -34,15 +34,21 @@ struct K1Params {
     uint32_t radius;      // threshold_window
 };
 struct K1Tuning {
-    uint32_t strip_cols;  // core columns per strip (multiple of 32); 0 = auto
-    uint32_t seg_rows;    // output rows per CTA; 0 = auto
-    int force_no_tma;     // 1 = take the plain-load path even when the bulk-copy path is legal (tests)
+    uint32_t strip_cols;  // generic kernel: core columns per strip (multiple of 32); 0 = auto
+    uint32_t seg_rows;    // output rows per row segment; 0 = auto
+    int force_no_tma;     // generic kernel: 1 = plain loads even when the bulk-copy path is legal (tests)
+    int force_generic;    // 1 = never take the warp-strip kernel (k1_strips.cu)
+    uint32_t tma_rows;    // warp-strip kernel: rows per TMA box (1, 2 or 4); 0 = default
+    uint32_t tma_stages;  // warp-strip kernel: TMA ring depth per warp; 0 = default
 };
 struct K1LaunchInfo {
     uint32_t grid, block, smem_bytes, strips, segs, strip_cols, seg_rows;
     int tma, specialised_radius;
 };
 cudaError_t k1_gray_threshold(const K1Params &p, const K1Tuning *tuning, cudaStream_t stream, K1LaunchInfo *info);
+// warp-strip fast path (k1_strips.cu): radius 7, 16-byte aligned rows, width % 4 == 0
+bool k1_strips_eligible(const K1Params &p);
+cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t stream, K1LaunchInfo *info);
 
 // ---- K2: per-candidate homography + warp + otsu + resize + bits + dictionary match (k2_decode.cu) ----
 struct K2Params {

@@ -1,0 +1,404 @@
+// K1 (fast path) — fused `into_luma8` + `adaptive_threshold(radius 7)` over a batch of frames, sm_100a.
+//
+// Replaces, bit for bit, /root/reference/src/aruco.rs:60-61 (image 0.25 `into_luma8`, imageproc 0.25
+// `adaptive_threshold`; semantics in SURVEY.md A.1-A.2).  Same results as the generic kernel in k1_threshold.cu, which
+// stays the path for unaligned inputs and other radii.
+//
+// Shape: the kernel was issue-bound, not HBM-bound (ncu, profiles/r01a_*: alu pipe 71 %, dram 20 %), so this version
+// is organised around instructions per pixel and has no block-wide barrier at all:
+//   * a WARP owns a 256-column strip (240 output columns + an 8-column halo on each side) of one row segment of one
+//     frame and marches down it; lane l owns 8 adjacent columns.  Warps never talk to each other.
+//   * RGB rows arrive through TMA: one `cp.async.bulk.tensor.3d` box of {256 px, kRows rows, 1 frame} per step into a
+//     per-warp ring of stages guarded by mbarriers (SASS UTMALDG).  The tensor map is over the byte plane viewed as
+//     u32 [n][h][pitch/4]; out-of-image rows and columns are zero-filled by the TMA unit, which is exactly the
+//     clipped-window semantics of the reference (a clipped window sums only in-image pixels), so the inner loop has
+//     no bounds checks on its loads.
+//   * luma: v = 2126 R + 7152 G + 722 B by two dp4a (byte-split weights), grey = umulhi(v, ceil(2^40/10^4)) >> 8
+//     (exact for every v <= 2 550 000, tests/test_k1_identities.py); no per-channel byte extraction.
+//   * vertical 15-row column sums live in registers as u16 pairs (one IADD3 per pair per row: + new - old); the 15
+//     previous grey rows of the lane's 8 columns are a lane-private shared-memory ring (8 B per lane per row).
+//   * horizontal 15-column sums: the 8 neighbouring column sums on each side come from lanes l-1 / l+1 by warp
+//     shuffles; pair sums by dp2a; a sliding 7-pair window T; S(even) = T + hi(pair before), S(odd) = T + lo(pair after).
+//   * `pix >= floor(S / cnt)`  <=>  `S < (pix + 1) * cnt`  <=>  sign of  S - 256 cnt + (255 - pix) * cnt, evaluated as
+//     dp4a(~pix4, cnt << 8j, dp2a(neighbour pair, T - 256 cnt)): one dp4a picks the pixel's byte and multiplies it,
+//     the sign bits are collected with funnel shifts.  cnt = nx * ny is the clipped window area (<= 225, one byte).
+//   * outputs: grey 8 B / lane / row, optional byte mask 8 B / lane / row, optional 1-bit mask 1 B / lane / row.
+// Algorithmic traffic: 3 B read + 1 B grey + 1 B mask = 5 B / pixel; with the 1-bit mask the kernel
+// moves 3 + 1 + 1/8 B / pixel (+ the row / column halos, served mostly by L2).
+#include <cuda.h>
+
+#include "a3_internal.h"
+
+namespace a3 {
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kRing = 16;          // >= 2 * 7 + 1 grey rows; a power of two so ring slots are `row & 15`
+constexpr int kCore = 240;         // output columns per warp
+constexpr int kHalo = 8;           // >= radius, keeps every lane's 8 columns 8-px aligned
+constexpr uint32_t kMagic = 109951163u;  // ceil(2^40 / 10000)
+
+struct StripArgs {
+    uint8_t *grey, *mask, *bits;   // bits addressed by byte: byte (x >> 3) of row, bit x & 7
+    uint32_t n, w, h;
+    uint32_t nstrips, nsegs, seg_rows, njobs;
+    uint32_t bits_row_bytes;       // 4 * ceil(w / 32)
+    uint32_t stages;               // TMA ring depth per warp
+    int wide_stores;               // w % 8 == 0 and grey / mask bases 8-byte aligned
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "K1S_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra K1S_DONE;\n"
+        "bra K1S_WAIT;\n"
+        "K1S_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA: box {box_x u32, kRows, 1} of the [n][h][pitch/4] u32 view at element coordinates (cx, cy, cz); out-of-range
+// elements are written as zero.
+__device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *map, int cx, int cy, int cz, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(cx), "r"(cy), "r"(cz), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// The TMA unit wants the first byte of a box 16-byte aligned in global memory, so a box starts at the 16-px boundary
+// at or before the warp's first column (x0 = 240 s - 8  ->  240 s - 16) and is 16 px wider than the 256 columns when
+// 8 px are not 16 bytes (RGB8, LUMA8).
+template <int FMT>
+struct Fmt {
+    static constexpr int bpp = FMT == A3_FMT_RGB8 ? 3 : (FMT == A3_FMT_RGBA8 ? 4 : 1);
+    static constexpr int lead_px = FMT == A3_FMT_RGBA8 ? 0 : 8;          // columns staged before x0
+    static constexpr int lead_bytes = lead_px * bpp;                      // 24 / 0 / 8: keeps 8-byte alignment of lane loads
+    static constexpr int row_bytes = (256 + 2 * lead_px) * bpp;           // 816 / 1024 / 272 (multiples of 16)
+    static constexpr int box_x = row_bytes / 4;                           // box width in u32 elements (<= 256)
+};
+
+// grey of one [R,G,B,x] word, left in byte 1 of the result (bytes 2 and 3 are zero)
+__device__ __forceinline__ uint32_t luma_h(uint32_t px) {
+    const uint32_t hi = __dp4a(px, 0x00021b08u, 0u);              // 8 R + 27 G + 2 B
+    const uint32_t v = __dp4a(px, 0x00d2f04eu, hi << 8);          // + 78 R + 240 G + 210 B  = 2126 R + 7152 G + 722 B
+    return __umulhi(v, kMagic);                                    // floor(v / 10000) << 8 | fraction byte
+}
+
+// the lane's 8 greys of one staged row: p01..p67 = u16 pairs (g_even | g_odd << 16), g03 / g47 = packed bytes
+template <int FMT>
+__device__ __forceinline__ void load_grey8(const uint8_t *row, int lane, uint32_t &p01, uint32_t &p23, uint32_t &p45, uint32_t &p67,
+                                           uint32_t &g03, uint32_t &g47) {
+    if constexpr (FMT == A3_FMT_LUMA8) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(row + Fmt<FMT>::lead_bytes + lane * 8);
+        g03 = v.x; g47 = v.y;
+        p01 = __byte_perm(v.x, 0u, 0x4140); p23 = __byte_perm(v.x, 0u, 0x4342);
+        p45 = __byte_perm(v.y, 0u, 0x4140); p67 = __byte_perm(v.y, 0u, 0x4342);
+    } else {
+        uint32_t h[8];
+        if constexpr (FMT == A3_FMT_RGB8) {
+            const uint2 *s = reinterpret_cast<const uint2 *>(row + Fmt<FMT>::lead_bytes + lane * 24);
+            const uint2 a = s[0], b = s[1], c = s[2];
+            // 12 bytes -> 4 pixel words; the 4th byte of each word has weight 0
+            h[0] = luma_h(a.x);
+            h[1] = luma_h(__byte_perm(a.x, a.y, 0x6543));
+            h[2] = luma_h(__byte_perm(a.y, b.x, 0x5432));
+            h[3] = luma_h(b.x >> 8);
+            h[4] = luma_h(b.y);
+            h[5] = luma_h(__byte_perm(b.y, c.x, 0x6543));
+            h[6] = luma_h(__byte_perm(c.x, c.y, 0x5432));
+            h[7] = luma_h(c.y >> 8);
+        } else {
+            const uint4 *s = reinterpret_cast<const uint4 *>(row + lane * 32);
+            const uint4 a = s[0], b = s[1];
+            h[0] = luma_h(a.x); h[1] = luma_h(a.y); h[2] = luma_h(a.z); h[3] = luma_h(a.w);
+            h[4] = luma_h(b.x); h[5] = luma_h(b.y); h[6] = luma_h(b.z); h[7] = luma_h(b.w);
+        }
+        p01 = __byte_perm(h[0], h[1], 0x6521); p23 = __byte_perm(h[2], h[3], 0x6521);
+        p45 = __byte_perm(h[4], h[5], 0x6521); p67 = __byte_perm(h[6], h[7], 0x6521);
+        g03 = __byte_perm(p01, p23, 0x6420); g47 = __byte_perm(p45, p67, 0x6420);
+    }
+}
+
+// 4 mask bits -> 4 bytes of 0 / 255
+__device__ __forceinline__ uint32_t expand4(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xffu; }
+
+template <int FMT, int ROWS, bool MASK, bool BITS>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k1_strips_kernel(const __grid_constant__ CUtensorMap tmap, const StripArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int kTxBytes = ROWS * Fmt<FMT>::row_bytes;            // bytes one box delivers
+    constexpr int kStageBytes = (kTxBytes + 127) & ~127;            // stage stride: TMA destinations are 128-byte aligned
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t job = blockIdx.x * kWarpsPerCta + warp;
+    // per-warp carve: [stages * kStageBytes] TMA ring (128-B aligned) | [16 * 256] grey ring | [stages] mbarriers
+    const uint32_t per_warp = a.stages * kStageBytes + kRing * 256 + 8 * a.stages;
+    uint8_t *base = smem + (size_t)warp * ((per_warp + 127) & ~127u);
+    uint8_t *stage_mem = base;
+    uint2 *ring = reinterpret_cast<uint2 *>(base + a.stages * kStageBytes) + lane;  // slot s at ring[32 * s]
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + a.stages * kStageBytes + kRing * 256);
+    if (job >= a.njobs) return;  // whole warp; warps are independent (no block-wide barrier anywhere)
+
+    const uint32_t strip = job % a.nstrips;
+    const uint32_t seg = (job / a.nstrips) % a.nsegs;
+    const uint32_t frame = job / (a.nstrips * a.nsegs);
+    const int x0 = (int)strip * kCore - kHalo;        // first column of the warp's 256
+    const int x = x0 + 8 * lane;                      // first of this lane's 8 columns
+    const int ys = (int)(seg * a.seg_rows);
+    const int ye = min((int)a.h, ys + (int)a.seg_rows);
+    const int total_rows = (ye - ys) + 14;            // input rows ys-7 .. ye+6
+    const int nblocks = (total_rows + ROWS - 1) / ROWS;
+    const int cx = (x0 - Fmt<FMT>::lead_px) * Fmt<FMT>::bpp / 4;  // u32 element coordinate of the box, a multiple of 4
+
+    if (lane == 0) {
+        for (uint32_t s = 0; s < a.stages; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#pragma unroll
+    for (int s = 0; s < kRing; s++) ring[32 * s] = make_uint2(0u, 0u);
+    __syncwarp();
+    if (lane == 0) {
+        for (int b = 0; b < (int)a.stages && b < nblocks; b++) {
+            mbar_expect_tx(&full[b], kTxBytes);
+            tma_load_box(stage_mem + b * kStageBytes, &tmap, cx, ys - 7 + b * ROWS, (int)frame, &full[b]);
+        }
+    }
+
+    // clipped window widths of the lane's 8 columns (fixed for the whole march); 0 outside the image
+    uint32_t nx[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int xx = x + j;
+        nx[j] = (xx >= 0 && xx < (int)a.w) ? (uint32_t)(min((int)a.w - 1, xx + 7) - max(0, xx - 7) + 1) : 0u;
+    }
+    uint32_t cvec[8], tbase[8];  // cnt << 8 (j & 3)  and  -256 cnt,  cnt = nx * ny of the current output row
+    uint32_t ny_cur = 0xffffffffu;
+    const bool lane_core = lane >= 1 && lane <= 30 && x < (int)a.w;
+    uint32_t valid8 = 0;          // which of the lane's 8 pixels are output pixels
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (lane_core && x + j < (int)a.w) valid8 |= 1u << j;
+
+    uint32_t cs0 = 0, cs1 = 0, cs2 = 0, cs3 = 0;  // running 15-row column sums, u16 pairs
+    uint32_t stage = 0, parity = 0;
+    // output pointers of the lane's 8 pixels in row ys, advanced by one row per output row
+    size_t o_px = ((size_t)frame * a.h + ys) * a.w + x;
+    size_t o_bits = ((size_t)frame * a.h + ys) * a.bits_row_bytes + (x >> 3);
+
+    for (int b = 0; b < nblocks; b++) {
+        mbar_wait(&full[stage], parity);
+        const uint8_t *srow = stage_mem + stage * kStageBytes;
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const int k = b * ROWS + r;
+            if (k < total_rows) {  // warp-uniform
+                uint32_t p01, p23, p45, p67, g03, g47;
+                load_grey8<FMT>(srow + r * Fmt<FMT>::row_bytes, lane, p01, p23, p45, p67, g03, g47);
+                // input row k lives in ring slot k & 15; the row leaving the 15-row window is k - 15
+                const uint2 old = ring[32 * ((k + 1) & 15)];
+                ring[32 * (k & 15)] = make_uint2(g03, g47);
+                cs0 = cs0 + p01 - __byte_perm(old.x, 0u, 0x4140);
+                cs1 = cs1 + p23 - __byte_perm(old.x, 0u, 0x4342);
+                cs2 = cs2 + p45 - __byte_perm(old.y, 0u, 0x4140);
+                cs3 = cs3 + p67 - __byte_perm(old.y, 0u, 0x4342);
+                if (k >= 14) {
+                    const int yo = ys + k - 14;
+                    const uint32_t ny = (uint32_t)(min((int)a.h - 1, yo + 7) - max(0, yo - 7) + 1);
+                    if (ny != ny_cur) {  // only in the top / bottom 7 rows of the frame
+                        ny_cur = ny;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t c = nx[j] * ny;
+                            cvec[j] = c << (8 * (j & 3));
+                            tbase[j] = 0u - 256u * c;
+                        }
+                    }
+                    // pair words of columns -8..15 relative to the lane's first column
+                    uint32_t w[12];
+                    w[0] = __shfl_up_sync(0xffffffffu, cs0, 1); w[1] = __shfl_up_sync(0xffffffffu, cs1, 1);
+                    w[2] = __shfl_up_sync(0xffffffffu, cs2, 1); w[3] = __shfl_up_sync(0xffffffffu, cs3, 1);
+                    w[4] = cs0; w[5] = cs1; w[6] = cs2; w[7] = cs3;
+                    w[8] = __shfl_down_sync(0xffffffffu, cs0, 1); w[9] = __shfl_down_sync(0xffffffffu, cs1, 1);
+                    w[10] = __shfl_down_sync(0xffffffffu, cs2, 1); w[11] = __shfl_down_sync(0xffffffffu, cs3, 1);
+                    uint32_t f[12];
+#pragma unroll
+                    for (int i = 1; i <= 10; i++) f[i] = __dp2a_lo(w[i], 0x0101u, 0u);  // lo + hi
+                    uint32_t T[4];
+                    T[0] = (f[1] + f[2] + f[3]) + (f[4] + f[5] + f[6]) + f[7];
+                    T[1] = T[0] + f[8] - f[1];
+                    T[2] = T[1] + f[9] - f[2];
+                    T[3] = T[2] + f[10] - f[3];
+                    const uint2 pix = ring[32 * ((k + 9) & 15)];  // row k - 7 = the output row
+                    const uint32_t pc0 = ~pix.x, pc1 = ~pix.y;
+                    uint32_t bits8 = 0;
+#pragma unroll
+                    for (int j = 7; j >= 0; j--) {
+                        // S - 256 cnt:  even column j: T[j/2] + hi(w[j/2]);  odd: T[j/2] + lo(w[(j+15)/2])
+                        const uint32_t acc = (j & 1) ? __dp2a_lo(w[(j + 15) / 2], 0x0001u, T[j / 2] + tbase[j])
+                                                     : __dp2a_lo(w[j / 2], 0x0100u, T[j / 2] + tbase[j]);
+                        const uint32_t u = __dp4a(j < 4 ? pc0 : pc1, cvec[j], acc);  // + (255 - pix) * cnt
+                        bits8 = __funnelshift_l(u, bits8, 1);                        // sign bit: S < (pix + 1) * cnt
+                    }
+                    bits8 &= valid8;
+                    if (lane_core) {
+                        const size_t o = o_px;
+                        if (a.wide_stores && valid8 == 0xffu) {
+                            *reinterpret_cast<uint2 *>(a.grey + o) = pix;
+                            if constexpr (MASK) *reinterpret_cast<uint2 *>(a.mask + o) = make_uint2(expand4(bits8 & 15u), expand4(bits8 >> 4));
+                        } else {
+                            if (valid8 & 0x0fu) {
+                                *reinterpret_cast<uint32_t *>(a.grey + o) = pix.x;
+                                if constexpr (MASK) *reinterpret_cast<uint32_t *>(a.mask + o) = expand4(bits8 & 15u);
+                            }
+                            if (valid8 & 0xf0u) {
+                                *reinterpret_cast<uint32_t *>(a.grey + o + 4) = pix.y;
+                                if constexpr (MASK) *reinterpret_cast<uint32_t *>(a.mask + o + 4) = expand4(bits8 >> 4);
+                            }
+                        }
+                        if constexpr (BITS) a.bits[o_bits] = (uint8_t)bits8;
+                    }
+                    o_px += a.w;
+                    o_bits += a.bits_row_bytes;
+                }
+            }
+        }
+        // every lane has consumed the stage (its values are in registers): refill it with the block `stages` ahead
+        __syncwarp();
+        if (lane == 0 && b + (int)a.stages < nblocks) {
+            mbar_expect_tx(&full[stage], kTxBytes);
+            tma_load_box(stage_mem + stage * kStageBytes, &tmap, cx, ys - 7 + (b + (int)a.stages) * ROWS, (int)frame, &full[stage]);
+        }
+        if (++stage == a.stages) { stage = 0; parity ^= 1u; }
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+template <int FMT, int ROWS>
+cudaError_t launch_strips(const CUtensorMap &map, const StripArgs &a, bool mask, bool bits, uint32_t grid, size_t smem, cudaStream_t stream) {
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kWarpsPerCta * 32, smem, stream>>>(map, a);
+        return cudaGetLastError();
+    };
+    if (mask) return bits ? go(k1_strips_kernel<FMT, ROWS, true, true>) : go(k1_strips_kernel<FMT, ROWS, true, false>);
+    return bits ? go(k1_strips_kernel<FMT, ROWS, false, true>) : go(k1_strips_kernel<FMT, ROWS, false, false>);
+}
+
+}  // namespace
+
+bool k1_strips_eligible(const K1Params &p) {
+    const uint32_t bpp = p.format == A3_FMT_RGB8 ? 3 : (p.format == A3_FMT_RGBA8 ? 4 : 1);
+    return p.radius == 7 && p.grey != nullptr && p.w % 4 == 0 && p.w >= 4 && p.pitch % 16 == 0 && p.frame_stride % 16 == 0 &&
+           p.frame_stride % p.pitch == 0 && (uintptr_t)p.src % 16 == 0 && (uintptr_t)p.grey % 4 == 0 && (uintptr_t)p.mask % 4 == 0 &&
+           (uint64_t)p.w * bpp <= p.pitch && p.n <= 0x7fffffffu && encode_tiled_fn() != nullptr;
+}
+
+cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t stream, K1LaunchInfo *info) {
+    const uint32_t bpp = p.format == A3_FMT_RGB8 ? 3 : (p.format == A3_FMT_RGBA8 ? 4 : 1);
+    const uint32_t rows = tuning && tuning->tma_rows ? tuning->tma_rows : 2;
+    const uint32_t stages = tuning && tuning->tma_stages ? tuning->tma_stages : 2;
+    if (rows != 1 && rows != 2 && rows != 4) return cudaErrorInvalidValue;
+
+    // ---- tensor map over the frames viewed as u32 [n][h][pitch / 4]; dim 0 stops at the last pixel's bytes ----
+    CUtensorMap map;
+    const cuuint64_t gdim[3] = {(cuuint64_t)p.w * bpp / 4, p.h, p.n};
+    const cuuint64_t gstride[2] = {p.pitch, p.frame_stride};
+    const uint32_t row_bytes = (256u + (p.format == A3_FMT_RGBA8 ? 0u : 16u)) * bpp;  // Fmt<>::row_bytes
+    const cuuint32_t box[3] = {row_bytes / 4, rows, 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    const CUresult cr = encode_tiled_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(p.src), gdim, gstride, box, estride,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
+
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t stage_bytes = (rows * row_bytes + 127) & ~127u;
+    const uint32_t per_warp = ((stages * stage_bytes + kRing * 256 + 8 * stages) + 127) & ~127u;
+    const size_t smem = (size_t)per_warp * kWarpsPerCta;
+    if (smem > 220 * 1024) return cudaErrorInvalidValue;
+    uint32_t ctas_per_sm = (uint32_t)((227 * 1024) / (smem + 1024));
+    if (ctas_per_sm > 16) ctas_per_sm = 16;  // 64 warps per SM
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const uint32_t slots = (uint32_t)sms * ctas_per_sm * kWarpsPerCta;  // warps resident at once
+
+    StripArgs a;
+    a.grey = p.grey; a.mask = p.mask; a.bits = reinterpret_cast<uint8_t *>(p.bits);
+    a.n = p.n; a.w = p.w; a.h = p.h;
+    a.nstrips = (p.w + kCore - 1) / kCore;
+    // row segments: one resident wave when the batch is small (largest segment count that still fits), whole
+    // frames otherwise; every segment re-reads a 14-row halo, so segments stay >= 64 rows
+    uint32_t nsegs = tuning && tuning->seg_rows ? (p.h + tuning->seg_rows - 1) / tuning->seg_rows : 0;
+    if (nsegs == 0) {
+        const uint64_t per_seg = (uint64_t)p.n * a.nstrips;
+        nsegs = per_seg >= slots ? 1 : (uint32_t)(slots / per_seg);
+        const uint32_t max_segs = p.h / 64 ? p.h / 64 : 1;
+        if (nsegs > max_segs) nsegs = max_segs;
+    }
+    a.seg_rows = (p.h + nsegs - 1) / nsegs;
+    a.nsegs = (p.h + a.seg_rows - 1) / a.seg_rows;
+    const uint64_t njobs = (uint64_t)p.n * a.nsegs * a.nstrips;
+    if (njobs > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    a.njobs = (uint32_t)njobs;
+    a.bits_row_bytes = 4 * ((p.w + 31) / 32);
+    a.stages = stages;
+    a.wide_stores = (p.w % 8 == 0) && ((uintptr_t)p.grey % 8 == 0) && ((uintptr_t)p.mask % 8 == 0);
+    const uint32_t grid = (a.njobs + kWarpsPerCta - 1) / kWarpsPerCta;
+
+    // the kernel writes the 1-bit mask by bytes; when w is not a multiple of 32 the tail bytes of each row's last
+    // word are never touched by it and must read as zero
+    if (p.bits && p.w % 32 != 0) {
+        const size_t tail = a.bits_row_bytes - 4;
+        cudaError_t e = cudaMemset2DAsync(reinterpret_cast<uint8_t *>(p.bits) + tail, a.bits_row_bytes, 0, 4, (size_t)p.n * p.h, stream);
+        if (e != cudaSuccess) return e;
+    }
+    if (info) {
+        info->grid = grid; info->block = kWarpsPerCta * 32; info->smem_bytes = (uint32_t)smem; info->strips = a.nstrips; info->segs = a.nsegs;
+        info->strip_cols = kCore; info->seg_rows = a.seg_rows; info->tma = 2; info->specialised_radius = 1;
+    }
+    const bool mask = p.mask != nullptr, bits = p.bits != nullptr;
+    switch (p.format) {
+        case A3_FMT_RGB8:
+            return rows == 1   ? launch_strips<A3_FMT_RGB8, 1>(map, a, mask, bits, grid, smem, stream)
+                   : rows == 2 ? launch_strips<A3_FMT_RGB8, 2>(map, a, mask, bits, grid, smem, stream)
+                               : launch_strips<A3_FMT_RGB8, 4>(map, a, mask, bits, grid, smem, stream);
+        case A3_FMT_RGBA8:
+            return rows == 1   ? launch_strips<A3_FMT_RGBA8, 1>(map, a, mask, bits, grid, smem, stream)
+                   : rows == 2 ? launch_strips<A3_FMT_RGBA8, 2>(map, a, mask, bits, grid, smem, stream)
+                               : launch_strips<A3_FMT_RGBA8, 4>(map, a, mask, bits, grid, smem, stream);
+        case A3_FMT_LUMA8:
+            return rows == 1   ? launch_strips<A3_FMT_LUMA8, 1>(map, a, mask, bits, grid, smem, stream)
+                   : rows == 2 ? launch_strips<A3_FMT_LUMA8, 2>(map, a, mask, bits, grid, smem, stream)
+                               : launch_strips<A3_FMT_LUMA8, 4>(map, a, mask, bits, grid, smem, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace a3

@@ -321,6 +321,7 @@ inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 cudaError_t k1_gray_threshold(const K1Params &p, const K1Tuning *tuning, cudaStream_t stream, K1LaunchInfo *info) {
     if (p.n == 0 || p.w == 0 || p.h == 0) return cudaSuccess;
     if (p.radius == 0 || p.radius > (uint32_t)kMaxRadius) return cudaErrorInvalidValue;
+    if (!(tuning && tuning->force_generic) && k1_strips_eligible(p)) return k1_strips(p, tuning, stream, info);
     const uint32_t r = p.radius;
     const uint32_t bpp = p.format == A3_FMT_RGB8 ? 3 : (p.format == A3_FMT_RGBA8 ? 4 : 1);
     const uint32_t max_core = 4 * kMaxThreads - 64;  // leave room for the 32-aligned left halo and the right halo

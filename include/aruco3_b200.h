@@ -136,6 +136,19 @@ void a3_detector_destroy(a3_detector *det);
 /* number of host threads used for the contour / quad stage (default: all cores, capped at 64) */
 a3_status a3_detector_set_host_threads(a3_detector *det, uint32_t threads);
 
+/* Launch-shape knobs of the pixel kernel (benchmark sweeps and tests; results never depend on them). 0 = automatic. */
+typedef struct a3_k1_tuning {
+    uint32_t strip_cols;    /* generic kernel: output columns per CTA strip */
+    uint32_t seg_rows;      /* output rows per row segment */
+    uint32_t force_no_tma;  /* generic kernel: plain loads instead of bulk copies */
+    uint32_t force_generic; /* never take the warp-strip kernel */
+    uint32_t tma_rows;      /* warp-strip kernel: rows per TMA box (1, 2 or 4) */
+    uint32_t tma_stages;    /* warp-strip kernel: TMA ring depth per warp */
+    uint32_t chunk_frames;  /* a3_detect_batch: frames per pipeline chunk */
+    uint32_t reserved;
+} a3_k1_tuning;
+a3_status a3_detector_set_k1_tuning(a3_detector *det, const a3_k1_tuning *tuning); /* NULL restores the defaults */
+
 /* Detector::detect over a batch of n equally sized frames (src/aruco.rs:52-121 per frame).
  * markers are written frame-major, in candidate order within a frame (the order of Detection.markers).
  * Returns A3_ERR_CAPACITY (with *n_markers = the number found) when marker_capacity is too small. */
