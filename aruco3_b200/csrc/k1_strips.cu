@@ -33,6 +33,7 @@ namespace a3 {
 namespace {
 
 constexpr int kWarpsPerCta = 4;
+constexpr int kMinCtasPerSm = 7;   // register cap: 65536 / (128 * 7) -> 72 per thread, matches the 7 CTAs the shared memory allows
 constexpr int kRing = 16;          // >= 2 * 7 + 1 grey rows; a power of two so ring slots are `row & 15`
 constexpr int kCore = 240;         // output columns per warp
 constexpr int kHalo = 8;           // >= radius, keeps every lane's 8 columns 8-px aligned
@@ -43,7 +44,7 @@ struct StripArgs {
     uint32_t n, w, h;
     uint32_t nstrips, nsegs, seg_rows, njobs;
     uint32_t bits_row_bytes;       // 4 * ceil(w / 32)
-    uint32_t stages;               // TMA ring depth per warp
+    uint32_t stages;               // TMA ring depth per warp (kStages)
     int wide_stores;               // w % 8 == 0 and grey / mask bases 8-byte aligned
 };
 
@@ -96,20 +97,32 @@ __device__ __forceinline__ uint32_t luma_h(uint32_t px) {
     return __umulhi(v, kMagic);                                    // floor(v / 10000) << 8 | fraction byte
 }
 
-// the lane's 8 greys of one staged row: p01..p67 = u16 pairs (g_even | g_odd << 16), g03 / g47 = packed bytes
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// the lane's 8 greys of one staged row (shared address `row` = first byte of the lane's pixels):
+// p01..p67 = u16 pairs (g_even | g_odd << 16), g = packed bytes
 template <int FMT>
-__device__ __forceinline__ void load_grey8(const uint8_t *row, int lane, uint32_t &p01, uint32_t &p23, uint32_t &p45, uint32_t &p67,
-                                           uint32_t &g03, uint32_t &g47) {
+__device__ __forceinline__ void load_grey8(uint32_t row, uint32_t &p01, uint32_t &p23, uint32_t &p45, uint32_t &p67, uint2 &g) {
     if constexpr (FMT == A3_FMT_LUMA8) {
-        const uint2 v = *reinterpret_cast<const uint2 *>(row + Fmt<FMT>::lead_bytes + lane * 8);
-        g03 = v.x; g47 = v.y;
-        p01 = __byte_perm(v.x, 0u, 0x4140); p23 = __byte_perm(v.x, 0u, 0x4342);
-        p45 = __byte_perm(v.y, 0u, 0x4140); p67 = __byte_perm(v.y, 0u, 0x4342);
+        g = lds64(row);
+        p01 = __byte_perm(g.x, 0u, 0x4140); p23 = __byte_perm(g.x, 0u, 0x4342);
+        p45 = __byte_perm(g.y, 0u, 0x4140); p67 = __byte_perm(g.y, 0u, 0x4342);
     } else {
         uint32_t h[8];
         if constexpr (FMT == A3_FMT_RGB8) {
-            const uint2 *s = reinterpret_cast<const uint2 *>(row + Fmt<FMT>::lead_bytes + lane * 24);
-            const uint2 a = s[0], b = s[1], c = s[2];
+            const uint2 a = lds64(row), b = lds64(row + 8), c = lds64(row + 16);
             // 12 bytes -> 4 pixel words; the 4th byte of each word has weight 0
             h[0] = luma_h(a.x);
             h[1] = luma_h(__byte_perm(a.x, a.y, 0x6543));
@@ -120,165 +133,258 @@ __device__ __forceinline__ void load_grey8(const uint8_t *row, int lane, uint32_
             h[6] = luma_h(__byte_perm(c.x, c.y, 0x5432));
             h[7] = luma_h(c.y >> 8);
         } else {
-            const uint4 *s = reinterpret_cast<const uint4 *>(row + lane * 32);
-            const uint4 a = s[0], b = s[1];
+            const uint4 a = lds128(row), b = lds128(row + 16);
             h[0] = luma_h(a.x); h[1] = luma_h(a.y); h[2] = luma_h(a.z); h[3] = luma_h(a.w);
             h[4] = luma_h(b.x); h[5] = luma_h(b.y); h[6] = luma_h(b.z); h[7] = luma_h(b.w);
         }
         p01 = __byte_perm(h[0], h[1], 0x6521); p23 = __byte_perm(h[2], h[3], 0x6521);
         p45 = __byte_perm(h[4], h[5], 0x6521); p67 = __byte_perm(h[6], h[7], 0x6521);
-        g03 = __byte_perm(p01, p23, 0x6420); g47 = __byte_perm(p45, p67, 0x6420);
+        g.x = __byte_perm(p01, p23, 0x6420); g.y = __byte_perm(p45, p67, 0x6420);
     }
 }
 
 // 4 mask bits -> 4 bytes of 0 / 255
 __device__ __forceinline__ uint32_t expand4(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xffu; }
 
-template <int FMT, int ROWS, bool MASK, bool BITS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k1_strips_kernel(const __grid_constant__ CUtensorMap tmap, const StripArgs a) {
+// Per-lane marching state (registers).
+struct Lane {
+    uint32_t cs0, cs1, cs2, cs3;   // running 15-row column sums of the lane's 8 columns, u16 pairs
+    uint32_t cvec[8], tbase[8];    // cnt << 8 (j & 3)  and  -256 cnt,  cnt = nx * ny of the current output row
+    uint32_t ny_cur;
+    uint32_t valid8;               // which of the lane's 8 pixels are output pixels
+    int store_mode;                // 0 nothing, 1 one 8-byte store per array, 2 4-byte stores
+    uint8_t *grey, *mask, *bits;   // output addresses of the lane's pixels in the next output row
+    uint32_t row_px, row_bits;     // bytes per output row
+};
+
+// Warp-uniform marching context.
+struct March {
+    const CUtensorMap *tmap;
+    uint32_t base;       // shared address of the warp's carve: stages, then the grey ring, then the mbarriers
+    uint32_t ring;       // this lane's slot 0 of the grey ring (slot s at ring + 256 s)
+    uint32_t full;       // mbarrier of stage s at full + 8 s
+    uint32_t lane_src;   // shared address of the lane's pixels in row 0 of stage 0
+    int x, w, h, ys, total_rows, nboxes, cx, cy0, frame, lane;
+};
+
+// cnt = nx * ny of the lane's 8 columns for an output row with ny window rows (nx: clipped window width, 0 outside)
+__device__ __forceinline__ void set_ny(Lane &L, const March &m, uint32_t ny) {
+    L.ny_cur = ny;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int xx = m.x + j;
+        const uint32_t nx = (xx >= 0 && xx < m.w) ? (uint32_t)(min(m.w - 1, xx + 7) - max(0, xx - 7) + 1) : 0u;
+        const uint32_t c = nx * ny;
+        L.cvec[j] = c << (8 * (j & 3));
+        L.tbase[j] = 0u - 256u * c;
+    }
+}
+
+// The march is organised in bodies of 8 input rows = 4 TMA boxes of 2 rows over a 2-stage ring, so that inside a
+// body every ring slot, stage and mbarrier phase is a compile-time constant.
+constexpr int kBody = 8, kBoxRows = 2, kStages = 2;
+template <int FMT>
+struct Stage {
+    static constexpr int tx_bytes = kBoxRows * Fmt<FMT>::row_bytes;  // bytes one box delivers
+    static constexpr int bytes = (tx_bytes + 127) & ~127;            // stage stride: TMA destinations are 128-byte aligned
+    static constexpr int per_warp = (kStages * bytes + kRing * 256 + 8 * kStages + 127) & ~127;
+};
+
+template <int FMT>
+__device__ __forceinline__ void arm_box(const March &m, int box) {  // lane 0: request rows cy0 + 2 box .. into stage box & 1
+    const uint32_t st = (uint32_t)box & 1u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m.full + 8 * st), "r"(Stage<FMT>::tx_bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            m.base + st * Stage<FMT>::bytes),
+        "l"(m.tmap), "r"(m.cx), "r"(m.cy0 + box * kBoxRows), "r"(m.frame), "r"(m.full + 8 * st)
+        : "memory");
+}
+__device__ __forceinline__ void wait_box(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "K1S_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra K1S_DONE;\n"
+        "bra K1S_WAIT;\n"
+        "K1S_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+// Consume one staged input row: update the column sums and, when OUT, emit the output row 7 rows behind it.
+// src: the lane's pixels of the row; ring_new / ring_old / ring_pix: the lane's ring slots of this row, of the row
+// 15 behind (leaving the window) and of the row 7 behind (the output row).
+template <int FMT, bool MASK, bool BITS, bool OUT>
+__device__ __forceinline__ void row_step(Lane &L, uint32_t src, uint32_t ring_new, uint32_t ring_old, uint32_t ring_pix) {
+    uint32_t p01, p23, p45, p67;
+    uint2 g;
+    load_grey8<FMT>(src, p01, p23, p45, p67, g);
+    const uint2 old = lds64(ring_old);
+    sts64(ring_new, g);
+    L.cs0 = L.cs0 + p01 - __byte_perm(old.x, 0u, 0x4140);
+    L.cs1 = L.cs1 + p23 - __byte_perm(old.x, 0u, 0x4342);
+    L.cs2 = L.cs2 + p45 - __byte_perm(old.y, 0u, 0x4140);
+    L.cs3 = L.cs3 + p67 - __byte_perm(old.y, 0u, 0x4342);
+    if constexpr (OUT) {
+        const uint2 pix = lds64(ring_pix);
+        // pair words of columns -8..15 relative to the lane's first column
+        uint32_t w[12];
+        w[0] = __shfl_up_sync(0xffffffffu, L.cs0, 1); w[1] = __shfl_up_sync(0xffffffffu, L.cs1, 1);
+        w[2] = __shfl_up_sync(0xffffffffu, L.cs2, 1); w[3] = __shfl_up_sync(0xffffffffu, L.cs3, 1);
+        w[4] = L.cs0; w[5] = L.cs1; w[6] = L.cs2; w[7] = L.cs3;
+        w[8] = __shfl_down_sync(0xffffffffu, L.cs0, 1); w[9] = __shfl_down_sync(0xffffffffu, L.cs1, 1);
+        w[10] = __shfl_down_sync(0xffffffffu, L.cs2, 1); w[11] = __shfl_down_sync(0xffffffffu, L.cs3, 1);
+        uint32_t f[12];
+#pragma unroll
+        for (int i = 1; i <= 10; i++) f[i] = __dp2a_lo(w[i], 0x0101u, 0u);  // lo + hi
+        uint32_t T[4];
+        T[0] = (f[1] + f[2] + f[3]) + (f[4] + f[5] + f[6]) + f[7];
+        T[1] = T[0] + f[8] - f[1];
+        T[2] = T[1] + f[9] - f[2];
+        T[3] = T[2] + f[10] - f[3];
+        const uint32_t pc0 = ~pix.x, pc1 = ~pix.y;
+        uint32_t bits8 = 0;
+#pragma unroll
+        for (int j = 7; j >= 0; j--) {
+            // S - 256 cnt:  even column j: T[j/2] + hi(w[j/2]);  odd: T[j/2] + lo(w[(j+15)/2])
+            const uint32_t acc = (j & 1) ? __dp2a_lo(w[(j + 15) / 2], 0x0001u, T[j / 2] + L.tbase[j])
+                                         : __dp2a_lo(w[j / 2], 0x0100u, T[j / 2] + L.tbase[j]);
+            const uint32_t u = __dp4a(j < 4 ? pc0 : pc1, L.cvec[j], acc);  // + (255 - pix) * cnt
+            bits8 = __funnelshift_l(u, bits8, 1);                          // sign bit: S < (pix + 1) * cnt
+        }
+        bits8 &= L.valid8;
+        if (L.store_mode == 1) {
+            *reinterpret_cast<uint2 *>(L.grey) = pix;
+            if constexpr (MASK) *reinterpret_cast<uint2 *>(L.mask) = make_uint2(expand4(bits8 & 15u), expand4(bits8 >> 4));
+            if constexpr (BITS) *L.bits = (uint8_t)bits8;
+        } else if (L.store_mode == 2) {
+            if (L.valid8 & 0x0fu) {
+                *reinterpret_cast<uint32_t *>(L.grey) = pix.x;
+                if constexpr (MASK) *reinterpret_cast<uint32_t *>(L.mask) = expand4(bits8 & 15u);
+            }
+            if (L.valid8 & 0xf0u) {
+                *reinterpret_cast<uint32_t *>(L.grey + 4) = pix.y;
+                if constexpr (MASK) *reinterpret_cast<uint32_t *>(L.mask + 4) = expand4(bits8 >> 4);
+            }
+            if constexpr (BITS) *L.bits = (uint8_t)bits8;
+        }
+        L.grey += L.row_px;
+        if constexpr (MASK) L.mask += L.row_px;
+        if constexpr (BITS) L.bits += L.row_bits;
+    }
+}
+
+// Rows R .. 7 of the body that starts at input row k0 (k0 % 8 == 0).  FAST: all 8 rows exist, all emit output and all
+// output rows have ny == 15 (already in L.cvec / L.tbase); otherwise every row is guarded.
+// ring_lo: the lane's slot (k0 & 8); ring_hi: slot (k0 & 8) ^ 8.
+template <int FMT, bool MASK, bool BITS, bool FAST, int R>
+__device__ __forceinline__ void body_rows(Lane &L, const March &m, int k0, uint32_t ring_lo, uint32_t ring_hi) {
+    if constexpr (R < kBody) {
+        constexpr int box_in_body = R / kBoxRows;
+        constexpr uint32_t st = box_in_body & 1;
+        const bool row_ok = FAST || (k0 + R < m.total_rows);  // warp-uniform
+        if constexpr (R % kBoxRows == 0) {
+            if (row_ok) wait_box(m.full + 8 * st, (uint32_t)(box_in_body >> 1) & 1u);  // each stage completes twice per body
+        }
+        if (row_ok) {
+            const uint32_t src = m.lane_src + st * Stage<FMT>::bytes + (R % kBoxRows) * Fmt<FMT>::row_bytes;
+            const uint32_t rn = ring_lo + 256 * R;                                   // row k        -> slot (k0 & 8) + R
+            const uint32_t ro = R < 7 ? ring_lo + 256 * (R + 1) : ring_hi;           // row k - 15
+            const uint32_t rp = R < 7 ? ring_hi + 256 * (R + 1) : ring_lo;           // row k - 7
+            if constexpr (FAST) {
+                row_step<FMT, MASK, BITS, true>(L, src, rn, ro, rp);
+            } else {
+                if (k0 + R >= 14) {
+                    const int yo = m.ys + k0 + R - 14;
+                    const uint32_t ny = (uint32_t)(min(m.h - 1, yo + 7) - max(0, yo - 7) + 1);
+                    if (ny != L.ny_cur) set_ny(L, m, ny);  // only in the top / bottom 7 rows of the frame
+                    row_step<FMT, MASK, BITS, true>(L, src, rn, ro, rp);
+                } else {
+                    row_step<FMT, MASK, BITS, false>(L, src, rn, ro, rp);
+                }
+            }
+        }
+        if constexpr (R % kBoxRows == kBoxRows - 1) {
+            // every lane has consumed the box (its values are in registers): refill the stage with the box 2 ahead
+            __syncwarp();
+            const int box = (k0 + R) / kBoxRows;
+            if (m.lane == 0 && box + kStages < m.nboxes) arm_box<FMT>(m, box + kStages);
+        }
+        body_rows<FMT, MASK, BITS, FAST, R + 1>(L, m, k0, ring_lo, ring_hi);
+    }
+}
+
+template <int FMT, bool MASK, bool BITS>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) k1_strips_kernel(const __grid_constant__ CUtensorMap tmap, const StripArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int kTxBytes = ROWS * Fmt<FMT>::row_bytes;            // bytes one box delivers
-    constexpr int kStageBytes = (kTxBytes + 127) & ~127;            // stage stride: TMA destinations are 128-byte aligned
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t job = blockIdx.x * kWarpsPerCta + warp;
-    // per-warp carve: [stages * kStageBytes] TMA ring (128-B aligned) | [16 * 256] grey ring | [stages] mbarriers
-    const uint32_t per_warp = a.stages * kStageBytes + kRing * 256 + 8 * a.stages;
-    uint8_t *base = smem + (size_t)warp * ((per_warp + 127) & ~127u);
-    uint8_t *stage_mem = base;
-    uint2 *ring = reinterpret_cast<uint2 *>(base + a.stages * kStageBytes) + lane;  // slot s at ring[32 * s]
-    uint64_t *full = reinterpret_cast<uint64_t *>(base + a.stages * kStageBytes + kRing * 256);
     if (job >= a.njobs) return;  // whole warp; warps are independent (no block-wide barrier anywhere)
-
     const uint32_t strip = job % a.nstrips;
     const uint32_t seg = (job / a.nstrips) % a.nsegs;
     const uint32_t frame = job / (a.nstrips * a.nsegs);
     const int x0 = (int)strip * kCore - kHalo;        // first column of the warp's 256
-    const int x = x0 + 8 * lane;                      // first of this lane's 8 columns
-    const int ys = (int)(seg * a.seg_rows);
-    const int ye = min((int)a.h, ys + (int)a.seg_rows);
-    const int total_rows = (ye - ys) + 14;            // input rows ys-7 .. ye+6
-    const int nblocks = (total_rows + ROWS - 1) / ROWS;
-    const int cx = (x0 - Fmt<FMT>::lead_px) * Fmt<FMT>::bpp / 4;  // u32 element coordinate of the box, a multiple of 4
+
+    March m;
+    m.tmap = &tmap;
+    m.base = smem_u32(smem) + (uint32_t)warp * Stage<FMT>::per_warp;
+    m.ring = m.base + kStages * Stage<FMT>::bytes + 8 * lane;
+    m.full = m.base + kStages * Stage<FMT>::bytes + kRing * 256;
+    m.lane_src = m.base + Fmt<FMT>::lead_bytes + lane * 8 * Fmt<FMT>::bpp;
+    m.x = x0 + 8 * lane;                              // first of this lane's 8 columns
+    m.w = (int)a.w; m.h = (int)a.h;
+    m.ys = (int)(seg * a.seg_rows);
+    const int ye = min(m.h, m.ys + (int)a.seg_rows);
+    m.total_rows = (ye - m.ys) + 14;                  // input rows ys-7 .. ye+6
+    m.nboxes = (m.total_rows + kBoxRows - 1) / kBoxRows;
+    m.cx = (x0 - Fmt<FMT>::lead_px) * Fmt<FMT>::bpp / 4;  // u32 element coordinate of the box, a multiple of 4
+    m.cy0 = m.ys - 7;
+    m.frame = (int)frame;
+    m.lane = lane;
 
     if (lane == 0) {
-        for (uint32_t s = 0; s < a.stages; s++) mbar_init(&full[s], 1);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(m.full));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(m.full + 8));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 #pragma unroll
-    for (int s = 0; s < kRing; s++) ring[32 * s] = make_uint2(0u, 0u);
+    for (int s = 0; s < kRing; s++) sts64(m.ring + 256 * s, make_uint2(0u, 0u));
     __syncwarp();
     if (lane == 0) {
-        for (int b = 0; b < (int)a.stages && b < nblocks; b++) {
-            mbar_expect_tx(&full[b], kTxBytes);
-            tma_load_box(stage_mem + b * kStageBytes, &tmap, cx, ys - 7 + b * ROWS, (int)frame, &full[b]);
-        }
+        arm_box<FMT>(m, 0);
+        if (m.nboxes > 1) arm_box<FMT>(m, 1);
     }
 
-    // clipped window widths of the lane's 8 columns (fixed for the whole march); 0 outside the image
-    uint32_t nx[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int xx = x + j;
-        nx[j] = (xx >= 0 && xx < (int)a.w) ? (uint32_t)(min((int)a.w - 1, xx + 7) - max(0, xx - 7) + 1) : 0u;
-    }
-    uint32_t cvec[8], tbase[8];  // cnt << 8 (j & 3)  and  -256 cnt,  cnt = nx * ny of the current output row
-    uint32_t ny_cur = 0xffffffffu;
-    const bool lane_core = lane >= 1 && lane <= 30 && x < (int)a.w;
-    uint32_t valid8 = 0;          // which of the lane's 8 pixels are output pixels
+    Lane L;
+    L.cs0 = L.cs1 = L.cs2 = L.cs3 = 0;
+    set_ny(L, m, 15);
+    const bool lane_core = lane >= 1 && lane <= 30 && m.x < m.w;
+    L.valid8 = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++)
-        if (lane_core && x + j < (int)a.w) valid8 |= 1u << j;
+        if (lane_core && m.x + j < m.w) L.valid8 |= 1u << j;
+    L.store_mode = !lane_core ? 0 : ((a.wide_stores && L.valid8 == 0xffu) ? 1 : 2);
+    const size_t o_px = ((size_t)frame * a.h + m.ys) * a.w + m.x;
+    L.grey = a.grey + o_px;
+    L.mask = a.mask + o_px;
+    L.bits = a.bits + ((size_t)frame * a.h + m.ys) * a.bits_row_bytes + (m.x >> 3);
+    L.row_px = a.w;
+    L.row_bits = a.bits_row_bytes;
 
-    uint32_t cs0 = 0, cs1 = 0, cs2 = 0, cs3 = 0;  // running 15-row column sums, u16 pairs
-    uint32_t stage = 0, parity = 0;
-    // output pointers of the lane's 8 pixels in row ys, advanced by one row per output row
-    size_t o_px = ((size_t)frame * a.h + ys) * a.w + x;
-    size_t o_bits = ((size_t)frame * a.h + ys) * a.bits_row_bytes + (x >> 3);
-
-    for (int b = 0; b < nblocks; b++) {
-        mbar_wait(&full[stage], parity);
-        const uint8_t *srow = stage_mem + stage * kStageBytes;
-#pragma unroll
-        for (int r = 0; r < ROWS; r++) {
-            const int k = b * ROWS + r;
-            if (k < total_rows) {  // warp-uniform
-                uint32_t p01, p23, p45, p67, g03, g47;
-                load_grey8<FMT>(srow + r * Fmt<FMT>::row_bytes, lane, p01, p23, p45, p67, g03, g47);
-                // input row k lives in ring slot k & 15; the row leaving the 15-row window is k - 15
-                const uint2 old = ring[32 * ((k + 1) & 15)];
-                ring[32 * (k & 15)] = make_uint2(g03, g47);
-                cs0 = cs0 + p01 - __byte_perm(old.x, 0u, 0x4140);
-                cs1 = cs1 + p23 - __byte_perm(old.x, 0u, 0x4342);
-                cs2 = cs2 + p45 - __byte_perm(old.y, 0u, 0x4140);
-                cs3 = cs3 + p67 - __byte_perm(old.y, 0u, 0x4342);
-                if (k >= 14) {
-                    const int yo = ys + k - 14;
-                    const uint32_t ny = (uint32_t)(min((int)a.h - 1, yo + 7) - max(0, yo - 7) + 1);
-                    if (ny != ny_cur) {  // only in the top / bottom 7 rows of the frame
-                        ny_cur = ny;
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const uint32_t c = nx[j] * ny;
-                            cvec[j] = c << (8 * (j & 3));
-                            tbase[j] = 0u - 256u * c;
-                        }
-                    }
-                    // pair words of columns -8..15 relative to the lane's first column
-                    uint32_t w[12];
-                    w[0] = __shfl_up_sync(0xffffffffu, cs0, 1); w[1] = __shfl_up_sync(0xffffffffu, cs1, 1);
-                    w[2] = __shfl_up_sync(0xffffffffu, cs2, 1); w[3] = __shfl_up_sync(0xffffffffu, cs3, 1);
-                    w[4] = cs0; w[5] = cs1; w[6] = cs2; w[7] = cs3;
-                    w[8] = __shfl_down_sync(0xffffffffu, cs0, 1); w[9] = __shfl_down_sync(0xffffffffu, cs1, 1);
-                    w[10] = __shfl_down_sync(0xffffffffu, cs2, 1); w[11] = __shfl_down_sync(0xffffffffu, cs3, 1);
-                    uint32_t f[12];
-#pragma unroll
-                    for (int i = 1; i <= 10; i++) f[i] = __dp2a_lo(w[i], 0x0101u, 0u);  // lo + hi
-                    uint32_t T[4];
-                    T[0] = (f[1] + f[2] + f[3]) + (f[4] + f[5] + f[6]) + f[7];
-                    T[1] = T[0] + f[8] - f[1];
-                    T[2] = T[1] + f[9] - f[2];
-                    T[3] = T[2] + f[10] - f[3];
-                    const uint2 pix = ring[32 * ((k + 9) & 15)];  // row k - 7 = the output row
-                    const uint32_t pc0 = ~pix.x, pc1 = ~pix.y;
-                    uint32_t bits8 = 0;
-#pragma unroll
-                    for (int j = 7; j >= 0; j--) {
-                        // S - 256 cnt:  even column j: T[j/2] + hi(w[j/2]);  odd: T[j/2] + lo(w[(j+15)/2])
-                        const uint32_t acc = (j & 1) ? __dp2a_lo(w[(j + 15) / 2], 0x0001u, T[j / 2] + tbase[j])
-                                                     : __dp2a_lo(w[j / 2], 0x0100u, T[j / 2] + tbase[j]);
-                        const uint32_t u = __dp4a(j < 4 ? pc0 : pc1, cvec[j], acc);  // + (255 - pix) * cnt
-                        bits8 = __funnelshift_l(u, bits8, 1);                        // sign bit: S < (pix + 1) * cnt
-                    }
-                    bits8 &= valid8;
-                    if (lane_core) {
-                        const size_t o = o_px;
-                        if (a.wide_stores && valid8 == 0xffu) {
-                            *reinterpret_cast<uint2 *>(a.grey + o) = pix;
-                            if constexpr (MASK) *reinterpret_cast<uint2 *>(a.mask + o) = make_uint2(expand4(bits8 & 15u), expand4(bits8 >> 4));
-                        } else {
-                            if (valid8 & 0x0fu) {
-                                *reinterpret_cast<uint32_t *>(a.grey + o) = pix.x;
-                                if constexpr (MASK) *reinterpret_cast<uint32_t *>(a.mask + o) = expand4(bits8 & 15u);
-                            }
-                            if (valid8 & 0xf0u) {
-                                *reinterpret_cast<uint32_t *>(a.grey + o + 4) = pix.y;
-                                if constexpr (MASK) *reinterpret_cast<uint32_t *>(a.mask + o + 4) = expand4(bits8 >> 4);
-                            }
-                        }
-                        if constexpr (BITS) a.bits[o_bits] = (uint8_t)bits8;
-                    }
-                    o_px += a.w;
-                    o_bits += a.bits_row_bytes;
-                }
-            }
+    for (int k0 = 0; k0 < m.total_rows; k0 += kBody) {
+        const uint32_t ring_lo = m.ring + ((uint32_t)(k0 & 8) << 8);
+        const uint32_t ring_hi = m.ring + ((uint32_t)((k0 & 8) ^ 8) << 8);
+        const int yo_first = m.ys + k0 - 14;  // output row of the body's first input row
+        const bool fast = k0 >= 16 && k0 + kBody <= m.total_rows && yo_first >= 7 && yo_first + 7 <= m.h - 8;
+        if (fast) {
+            if (L.ny_cur != 15u) set_ny(L, m, 15);
+            body_rows<FMT, MASK, BITS, true, 0>(L, m, k0, ring_lo, ring_hi);
+        } else {
+            body_rows<FMT, MASK, BITS, false, 0>(L, m, k0, ring_lo, ring_hi);
         }
-        // every lane has consumed the stage (its values are in registers): refill it with the block `stages` ahead
-        __syncwarp();
-        if (lane == 0 && b + (int)a.stages < nblocks) {
-            mbar_expect_tx(&full[stage], kTxBytes);
-            tma_load_box(stage_mem + stage * kStageBytes, &tmap, cx, ys - 7 + (b + (int)a.stages) * ROWS, (int)frame, &full[stage]);
-        }
-        if (++stage == a.stages) { stage = 0; parity ^= 1u; }
     }
 }
 
@@ -298,7 +404,7 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-template <int FMT, int ROWS>
+template <int FMT>
 cudaError_t launch_strips(const CUtensorMap &map, const StripArgs &a, bool mask, bool bits, uint32_t grid, size_t smem, cudaStream_t stream) {
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -306,8 +412,8 @@ cudaError_t launch_strips(const CUtensorMap &map, const StripArgs &a, bool mask,
         kern<<<grid, kWarpsPerCta * 32, smem, stream>>>(map, a);
         return cudaGetLastError();
     };
-    if (mask) return bits ? go(k1_strips_kernel<FMT, ROWS, true, true>) : go(k1_strips_kernel<FMT, ROWS, true, false>);
-    return bits ? go(k1_strips_kernel<FMT, ROWS, false, true>) : go(k1_strips_kernel<FMT, ROWS, false, false>);
+    if (mask) return bits ? go(k1_strips_kernel<FMT, true, true>) : go(k1_strips_kernel<FMT, true, false>);
+    return bits ? go(k1_strips_kernel<FMT, false, true>) : go(k1_strips_kernel<FMT, false, false>);
 }
 
 }  // namespace
@@ -321,16 +427,13 @@ bool k1_strips_eligible(const K1Params &p) {
 
 cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t stream, K1LaunchInfo *info) {
     const uint32_t bpp = p.format == A3_FMT_RGB8 ? 3 : (p.format == A3_FMT_RGBA8 ? 4 : 1);
-    const uint32_t rows = tuning && tuning->tma_rows ? tuning->tma_rows : 2;
-    const uint32_t stages = tuning && tuning->tma_stages ? tuning->tma_stages : 2;
-    if (rows != 1 && rows != 2 && rows != 4) return cudaErrorInvalidValue;
 
     // ---- tensor map over the frames viewed as u32 [n][h][pitch / 4]; dim 0 stops at the last pixel's bytes ----
     CUtensorMap map;
     const cuuint64_t gdim[3] = {(cuuint64_t)p.w * bpp / 4, p.h, p.n};
     const cuuint64_t gstride[2] = {p.pitch, p.frame_stride};
     const uint32_t row_bytes = (256u + (p.format == A3_FMT_RGBA8 ? 0u : 16u)) * bpp;  // Fmt<>::row_bytes
-    const cuuint32_t box[3] = {row_bytes / 4, rows, 1};
+    const cuuint32_t box[3] = {row_bytes / 4, (cuuint32_t)kBoxRows, 1};
     const cuuint32_t estride[3] = {1, 1, 1};
     const CUresult cr = encode_tiled_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(p.src), gdim, gstride, box, estride,
                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -340,12 +443,12 @@ cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t st
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t stage_bytes = (rows * row_bytes + 127) & ~127u;
-    const uint32_t per_warp = ((stages * stage_bytes + kRing * 256 + 8 * stages) + 127) & ~127u;
+    const uint32_t per_warp = p.format == A3_FMT_RGB8 ? Stage<A3_FMT_RGB8>::per_warp
+                              : (p.format == A3_FMT_RGBA8 ? Stage<A3_FMT_RGBA8>::per_warp : Stage<A3_FMT_LUMA8>::per_warp);
     const size_t smem = (size_t)per_warp * kWarpsPerCta;
-    if (smem > 220 * 1024) return cudaErrorInvalidValue;
     uint32_t ctas_per_sm = (uint32_t)((227 * 1024) / (smem + 1024));
-    if (ctas_per_sm > 16) ctas_per_sm = 16;  // 64 warps per SM
+    const uint32_t reg_limit = 65536u / (kWarpsPerCta * 32u * 80u);  // ~80 registers per thread
+    if (ctas_per_sm > reg_limit) ctas_per_sm = reg_limit;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const uint32_t slots = (uint32_t)sms * ctas_per_sm * kWarpsPerCta;  // warps resident at once
 
@@ -353,13 +456,13 @@ cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t st
     a.grey = p.grey; a.mask = p.mask; a.bits = reinterpret_cast<uint8_t *>(p.bits);
     a.n = p.n; a.w = p.w; a.h = p.h;
     a.nstrips = (p.w + kCore - 1) / kCore;
-    // row segments: one resident wave when the batch is small (largest segment count that still fits), whole
-    // frames otherwise; every segment re-reads a 14-row halo, so segments stay >= 64 rows
+    // row segments: as many as still fit in ONE wave of resident warps (measured best on B200: 64 x 1080p -> 8
+    // segments, 256 x 1080p -> 2); every segment re-reads a 14-row halo, so they stay >= 128 rows
     uint32_t nsegs = tuning && tuning->seg_rows ? (p.h + tuning->seg_rows - 1) / tuning->seg_rows : 0;
     if (nsegs == 0) {
         const uint64_t per_seg = (uint64_t)p.n * a.nstrips;
         nsegs = per_seg >= slots ? 1 : (uint32_t)(slots / per_seg);
-        const uint32_t max_segs = p.h / 64 ? p.h / 64 : 1;
+        const uint32_t max_segs = p.h / 128 ? p.h / 128 : 1;
         if (nsegs > max_segs) nsegs = max_segs;
     }
     a.seg_rows = (p.h + nsegs - 1) / nsegs;
@@ -368,7 +471,7 @@ cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t st
     if (njobs > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     a.njobs = (uint32_t)njobs;
     a.bits_row_bytes = 4 * ((p.w + 31) / 32);
-    a.stages = stages;
+    a.stages = kStages;
     a.wide_stores = (p.w % 8 == 0) && ((uintptr_t)p.grey % 8 == 0) && ((uintptr_t)p.mask % 8 == 0);
     const uint32_t grid = (a.njobs + kWarpsPerCta - 1) / kWarpsPerCta;
 
@@ -385,18 +488,9 @@ cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t st
     }
     const bool mask = p.mask != nullptr, bits = p.bits != nullptr;
     switch (p.format) {
-        case A3_FMT_RGB8:
-            return rows == 1   ? launch_strips<A3_FMT_RGB8, 1>(map, a, mask, bits, grid, smem, stream)
-                   : rows == 2 ? launch_strips<A3_FMT_RGB8, 2>(map, a, mask, bits, grid, smem, stream)
-                               : launch_strips<A3_FMT_RGB8, 4>(map, a, mask, bits, grid, smem, stream);
-        case A3_FMT_RGBA8:
-            return rows == 1   ? launch_strips<A3_FMT_RGBA8, 1>(map, a, mask, bits, grid, smem, stream)
-                   : rows == 2 ? launch_strips<A3_FMT_RGBA8, 2>(map, a, mask, bits, grid, smem, stream)
-                               : launch_strips<A3_FMT_RGBA8, 4>(map, a, mask, bits, grid, smem, stream);
-        case A3_FMT_LUMA8:
-            return rows == 1   ? launch_strips<A3_FMT_LUMA8, 1>(map, a, mask, bits, grid, smem, stream)
-                   : rows == 2 ? launch_strips<A3_FMT_LUMA8, 2>(map, a, mask, bits, grid, smem, stream)
-                               : launch_strips<A3_FMT_LUMA8, 4>(map, a, mask, bits, grid, smem, stream);
+        case A3_FMT_RGB8: return launch_strips<A3_FMT_RGB8>(map, a, mask, bits, grid, smem, stream);
+        case A3_FMT_RGBA8: return launch_strips<A3_FMT_RGBA8>(map, a, mask, bits, grid, smem, stream);
+        case A3_FMT_LUMA8: return launch_strips<A3_FMT_LUMA8>(map, a, mask, bits, grid, smem, stream);
         default: return cudaErrorInvalidValue;
     }
 }
