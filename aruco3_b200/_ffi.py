@@ -42,7 +42,7 @@ class A3Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_frames", "n_contours", "n_contour_points", "n_candidates_before_discard",
                                           "n_candidates", "n_markers")] + \
                [(n, C.c_double) for n in ("ms_h2d", "ms_pixel_kernel", "ms_mask_d2h", "ms_host_quads",
-                                          "ms_decode_kernel", "ms_d2h", "ms_total")] + \
+                                          "ms_decode_kernel", "ms_host_cpu", "ms_total")] + \
                [(n, C.c_uint32) for n in ("pixel_kernel_launches", "decode_kernel_launches", "host_threads", "reserved")]
 
     def as_dict(self):
@@ -56,8 +56,8 @@ class A3Outputs(C.Structure):
 
 
 class A3K1Tuning(C.Structure):
-    _fields_ = [(n, C.c_uint32) for n in ("strip_cols", "seg_rows", "force_no_tma", "force_generic", "tma_rows", "tma_stages",
-                                          "chunk_frames", "reserved")]
+    _fields_ = [(n, C.c_uint32) for n in ("strip_cols", "seg_rows", "force_no_tma", "force_generic", "chunk_frames")] + \
+               [("reserved", C.c_uint32 * 3)]
 
 
 class A3Error(RuntimeError):

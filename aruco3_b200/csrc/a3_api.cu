@@ -1,16 +1,26 @@
 // C ABI of the detection path (include/aruco3_b200.h): detector handle, the batched pipeline and the stage probes.
 //
-// Pipeline of a3_detect_batch, per chunk of frames (frames are independent, src/aruco.rs:52-121 is a pure
-// function of one image, so chunks — and GPUs — never exchange data):
-//   H2D frames (skipped for device input) -> K1 (grey + 1-bit mask) -> D2H mask bits
-//   -> host threads: border following + quad filters, one frame per task (host_quads.cpp)
-//   -> H2D quads -> K2 (warp, otsu, bits, dictionary match) -> D2H decode records -> markers in candidate order.
-// Two chunk slots are kept in flight so the host stage of chunk c overlaps the device stages of chunk c+1.
+// Pipeline of a3_detect_batch (frames are independent — src/aruco.rs:52-121 is a pure function of one image — so
+// frames, chunks and GPUs never exchange data):
+//
+//   copy stream     H2D of front-end chunk j into a staging ring            (host input only)
+//   pixel stream    K1 (grey + 1-bit mask, k1_strips.cu) -> D2H of the mask bits -> event[j]
+//   host pool       persistent threads; frame f becomes runnable when event[chunk of f] has fired; one task = border
+//                   following + quad filters of one frame (host_quads.cpp)
+//   decode stream   per group of frames whose quads are ready: H2D quads -> K2 (k2_decode.cu) -> D2H decode records
+//   caller thread   feeds the pool, launches decode groups, finally assembles markers in frame / candidate order
+//
+// Device input runs K1 once over the whole (super-)batch; host input runs it per front-end chunk right behind the
+// copy, so the PCIe transfer, the host stage and the decode kernel all overlap.
 // There is no CPU fallback: without a CUDA device every compute entry point returns A3_ERR_CUDA.
 #include <string.h>
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -59,14 +69,96 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-struct Slot {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_h2d = nullptr, ev_k1 = nullptr, ev_bits = nullptr, ev_k2a = nullptr, ev_k2b = nullptr;
-    DevBuf<uint8_t> d_src, d_grey, d_mask, d_patches;
-    DevBuf<uint32_t> d_bits, d_quads, d_qframe;
-    DevBuf<a3_decode> d_dec;
-    PinBuf<uint32_t> h_bits, h_quads, h_qframe;
+// Persistent host threads.  A job is a function of a frame index; indices [0, ready) may be claimed.
+class WorkerPool {
+public:
+    ~WorkerPool() { stop(); }
+    void resize(uint32_t threads) {
+        if (threads == workers_.size()) return;
+        stop();
+        quit_ = false;
+        for (uint32_t t = 0; t < threads; t++) workers_.emplace_back([this] { loop(); });
+    }
+    uint32_t size() const { return (uint32_t)workers_.size(); }
+    void begin(std::function<void(uint32_t)> fn, uint32_t total) {
+        std::lock_guard<std::mutex> lk(mu_);
+        fn_ = std::move(fn); total_ = total; next_ = 0; ready_ = 0; done_ = 0;
+    }
+    void publish(uint32_t upto) {
+        { std::lock_guard<std::mutex> lk(mu_); if (upto > ready_) ready_ = upto; }
+        cv_.notify_all();
+    }
+    // Tasks do not finish in index order; callers keep their own counters inside the job function and sleep on them
+    // with wait_caller(); the job calls notify_caller() when a counter reaches its goal.
+    void notify_caller() { { std::lock_guard<std::mutex> lk(mu_); } cv_done_.notify_all(); }
+    template <typename Pred>
+    void wait_caller(Pred pred) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, pred);
+    }
+    void finish() {  // block until all `total` tasks are done
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [this] { return done_ >= total_; });
+        fn_ = nullptr;
+    }
+
+private:
+    void loop() {
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_.wait(lk, [this] { return quit_ || (fn_ && next_ < ready_); });
+            if (quit_) return;
+            const uint32_t i = next_++;
+            lk.unlock();
+            fn_(i);  // fn_ stays alive until finish(), which waits for this task
+            lk.lock();
+            if (++done_ >= total_) cv_done_.notify_all();
+        }
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(mu_); quit_ = true; }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+        workers_.clear();
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, cv_done_;
+    std::function<void(uint32_t)> fn_;
+    uint32_t total_ = 0, next_ = 0, ready_ = 0, done_ = 0;
+    bool quit_ = false;
+};
+
+// Buffers of one decode group (the quads of a few frames); kept for reuse across calls.
+struct DecodeBlock {
+    PinBuf<uint32_t> h_quads, h_qframe;
     PinBuf<a3_decode> h_dec;
+    DevBuf<uint32_t> d_quads, d_qframe;
+    DevBuf<a3_decode> d_dec;
+    DevBuf<uint8_t> d_patches;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    uint32_t n_quads = 0;
+    void release() {
+        h_quads.release(); h_qframe.release(); h_dec.release(); d_quads.release(); d_qframe.release(); d_dec.release(); d_patches.release();
+        for (cudaEvent_t *e : {&ev_a, &ev_b}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
+    }
+};
+
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    cudaError_t get(cudaEvent_t *out) {
+        if (used == ev.size()) {
+            cudaEvent_t e;
+            cudaError_t r = cudaEventCreate(&e);
+            if (r != cudaSuccess) return r;
+            ev.push_back(e);
+        }
+        *out = ev[used++];
+        return cudaSuccess;
+    }
+    void reset() { used = 0; }
+    void release() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); used = 0; }
 };
 
 }  // namespace
@@ -79,13 +171,20 @@ struct a3_detector {
     uint32_t host_threads = 1;
     uint32_t mark_size = 0;
     uint32_t max_taps = 0;
-    a3::Slot slot[2];
     a3::K1Tuning k1_tuning{};
     bool has_tuning = false;
     uint32_t chunk_override = 0;
+    cudaStream_t s_copy = nullptr, s_pixel = nullptr, s_decode = nullptr;
+    a3::DevBuf<uint8_t> d_src, d_grey, d_mask, d_patches;
+    a3::DevBuf<uint32_t> d_bits, d_quads, d_qframe;
+    a3::DevBuf<a3_decode> d_dec;
+    a3::PinBuf<uint32_t> h_bits;
     a3::DevBuf<uint64_t> d_codes;
     a3::DevBuf<float> d_taps;
     a3::DevBuf<int> d_meta;
+    a3::EventPool events;
+    std::vector<std::unique_ptr<a3::DecodeBlock>> blocks;
+    a3::WorkerPool pool;
 };
 
 namespace a3 {
@@ -103,40 +202,17 @@ a3_status check_config(const a3_config &c) {
 
 uint32_t bytes_per_pixel(a3_format f) { return f == A3_FMT_RGB8 ? 3 : (f == A3_FMT_RGBA8 ? 4 : 1); }
 
-// frames per chunk: bounded device footprint, enough CTAs per launch
-uint32_t chunk_frames(uint32_t n, uint32_t w, uint32_t h, uint32_t bpp) {
-    const size_t per_frame = (size_t)w * h * (bpp + 2);
-    size_t c = ((size_t)768 << 20) / (per_frame ? per_frame : 1);
-    if (c < 1) c = 1;
-    if (c > 64) c = 64;
-    if (c > n) c = n;
-    return (uint32_t)c;
-}
-
-// run fn(i) for i in [0, n) on `threads` host threads
-template <typename F>
-void parallel_for(uint32_t n, uint32_t threads, F fn) {
-    if (threads <= 1 || n <= 1) {
-        for (uint32_t i = 0; i < n; i++) fn(i);
-        return;
-    }
-    if (threads > n) threads = n;
-    std::atomic<uint32_t> next{0};
-    std::vector<std::thread> pool;
-    pool.reserve(threads);
-    for (uint32_t t = 0; t < threads; t++)
-        pool.emplace_back([&] {
-            for (;;) {
-                const uint32_t i = next.fetch_add(1);
-                if (i >= n) break;
-                fn(i);
-            }
-        });
-    for (auto &th : pool) th.join();
-}
-
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+K2Params k2_params(const a3_detector *d, const uint8_t *grey, uint32_t w, uint32_t h) {
+    K2Params p;
+    p.grey = grey; p.w = w; p.h = h; p.quads = nullptr; p.quad_frame = nullptr; p.n_quads = 0;
+    p.patch_size = d->cfg.homography_sample_size; p.mark_size = d->mark_size; p.codes = d->d_codes.p;
+    p.n_codes = d->dict.n_codes; p.tau = d->dict.tau; p.filter_high_bit_errors = d->cfg.filter_high_bit_errors;
+    p.resize_w = d->d_taps.p; p.resize_meta = d->d_meta.p; p.decodes = nullptr; p.patches = nullptr;
+    return p;
 }
 
 }  // namespace
@@ -202,11 +278,8 @@ a3_status a3_detector_create(const a3_config *cfg, const a3_dictionary *dict, in
     if (e == cudaSuccess) e = cudaMemcpy(d->d_taps.p, tp.weights.data(), tp.weights.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = d->d_meta.reserve(tp.meta.size());
     if (e == cudaSuccess) e = cudaMemcpy(d->d_meta.p, tp.meta.data(), tp.meta.size() * 4, cudaMemcpyHostToDevice);
-    for (auto &s : d->slot) {
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
-        for (cudaEvent_t *ev : {&s.ev_start, &s.ev_h2d, &s.ev_k1, &s.ev_bits, &s.ev_k2a, &s.ev_k2b})
-            if (e == cudaSuccess) e = cudaEventCreate(ev);
-    }
+    for (cudaStream_t *s : {&d->s_copy, &d->s_pixel, &d->s_decode})
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         a3_detector_destroy(d);
         return cuda_fail(e, "a3_detector_create");
@@ -218,15 +291,13 @@ a3_status a3_detector_create(const a3_config *cfg, const a3_dictionary *dict, in
 void a3_detector_destroy(a3_detector *d) {
     if (!d) return;
     cudaSetDevice(d->device);
-    for (auto &s : d->slot) {
-        if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
-        for (cudaEvent_t ev : {s.ev_start, s.ev_h2d, s.ev_k1, s.ev_bits, s.ev_k2a, s.ev_k2b})
-            if (ev) cudaEventDestroy(ev);
-        s.d_src.release(); s.d_grey.release(); s.d_mask.release(); s.d_patches.release();
-        s.d_bits.release(); s.d_quads.release(); s.d_qframe.release(); s.d_dec.release();
-        s.h_bits.release(); s.h_quads.release(); s.h_qframe.release(); s.h_dec.release();
-    }
+    for (cudaStream_t s : {d->s_copy, d->s_pixel, d->s_decode})
+        if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    d->d_src.release(); d->d_grey.release(); d->d_mask.release(); d->d_patches.release();
+    d->d_bits.release(); d->d_quads.release(); d->d_qframe.release(); d->d_dec.release(); d->h_bits.release();
     d->d_codes.release(); d->d_taps.release(); d->d_meta.release();
+    d->events.release();
+    for (auto &b : d->blocks) b->release();
     delete d;
 }
 
@@ -242,10 +313,8 @@ a3_status a3_detector_set_k1_tuning(a3_detector *d, const a3_k1_tuning *t) {
     d->k1_tuning = K1Tuning{};
     d->chunk_override = 0;
     if (t) {
-        if (t->tma_rows != 0 && t->tma_rows != 1 && t->tma_rows != 2 && t->tma_rows != 4) return fail(A3_ERR_INVALID_ARGUMENT, "tma_rows must be 0, 1, 2 or 4");
-        if (t->tma_stages > 8) return fail(A3_ERR_INVALID_ARGUMENT, "tma_stages must be <= 8");
         d->k1_tuning.strip_cols = t->strip_cols; d->k1_tuning.seg_rows = t->seg_rows; d->k1_tuning.force_no_tma = (int)t->force_no_tma;
-        d->k1_tuning.force_generic = (int)t->force_generic; d->k1_tuning.tma_rows = t->tma_rows; d->k1_tuning.tma_stages = t->tma_stages;
+        d->k1_tuning.force_generic = (int)t->force_generic;
         d->chunk_override = t->chunk_frames;
     }
     return A3_OK;
@@ -260,32 +329,35 @@ a3_status a3_gray_threshold_batch(a3_detector *d, const void *frames, a3_format 
     const uint32_t bpp = bytes_per_pixel(format);
     if (pitch < (size_t)w * bpp || frame_stride < pitch * h) return fail(A3_ERR_INVALID_ARGUMENT, "pitch / frame_stride too small");
     A3_CUDA(cudaSetDevice(d->device));
+    const K1Tuning *tune = d->has_tuning ? &d->k1_tuning : nullptr;
     K1Params p;
     p.format = format; p.n = n; p.w = w; p.h = h; p.pitch = pitch; p.frame_stride = frame_stride; p.radius = d->cfg.threshold_window;
     if (mem == A3_MEM_DEVICE) {
         p.src = static_cast<const uint8_t *>(frames); p.grey = grey; p.mask = mask; p.bits = mask_bits;
-        A3_CUDA(k1_gray_threshold(p, d->has_tuning ? &d->k1_tuning : nullptr, static_cast<cudaStream_t>(cuda_stream), nullptr));
+        A3_CUDA(k1_gray_threshold(p, tune, static_cast<cudaStream_t>(cuda_stream), nullptr));
         return A3_OK;
     }
-    // host pointers: stage through slot 0, chunk by chunk, synchronously
-    Slot &s = d->slot[0];
+    // host pointers: stage chunk by chunk, synchronously
+    cudaStream_t s = d->s_pixel;
     const size_t px = (size_t)w * h, wpr = (w + 31) / 32;
-    const uint32_t chunk = chunk_frames(n, w, h, bpp);
-    for (uint32_t f0 = 0; f0 < n; f0 += chunk) {
-        const uint32_t c = n - f0 < chunk ? n - f0 : chunk;
-        A3_CUDA(s.d_src.reserve((size_t)c * frame_stride));
-        A3_CUDA(cudaMemcpyAsync(s.d_src.p, static_cast<const uint8_t *>(frames) + (size_t)f0 * frame_stride, (size_t)c * frame_stride,
-                                cudaMemcpyHostToDevice, s.stream));
-        if (grey) A3_CUDA(s.d_grey.reserve(c * px));
-        if (mask) A3_CUDA(s.d_mask.reserve(c * px));
-        if (mask_bits) A3_CUDA(s.d_bits.reserve(c * wpr * h));
-        p.src = s.d_src.p; p.n = c;
-        p.grey = grey ? s.d_grey.p : nullptr; p.mask = mask ? s.d_mask.p : nullptr; p.bits = mask_bits ? s.d_bits.p : nullptr;
-        A3_CUDA(k1_gray_threshold(p, d->has_tuning ? &d->k1_tuning : nullptr, s.stream, nullptr));
-        if (grey) A3_CUDA(cudaMemcpyAsync(grey + f0 * px, s.d_grey.p, c * px, cudaMemcpyDeviceToHost, s.stream));
-        if (mask) A3_CUDA(cudaMemcpyAsync(mask + f0 * px, s.d_mask.p, c * px, cudaMemcpyDeviceToHost, s.stream));
-        if (mask_bits) A3_CUDA(cudaMemcpyAsync(mask_bits + f0 * wpr * h, s.d_bits.p, c * wpr * h * 4, cudaMemcpyDeviceToHost, s.stream));
-        A3_CUDA(cudaStreamSynchronize(s.stream));
+    size_t chunk = ((size_t)512 << 20) / (frame_stride + 2 * px + 1);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    for (uint32_t f0 = 0; f0 < n; f0 += (uint32_t)chunk) {
+        const uint32_t c = n - f0 < chunk ? n - f0 : (uint32_t)chunk;
+        A3_CUDA(d->d_src.reserve((size_t)c * frame_stride));
+        A3_CUDA(cudaMemcpyAsync(d->d_src.p, static_cast<const uint8_t *>(frames) + (size_t)f0 * frame_stride, (size_t)c * frame_stride,
+                                cudaMemcpyHostToDevice, s));
+        if (grey) A3_CUDA(d->d_grey.reserve(c * px));
+        if (mask) A3_CUDA(d->d_mask.reserve(c * px));
+        if (mask_bits) A3_CUDA(d->d_bits.reserve(c * wpr * h));
+        p.src = d->d_src.p; p.n = c;
+        p.grey = grey ? d->d_grey.p : nullptr; p.mask = mask ? d->d_mask.p : nullptr; p.bits = mask_bits ? d->d_bits.p : nullptr;
+        A3_CUDA(k1_gray_threshold(p, tune, s, nullptr));
+        if (grey) A3_CUDA(cudaMemcpyAsync(grey + f0 * px, d->d_grey.p, c * px, cudaMemcpyDeviceToHost, s));
+        if (mask) A3_CUDA(cudaMemcpyAsync(mask + f0 * px, d->d_mask.p, c * px, cudaMemcpyDeviceToHost, s));
+        if (mask_bits) A3_CUDA(cudaMemcpyAsync(mask_bits + f0 * wpr * h, d->d_bits.p, c * wpr * h * 4, cudaMemcpyDeviceToHost, s));
+        A3_CUDA(cudaStreamSynchronize(s));
     }
     return A3_OK;
 }
@@ -318,25 +390,23 @@ a3_status a3_decode_candidates(a3_detector *d, const uint8_t *grey, uint32_t n_f
     for (uint32_t i = 0; quad_frame && i < n_quads; i++)
         if (quad_frame[i] >= n_frames) return fail(A3_ERR_INVALID_ARGUMENT, "a3_decode_candidates: quad_frame out of range");
     A3_CUDA(cudaSetDevice(d->device));
-    Slot &s = d->slot[0];
+    cudaStream_t s = d->s_decode;
     const size_t px = (size_t)w * h, np = (size_t)d->cfg.homography_sample_size * d->cfg.homography_sample_size;
-    A3_CUDA(s.d_grey.reserve(px * n_frames));
-    A3_CUDA(s.d_quads.reserve((size_t)n_quads * 8));
-    A3_CUDA(s.d_qframe.reserve(n_quads));
-    A3_CUDA(s.d_dec.reserve(n_quads));
-    if (patches) A3_CUDA(s.d_patches.reserve(n_quads * np));
-    A3_CUDA(cudaMemcpyAsync(s.d_grey.p, grey, px * n_frames, cudaMemcpyHostToDevice, s.stream));
-    A3_CUDA(cudaMemcpyAsync(s.d_quads.p, quads, (size_t)n_quads * 32, cudaMemcpyHostToDevice, s.stream));
-    if (quad_frame) A3_CUDA(cudaMemcpyAsync(s.d_qframe.p, quad_frame, (size_t)n_quads * 4, cudaMemcpyHostToDevice, s.stream));
-    K2Params p;
-    p.grey = s.d_grey.p; p.w = w; p.h = h; p.quads = s.d_quads.p; p.quad_frame = quad_frame ? s.d_qframe.p : nullptr;
-    p.n_quads = n_quads; p.patch_size = d->cfg.homography_sample_size; p.mark_size = d->mark_size;
-    p.codes = d->d_codes.p; p.n_codes = d->dict.n_codes; p.tau = d->dict.tau; p.filter_high_bit_errors = d->cfg.filter_high_bit_errors;
-    p.resize_w = d->d_taps.p; p.resize_meta = d->d_meta.p; p.decodes = s.d_dec.p; p.patches = patches ? s.d_patches.p : nullptr;
-    A3_CUDA(k2_decode(p, s.stream));
-    A3_CUDA(cudaMemcpyAsync(decodes, s.d_dec.p, (size_t)n_quads * sizeof(a3_decode), cudaMemcpyDeviceToHost, s.stream));
-    if (patches) A3_CUDA(cudaMemcpyAsync(patches, s.d_patches.p, n_quads * np, cudaMemcpyDeviceToHost, s.stream));
-    A3_CUDA(cudaStreamSynchronize(s.stream));
+    A3_CUDA(d->d_grey.reserve(px * n_frames));
+    A3_CUDA(d->d_quads.reserve((size_t)n_quads * 8));
+    A3_CUDA(d->d_qframe.reserve(n_quads));
+    A3_CUDA(d->d_dec.reserve(n_quads));
+    if (patches) A3_CUDA(d->d_patches.reserve(n_quads * np));
+    A3_CUDA(cudaMemcpyAsync(d->d_grey.p, grey, px * n_frames, cudaMemcpyHostToDevice, s));
+    A3_CUDA(cudaMemcpyAsync(d->d_quads.p, quads, (size_t)n_quads * 32, cudaMemcpyHostToDevice, s));
+    if (quad_frame) A3_CUDA(cudaMemcpyAsync(d->d_qframe.p, quad_frame, (size_t)n_quads * 4, cudaMemcpyHostToDevice, s));
+    K2Params p = k2_params(d, d->d_grey.p, w, h);
+    p.quads = d->d_quads.p; p.quad_frame = quad_frame ? d->d_qframe.p : nullptr; p.n_quads = n_quads;
+    p.decodes = d->d_dec.p; p.patches = patches ? d->d_patches.p : nullptr;
+    A3_CUDA(k2_decode(p, s));
+    A3_CUDA(cudaMemcpyAsync(decodes, d->d_dec.p, (size_t)n_quads * sizeof(a3_decode), cudaMemcpyDeviceToHost, s));
+    if (patches) A3_CUDA(cudaMemcpyAsync(patches, d->d_patches.p, n_quads * np, cudaMemcpyDeviceToHost, s));
+    A3_CUDA(cudaStreamSynchronize(s));
     return A3_OK;
 }
 
@@ -356,154 +426,235 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
     if (pitch < (size_t)w * bpp || frame_stride < pitch * h) return fail(A3_ERR_INVALID_ARGUMENT, "pitch / frame_stride too small");
     A3_CUDA(cudaSetDevice(d->device));
     const double t_begin = now_ms();
-    const size_t px = (size_t)w * h, wpr = (w + 31) / 32, np = (size_t)d->cfg.homography_sample_size * d->cfg.homography_sample_size;
-    uint32_t chunk = chunk_frames(n, w, h, bpp);
-    if (d->chunk_override) chunk = d->chunk_override < n ? d->chunk_override : n;
-    const uint32_t nchunks = (n + chunk - 1) / chunk;
+    const size_t px = (size_t)w * h, wpr = (w + 31) / 32, bits_words = wpr * h;
+    const size_t np = (size_t)d->cfg.homography_sample_size * d->cfg.homography_sample_size;
     const bool want_mask = outs && outs->mask, want_grey = outs && outs->grey, want_patches = outs && outs->homographies;
+    const K1Tuning *tune = d->has_tuning ? &d->k1_tuning : nullptr;
+    const uint8_t *src_all = static_cast<const uint8_t *>(frames);
     a3_stats st;
     memset(&st, 0, sizeof(st));
     st.n_frames = n;
     st.host_threads = d->host_threads;
+    if (d->pool.size() != d->host_threads) d->pool.resize(d->host_threads);
 
-    auto issue = [&](uint32_t c) -> a3_status {  // device front end of chunk c
-        Slot &s = d->slot[c & 1];
-        const uint32_t f0 = c * chunk, cn = n - f0 < chunk ? n - f0 : chunk;
-        const uint8_t *src = static_cast<const uint8_t *>(frames) + (size_t)f0 * frame_stride;
-        A3_CUDA(cudaEventRecord(s.ev_start, s.stream));
-        if (mem == A3_MEM_HOST) {
-            A3_CUDA(s.d_src.reserve((size_t)cn * frame_stride));
-            A3_CUDA(cudaMemcpyAsync(s.d_src.p, src, (size_t)cn * frame_stride, cudaMemcpyHostToDevice, s.stream));
-            src = s.d_src.p;
-        }
-        A3_CUDA(cudaEventRecord(s.ev_h2d, s.stream));
-        A3_CUDA(s.d_grey.reserve(cn * px));
-        A3_CUDA(s.d_bits.reserve(cn * wpr * h));
-        A3_CUDA(s.h_bits.reserve(cn * wpr * h));
-        if (want_mask) A3_CUDA(s.d_mask.reserve(cn * px));
-        K1Params p;
-        p.src = src; p.format = format; p.n = cn; p.w = w; p.h = h; p.pitch = pitch; p.frame_stride = frame_stride;
-        p.grey = s.d_grey.p; p.mask = want_mask ? s.d_mask.p : nullptr; p.bits = s.d_bits.p; p.radius = d->cfg.threshold_window;
-        A3_CUDA(k1_gray_threshold(p, d->has_tuning ? &d->k1_tuning : nullptr, s.stream, nullptr));
-        st.pixel_kernel_launches++;
-        A3_CUDA(cudaEventRecord(s.ev_k1, s.stream));
-        A3_CUDA(cudaMemcpyAsync(s.h_bits.p, s.d_bits.p, cn * wpr * h * 4, cudaMemcpyDeviceToHost, s.stream));
-        if (want_grey) A3_CUDA(cudaMemcpyAsync(outs->grey + f0 * px, s.d_grey.p, cn * px, cudaMemcpyDeviceToHost, s.stream));
-        if (want_mask) A3_CUDA(cudaMemcpyAsync(outs->mask + f0 * px, s.d_mask.p, cn * px, cudaMemcpyDeviceToHost, s.stream));
-        A3_CUDA(cudaEventRecord(s.ev_bits, s.stream));
-        return A3_OK;
-    };
+    // ---- sizes: super-batch (device footprint), front-end chunk (copy / event granularity), decode group ----
+    size_t sb = ((size_t)3 << 30) / (px + bits_words * 4 + (want_mask ? px : 0));  // grey + bits (+ mask) stay resident per frame
+    if (sb < 1) sb = 1;
+    if (sb > n) sb = n;
+    size_t fe = ((size_t)96 << 20) / (frame_stride ? frame_stride : 1);           // ~96 MB of input per front-end chunk
+    if (d->chunk_override) fe = d->chunk_override;
+    if (fe < 1) fe = 1;
+    if (fe > 64) fe = 64;
+    if (fe > sb) fe = sb;
+    const uint32_t group = 32;    // frames per decode launch
+    const uint32_t kStaging = 3;  // staging ring depth (host input)
 
     uint32_t total_markers = 0, total_cands = 0;
     bool overflow = false;
-    if (a3_status s0 = issue(0)) return s0;
     std::vector<std::vector<uint32_t>> frame_quads;
     std::vector<QuadStats> frame_stats;
-    for (uint32_t c = 0; c < nchunks; c++) {
-        if (c + 1 < nchunks)
-            if (a3_status s1 = issue(c + 1)) return s1;
-        Slot &s = d->slot[c & 1];
-        const uint32_t f0 = c * chunk, cn = n - f0 < chunk ? n - f0 : chunk;
-        A3_CUDA(cudaEventSynchronize(s.ev_bits));
+    std::vector<double> frame_ms;
+
+    for (uint32_t s0 = 0; s0 < n; s0 += (uint32_t)sb) {
+        const uint32_t sn = n - s0 < sb ? n - s0 : (uint32_t)sb;
+        const uint32_t nfe = (sn + (uint32_t)fe - 1) / (uint32_t)fe, ngroups = (sn + group - 1) / group;
+        A3_CUDA(d->d_grey.reserve(sn * px));
+        A3_CUDA(d->d_bits.reserve(sn * bits_words));
+        A3_CUDA(d->h_bits.reserve(sn * bits_words));
+        if (want_mask) A3_CUDA(d->d_mask.reserve(sn * px));
+        if (mem == A3_MEM_HOST) A3_CUDA(d->d_src.reserve((size_t)kStaging * fe * frame_stride));
+        while (d->blocks.size() < ngroups) d->blocks.emplace_back(new DecodeBlock());
+        d->events.reset();
+        std::vector<cudaEvent_t> ev_fe(nfe), ev_k1a(nfe), ev_k1b(nfe), ev_h2da(nfe), ev_h2db(nfe);
+        for (uint32_t j = 0; j < nfe; j++) {
+            A3_CUDA(d->events.get(&ev_fe[j])); A3_CUDA(d->events.get(&ev_k1a[j])); A3_CUDA(d->events.get(&ev_k1b[j]));
+            A3_CUDA(d->events.get(&ev_h2da[j])); A3_CUDA(d->events.get(&ev_h2db[j]));
+        }
+        frame_quads.assign(sn, {});
+        frame_stats.assign(sn, QuadStats());
+        frame_ms.assign(sn, 0.0);
+        std::unique_ptr<std::atomic<uint32_t>[]> group_done(new std::atomic<uint32_t>[ngroups]);
+        for (uint32_t g = 0; g < ngroups; g++) group_done[g].store(0);
+        auto group_size = [&](uint32_t g) { return (g + 1) * group <= sn ? group : sn - g * group; };
+
+        // ---- device front end of chunk j (asynchronous) ----
+        auto k1_launch = [&](const uint8_t *src, uint32_t f0, uint32_t cn, uint32_t j) -> a3_status {
+            K1Params p;
+            p.src = src; p.format = format; p.n = cn; p.w = w; p.h = h; p.pitch = pitch; p.frame_stride = frame_stride;
+            p.grey = d->d_grey.p + (size_t)f0 * px; p.mask = want_mask ? d->d_mask.p + (size_t)f0 * px : nullptr;
+            p.bits = d->d_bits.p + (size_t)f0 * bits_words; p.radius = d->cfg.threshold_window;
+            A3_CUDA(cudaEventRecord(ev_k1a[j], d->s_pixel));
+            A3_CUDA(k1_gray_threshold(p, tune, d->s_pixel, nullptr));
+            A3_CUDA(cudaEventRecord(ev_k1b[j], d->s_pixel));
+            st.pixel_kernel_launches++;
+            return A3_OK;
+        };
+        auto bits_d2h = [&](uint32_t f0, uint32_t cn, uint32_t j) -> a3_status {
+            A3_CUDA(cudaMemcpyAsync(d->h_bits.p + (size_t)f0 * bits_words, d->d_bits.p + (size_t)f0 * bits_words, (size_t)cn * bits_words * 4,
+                                    cudaMemcpyDeviceToHost, d->s_pixel));
+            A3_CUDA(cudaEventRecord(ev_fe[j], d->s_pixel));
+            if (want_grey)
+                A3_CUDA(cudaMemcpyAsync(outs->grey + (size_t)(s0 + f0) * px, d->d_grey.p + (size_t)f0 * px, (size_t)cn * px, cudaMemcpyDeviceToHost, d->s_pixel));
+            if (want_mask)
+                A3_CUDA(cudaMemcpyAsync(outs->mask + (size_t)(s0 + f0) * px, d->d_mask.p + (size_t)f0 * px, (size_t)cn * px, cudaMemcpyDeviceToHost, d->s_pixel));
+            return A3_OK;
+        };
+        uint32_t issued = 0;
+        auto issue = [&](uint32_t j) -> a3_status {
+            const uint32_t f0 = j * (uint32_t)fe, cn = sn - f0 < fe ? sn - f0 : (uint32_t)fe;
+            if (mem == A3_MEM_HOST) {
+                uint8_t *slot = d->d_src.p + (size_t)(j % kStaging) * fe * frame_stride;
+                if (j >= kStaging) A3_CUDA(cudaStreamWaitEvent(d->s_copy, ev_k1b[j - kStaging], 0));  // the slot's previous K1 is done
+                A3_CUDA(cudaEventRecord(ev_h2da[j], d->s_copy));
+                A3_CUDA(cudaMemcpyAsync(slot, src_all + (size_t)(s0 + f0) * frame_stride, (size_t)cn * frame_stride, cudaMemcpyHostToDevice, d->s_copy));
+                A3_CUDA(cudaEventRecord(ev_h2db[j], d->s_copy));
+                A3_CUDA(cudaStreamWaitEvent(d->s_pixel, ev_h2db[j], 0));
+                if (a3_status s = k1_launch(slot, f0, cn, j)) return s;
+            } else if (j == 0) {
+                // resident input: one K1 launch over the whole super-batch
+                if (a3_status s = k1_launch(src_all + (size_t)s0 * frame_stride, 0, sn, 0)) return s;
+            }
+            return bits_d2h(f0, cn, j);
+        };
+
+        // ---- host stage: one task per frame ----
+        const a3_config cfg = d->cfg;
+        uint32_t *h_bits = d->h_bits.p;
+        a3_detector *det = d;
+        d->pool.begin([&, h_bits, cfg, det](uint32_t i) {
+            const double t0 = now_ms();
+            quads_from_bits(h_bits + (size_t)i * bits_words, (uint32_t)wpr, w, h, cfg, frame_quads[i], &frame_stats[i]);
+            frame_ms[i] = now_ms() - t0;
+            const uint32_t g = i / group;
+            if (group_done[g].fetch_add(1) + 1 == group_size(g)) det->pool.notify_caller();
+        }, sn);
+
+        // ---- decode of group g (asynchronous) ----
+        auto launch_group = [&](uint32_t g) -> a3_status {
+            DecodeBlock &b = *d->blocks[g];
+            const uint32_t f0 = g * group, f1 = f0 + group_size(g);
+            uint32_t nq = 0;
+            for (uint32_t i = f0; i < f1; i++) nq += (uint32_t)(frame_quads[i].size() / 8);
+            b.n_quads = nq;
+            if (!b.ev_a) { A3_CUDA(cudaEventCreate(&b.ev_a)); A3_CUDA(cudaEventCreate(&b.ev_b)); }
+            if (nq == 0) return A3_OK;
+            A3_CUDA(b.h_quads.reserve((size_t)nq * 8)); A3_CUDA(b.h_qframe.reserve(nq)); A3_CUDA(b.h_dec.reserve(nq));
+            A3_CUDA(b.d_quads.reserve((size_t)nq * 8)); A3_CUDA(b.d_qframe.reserve(nq)); A3_CUDA(b.d_dec.reserve(nq));
+            if (want_patches) A3_CUDA(b.d_patches.reserve(nq * np));
+            uint32_t k = 0;
+            for (uint32_t i = f0; i < f1; i++) {
+                const uint32_t m = (uint32_t)(frame_quads[i].size() / 8);
+                if (m) memcpy(b.h_quads.p + (size_t)k * 8, frame_quads[i].data(), (size_t)m * 32);
+                for (uint32_t q = 0; q < m; q++) b.h_qframe.p[k + q] = i;
+                k += m;
+            }
+            A3_CUDA(cudaMemcpyAsync(b.d_quads.p, b.h_quads.p, (size_t)nq * 32, cudaMemcpyHostToDevice, d->s_decode));
+            A3_CUDA(cudaMemcpyAsync(b.d_qframe.p, b.h_qframe.p, (size_t)nq * 4, cudaMemcpyHostToDevice, d->s_decode));
+            K2Params p = k2_params(d, d->d_grey.p, w, h);
+            p.quads = b.d_quads.p; p.quad_frame = b.d_qframe.p; p.n_quads = nq; p.decodes = b.d_dec.p;
+            p.patches = want_patches ? b.d_patches.p : nullptr;
+            A3_CUDA(cudaEventRecord(b.ev_a, d->s_decode));
+            A3_CUDA(k2_decode(p, d->s_decode));
+            A3_CUDA(cudaEventRecord(b.ev_b, d->s_decode));
+            st.decode_kernel_launches++;
+            A3_CUDA(cudaMemcpyAsync(b.h_dec.p, b.d_dec.p, (size_t)nq * sizeof(a3_decode), cudaMemcpyDeviceToHost, d->s_decode));
+            return A3_OK;
+        };
+        auto drain = [&](a3_status s) {  // an error: let the pool and the streams finish before the buffers go away
+            d->pool.publish(sn);
+            d->pool.finish();
+            cudaStreamSynchronize(d->s_copy); cudaStreamSynchronize(d->s_pixel); cudaStreamSynchronize(d->s_decode);
+            return s;
+        };
+
+        // ---- drive: front end `kStaging` chunks ahead, feed the pool, launch decode groups as they complete ----
+        const double t_host0 = now_ms();
+        a3_status err = A3_OK;
+        uint32_t next_group = 0;
+        for (uint32_t j = 0; j < nfe && !err; j++) {
+            while (issued < nfe && issued < j + kStaging && !err) err = issue(issued++);
+            if (err) break;
+            const cudaError_t e = cudaEventSynchronize(ev_fe[j]);
+            if (e != cudaSuccess) { err = cuda_fail(e, "cudaEventSynchronize(front end)"); break; }
+            const uint32_t upto = (j + 1) * (uint32_t)fe < sn ? (j + 1) * (uint32_t)fe : sn;
+            d->pool.publish(upto);
+            while (next_group < ngroups && !err && group_done[next_group].load() == group_size(next_group)) err = launch_group(next_group++);
+        }
+        if (err) return drain(err);
+        for (; next_group < ngroups; next_group++) {
+            const uint32_t g = next_group;
+            d->pool.wait_caller([&] { return group_done[g].load() == group_size(g); });
+            if ((err = launch_group(g))) return drain(err);
+        }
+        d->pool.finish();
+        st.ms_host_quads += now_ms() - t_host0;
+
+        // ---- gather: stage timings, then markers in frame / candidate order (src/aruco.rs:75-113) ----
+        A3_CUDA(cudaStreamSynchronize(d->s_decode));
+        A3_CUDA(cudaStreamSynchronize(d->s_pixel));
         float ms = 0;
-        cudaEventElapsedTime(&ms, s.ev_start, s.ev_h2d); st.ms_h2d += ms;
-        cudaEventElapsedTime(&ms, s.ev_h2d, s.ev_k1); st.ms_pixel_kernel += ms;
-        cudaEventElapsedTime(&ms, s.ev_k1, s.ev_bits); st.ms_mask_d2h += ms;
-        // ---- host stage: one frame per task ----
-        const double th0 = now_ms();
-        frame_quads.assign(cn, {});
-        frame_stats.assign(cn, QuadStats());
-        parallel_for(cn, d->host_threads, [&](uint32_t i) {
-            quads_from_bits(s.h_bits.p + (size_t)i * wpr * h, (uint32_t)wpr, w, h, d->cfg, frame_quads[i], &frame_stats[i]);
-        });
-        uint32_t nq = 0;
-        for (uint32_t i = 0; i < cn; i++) {
-            nq += (uint32_t)(frame_quads[i].size() / 8);
+        for (uint32_t j = 0; j < nfe; j++) {
+            if (mem == A3_MEM_HOST) { cudaEventElapsedTime(&ms, ev_h2da[j], ev_h2db[j]); st.ms_h2d += ms; }
+            if (mem == A3_MEM_HOST || j == 0) { cudaEventElapsedTime(&ms, ev_k1a[j], ev_k1b[j]); st.ms_pixel_kernel += ms; }
+            cudaEventElapsedTime(&ms, (mem == A3_MEM_HOST || j == 0) ? ev_k1b[j] : ev_fe[j - 1], ev_fe[j]);
+            st.ms_mask_d2h += ms;
+        }
+        for (uint32_t i = 0; i < sn; i++) {
             st.n_contours += frame_stats[i].n_contours;
             st.n_contour_points += frame_stats[i].n_contour_points;
             st.n_candidates_before_discard += frame_stats[i].n_before_discard;
+            st.ms_host_cpu += frame_ms[i];
         }
-        st.ms_host_quads += now_ms() - th0;
-        st.n_candidates += nq;
-        // ---- decode ----
-        if (nq) {
-            A3_CUDA(s.h_quads.reserve((size_t)nq * 8));
-            A3_CUDA(s.h_qframe.reserve(nq));
-            A3_CUDA(s.h_dec.reserve(nq));
-            A3_CUDA(s.d_quads.reserve((size_t)nq * 8));
-            A3_CUDA(s.d_qframe.reserve(nq));
-            A3_CUDA(s.d_dec.reserve(nq));
-            if (want_patches) A3_CUDA(s.d_patches.reserve(nq * np));
+        for (uint32_t g = 0; g < ngroups; g++) {
+            DecodeBlock &b = *d->blocks[g];
+            if (b.n_quads) { cudaEventElapsedTime(&ms, b.ev_a, b.ev_b); st.ms_decode_kernel += ms; }
+            const uint32_t f0 = g * group, f1 = f0 + group_size(g);
+            if (want_patches && b.n_quads && total_cands < outs->cand_capacity) {
+                const uint32_t room = outs->cand_capacity - total_cands, m = b.n_quads < room ? b.n_quads : room;
+                A3_CUDA(cudaMemcpy(outs->homographies + (size_t)total_cands * np, b.d_patches.p, (size_t)m * np, cudaMemcpyDeviceToHost));
+            }
             uint32_t k = 0;
-            for (uint32_t i = 0; i < cn; i++) {
+            for (uint32_t i = f0; i < f1; i++) {
+                if (outs && outs->frame_marker_offsets) outs->frame_marker_offsets[s0 + i] = total_markers;
                 const uint32_t m = (uint32_t)(frame_quads[i].size() / 8);
-                if (m) memcpy(s.h_quads.p + (size_t)k * 8, frame_quads[i].data(), (size_t)m * 32);
-                for (uint32_t j = 0; j < m; j++) s.h_qframe.p[k + j] = i;
-                k += m;
-            }
-            A3_CUDA(cudaMemcpyAsync(s.d_quads.p, s.h_quads.p, (size_t)nq * 32, cudaMemcpyHostToDevice, s.stream));
-            A3_CUDA(cudaMemcpyAsync(s.d_qframe.p, s.h_qframe.p, (size_t)nq * 4, cudaMemcpyHostToDevice, s.stream));
-            K2Params p;
-            p.grey = s.d_grey.p; p.w = w; p.h = h; p.quads = s.d_quads.p; p.quad_frame = s.d_qframe.p; p.n_quads = nq;
-            p.patch_size = d->cfg.homography_sample_size; p.mark_size = d->mark_size; p.codes = d->d_codes.p;
-            p.n_codes = d->dict.n_codes; p.tau = d->dict.tau; p.filter_high_bit_errors = d->cfg.filter_high_bit_errors;
-            p.resize_w = d->d_taps.p; p.resize_meta = d->d_meta.p; p.decodes = s.d_dec.p;
-            p.patches = want_patches ? s.d_patches.p : nullptr;
-            A3_CUDA(cudaEventRecord(s.ev_k2a, s.stream));
-            A3_CUDA(k2_decode(p, s.stream));
-            st.decode_kernel_launches++;
-            A3_CUDA(cudaEventRecord(s.ev_k2b, s.stream));
-            A3_CUDA(cudaMemcpyAsync(s.h_dec.p, s.d_dec.p, (size_t)nq * sizeof(a3_decode), cudaMemcpyDeviceToHost, s.stream));
-            if (want_patches && total_cands < outs->cand_capacity) {
-                const uint32_t room = outs->cand_capacity - total_cands, m = nq < room ? nq : room;
-                A3_CUDA(cudaMemcpyAsync(outs->homographies + (size_t)total_cands * np, s.d_patches.p, (size_t)m * np,
-                                        cudaMemcpyDeviceToHost, s.stream));
-            }
-            A3_CUDA(cudaStreamSynchronize(s.stream));
-            cudaEventElapsedTime(&ms, s.ev_k2a, s.ev_k2b); st.ms_decode_kernel += ms;
-        }
-        // ---- markers, in candidate order (src/aruco.rs:75-113) ----
-        uint32_t k = 0;
-        for (uint32_t i = 0; i < cn; i++) {
-            if (outs && outs->frame_marker_offsets) outs->frame_marker_offsets[f0 + i] = total_markers;
-            const uint32_t m = (uint32_t)(frame_quads[i].size() / 8);
-            for (uint32_t j = 0; j < m; j++, k++) {
-                const a3_decode &dc = s.h_dec.p[k];
-                const uint32_t *q = &frame_quads[i][(size_t)j * 8];
-                if (outs && total_cands < outs->cand_capacity) {
-                    if (outs->candidates) memcpy(outs->candidates + (size_t)total_cands * 8, q, 32);
-                    if (outs->candidate_frame) outs->candidate_frame[total_cands] = f0 + i;
-                    if (outs->decodes) outs->decodes[total_cands] = dc;
-                } else if (outs && (outs->candidates || outs->decodes || outs->homographies)) {
-                    overflow = true;
-                }
-                total_cands++;
-                if (!dc.accepted) continue;
-                if (markers && total_markers < marker_capacity) {
-                    a3_marker &mk = markers[total_markers];
-                    memset(&mk, 0, sizeof(mk));
-                    mk.id = dc.id;
-                    mk.code = dc.codes[dc.rotation & 3];
-                    mk.frame = f0 + i;
-                    mk.candidate = j;
-                    mk.hamming_distance = dc.hamming_distance;
-                    mk.rotation = dc.rotation;
-                    for (uint32_t cidx = 0; cidx < 4; cidx++) {  // corners.rotate_left(min_rotation)
-                        const uint32_t sidx = (cidx + dc.rotation) & 3;
-                        mk.corners[2 * cidx] = q[2 * sidx];
-                        mk.corners[2 * cidx + 1] = q[2 * sidx + 1];
+                for (uint32_t j = 0; j < m; j++, k++) {
+                    const a3_decode &dc = b.h_dec.p[k];
+                    const uint32_t *q = &frame_quads[i][(size_t)j * 8];
+                    if (outs && total_cands < outs->cand_capacity) {
+                        if (outs->candidates) memcpy(outs->candidates + (size_t)total_cands * 8, q, 32);
+                        if (outs->candidate_frame) outs->candidate_frame[total_cands] = s0 + i;
+                        if (outs->decodes) outs->decodes[total_cands] = dc;
+                    } else if (outs && (outs->candidates || outs->decodes || outs->homographies)) {
+                        overflow = true;
                     }
-                } else {
-                    overflow = true;
+                    total_cands++;
+                    if (!dc.accepted) continue;
+                    if (markers && total_markers < marker_capacity) {
+                        a3_marker &mk = markers[total_markers];
+                        memset(&mk, 0, sizeof(mk));
+                        mk.id = dc.id;
+                        mk.code = dc.codes[dc.rotation & 3];
+                        mk.frame = s0 + i;
+                        mk.candidate = j;
+                        mk.hamming_distance = dc.hamming_distance;
+                        mk.rotation = dc.rotation;
+                        for (uint32_t cidx = 0; cidx < 4; cidx++) {  // corners.rotate_left(min_rotation)
+                            const uint32_t sidx = (cidx + dc.rotation) & 3;
+                            mk.corners[2 * cidx] = q[2 * sidx];
+                            mk.corners[2 * cidx + 1] = q[2 * sidx + 1];
+                        }
+                    } else {
+                        overflow = true;
+                    }
+                    total_markers++;
                 }
-                total_markers++;
             }
         }
-        if (want_grey || want_mask) A3_CUDA(cudaStreamSynchronize(s.stream));
     }
     if (outs && outs->frame_marker_offsets) outs->frame_marker_offsets[n] = total_markers;
     if (outs) outs->n_candidates = total_cands;
     *n_markers = total_markers;
+    st.n_candidates = total_cands;
     st.n_markers = total_markers;
     st.ms_total = now_ms() - t_begin;
     if (stats) *stats = st;

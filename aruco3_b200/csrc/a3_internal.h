@@ -38,8 +38,6 @@ struct K1Tuning {
     uint32_t seg_rows;    // output rows per row segment; 0 = auto
     int force_no_tma;     // generic kernel: 1 = plain loads even when the bulk-copy path is legal (tests)
     int force_generic;    // 1 = never take the warp-strip kernel (k1_strips.cu)
-    uint32_t tma_rows;    // warp-strip kernel: rows per TMA box (1, 2 or 4); 0 = default
-    uint32_t tma_stages;  // warp-strip kernel: TMA ring depth per warp; 0 = default
 };
 struct K1LaunchInfo {
     uint32_t grid, block, smem_bytes, strips, segs, strip_cols, seg_rows;

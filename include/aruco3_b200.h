@@ -93,7 +93,9 @@ typedef struct a3_decode {
 /* Counters + device-side stage times of the last call (CUDA events; host stage by steady_clock). */
 typedef struct a3_stats {
     uint64_t n_frames, n_contours, n_contour_points, n_candidates_before_discard, n_candidates, n_markers;
-    double ms_h2d, ms_pixel_kernel, ms_mask_d2h, ms_host_quads, ms_decode_kernel, ms_d2h, ms_total;
+    /* ms_h2d / ms_pixel_kernel / ms_mask_d2h / ms_decode_kernel: sums of CUDA-event intervals on the stream each runs on;
+     * ms_host_quads: wall time the host stage was active (overlaps the others); ms_host_cpu: CPU time summed over frames */
+    double ms_h2d, ms_pixel_kernel, ms_mask_d2h, ms_host_quads, ms_decode_kernel, ms_host_cpu, ms_total;
     uint32_t pixel_kernel_launches, decode_kernel_launches, host_threads, reserved;
 } a3_stats;
 
@@ -139,13 +141,11 @@ a3_status a3_detector_set_host_threads(a3_detector *det, uint32_t threads);
 /* Launch-shape knobs of the pixel kernel (benchmark sweeps and tests; results never depend on them). 0 = automatic. */
 typedef struct a3_k1_tuning {
     uint32_t strip_cols;    /* generic kernel: output columns per CTA strip */
-    uint32_t seg_rows;      /* output rows per row segment */
+    uint32_t seg_rows;      /* output rows per row segment (both kernels) */
     uint32_t force_no_tma;  /* generic kernel: plain loads instead of bulk copies */
-    uint32_t force_generic; /* never take the warp-strip kernel */
-    uint32_t tma_rows;      /* warp-strip kernel: rows per TMA box (1, 2 or 4) */
-    uint32_t tma_stages;    /* warp-strip kernel: TMA ring depth per warp */
-    uint32_t chunk_frames;  /* a3_detect_batch: frames per pipeline chunk */
-    uint32_t reserved;
+    uint32_t force_generic; /* never take the warp-strip kernel (k1_strips.cu) */
+    uint32_t chunk_frames;  /* a3_detect_batch: frames per front-end chunk (copy / event granularity) */
+    uint32_t reserved[3];
 } a3_k1_tuning;
 a3_status a3_detector_set_k1_tuning(a3_detector *det, const a3_k1_tuning *tuning); /* NULL restores the defaults */
 

@@ -23,8 +23,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", default="64,256")
     ap.add_argument("--mask", action="store_true", help="also write the byte mask (5 B/px of traffic)")
-    ap.add_argument("--rows", default="2,4")
-    ap.add_argument("--stages", default="2,3,4")
     ap.add_argument("--segs", default="0")
     ap.add_argument("--reps", type=int, default=10)
     args = ap.parse_args()
@@ -56,10 +54,7 @@ def main():
     ref_grey, ref_bits = grey.clone(), bits.clone()
     ref_mask = mask.clone() if args.mask else None
     bpp_moved = 3 + 1 + 0.125 + (1 if args.mask else 0)
-    settings = [dict(force_generic=1)] + [dict(tma_rows=r, tma_stages=s, seg_rows=g)
-                                          for r, s, g in itertools.product([int(v) for v in args.rows.split(",")],
-                                                                           [int(v) for v in args.stages.split(",")],
-                                                                           [int(v) for v in args.segs.split(",")])]
+    settings = [dict(force_generic=1)] + [dict(seg_rows=g) for g in [int(v) for v in args.segs.split(",")]]
     for n in [int(v) for v in args.frames.split(",")]:
         for kw in settings:
             tune(**kw)
