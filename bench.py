@@ -169,8 +169,11 @@ def main():
     n, h, w = args.batch, 1080, 1920
 
     # ---- synthetic frames: pinned host copy (e2e arm) and a resident device copy (value arm) ----
+    from aruco3_b200.sharding import shard_range
+    lo, hi = shard_range(n * world, rank, world)  # this rank's contiguous block of the global batch (weak scaling: 256 per GPU)
+    assert hi - lo == n
     pinned = torch.empty((n, h, w, 3), dtype=torch.uint8, pin_memory=True)
-    render(n, rank * n, pinned.numpy())
+    render(n, lo, pinned.numpy())
     resident = pinned.cuda(non_blocking=False)
     torch.cuda.synchronize()
 
