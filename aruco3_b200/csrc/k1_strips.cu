@@ -446,9 +446,9 @@ cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t st
     const uint32_t per_warp = p.format == A3_FMT_RGB8 ? Stage<A3_FMT_RGB8>::per_warp
                               : (p.format == A3_FMT_RGBA8 ? Stage<A3_FMT_RGBA8>::per_warp : Stage<A3_FMT_LUMA8>::per_warp);
     const size_t smem = (size_t)per_warp * kWarpsPerCta;
+    // resident CTAs per SM: bounded by shared memory (~30 KB per CTA) and by the register cap of __launch_bounds__
     uint32_t ctas_per_sm = (uint32_t)((227 * 1024) / (smem + 1024));
-    const uint32_t reg_limit = 65536u / (kWarpsPerCta * 32u * 80u);  // ~80 registers per thread
-    if (ctas_per_sm > reg_limit) ctas_per_sm = reg_limit;
+    if (ctas_per_sm > (uint32_t)kMinCtasPerSm) ctas_per_sm = kMinCtasPerSm;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const uint32_t slots = (uint32_t)sms * ctas_per_sm * kWarpsPerCta;  // warps resident at once
 

@@ -1,0 +1,212 @@
+// aruco3_b200.hpp — header-only C++ mirror of the reference's detection API over the C ABI (aruco3_b200.h).
+//
+// The reference is a Rust crate; Rust is not available in this build environment, so the host side above the C ABI is
+// C++ with the reference's names, argument meaning and error behaviour:
+//   DetectorConfig   /root/reference/src/aruco.rs:23-43        Detector    /root/reference/src/aruco.rs:46-52
+//   Detection        /root/reference/src/aruco.rs:16-21        Marker      /root/reference/src/aruco.rs:8-13
+//   ARDictionary     /root/reference/src/dictionaries.rs:22-28, 115-232
+// Where the reference panics (unknown dictionary name, threshold_window == 0, epsilon <= 0) this mirror throws
+// aruco3::Error.  Link with -laruco3_b200.  No CPU fallback: constructing a Detector without a CUDA device throws.
+#ifndef ARUCO3_B200_HPP
+#define ARUCO3_B200_HPP
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "aruco3_b200.h"
+
+namespace aruco3 {
+
+struct Error : std::runtime_error {
+    a3_status status;
+    Error(a3_status s, const std::string &what) : std::runtime_error(what), status(s) {}
+};
+inline void check(a3_status s) {
+    if (s != A3_OK) throw Error(s, std::string(a3_status_string(s)) + ": " + a3_last_error());
+}
+
+// src/lib.rs:11-21
+inline uint8_t hamming_distance(uint64_t a, uint64_t b) { return a3_hamming_distance(a, b); }
+
+// src/dictionaries.rs:22-28
+class ARDictionary {
+public:
+    uint8_t num_bits = 0;
+    uint8_t tau = 0;
+    const uint64_t *code_list = nullptr;  // static storage inside the library
+    size_t code_count = 0;
+
+    // src/dictionaries.rs:140-145 (case-insensitive; the reference panics on an unknown name)
+    static ARDictionary new_from_named_dict(const std::string &name) {
+        ARDictionary d;
+        check(a3_dictionary_by_name(name.c_str(), &d.c_));
+        d.num_bits = d.c_.num_bits; d.tau = d.c_.tau; d.code_list = d.c_.codes; d.code_count = d.c_.n_codes;
+        return d;
+    }
+    // src/dictionaries.rs:147-149
+    static std::vector<std::string> get_dictionary_names() {
+        std::vector<std::string> v;
+        for (int32_t i = 0; i < a3_dictionary_count(); i++) v.emplace_back(a3_dictionary_name(i));
+        return v;
+    }
+    uint8_t get_mark_size() const { return a3_dictionary_mark_size(&c_); }  // :154-156
+    std::pair<size_t, uint8_t> find_nearest(uint64_t bits) const {          // :160-196
+        uint64_t i; uint8_t dist;
+        a3_find_nearest(&c_, bits, &i, &dist);
+        return {(size_t)i, dist};
+    }
+    bool try_find_nearest(uint64_t bits, size_t *index, uint8_t *dist) const {  // :200-207 (Option -> bool)
+        uint64_t i; uint8_t dd;
+        const bool ok = a3_try_find_nearest(&c_, bits, &i, &dd) != 0;
+        if (index) *index = (size_t)i;
+        if (dist) *dist = dd;
+        return ok;
+    }
+    std::pair<std::vector<bool>, uint8_t> make_binary_image(size_t marker_id) const {  // :212-232
+        uint8_t buf[256]; uint32_t n = 0;
+        const uint8_t w = a3_make_binary_image(&c_, marker_id, buf, sizeof(buf), &n);
+        return {std::vector<bool>(buf, buf + (n < sizeof(buf) ? n : sizeof(buf))), w};
+    }
+    const a3_dictionary &c() const { return c_; }
+
+private:
+    a3_dictionary c_{};
+};
+
+// src/aruco.rs:23-30; defaults :32-43
+struct DetectorConfig {
+    uint32_t threshold_window = 7;
+    double contour_simplification_epsilon = 0.05;
+    float min_side_length_factor = 0.2f;
+    float min_corner_separation_factor = 0.1f;
+    size_t homography_sample_size = 49;
+    bool filter_high_bit_errors = true;
+};
+
+// src/aruco.rs:8-13
+struct Marker {
+    size_t id = 0;
+    uint64_t code = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> corners;  // 4, already rotate_left(rotation)
+    uint8_t hamming_distance = 0;
+};
+
+struct GrayImage {  // image::GrayImage: tightly packed, row-major
+    uint32_t width = 0, height = 0;
+    std::vector<uint8_t> data;
+};
+
+// src/aruco.rs:16-21
+struct Detection {
+    GrayImage grey;                                                    // always present, like Some(grey)
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> candidates;
+    std::vector<GrayImage> homographies;                               // 1x1 when the projection failed (src/aruco.rs:256)
+    std::vector<Marker> markers;
+};
+
+enum class PixelFormat { Rgb8 = A3_FMT_RGB8, Rgba8 = A3_FMT_RGBA8, Luma8 = A3_FMT_LUMA8 };
+
+// `Detector { config, dictionary }` (src/aruco.rs:46-49) bound to one CUDA device.  Thread-compatible: one per
+// (host thread, device).  Public fields are read at construction; call rebuild() after changing them.
+class Detector {
+public:
+    DetectorConfig config;
+    ARDictionary dictionary;
+
+    Detector(const DetectorConfig &cfg, const ARDictionary &dict, int device = 0) : config(cfg), dictionary(dict), device_(device) { rebuild(); }
+    ~Detector() { a3_detector_destroy(h_); }
+    Detector(const Detector &) = delete;
+    Detector &operator=(const Detector &) = delete;
+
+    void rebuild() {
+        a3_detector_destroy(h_);
+        h_ = nullptr;
+        a3_config c;
+        c.threshold_window = config.threshold_window;
+        c.contour_simplification_epsilon = config.contour_simplification_epsilon;
+        c.min_side_length_factor = config.min_side_length_factor;
+        c.min_corner_separation_factor = config.min_corner_separation_factor;
+        c.homography_sample_size = (uint32_t)config.homography_sample_size;
+        c.filter_high_bit_errors = config.filter_high_bit_errors ? 1 : 0;
+        check(a3_detector_create(&c, &dictionary.c(), device_, &h_));
+    }
+
+    // Detector::detect(&self, image: DynamicImage) -> Detection (src/aruco.rs:52-121): one tightly packed image.
+    Detection detect(const uint8_t *pixels, uint32_t width, uint32_t height, PixelFormat fmt = PixelFormat::Rgb8) const {
+        std::vector<Detection> v = detect_batch(pixels, 1, width, height, fmt, /*full=*/true);
+        return std::move(v[0]);
+    }
+
+    // The same over n equally sized frames; `full` fills grey / candidates / homographies, otherwise only markers.
+    std::vector<Detection> detect_batch(const uint8_t *frames, uint32_t n, uint32_t width, uint32_t height,
+                                        PixelFormat fmt = PixelFormat::Rgb8, bool full = false, a3_stats *stats = nullptr) const {
+        const uint32_t bpp = fmt == PixelFormat::Rgb8 ? 3 : (fmt == PixelFormat::Rgba8 ? 4 : 1);
+        const size_t pitch = (size_t)width * bpp, stride = pitch * height, px = (size_t)width * height;
+        const size_t hs = config.homography_sample_size, np = hs * hs;
+        std::vector<Detection> out(n);
+        uint32_t cap_m = 64 * n + 1024, cap_c = 128 * n + 2048;
+        for (;;) {
+            std::vector<a3_marker> markers(cap_m);
+            std::vector<uint8_t> grey, patches;
+            std::vector<uint32_t> cands, cframe, offsets(n + 1);
+            std::vector<a3_decode> decs;
+            a3_outputs o{};
+            o.frame_marker_offsets = offsets.data();
+            if (full) {
+                grey.resize(n * px); cands.resize((size_t)cap_c * 8); cframe.resize(cap_c); patches.resize((size_t)cap_c * np); decs.resize(cap_c);
+                o.grey = grey.data(); o.candidates = cands.data(); o.candidate_frame = cframe.data();
+                o.homographies = patches.data(); o.decodes = decs.data(); o.cand_capacity = cap_c;
+            }
+            uint32_t nm = 0;
+            const a3_status s = a3_detect_batch(h_, frames, (a3_format)fmt, A3_MEM_HOST, n, width, height, pitch, stride, markers.data(),
+                                                cap_m, &nm, &o, stats);
+            if (s == A3_ERR_CAPACITY) {  // counts are valid: size once more
+                cap_m = nm > cap_m ? nm : cap_m;
+                cap_c = o.n_candidates > cap_c ? o.n_candidates : cap_c;
+                continue;
+            }
+            check(s);
+            for (uint32_t i = 0; i < nm; i++) {
+                const a3_marker &m = markers[i];
+                Marker mk;
+                mk.id = (size_t)m.id; mk.code = m.code; mk.hamming_distance = m.hamming_distance;
+                for (int k = 0; k < 4; k++) mk.corners.emplace_back(m.corners[2 * k], m.corners[2 * k + 1]);
+                out[m.frame].markers.push_back(std::move(mk));
+            }
+            if (full) {
+                for (uint32_t f = 0; f < n; f++) {
+                    out[f].grey.width = width; out[f].grey.height = height;
+                    out[f].grey.data.assign(grey.begin() + f * px, grey.begin() + (f + 1) * px);
+                }
+                for (uint32_t k = 0; k < o.n_candidates; k++) {
+                    Detection &d = out[cframe[k]];
+                    std::vector<std::pair<uint32_t, uint32_t>> poly;
+                    for (int j = 0; j < 4; j++) poly.emplace_back(cands[(size_t)k * 8 + 2 * j], cands[(size_t)k * 8 + 2 * j + 1]);
+                    d.candidates.push_back(std::move(poly));
+                    GrayImage g;
+                    if (decs[k].homography_ok) {
+                        g.width = g.height = (uint32_t)hs;
+                        g.data.assign(patches.begin() + (size_t)k * np, patches.begin() + (size_t)(k + 1) * np);
+                    } else {
+                        g.width = g.height = 1;
+                        g.data.assign(1, 0);
+                    }
+                    d.homographies.push_back(std::move(g));
+                }
+            }
+            return out;
+        }
+    }
+
+    a3_detector *handle() const { return h_; }
+
+private:
+    int device_ = 0;
+    a3_detector *h_ = nullptr;
+};
+
+}  // namespace aruco3
+#endif  // ARUCO3_B200_HPP

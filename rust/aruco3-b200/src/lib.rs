@@ -1,0 +1,195 @@
+//! Drop-in for the detection path of `aruco3` (reference `src/aruco.rs`, `src/dictionaries.rs`): same public
+//! types, field names and conventions; the work happens in libaruco3_b200.so (CUDA, sm_100a).
+//! Not compiled in this repository's environment (no Rust toolchain there).
+use std::ffi::{CStr, CString};
+use std::ptr;
+
+use aruco3_b200_sys as sys;
+use image::{DynamicImage, GrayImage};
+use imageproc::point::Point;
+
+/// reference `src/aruco.rs:8-13`
+#[derive(Debug)]
+pub struct Marker {
+    pub id: usize,
+    pub code: u64,
+    pub corners: Vec<(u32, u32)>,
+    pub hamming_distance: u8,
+}
+
+/// reference `src/aruco.rs:16-21`
+#[derive(Default)]
+pub struct Detection {
+    pub grey: Option<GrayImage>,
+    pub candidates: Vec<Vec<Point<u32>>>,
+    pub homographies: Vec<GrayImage>,
+    pub markers: Vec<Marker>,
+}
+
+/// reference `src/aruco.rs:23-43`
+pub struct DetectorConfig {
+    pub threshold_window: u32,
+    pub contour_simplification_epsilon: f64,
+    pub min_side_length_factor: f32,
+    pub min_corner_separation_factor: f32,
+    pub homography_sample_size: usize,
+    pub filter_high_bit_errors: bool,
+}
+
+impl Default for DetectorConfig {
+    fn default() -> Self {
+        DetectorConfig {
+            threshold_window: 7,
+            contour_simplification_epsilon: 0.05,
+            min_side_length_factor: 0.2,
+            min_corner_separation_factor: 0.1f32,
+            homography_sample_size: 49,
+            filter_high_bit_errors: true,
+        }
+    }
+}
+
+/// reference `src/dictionaries.rs:22-28`
+#[derive(Clone, Debug)]
+pub struct ARDictionary {
+    pub num_bits: u8,
+    pub tau: u8,
+    pub code_list: &'static [u64],
+    raw: sys::a3_dictionary,
+}
+
+fn last_error() -> String {
+    unsafe { CStr::from_ptr(sys::a3_last_error()).to_string_lossy().into_owned() }
+}
+
+impl ARDictionary {
+    /// reference `src/dictionaries.rs:140-145`: panics on an unknown name, like the reference.
+    pub fn new_from_named_dict(name: &str) -> Self {
+        let c = CString::new(name).expect("dictionary name");
+        let mut raw = sys::a3_dictionary { num_bits: 0, tau: 0, n_codes: 0, codes: ptr::null() };
+        let st = unsafe { sys::a3_dictionary_by_name(c.as_ptr(), &mut raw) };
+        if st != sys::A3_OK {
+            panic!("{}", last_error());
+        }
+        let code_list: &'static [u64] = unsafe { std::slice::from_raw_parts(raw.codes, raw.n_codes as usize) };
+        ARDictionary { num_bits: raw.num_bits, tau: raw.tau, code_list, raw }
+    }
+    pub fn get_mark_size(&self) -> u8 {
+        unsafe { sys::a3_dictionary_mark_size(&self.raw) }
+    }
+    pub fn find_nearest(&self, bits: u64) -> (usize, u8) {
+        let (mut i, mut d) = (0u64, 0u8);
+        unsafe { sys::a3_find_nearest(&self.raw, bits, &mut i, &mut d) };
+        (i as usize, d)
+    }
+    pub fn try_find_nearest(&self, bits: u64) -> Option<(usize, u8)> {
+        let (mut i, mut d) = (0u64, 0u8);
+        let ok = unsafe { sys::a3_try_find_nearest(&self.raw, bits, &mut i, &mut d) };
+        if ok != 0 { Some((i as usize, d)) } else { None }
+    }
+}
+
+/// reference `src/aruco.rs:46-49`. The CUDA handle is created lazily from the public fields on first use.
+pub struct Detector {
+    pub config: DetectorConfig,
+    pub dictionary: ARDictionary,
+}
+
+struct Handle(*mut sys::a3_detector);
+impl Drop for Handle {
+    fn drop(&mut self) {
+        unsafe { sys::a3_detector_destroy(self.0) }
+    }
+}
+
+impl Detector {
+    fn handle(&self) -> Handle {
+        let cfg = sys::a3_config {
+            threshold_window: self.config.threshold_window,
+            contour_simplification_epsilon: self.config.contour_simplification_epsilon,
+            min_side_length_factor: self.config.min_side_length_factor,
+            min_corner_separation_factor: self.config.min_corner_separation_factor,
+            homography_sample_size: self.config.homography_sample_size as u32,
+            filter_high_bit_errors: self.config.filter_high_bit_errors as u8,
+        };
+        let mut h = ptr::null_mut();
+        let st = unsafe { sys::a3_detector_create(&cfg, &self.dictionary.raw, 0, &mut h) };
+        if st != sys::A3_OK {
+            panic!("{}", last_error()); // threshold_window == 0 / epsilon <= 0 panic inside imageproc in the reference
+        }
+        Handle(h)
+    }
+
+    /// reference `src/aruco.rs:52-121`
+    pub fn detect(&self, image: DynamicImage) -> Detection {
+        let (w, h) = (image.width(), image.height());
+        let (buf, fmt, bpp): (Vec<u8>, i32, usize) = match image {
+            DynamicImage::ImageLuma8(g) => (g.into_raw(), sys::A3_FMT_LUMA8, 1),
+            DynamicImage::ImageRgba8(i) => (i.into_raw(), sys::A3_FMT_RGBA8, 4),
+            DynamicImage::ImageRgb8(i) => (i.into_raw(), sys::A3_FMT_RGB8, 3),
+            // documented deviation: other variants go through Rgb8 first (the reference converts them directly to Luma8)
+            other => (other.into_rgb8().into_raw(), sys::A3_FMT_RGB8, 3),
+        };
+        self.detect_batch(&buf, fmt, 1, w, h, bpp).pop().unwrap()
+    }
+
+    /// `detect` over `n` equally sized, tightly packed frames (not in the reference).
+    pub fn detect_batch(&self, frames: &[u8], fmt: i32, n: u32, w: u32, h: u32, bpp: usize) -> Vec<Detection> {
+        let hd = self.handle();
+        let hs = self.config.homography_sample_size;
+        let (px, np) = ((w as usize) * (h as usize), hs * hs);
+        let (mut cap_m, mut cap_c) = (64 * n as usize + 1024, 128 * n as usize + 2048);
+        loop {
+            let mut markers: Vec<sys::a3_marker> = Vec::with_capacity(cap_m);
+            let mut grey = vec![0u8; n as usize * px];
+            let mut cands = vec![0u32; cap_c * 8];
+            let mut cframe = vec![0u32; cap_c];
+            let mut patches = vec![0u8; cap_c * np];
+            let mut decs: Vec<sys::a3_decode> = Vec::with_capacity(cap_c);
+            let mut out = sys::a3_outputs {
+                grey: grey.as_mut_ptr(), mask: ptr::null_mut(), candidates: cands.as_mut_ptr(), candidate_frame: cframe.as_mut_ptr(),
+                homographies: patches.as_mut_ptr(), decodes: decs.as_mut_ptr(), cand_capacity: cap_c as u32, n_candidates: 0,
+                frame_marker_offsets: ptr::null_mut(),
+            };
+            let mut nm = 0u32;
+            let st = unsafe {
+                sys::a3_detect_batch(hd.0, frames.as_ptr() as *const _, fmt, sys::A3_MEM_HOST, n, w, h, w as usize * bpp,
+                                     w as usize * bpp * h as usize, markers.as_mut_ptr(), cap_m as u32, &mut nm, &mut out, ptr::null_mut())
+            };
+            if st == sys::A3_ERR_CAPACITY {
+                cap_m = cap_m.max(nm as usize);
+                cap_c = cap_c.max(out.n_candidates as usize);
+                continue;
+            }
+            if st != sys::A3_OK {
+                panic!("{}", last_error());
+            }
+            unsafe {
+                markers.set_len(nm as usize);
+                decs.set_len(out.n_candidates as usize);
+            }
+            let mut dets: Vec<Detection> = (0..n).map(|_| Detection::default()).collect();
+            for f in 0..n as usize {
+                dets[f].grey = GrayImage::from_raw(w, h, grey[f * px..(f + 1) * px].to_vec());
+            }
+            for k in 0..out.n_candidates as usize {
+                let d = &mut dets[cframe[k] as usize];
+                d.candidates.push((0..4).map(|j| Point::new(cands[k * 8 + 2 * j], cands[k * 8 + 2 * j + 1])).collect());
+                d.homographies.push(if decs[k].homography_ok != 0 {
+                    GrayImage::from_raw(hs as u32, hs as u32, patches[k * np..(k + 1) * np].to_vec()).unwrap()
+                } else {
+                    GrayImage::new(1, 1) // reference src/aruco.rs:256
+                });
+            }
+            for m in &markers {
+                dets[m.frame as usize].markers.push(Marker {
+                    id: m.id as usize,
+                    code: m.code,
+                    corners: (0..4).map(|k| (m.corners[2 * k], m.corners[2 * k + 1])).collect(),
+                    hamming_distance: m.hamming_distance,
+                });
+            }
+            return dets;
+        }
+    }
+}

@@ -1,0 +1,66 @@
+"""include/aruco3_b200.hpp — the C++ host mirror of `Detector { config, dictionary }.detect(img)` — compiled with g++,
+run on the GPU and compared with the oracle (markers, candidates, grey) on a seeded frame."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+PROGRAM = r'''
+#include <cstdio>
+#include <vector>
+#include "aruco3_b200.hpp"
+int main(int argc, char **argv) {
+    const uint32_t w = 640, h = 480;
+    std::vector<uint8_t> rgb((size_t)w * h * 3);
+    FILE *f = fopen(argv[1], "rb");
+    if (!f || fread(rgb.data(), 1, rgb.size(), f) != rgb.size()) return 2;
+    fclose(f);
+    try {
+        aruco3::ARDictionary::new_from_named_dict("no such dictionary");
+        return 3;
+    } catch (const aruco3::Error &e) {
+        if (e.status != A3_ERR_UNKNOWN_DICTIONARY) return 4;
+    }
+    aruco3::Detector detector(aruco3::DetectorConfig(), aruco3::ARDictionary::new_from_named_dict("ARUCO"));
+    aruco3::Detection d = detector.detect(rgb.data(), w, h);
+    unsigned long long sum = 0;
+    for (uint8_t v : d.grey.data) sum += v;
+    printf("grey %u %u %llu\n", d.grey.width, d.grey.height, sum);
+    for (auto &c : d.candidates) printf("cand %u %u %u %u %u %u %u %u\n", c[0].first, c[0].second, c[1].first, c[1].second, c[2].first, c[2].second, c[3].first, c[3].second);
+    for (auto &p : d.homographies) printf("patch %u\n", p.width);
+    for (auto &m : d.markers)
+        printf("marker %zu %llu %u %u %u %u %u %u %u %u %u\n", m.id, (unsigned long long)m.code, m.hamming_distance, m.corners[0].first, m.corners[0].second,
+               m.corners[1].first, m.corners[1].second, m.corners[2].first, m.corners[2].second, m.corners[3].first, m.corners[3].second);
+    return 0;
+}
+'''
+
+
+def test_header_compiles_without_gpu(tmp_path):
+    src = tmp_path / "mirror.cpp"
+    src.write_text(PROGRAM)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-I", str(ROOT / "include"), "-c", str(src), "-o", str(tmp_path / "mirror.o")], check=True)
+
+
+@pytest.mark.gpu
+def test_cpp_detector_matches_oracle(oracle, tmp_path):
+    from aruco3_b200 import _ffi, synth
+    _ffi.lib()
+    img, _ = synth.render_frame(synth.CONFIGS["C1"], 0)
+    (tmp_path / "frame.rgb").write_bytes(img.tobytes())
+    src, exe = tmp_path / "mirror.cpp", tmp_path / "mirror"
+    src.write_text(PROGRAM)
+    lib_dir = ROOT / "aruco3_b200"
+    subprocess.run(["g++", "-std=c++17", "-I", str(ROOT / "include"), str(src), "-o", str(exe), f"-L{lib_dir}", "-laruco3_b200",
+                    f"-Wl,-rpath,{lib_dir}"], check=True)
+    out = subprocess.run([str(exe), str(tmp_path / "frame.rgb")], check=True, capture_output=True, text=True).stdout.splitlines()
+    ref = oracle.detect(img, "ARUCO")
+    assert out[0] == f"grey 640 480 {int(ref.grey.astype(np.uint64).sum())}"
+    cands = [[int(v) for v in ln.split()[1:]] for ln in out if ln.startswith("cand")]
+    assert cands == ref.candidates.tolist()
+    assert [int(ln.split()[1]) for ln in out if ln.startswith("patch")] == [49 if ok else 1 for ok in ref.homography_ok]
+    markers = [[int(v) for v in ln.split()[1:]] for ln in out if ln.startswith("marker")]
+    assert markers == [[m["id"], m["code"], m["hamming_distance"]] + m["corners"] for m in ref.markers]
