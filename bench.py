@@ -85,7 +85,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.02)
 
     def result(self):
         self.stop_flag.set()
