@@ -167,7 +167,7 @@ def find_contours(mask: np.ndarray):
     c = lib().a3ref_find_contours(mask.ctypes.data, mask.shape[1], mask.shape[0])
     cc = c.contents
     offs = np.ctypeslib.as_array(cc.offsets, (cc.n_contours + 1,)).copy()
-    pts = np.ctypeslib.as_array(cc.points, (max(cc.n_points, 1), 2))[:cc.n_points].copy()
+    pts = np.ctypeslib.as_array(cc.points, (cc.n_points, 2)).copy() if cc.n_points else np.zeros((0, 2), np.uint32)
     outer = np.ctypeslib.as_array(cc.is_outer, (max(cc.n_contours, 1),))[:cc.n_contours].copy() if cc.n_contours else np.zeros(0, np.uint8)
     lib().a3ref_contours_free(c)
     return [pts[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)], outer
