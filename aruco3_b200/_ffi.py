@@ -13,6 +13,7 @@ A3_OK, A3_ERR_INVALID_ARGUMENT, A3_ERR_UNKNOWN_DICTIONARY, A3_ERR_CUDA, A3_ERR_C
     A3_ERR_OUT_OF_MEMORY = range(7)
 FMT_RGB8, FMT_RGBA8, FMT_LUMA8 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
+CONTOURS_HOST, CONTOURS_DEVICE = 0, 1
 
 
 class A3Config(C.Structure):
@@ -41,9 +42,10 @@ class A3Decode(C.Structure):
 class A3Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_frames", "n_contours", "n_contour_points", "n_candidates_before_discard",
                                           "n_candidates", "n_markers")] + \
-               [(n, C.c_double) for n in ("ms_h2d", "ms_pixel_kernel", "ms_mask_d2h", "ms_host_quads",
+               [(n, C.c_double) for n in ("ms_h2d", "ms_pixel_kernel", "ms_contour_kernels", "ms_mask_d2h", "ms_host_quads",
                                           "ms_decode_kernel", "ms_host_cpu", "ms_total")] + \
-               [(n, C.c_uint32) for n in ("pixel_kernel_launches", "decode_kernel_launches", "host_threads", "reserved")]
+               [(n, C.c_uint32) for n in ("pixel_kernel_launches", "decode_kernel_launches", "host_threads", "contour_kernel_launches",
+                                          "host_fallback_frames", "reserved")]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_ if f != "reserved"}
@@ -113,11 +115,13 @@ def lib():
     L.a3_detector_destroy.restype = None
     L.a3_detector_destroy.argtypes = [vp]
     L.a3_detector_set_host_threads.argtypes = [vp, u32]
+    L.a3_detector_set_contour_mode.argtypes = [vp, u32]
     L.a3_detector_set_k1_tuning.argtypes = [vp, C.POINTER(A3K1Tuning)]
     L.a3_detect_batch.argtypes = [vp, vp, C.c_int, C.c_int, u32, u32, u32, sz, sz, vp, u32, C.POINTER(u32),
                                   C.POINTER(A3Outputs), C.POINTER(A3Stats)]
     L.a3_gray_threshold_batch.argtypes = [vp, vp, C.c_int, C.c_int, u32, u32, u32, sz, sz, vp, vp, vp, vp]
     L.a3_quads_from_mask.argtypes = [C.POINTER(A3Config), vp, u32, u32, vp, u32, C.POINTER(u32), C.POINTER(A3Stats)]
+    L.a3_quads_from_masks_device.argtypes = [vp, vp, u32, u32, u32, vp, u32, vp, vp, vp, vp]
     L.a3_decode_candidates.argtypes = [vp, vp, u32, u32, u32, vp, vp, u32, vp, vp]
     _lib = L
     return L

@@ -13,6 +13,7 @@
 // Device input runs K1 once over the whole (super-)batch; host input runs it per front-end chunk right behind the
 // copy, so the PCIe transfer, the host stage and the decode kernel all overlap.
 // There is no CPU fallback: without a CUDA device every compute entry point returns A3_ERR_CUDA.
+#include <math.h>
 #include <string.h>
 
 #include <atomic>
@@ -185,6 +186,15 @@ struct a3_detector {
     a3::EventPool events;
     std::vector<std::unique_ptr<a3::DecodeBlock>> blocks;
     a3::WorkerPool pool;
+    // GPU contour stage (K3)
+    uint32_t contour_mode = A3_CONTOURS_DEVICE;
+    a3::K3Workspace k3;
+    a3::DevBuf<uint32_t> d_planes, d_k3quads, d_k3counts, d_k3before, d_k3flags, d_k3contours;
+    a3::DevBuf<unsigned long long> d_k3points;
+    a3::PinBuf<uint32_t> h_k3quads, h_k3counts, h_k3before, h_k3flags, h_k3contours, h_plane;
+    a3::PinBuf<unsigned long long> h_k3points;
+    size_t planes_zeroed_words = 0;
+    uint32_t planes_w = 0, planes_h = 0;
 };
 
 namespace a3 {
@@ -296,6 +306,9 @@ void a3_detector_destroy(a3_detector *d) {
     d->d_src.release(); d->d_grey.release(); d->d_mask.release(); d->d_patches.release();
     d->d_bits.release(); d->d_quads.release(); d->d_qframe.release(); d->d_dec.release(); d->h_bits.release();
     d->d_codes.release(); d->d_taps.release(); d->d_meta.release();
+    d->d_planes.release(); d->d_k3quads.release(); d->d_k3counts.release(); d->d_k3before.release(); d->d_k3flags.release();
+    d->d_k3contours.release(); d->d_k3points.release(); d->h_k3quads.release(); d->h_k3counts.release(); d->h_k3before.release();
+    d->h_k3flags.release(); d->h_k3contours.release(); d->h_k3points.release(); d->h_plane.release();
     d->events.release();
     for (auto &b : d->blocks) b->release();
     delete d;
@@ -304,6 +317,12 @@ void a3_detector_destroy(a3_detector *d) {
 a3_status a3_detector_set_host_threads(a3_detector *d, uint32_t threads) {
     if (!d || threads == 0) return fail(A3_ERR_INVALID_ARGUMENT, "a3_detector_set_host_threads: bad argument");
     d->host_threads = threads > 256 ? 256 : threads;
+    return A3_OK;
+}
+
+a3_status a3_detector_set_contour_mode(a3_detector *d, uint32_t mode) {
+    if (!d || mode > A3_CONTOURS_DEVICE) return fail(A3_ERR_INVALID_ARGUMENT, "a3_detector_set_contour_mode: bad argument");
+    d->contour_mode = mode;
     return A3_OK;
 }
 
@@ -382,6 +401,46 @@ a3_status a3_quads_from_mask(const a3_config *cfg, const uint8_t *mask, uint32_t
     return A3_OK;
 }
 
+a3_status a3_quads_from_masks_device(a3_detector *d, const uint8_t *masks, uint32_t n, uint32_t w, uint32_t h, uint32_t *quads,
+                                     uint32_t quad_capacity, uint32_t *counts, uint32_t *flags, uint32_t *contours, uint64_t *points) {
+    if (!d || !masks || !quads || !counts || !flags || quad_capacity == 0)
+        return fail(A3_ERR_INVALID_ARGUMENT, "a3_quads_from_masks_device: null argument");
+    if (n == 0 || w == 0 || h == 0) return A3_OK;
+    if (w > 65535 || h > 65535) return fail(A3_ERR_UNSUPPORTED, "a3_quads_from_masks_device: frames larger than 65535 pixels a side");
+    A3_CUDA(cudaSetDevice(d->device));
+    const uint32_t wpr = (w + 31) / 32, S = wpr + 2;
+    const size_t plane_words = (size_t)(h + 2) * S;
+    std::vector<uint32_t> planes((size_t)n * plane_words, 0u);
+    for (uint32_t f = 0; f < n; f++)
+        for (uint32_t y = 0; y < h; y++)
+            for (uint32_t x = 0; x < w; x++)
+                if (masks[((size_t)f * h + y) * w + x]) planes[(size_t)f * plane_words + (size_t)(y + 1) * S + 1 + (x >> 5)] |= 1u << (x & 31);
+    cudaStream_t s = d->s_pixel;
+    d->planes_zeroed_words = 0;  // the pipeline's guard words are overwritten below
+    A3_CUDA(d->d_planes.reserve(planes.size()));
+    A3_CUDA(d->d_k3quads.reserve((size_t)n * quad_capacity * 8));
+    A3_CUDA(d->d_k3counts.reserve(n)); A3_CUDA(d->d_k3before.reserve(n)); A3_CUDA(d->d_k3flags.reserve(n));
+    A3_CUDA(d->d_k3contours.reserve(n)); A3_CUDA(d->d_k3points.reserve(n));
+    A3_CUDA(cudaMemcpyAsync(d->d_planes.p, planes.data(), planes.size() * 4, cudaMemcpyHostToDevice, s));
+    const uint32_t mn = w < h ? w : h;
+    K3Params kp;
+    kp.planes = d->d_planes.p; kp.n = n; kp.w = w; kp.h = h;
+    kp.eps_factor = d->cfg.contour_simplification_epsilon;
+    kp.min_edge_length = (uint32_t)((float)mn * d->cfg.min_side_length_factor);
+    kp.min_corner_separation = (float)mn * d->cfg.min_corner_separation_factor;
+    kp.min_points = (uint32_t)floor(sqrt(2.0 * (double)kp.min_edge_length));
+    kp.quad_cap = quad_capacity; kp.quads = d->d_k3quads.p; kp.quad_counts = d->d_k3counts.p; kp.before_discard = d->d_k3before.p;
+    kp.frame_flags = d->d_k3flags.p; kp.frame_contours = d->d_k3contours.p; kp.frame_points = d->d_k3points.p;
+    A3_CUDA(k3_quads(d->k3, kp, s));
+    A3_CUDA(cudaMemcpyAsync(quads, d->d_k3quads.p, (size_t)n * quad_capacity * 32, cudaMemcpyDeviceToHost, s));
+    A3_CUDA(cudaMemcpyAsync(counts, d->d_k3counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    A3_CUDA(cudaMemcpyAsync(flags, d->d_k3flags.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (contours) A3_CUDA(cudaMemcpyAsync(contours, d->d_k3contours.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (points) A3_CUDA(cudaMemcpyAsync(points, d->d_k3points.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    A3_CUDA(cudaStreamSynchronize(s));
+    return A3_OK;
+}
+
 a3_status a3_decode_candidates(a3_detector *d, const uint8_t *grey, uint32_t n_frames, uint32_t w, uint32_t h,
                                const uint32_t *quads, const uint32_t *quad_frame, uint32_t n_quads, a3_decode *decodes,
                                uint8_t *patches) {
@@ -448,6 +507,14 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
     if (fe > sb) fe = sb;
     const uint32_t group = 32;    // frames per decode launch
     const uint32_t kStaging = 3;  // staging ring depth (host input)
+    // contour stage on the device (K3) unless the caller asked for the host stage or the frame is too large for K3's 16-bit points
+    const bool gpu_contours = d->contour_mode == A3_CONTOURS_DEVICE && w <= 65535 && h <= 65535;
+    const uint32_t S = (uint32_t)wpr + 2;                    // guarded plane: words per row
+    const size_t plane_words = (size_t)(h + 2) * S;          // words per frame
+    const uint32_t quad_cap = 1024;                          // quads per frame K3 can return (more -> host stage)
+    const uint32_t mn = w < h ? w : h;
+    const uint32_t min_edge_length = (uint32_t)((float)mn * d->cfg.min_side_length_factor);   // src/aruco.rs:55
+    const float min_corner_separation = (float)mn * d->cfg.min_corner_separation_factor;      // src/aruco.rs:56
 
     uint32_t total_markers = 0, total_cands = 0;
     bool overflow = false;
@@ -459,16 +526,33 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         const uint32_t sn = n - s0 < sb ? n - s0 : (uint32_t)sb;
         const uint32_t nfe = (sn + (uint32_t)fe - 1) / (uint32_t)fe, ngroups = (sn + group - 1) / group;
         A3_CUDA(d->d_grey.reserve(sn * px));
-        A3_CUDA(d->d_bits.reserve(sn * bits_words));
-        A3_CUDA(d->h_bits.reserve(sn * bits_words));
+        if (gpu_contours) {
+            const size_t need = (size_t)sn * plane_words;
+            const bool fresh = need > d->d_planes.cap || d->planes_w != w || d->planes_h != h || need > d->planes_zeroed_words;
+            A3_CUDA(d->d_planes.reserve(need));
+            if (fresh) {  // guard words are written once and never touched by K1
+                A3_CUDA(cudaMemsetAsync(d->d_planes.p, 0, d->d_planes.cap * 4, d->s_pixel));
+                d->planes_zeroed_words = d->d_planes.cap; d->planes_w = w; d->planes_h = h;
+            }
+            A3_CUDA(d->d_k3quads.reserve((size_t)sn * quad_cap * 8)); A3_CUDA(d->h_k3quads.reserve((size_t)sn * quad_cap * 8));
+            A3_CUDA(d->d_k3counts.reserve(sn)); A3_CUDA(d->h_k3counts.reserve(sn));
+            A3_CUDA(d->d_k3before.reserve(sn)); A3_CUDA(d->h_k3before.reserve(sn));
+            A3_CUDA(d->d_k3flags.reserve(sn)); A3_CUDA(d->h_k3flags.reserve(sn));
+            A3_CUDA(d->d_k3contours.reserve(sn)); A3_CUDA(d->h_k3contours.reserve(sn));
+            A3_CUDA(d->d_k3points.reserve(sn)); A3_CUDA(d->h_k3points.reserve(sn));
+            A3_CUDA(d->h_plane.reserve(plane_words));
+        } else {
+            A3_CUDA(d->d_bits.reserve(sn * bits_words));
+            A3_CUDA(d->h_bits.reserve(sn * bits_words));
+        }
         if (want_mask) A3_CUDA(d->d_mask.reserve(sn * px));
         if (mem == A3_MEM_HOST) A3_CUDA(d->d_src.reserve((size_t)kStaging * fe * frame_stride));
         while (d->blocks.size() < ngroups) d->blocks.emplace_back(new DecodeBlock());
         d->events.reset();
-        std::vector<cudaEvent_t> ev_fe(nfe), ev_k1a(nfe), ev_k1b(nfe), ev_h2da(nfe), ev_h2db(nfe);
+        std::vector<cudaEvent_t> ev_fe(nfe), ev_k1a(nfe), ev_k1b(nfe), ev_h2da(nfe), ev_h2db(nfe), ev_k3(nfe);
         for (uint32_t j = 0; j < nfe; j++) {
             A3_CUDA(d->events.get(&ev_fe[j])); A3_CUDA(d->events.get(&ev_k1a[j])); A3_CUDA(d->events.get(&ev_k1b[j]));
-            A3_CUDA(d->events.get(&ev_h2da[j])); A3_CUDA(d->events.get(&ev_h2db[j]));
+            A3_CUDA(d->events.get(&ev_h2da[j])); A3_CUDA(d->events.get(&ev_h2db[j])); A3_CUDA(d->events.get(&ev_k3[j]));
         }
         frame_quads.assign(sn, {});
         frame_stats.assign(sn, QuadStats());
@@ -482,7 +566,13 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             K1Params p;
             p.src = src; p.format = format; p.n = cn; p.w = w; p.h = h; p.pitch = pitch; p.frame_stride = frame_stride;
             p.grey = d->d_grey.p + (size_t)f0 * px; p.mask = want_mask ? d->d_mask.p + (size_t)f0 * px : nullptr;
-            p.bits = d->d_bits.p + (size_t)f0 * bits_words; p.radius = d->cfg.threshold_window;
+            p.radius = d->cfg.threshold_window;
+            if (gpu_contours) {  // straight into the guarded planes K3 reads
+                p.bits = d->d_planes.p + (size_t)f0 * plane_words + S + 1;
+                p.bits_row_words = S; p.bits_frame_words = plane_words;
+            } else {
+                p.bits = d->d_bits.p + (size_t)f0 * bits_words;
+            }
             A3_CUDA(cudaEventRecord(ev_k1a[j], d->s_pixel));
             A3_CUDA(k1_gray_threshold(p, tune, d->s_pixel, nullptr));
             A3_CUDA(cudaEventRecord(ev_k1b[j], d->s_pixel));
@@ -490,8 +580,32 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             return A3_OK;
         };
         auto bits_d2h = [&](uint32_t f0, uint32_t cn, uint32_t j) -> a3_status {
-            A3_CUDA(cudaMemcpyAsync(d->h_bits.p + (size_t)f0 * bits_words, d->d_bits.p + (size_t)f0 * bits_words, (size_t)cn * bits_words * 4,
-                                    cudaMemcpyDeviceToHost, d->s_pixel));
+            if (gpu_contours) {
+                if (mem == A3_MEM_HOST || j == 0) {  // K3 over the frames K1 just produced (everything for resident input)
+                    const uint32_t kn = mem == A3_MEM_HOST ? cn : sn;
+                    K3Params kp;
+                    kp.planes = d->d_planes.p + (size_t)f0 * plane_words; kp.n = kn; kp.w = w; kp.h = h;
+                    kp.eps_factor = d->cfg.contour_simplification_epsilon; kp.min_edge_length = min_edge_length;
+                    kp.min_corner_separation = min_corner_separation;
+                    kp.min_points = (uint32_t)floor(sqrt(2.0 * (double)min_edge_length));
+                    kp.quad_cap = quad_cap; kp.quads = d->d_k3quads.p + (size_t)f0 * quad_cap * 8; kp.quad_counts = d->d_k3counts.p + f0;
+                    kp.before_discard = d->d_k3before.p + f0; kp.frame_flags = d->d_k3flags.p + f0;
+                    kp.frame_contours = d->d_k3contours.p + f0; kp.frame_points = d->d_k3points.p + f0;
+                    A3_CUDA(k3_quads(d->k3, kp, d->s_pixel));
+                    A3_CUDA(cudaEventRecord(ev_k3[j], d->s_pixel));
+                    st.contour_kernel_launches++;
+                    A3_CUDA(cudaMemcpyAsync(d->h_k3counts.p + f0, d->d_k3counts.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+                    A3_CUDA(cudaMemcpyAsync(d->h_k3before.p + f0, d->d_k3before.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+                    A3_CUDA(cudaMemcpyAsync(d->h_k3flags.p + f0, d->d_k3flags.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+                    A3_CUDA(cudaMemcpyAsync(d->h_k3contours.p + f0, d->d_k3contours.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+                    A3_CUDA(cudaMemcpyAsync(d->h_k3points.p + f0, d->d_k3points.p + f0, (size_t)kn * 8, cudaMemcpyDeviceToHost, d->s_pixel));
+                    A3_CUDA(cudaMemcpyAsync(d->h_k3quads.p + (size_t)f0 * quad_cap * 8, d->d_k3quads.p + (size_t)f0 * quad_cap * 8,
+                                            (size_t)kn * quad_cap * 32, cudaMemcpyDeviceToHost, d->s_pixel));
+                }
+            } else {
+                A3_CUDA(cudaMemcpyAsync(d->h_bits.p + (size_t)f0 * bits_words, d->d_bits.p + (size_t)f0 * bits_words, (size_t)cn * bits_words * 4,
+                                        cudaMemcpyDeviceToHost, d->s_pixel));
+            }
             A3_CUDA(cudaEventRecord(ev_fe[j], d->s_pixel));
             if (want_grey)
                 A3_CUDA(cudaMemcpyAsync(outs->grey + (size_t)(s0 + f0) * px, d->d_grey.p + (size_t)f0 * px, (size_t)cn * px, cudaMemcpyDeviceToHost, d->s_pixel));
@@ -499,15 +613,29 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                 A3_CUDA(cudaMemcpyAsync(outs->mask + (size_t)(s0 + f0) * px, d->d_mask.p + (size_t)f0 * px, (size_t)cn * px, cudaMemcpyDeviceToHost, d->s_pixel));
             return A3_OK;
         };
-        uint32_t issued = 0;
+        // the copy of chunk j (host input) is queued `kStaging` chunks ahead of its compute, so the PCIe link never idles
+        // even though K3 synchronises the pixel stream once per chunk
+        uint32_t copies_issued = 0, issued = 0;
+        const uint32_t lookahead = gpu_contours ? 1 : kStaging;  // chunks whose compute is queued ahead of the one being consumed
+        auto issue_copy = [&](uint32_t j) -> a3_status {
+            const uint32_t f0 = j * (uint32_t)fe, cn = sn - f0 < fe ? sn - f0 : (uint32_t)fe;
+            uint8_t *slot = d->d_src.p + (size_t)(j % kStaging) * fe * frame_stride;
+            if (j >= kStaging) A3_CUDA(cudaStreamWaitEvent(d->s_copy, ev_k1b[j - kStaging], 0));  // the slot's previous K1 is done
+            A3_CUDA(cudaEventRecord(ev_h2da[j], d->s_copy));
+            A3_CUDA(cudaMemcpyAsync(slot, src_all + (size_t)(s0 + f0) * frame_stride, (size_t)cn * frame_stride, cudaMemcpyHostToDevice, d->s_copy));
+            A3_CUDA(cudaEventRecord(ev_h2db[j], d->s_copy));
+            return A3_OK;
+        };
         auto issue = [&](uint32_t j) -> a3_status {
             const uint32_t f0 = j * (uint32_t)fe, cn = sn - f0 < fe ? sn - f0 : (uint32_t)fe;
             if (mem == A3_MEM_HOST) {
+                // copy c reuses the slot of chunk c - kStaging and waits for that chunk's K1, whose event exists once
+                // issue(c - kStaging) has run: c < j + kStaging
+                while (copies_issued < nfe && copies_issued < j + kStaging) {
+                    if (a3_status s = issue_copy(copies_issued)) return s;
+                    copies_issued++;
+                }
                 uint8_t *slot = d->d_src.p + (size_t)(j % kStaging) * fe * frame_stride;
-                if (j >= kStaging) A3_CUDA(cudaStreamWaitEvent(d->s_copy, ev_k1b[j - kStaging], 0));  // the slot's previous K1 is done
-                A3_CUDA(cudaEventRecord(ev_h2da[j], d->s_copy));
-                A3_CUDA(cudaMemcpyAsync(slot, src_all + (size_t)(s0 + f0) * frame_stride, (size_t)cn * frame_stride, cudaMemcpyHostToDevice, d->s_copy));
-                A3_CUDA(cudaEventRecord(ev_h2db[j], d->s_copy));
                 A3_CUDA(cudaStreamWaitEvent(d->s_pixel, ev_h2db[j], 0));
                 if (a3_status s = k1_launch(slot, f0, cn, j)) return s;
             } else if (j == 0) {
@@ -517,17 +645,38 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             return bits_d2h(f0, cn, j);
         };
 
-        // ---- host stage: one task per frame ----
+        // ---- host stage: one task per frame (host-contour mode; in device-contour mode only flagged frames, inline) ----
         const a3_config cfg = d->cfg;
         uint32_t *h_bits = d->h_bits.p;
         a3_detector *det = d;
-        d->pool.begin([&, h_bits, cfg, det](uint32_t i) {
-            const double t0 = now_ms();
-            quads_from_bits(h_bits + (size_t)i * bits_words, (uint32_t)wpr, w, h, cfg, frame_quads[i], &frame_stats[i]);
-            frame_ms[i] = now_ms() - t0;
-            const uint32_t g = i / group;
-            if (group_done[g].fetch_add(1) + 1 == group_size(g)) det->pool.notify_caller();
-        }, sn);
+        if (!gpu_contours) {
+            d->pool.begin([&, h_bits, cfg, det](uint32_t i) {
+                const double t0 = now_ms();
+                quads_from_bits(h_bits + (size_t)i * bits_words, (uint32_t)wpr, w, h, cfg, frame_quads[i], &frame_stats[i]);
+                frame_ms[i] = now_ms() - t0;
+                const uint32_t g = i / group;
+                if (group_done[g].fetch_add(1) + 1 == group_size(g)) det->pool.notify_caller();
+            }, sn);
+        }
+        // device-contour mode: take frame i's quads from K3's output, or redo the frame on the host when K3 flagged it
+        auto take_k3_frame = [&](uint32_t i) -> a3_status {
+            if (d->h_k3flags.p[i] == 0) {
+                const uint32_t m = d->h_k3counts.p[i];
+                frame_quads[i].assign(d->h_k3quads.p + (size_t)i * quad_cap * 8, d->h_k3quads.p + (size_t)i * quad_cap * 8 + (size_t)m * 8);
+                frame_stats[i].n_contours = d->h_k3contours.p[i];
+                frame_stats[i].n_contour_points = d->h_k3points.p[i];
+                frame_stats[i].n_before_discard = d->h_k3before.p[i];
+            } else {
+                const double t0 = now_ms();
+                A3_CUDA(cudaMemcpyAsync(d->h_plane.p, d->d_planes.p + (size_t)i * plane_words, plane_words * 4, cudaMemcpyDeviceToHost, d->s_decode));
+                A3_CUDA(cudaStreamSynchronize(d->s_decode));
+                quads_from_bits(d->h_plane.p + S + 1, (uint32_t)wpr, w, h, cfg, frame_quads[i], &frame_stats[i], S);
+                frame_ms[i] = now_ms() - t0;
+                st.host_fallback_frames++;
+            }
+            group_done[i / group].fetch_add(1);
+            return A3_OK;
+        };
 
         // ---- decode of group g (asynchronous) ----
         auto launch_group = [&](uint32_t g) -> a3_status {
@@ -561,8 +710,10 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             return A3_OK;
         };
         auto drain = [&](a3_status s) {  // an error: let the pool and the streams finish before the buffers go away
-            d->pool.publish(sn);
-            d->pool.finish();
+            if (!gpu_contours) {
+                d->pool.publish(sn);
+                d->pool.finish();
+            }
             cudaStreamSynchronize(d->s_copy); cudaStreamSynchronize(d->s_pixel); cudaStreamSynchronize(d->s_decode);
             return s;
         };
@@ -572,21 +723,26 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         a3_status err = A3_OK;
         uint32_t next_group = 0;
         for (uint32_t j = 0; j < nfe && !err; j++) {
-            while (issued < nfe && issued < j + kStaging && !err) err = issue(issued++);
+            while (issued < nfe && issued < j + lookahead && !err) err = issue(issued++);
             if (err) break;
             const cudaError_t e = cudaEventSynchronize(ev_fe[j]);
             if (e != cudaSuccess) { err = cuda_fail(e, "cudaEventSynchronize(front end)"); break; }
             const uint32_t upto = (j + 1) * (uint32_t)fe < sn ? (j + 1) * (uint32_t)fe : sn;
-            d->pool.publish(upto);
+            if (gpu_contours) {
+                if (mem == A3_MEM_HOST || j == 0)  // resident input: K3 ran once over everything
+                    for (uint32_t i = (mem == A3_MEM_HOST ? j * (uint32_t)fe : 0); i < (mem == A3_MEM_HOST ? upto : sn) && !err; i++) err = take_k3_frame(i);
+            } else {
+                d->pool.publish(upto);
+            }
             while (next_group < ngroups && !err && group_done[next_group].load() == group_size(next_group)) err = launch_group(next_group++);
         }
         if (err) return drain(err);
         for (; next_group < ngroups; next_group++) {
             const uint32_t g = next_group;
-            d->pool.wait_caller([&] { return group_done[g].load() == group_size(g); });
+            if (!gpu_contours) d->pool.wait_caller([&] { return group_done[g].load() == group_size(g); });
             if ((err = launch_group(g))) return drain(err);
         }
-        d->pool.finish();
+        if (!gpu_contours) d->pool.finish();
         st.ms_host_quads += now_ms() - t_host0;
 
         // ---- gather: stage timings, then markers in frame / candidate order (src/aruco.rs:75-113) ----
@@ -596,8 +752,15 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         for (uint32_t j = 0; j < nfe; j++) {
             if (mem == A3_MEM_HOST) { cudaEventElapsedTime(&ms, ev_h2da[j], ev_h2db[j]); st.ms_h2d += ms; }
             if (mem == A3_MEM_HOST || j == 0) { cudaEventElapsedTime(&ms, ev_k1a[j], ev_k1b[j]); st.ms_pixel_kernel += ms; }
-            cudaEventElapsedTime(&ms, (mem == A3_MEM_HOST || j == 0) ? ev_k1b[j] : ev_fe[j - 1], ev_fe[j]);
-            st.ms_mask_d2h += ms;
+            if (gpu_contours) {
+                if (mem == A3_MEM_HOST || j == 0) {
+                    cudaEventElapsedTime(&ms, ev_k1b[j], ev_k3[j]); st.ms_contour_kernels += ms;
+                    cudaEventElapsedTime(&ms, ev_k3[j], ev_fe[j]); st.ms_mask_d2h += ms;
+                }
+            } else {
+                cudaEventElapsedTime(&ms, (mem == A3_MEM_HOST || j == 0) ? ev_k1b[j] : ev_fe[j - 1], ev_fe[j]);
+                st.ms_mask_d2h += ms;
+            }
         }
         for (uint32_t i = 0; i < sn; i++) {
             st.n_contours += frame_stats[i].n_contours;

@@ -30,8 +30,10 @@ struct K1Params {
     size_t pitch, frame_stride;
     uint8_t *grey;        // device n*h*w or null
     uint8_t *mask;        // device n*h*w or null
-    uint32_t *bits;       // device n*h*ceil(w/32) or null
+    uint32_t *bits;       // device 1-bit mask or null: word of pixel (x, y) of frame f = bits[f * bits_frame_words + y * bits_row_words + (x >> 5)]
     uint32_t radius;      // threshold_window
+    size_t bits_row_words = 0;    // 0 = ceil(w/32) (tightly packed rows)
+    size_t bits_frame_words = 0;  // 0 = h * bits_row_words
 };
 struct K1Tuning {
     uint32_t strip_cols;  // generic kernel: core columns per strip (multiple of 32); 0 = auto
@@ -78,6 +80,35 @@ struct ResizeTaps {
 };
 ResizeTaps make_resize_taps(uint32_t n_in, uint32_t n_out);
 
+// ---- K3: border following + quad filters on the device (k3_contours.cu) ----------------------------------------
+// Guarded bit planes: per frame (h + 2) rows of S = ceil(w/32) + 2 words, all guard words zero; pixel (x, y) is bit
+// x & 31 of word (y + 1) * S + 1 + (x >> 5).  K1 writes straight into this layout (bits_row_words = S,
+// bits_frame_words = (h + 2) * S, bits = plane + S + 1).
+struct K3Params {
+    const uint32_t *planes;       // device, n guarded planes
+    uint32_t n, w, h;
+    double eps_factor;            // contour_simplification_epsilon
+    uint32_t min_edge_length;     // (min(w,h) as f32 * min_side_length_factor) as u32
+    float min_corner_separation;  // min(w,h) as f32 * min_corner_separation_factor
+    uint32_t min_points;          // borders shorter than this cannot pass the edge test (see host_quads.cpp)
+    uint32_t quad_cap;            // quads per frame the output can hold
+    uint32_t *quads;              // device out: n * quad_cap * 8
+    uint32_t *quad_counts;        // device out: n (after discard_too_near)
+    uint32_t *before_discard;     // device out: n
+    uint32_t *frame_flags;        // device out: n; non-zero = redo this frame with the host stage
+    uint32_t *frame_contours;     // device out: n (borders followed) or null
+    unsigned long long *frame_points;  // device out: n or null
+};
+struct K3Workspace {
+    struct Impl;
+    Impl *impl;
+    K3Workspace();
+    ~K3Workspace();
+    K3Workspace(const K3Workspace &) = delete;
+    K3Workspace &operator=(const K3Workspace &) = delete;
+};
+cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream);  // synchronises the stream once (buffer sizing)
+
 // ---- host quad stage (host_quads.cpp) ---------------------------------------------------------------
 struct QuadStats {
     uint64_t n_contours = 0, n_contour_points = 0, n_before_discard = 0;
@@ -85,7 +116,7 @@ struct QuadStats {
 // mask bits: h rows of `words_per_row` little-endian 32-bit words (bit x&31 of word x>>5), zero beyond w.
 // Appends 8 uint32 per surviving quad (x0,y0..x3,y3) to `quads`.
 void quads_from_bits(const uint32_t *bits, uint32_t words_per_row, uint32_t w, uint32_t h, const a3_config &cfg,
-                     std::vector<uint32_t> &quads, QuadStats *stats);
+                     std::vector<uint32_t> &quads, QuadStats *stats, size_t row_stride_words = 0);
 void bits_from_mask(const uint8_t *mask, uint32_t w, uint32_t h, std::vector<uint32_t> &bits, uint32_t *words_per_row);
 
 // ---- dictionaries (a3_dictionary.cpp) ---------------------------------------------------------------

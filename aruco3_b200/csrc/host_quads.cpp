@@ -37,13 +37,13 @@ constexpr int kDirOf[9] = {1, 2, 3, 0, -1, 4, 7, 6, 5};
 struct Planes {
     std::vector<uint32_t> fg, seen, redge;
     uint32_t stride = 0, w = 0, h = 0;
-    void reset(const uint32_t *bits, uint32_t wpr, uint32_t w_, uint32_t h_) {
+    void reset(const uint32_t *bits, uint32_t wpr, uint32_t w_, uint32_t h_, size_t row_stride) {
         w = w_; h = h_; stride = wpr + 2;
         const size_t n = (size_t)stride * (h + 2);
         fg.assign(n, 0u);
         seen.assign(n, 0u);
         redge.assign(n, 0u);
-        for (uint32_t y = 0; y < h; y++) memcpy(&fg[(size_t)(y + 1) * stride + 1], bits + (size_t)y * wpr, (size_t)wpr * 4);
+        for (uint32_t y = 0; y < h; y++) memcpy(&fg[(size_t)(y + 1) * stride + 1], bits + (size_t)y * row_stride, (size_t)wpr * 4);
     }
     inline size_t word(int x, int y) const { return (size_t)(y + 1) * stride + 1 + (x >> 5); }
     // 3 bits of row y at columns x-1, x, x+1 (bit 0 = x-1); x in [0, w), y in [-1, h]
@@ -306,7 +306,7 @@ void bits_from_mask(const uint8_t *mask, uint32_t w, uint32_t h, std::vector<uin
 }
 
 void quads_from_bits(const uint32_t *bits, uint32_t wpr, uint32_t w, uint32_t h, const a3_config &cfg,
-                     std::vector<uint32_t> &quads_out, QuadStats *stats) {
+                     std::vector<uint32_t> &quads_out, QuadStats *stats, size_t row_stride_words) {
     const uint32_t mn = w < h ? w : h;
     const uint32_t min_edge_length = (uint32_t)((float)mn * cfg.min_side_length_factor);  // src/aruco.rs:55
     const float min_corner_separation = (float)mn * cfg.min_corner_separation_factor;     // src/aruco.rs:56
@@ -314,7 +314,7 @@ void quads_from_bits(const uint32_t *bits, uint32_t wpr, uint32_t w, uint32_t h,
 
     static thread_local Planes pl;  // per host thread scratch, reused across frames (no page faults after the first)
     static thread_local PtBuf contour;
-    pl.reset(bits, wpr, w, h);
+    pl.reset(bits, wpr, w, h, row_stride_words ? row_stride_words : wpr);
     const uint32_t S = pl.stride;
     const bool small = w <= 16384 && h <= 16384;
 

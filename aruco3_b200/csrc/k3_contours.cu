@@ -1,0 +1,613 @@
+// K3 — border following and quad filtering on the GPU, sm_100a.  Compile with -fmad=false.
+//
+// Replaces, with identical results, the host stage (host_quads.cpp) and therefore
+//   imageproc::contours::find_contours::<u32>                    call site /root/reference/src/aruco.rs:64
+//   contours_to_candidates / enforce_clockwise_corners / discard_too_near   /root/reference/src/aruco.rs:124-232
+// for every frame it does not flag; flagged frames are redone by the host stage.
+//
+// The reference algorithm (Suzuki-Abe with imageproc's start guards) is sequential: whether a pixel starts a border
+// depends on labels written by borders followed earlier in raster order.  tools/contour_parallel_proto.py restates
+// it without that dependence and checks the restatement against the oracle on random masks:
+//   * a border is a closed chain of cracks (foreground pixel + a side with a background 4-neighbour); following it
+//     from any of its cracks gives the same cyclic pixel sequence, because the step function reads no labels;
+//   * start candidates are west cracks with x > 0 (the reference's "outer" rule) and east cracks with x + 1 < w
+//     ("hole" rule); a border is followed exactly once, from its raster-first ELIGIBLE candidate;
+//   * eligibility can differ from "first candidate" only in frames that contain a border whose first candidate is a
+//     west crack that is not the raster-first pixel of that border (its natural start lies in column 0, where the
+//     outer rule is barred).  Such frames are FLAGGED and left to the sequential host stage.
+// So on the GPU every candidate decides alone: it walks its own border and survives iff it meets no raster-earlier
+// candidate crack of that border.  West candidates walk backwards (the pixel above on a left edge is an earlier
+// candidate: one step), east candidates forwards; only the one survivor of each border walks the full loop.
+//
+// Kernels:  k3_survivors (one thread per 32-pixel word of the 1-bit mask)  ->  prefix sums  ->  k3_emit (survivors of
+// borders long enough to matter write their points)  ->  k3_rdp (one warp per contour: Ramer-Douglas-Peucker, hull,
+// edge test)  ->  k3_finalize (one warp per frame: ordered compaction, clockwise, discard_too_near).
+#include <cub/device/device_scan.cuh>
+
+#include "a3_internal.h"
+
+namespace a3 {
+namespace {
+
+constexpr int kDx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};  // ring order w nw n ne e se s sw (screen clockwise)
+constexpr int kDy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+
+// step table entry: bits 0-2 direction of the next pixel, bit 3 west side examined, bit 4 east side examined,
+// bits 5-6 dx + 1, bits 7-8 dy + 1, bits 9-11 state at the next pixel (direction back to this one)
+struct StepTables {
+    uint16_t fwd[8][512];  // [ring direction of the previous border pixel][3x3 neighbourhood]
+    uint16_t bwd[8][512];  // [ring direction of the next border pixel][3x3 neighbourhood]
+};
+
+uint32_t ring_of_host(uint32_t hood9) {
+    const uint32_t t = hood9 & 7u, m = (hood9 >> 3) & 7u, b = hood9 >> 6;
+    return (m & 1u) | ((t & 1u) << 1) | ((t & 2u) << 1) | ((t & 4u) << 1) | ((m & 4u) << 2) | ((b & 4u) << 3) | ((b & 2u) << 5) | ((b & 1u) << 7);
+}
+
+void build_tables(StepTables &t) {
+    for (int state = 0; state < 8; state++)
+        for (int hood = 0; hood < 512; hood++) {
+            const uint32_t nb = ring_of_host((uint32_t)hood);
+            for (int back = 0; back < 2; back++) {
+                int d = state;
+                uint32_t examined = 0;
+                for (int k = 1; k <= 7; k++) {
+                    const int c = back ? (state + k) & 7 : (state - k) & 7;
+                    if ((nb >> c) & 1) { d = c; break; }
+                    examined |= 1u << c;
+                }
+                const uint16_t e = (uint16_t)(d | (((examined >> 0) & 1u) << 3) | (((examined >> 4) & 1u) << 4) | ((kDx[d] + 1) << 5) |
+                                              ((kDy[d] + 1) << 7) | (((d + 4) & 7) << 9));
+                (back ? t.bwd : t.fwd)[state][hood] = e;
+            }
+        }
+}
+
+__device__ __forceinline__ int ddx(int d) { return (d >= 3 && d <= 5) ? 1 : ((d == 2 || d == 6) ? 0 : -1); }
+__device__ __forceinline__ int ddy(int d) { return (d >= 1 && d <= 3) ? -1 : ((d == 0 || d == 4) ? 0 : 1); }
+
+struct Geo {
+    const uint32_t *planes;  // guarded bit planes: frame f at planes + f * frame_words, pixel (x, y) = bit x & 31 of word (y + 1) * S + 1 + (x >> 5)
+    uint32_t n, w, h, wpr, S;
+    size_t frame_words;
+};
+
+// 3x3 neighbourhood of (x, y): bits 0-2 row y-1, 3-5 row y, 6-8 row y+1 (bit 0 of each = column x-1)
+__device__ __forceinline__ uint32_t hood9(const uint32_t *plane, uint32_t S, int x, int y) {
+    const int o = x + 31;
+    const uint32_t *p = plane + (size_t)y * S + (o >> 5);  // row y-1 of the guarded plane
+    const int sh = o & 31;
+    const uint32_t t = __funnelshift_r(__ldg(p), __ldg(p + 1), sh) & 7u;
+    const uint32_t m = __funnelshift_r(__ldg(p + S), __ldg(p + S + 1), sh) & 7u;
+    const uint32_t b = __funnelshift_r(__ldg(p + 2 * S), __ldg(p + 2 * S + 1), sh) & 7u;
+    return t | (m << 3) | (b << 6);
+}
+__device__ __forceinline__ uint32_t ring_of(uint32_t hood) {
+    const uint32_t t = hood & 7u, m = (hood >> 3) & 7u, b = hood >> 6;
+    return (m & 1u) | ((t & 1u) << 1) | ((t & 2u) << 1) | ((t & 4u) << 1) | ((m & 4u) << 2) | ((b & 4u) << 3) | ((b & 2u) << 5) | ((b & 1u) << 7);
+}
+
+// The candidate (x, y, kind) walks its border.  Returns true iff it is the raster-first candidate crack of it.
+// n = number of points of the border; first_pixel = it is also the border's raster-first pixel.
+__device__ bool walk_border(const uint32_t *plane, const Geo &g, const uint16_t (*fwd)[512], const uint16_t (*bwd)[512], int sx, int sy, int kind,
+                            uint32_t &n, bool &first_pixel) {
+    const uint32_t me = ((uint32_t)(sy * (int)g.w + sx) << 1) | (uint32_t)kind;
+    const uint32_t nb0 = ring_of(hood9(plane, g.S, sx, sy));
+    const int adj = kind ? 4 : 0;
+    int pred = -1;
+    for (int k = 0; k < 8; k++) {  // clockwise from the zero neighbour: the previous pixel on the border
+        const int d = (adj + k) & 7;
+        if ((nb0 >> d) & 1) { pred = d; break; }
+    }
+    n = 1;
+    first_pixel = true;
+    if (pred < 0) return kind == 0 || sx == 0;  // isolated pixel: its west crack (if it is a candidate) comes first
+    const uint32_t start_pix = (uint32_t)(sy * (int)g.w + sx);
+    uint32_t min_pix = start_pix;
+    int x, y;
+    uint32_t state;
+    if (kind) {  // forwards from the start pixel, previous pixel in direction `pred` (this is the reference's own trace)
+        x = sx; y = sy; state = (uint32_t)pred;
+        n = 0;
+    } else {     // backwards: the start pixel's own visit owns the west crack and nothing raster-earlier
+        x = sx + ddx(pred); y = sy + ddy(pred); state = (uint32_t)((pred + 4) & 7);
+    }
+    const uint16_t (*lut)[512] = kind ? fwd : bwd;
+    for (;;) {
+        const uint32_t e = lut[state][hood9(plane, g.S, x, y)];
+        const uint32_t pix = (uint32_t)(y * (int)g.w + x);
+        if (kind) {
+            if (n && pix == start_pix && state == (uint32_t)pred) break;  // back in the starting state
+        } else {
+            if (pix == start_pix && (e & 8u)) break;                     // back at the visit that owns the west crack
+        }
+        // candidate cracks of this visit that come before me in raster order
+        if ((e & 8u) && x > 0 && (pix << 1) < me) return false;
+        if ((e & 16u) && x + 1 < (int)g.w && ((pix << 1) | 1u) < me) return false;
+        min_pix = min(min_pix, pix);
+        n++;
+        x += (int)((e >> 5) & 3u) - 1;
+        y += (int)((e >> 7) & 3u) - 1;
+        state = e >> 9;
+    }
+    first_pixel = min_pix == start_pix;
+    return true;
+}
+
+struct SurvOut {
+    uint32_t *long_w, *long_e;     // per word: survivors whose border has >= min_points points
+    unsigned long long *counts;    // per word: n_long << 40 | n_long_points
+    uint32_t *frame_contours;      // per frame: borders followed
+    unsigned long long *frame_points;  // per frame: their points
+    uint32_t *frame_flags;         // per frame: bit 0 barred start (host redo), bit 1 rdp stack overflow, bit 2 quad capacity
+};
+
+__global__ void __launch_bounds__(128) k3_survivors(const Geo g, const StepTables *tables, const uint32_t min_points, SurvOut o) {
+    __shared__ uint16_t fwd[8][512];
+    __shared__ uint16_t bwd[8][512];
+    for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) {
+        (&fwd[0][0])[i] = (&tables->fwd[0][0])[i];
+        (&bwd[0][0])[i] = (&tables->bwd[0][0])[i];
+    }
+    __syncthreads();
+    const size_t words_per_frame = (size_t)g.h * g.wpr;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= words_per_frame * g.n) return;
+    const uint32_t frame = (uint32_t)(gid / words_per_frame);
+    const uint32_t rem = (uint32_t)(gid % words_per_frame);
+    const uint32_t y = rem / g.wpr, k = rem % g.wpr;
+    const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+    const uint32_t *row = plane + (size_t)(y + 1) * g.S + 1;
+    const uint32_t f = row[k];
+    uint32_t lw = 0, le = 0, ncont = 0;
+    unsigned long long npts = 0, nlongpts = 0;
+    uint32_t flags = 0;
+    if (f) {
+        const uint32_t west = (f << 1) | (row[(int)k - 1] >> 31), east = (f >> 1) | (row[k + 1] << 31);
+        uint32_t og = f & ~west, hg = f & ~east;
+        if (k == 0) og &= ~1u;                                           // `x > 0`
+        if (k == (g.w - 1) >> 5) hg &= ~(1u << ((g.w - 1) & 31));        // `x + 1 < w`
+        uint32_t pending = og | hg;
+        while (pending) {
+            const uint32_t b = pending & (0u - pending);
+            pending ^= b;
+            const int x = (int)(k * 32 + __ffs(b) - 1);
+            for (int kind = 0; kind < 2; kind++) {
+                if (!((kind ? hg : og) & b)) continue;
+                uint32_t n;
+                bool first_pixel;
+                if (!walk_border(plane, g, fwd, bwd, x, (int)y, kind, n, first_pixel)) continue;
+                ncont++;
+                npts += n;
+                if (kind == 0 && !first_pixel) flags |= 1u;  // a west start below the top of its border: barred natural start
+                if (n >= min_points && n >= 4) {
+                    (kind ? le : lw) |= b;
+                    nlongpts += n;
+                }
+            }
+        }
+    }
+    o.long_w[gid] = lw;
+    o.long_e[gid] = le;
+    o.counts[gid] = ((unsigned long long)(__popc(lw) + __popc(le)) << 40) | nlongpts;
+    if (ncont) {
+        atomicAdd(&o.frame_contours[frame], ncont);
+        atomicAdd(&o.frame_points[frame], npts);
+    }
+    if (flags) atomicOr(&o.frame_flags[frame], flags);
+}
+
+struct Contour {
+    uint32_t frame, start, n, pad;     // start = x | y << 16
+    unsigned long long point_off;
+};
+
+// survivors of long borders write their points (x | y << 16) in the reference's order: the trace from the start pixel
+__global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *tables, const uint32_t *long_w, const uint32_t *long_e,
+                                               const unsigned long long *scan, Contour *contours, uint32_t *points) {
+    __shared__ uint16_t fwd[8][512];
+    for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) (&fwd[0][0])[i] = (&tables->fwd[0][0])[i];
+    __syncthreads();
+    const size_t words_per_frame = (size_t)g.h * g.wpr;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= words_per_frame * g.n) return;
+    const uint32_t lw = long_w[gid], le = long_e[gid];
+    if (!(lw | le)) return;
+    const uint32_t frame = (uint32_t)(gid / words_per_frame);
+    const uint32_t rem = (uint32_t)(gid % words_per_frame);
+    const int y0 = (int)(rem / g.wpr);
+    const uint32_t k = rem % g.wpr;
+    const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+    unsigned long long ci = scan[gid] >> 40, po = scan[gid] & ((1ull << 40) - 1);
+    uint32_t pending = lw | le;
+    while (pending) {
+        const uint32_t b = pending & (0u - pending);
+        pending ^= b;
+        const int sx = (int)(k * 32 + __ffs(b) - 1);
+        for (int kind = 0; kind < 2; kind++) {
+            if (!((kind ? le : lw) & b)) continue;
+            const uint32_t nb0 = ring_of(hood9(plane, g.S, sx, y0));
+            const int adj = kind ? 4 : 0;
+            int pred = 0;
+            for (int q = 0; q < 8; q++) {
+                const int d = (adj + q) & 7;
+                if ((nb0 >> d) & 1) { pred = d; break; }
+            }
+            int x = sx, y = y0;
+            uint32_t state = (uint32_t)pred, n = 0;
+            uint32_t *out = points + po;
+            for (;;) {
+                if (n && x == sx && y == y0 && state == (uint32_t)pred) break;
+                out[n++] = (uint32_t)x | ((uint32_t)y << 16);
+                const uint32_t e = fwd[state][hood9(plane, g.S, x, y)];
+                x += (int)((e >> 5) & 3u) - 1;
+                y += (int)((e >> 7) & 3u) - 1;
+                state = e >> 9;
+            }
+            Contour c;
+            c.frame = frame; c.start = (uint32_t)sx | ((uint32_t)y0 << 16); c.n = n; c.pad = 0; c.point_off = po;
+            contours[ci] = c;
+            ci++;
+            po += n;
+        }
+    }
+}
+
+struct Pt { int x, y; };
+__device__ __forceinline__ Pt unpack(uint32_t v) { return Pt{(int)(v & 0xffffu), (int)(v >> 16)}; }
+
+__device__ __forceinline__ int orient(Pt p, Pt q, Pt r) {
+    const int v = (q.y - p.y) * (r.x - q.x) - (q.x - p.x) * (r.y - q.y);
+    return v == 0 ? 0 : (v > 0 ? 1 : -1);
+}
+__device__ __forceinline__ double pdist(Pt p, Pt q) {
+    const double dx = (double)p.x - (double)q.x, dy = (double)p.y - (double)q.y;
+    return sqrt(dx * dx + dy * dy);
+}
+// imageproc::geometry::convex_hull on exactly four points (same steps as host_quads.cpp:hull4)
+__device__ bool hull4(Pt q[4]) {
+    int sp = 0;
+    for (int i = 1; i < 4; i++)
+        if (q[i].y < q[sp].y || (q[i].y == q[sp].y && q[i].x < q[sp].x)) sp = i;
+    const Pt start = q[sp];
+    Pt tmp[4] = {q[0], q[1], q[2], q[3]};
+    { const Pt t = tmp[0]; tmp[0] = tmp[sp]; tmp[sp] = t; }
+    Pt rest[3] = {tmp[1], tmp[2], tmp[3]};
+    for (int i = 1; i < 3; i++) {  // insertion sort with the sort_by closure (never Equal)
+        const Pt key = rest[i];
+        int j = i;
+        while (j > 0) {
+            const int o = orient(start, key, rest[j - 1]);
+            const bool less = o == 0 ? pdist(start, key) < pdist(start, rest[j - 1]) : o < 0;
+            if (!less) break;
+            rest[j] = rest[j - 1];
+            j--;
+        }
+        rest[j] = key;
+    }
+    Pt rem[3];
+    int nr = 0;
+    for (int i = 0; i < 3;) {
+        Pt p = rest[i++];
+        while (i < 3 && orient(start, p, rest[i]) == 0) p = rest[i++];
+        rem[nr++] = p;
+    }
+    Pt st[4];
+    int ns = 0;
+    st[ns++] = start;
+    for (int k = 0; k < nr; k++) {
+        while (ns > 1 && orient(st[ns - 2], st[ns - 1], rem[k]) != -1) ns--;
+        st[ns++] = rem[k];
+    }
+    if (ns != 4) return false;
+    for (int i = 0; i < 4; i++) q[i] = st[i];
+    return true;
+}
+
+constexpr int kRdpStack = 64;
+
+// One warp per contour: approximate_polygon_dp(points, n * eps, closed) -> exactly 4 vertices? -> hull -> edge test
+// (src/aruco.rs:133-159).  Same span order and the same "first strict maximum" rule as host_quads.cpp:simplify_closed.
+__global__ void __launch_bounds__(128) k3_rdp(const Contour *contours, const uint32_t *points, uint32_t n_contours, double eps_factor,
+                                              uint32_t min_edge_length, uint32_t *quads, uint32_t *frame_flags) {
+    __shared__ uint2 stacks[4][kRdpStack];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t ci = blockIdx.x * 4 + wid;
+    if (ci >= n_contours) return;
+    const Contour c = contours[ci];
+    const uint32_t *pts = points + c.point_off;
+    const double eps = (double)c.n * eps_factor;
+    uint2 *stack = stacks[wid];
+    int sp = 0;
+    if (lane == 0) stack[0] = make_uint2(0u, c.n - 1);
+    sp = 1;
+    uint32_t nout = 0;
+    Pt out[4];
+    bool overflow = false;
+    while (sp > 0) {
+        __syncwarp();
+        const uint2 s = stack[sp - 1];
+        sp--;
+        const Pt ps = unpack(pts[s.x]), pe = unpack(pts[s.y]);
+        const long long a = (long long)ps.y - pe.y, b = (long long)pe.x - ps.x, cc = (long long)ps.x * pe.y - (long long)pe.x * ps.y;
+        const double den = sqrt((double)a * (double)a + (double)b * (double)b);
+        // pass 1: largest numerator
+        long long best = 0;
+        for (uint32_t i = s.x + 1 + lane; i <= s.y; i += 32) {
+            const Pt p = unpack(pts[i]);
+            long long v = a * p.x + b * p.y + cc;
+            v = v < 0 ? -v : v;
+            best = v > best ? v : best;
+        }
+        for (int off = 16; off; off >>= 1) {
+            const long long other = __shfl_xor_sync(0xffffffffu, best, off);
+            best = other > best ? other : best;
+        }
+        double dmax = 0.0;
+        uint32_t index = 0;
+        if (best > 0) {
+            const double q = (double)best / den;
+            if (q > 0.0) {
+                long long t = best;  // smallest numerator whose quotient equals the maximum's
+                while (t > 1 && (double)(t - 1) / den == q) t--;
+                dmax = q;
+                uint32_t first = 0xffffffffu;
+                for (uint32_t i = s.x + 1 + lane; i <= s.y && first == 0xffffffffu; i += 32) {
+                    const Pt p = unpack(pts[i]);
+                    long long v = a * p.x + b * p.y + cc;
+                    v = v < 0 ? -v : v;
+                    if (v >= t) first = i;
+                }
+                for (int off = 16; off; off >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
+                index = first;
+            }
+        }
+        if (dmax > eps) {
+            if (sp + 2 > kRdpStack) { overflow = true; break; }
+            __syncwarp();
+            if (lane == 0) {
+                stack[sp] = make_uint2(index, s.y);
+                stack[sp + 1] = make_uint2(s.x, index);
+            }
+            sp += 2;
+        } else {
+            if (nout < 4) out[nout] = ps;
+            nout++;
+            if (nout > 4) break;
+        }
+    }
+    if (lane != 0) return;
+    uint32_t *q = quads + (size_t)ci * 8;
+    q[0] = 0xffffffffu;  // not a candidate
+    if (overflow) { atomicOr(&frame_flags[c.frame], 2u); return; }
+    if (nout != 4) return;
+    if (!hull4(out)) return;
+    uint32_t cmin = min_edge_length + 1;
+    for (int i = 0; i < 4; i++) {
+        const int j = (i + 1) & 3;
+        const int dx = out[i].x - out[j].x, dy = out[i].y - out[j].y;
+        cmin = min(cmin, (uint32_t)(dx * dx + dy * dy));
+    }
+    if (cmin < min_edge_length) return;  // squared vs unsquared on purpose
+    for (int i = 0; i < 4; i++) { q[2 * i] = (uint32_t)out[i].x; q[2 * i + 1] = (uint32_t)out[i].y; }
+}
+
+__device__ __forceinline__ float perimeter(const uint32_t *q) {
+    float p = 0.0f;
+    for (int i = 0; i < 4; i++) {
+        const int j = (i + 1) & 3;
+        const float dx = (float)q[2 * i] - (float)q[2 * j], dy = (float)q[2 * i + 1] - (float)q[2 * j + 1];
+        p += sqrtf((dx * dx) + (dy * dy));
+    }
+    return p;
+}
+
+// One warp per frame: the frame's quads in contour order, enforce_clockwise_corners, discard_too_near
+// (src/aruco.rs:168-232).  frame_first[f] .. frame_first[f + 1] = the frame's range of contours.
+__global__ void __launch_bounds__(32) k3_finalize(const uint32_t *contour_quads, const unsigned long long *scan, size_t words_per_frame,
+                                                  unsigned long long total_contours, uint32_t n_frames, float min_corner_separation,
+                                                  uint32_t quad_cap, uint32_t *out_quads, uint32_t *out_counts, uint32_t *out_before_discard,
+                                                  uint32_t *frame_flags, uint8_t *dead_scratch) {
+    const uint32_t f = blockIdx.x;
+    const int lane = threadIdx.x;
+    const unsigned long long c0 = scan[(size_t)f * words_per_frame] >> 40;
+    const unsigned long long c1 = f + 1 < n_frames ? scan[(size_t)(f + 1) * words_per_frame] >> 40 : total_contours;
+    uint32_t *dst = out_quads + (size_t)f * quad_cap * 8;
+    uint32_t nq = 0;
+    bool over = false;
+    for (unsigned long long base = c0; base < c1; base += 32) {
+        const unsigned long long ci = base + lane;
+        const bool valid = ci < c1 && contour_quads[ci * 8] != 0xffffffffu;
+        const uint32_t m = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const uint32_t slot = nq + __popc(m & ((1u << lane) - 1));
+            if (slot < quad_cap)
+                for (int i = 0; i < 8; i++) dst[(size_t)slot * 8 + i] = contour_quads[ci * 8 + i];
+            else
+                over = true;
+        }
+        nq += __popc(m);
+    }
+    over = __any_sync(0xffffffffu, over);
+    __syncwarp();
+    if (lane != 0) return;
+    if (over) { atomicOr(&frame_flags[f], 4u); nq = quad_cap; }
+    out_before_discard[f] = nq;
+    for (uint32_t i = 0; i < nq; i++) {  // enforce_clockwise_corners
+        uint32_t *p = dst + (size_t)i * 8;
+        const int dx1 = (int)p[2] - (int)p[0], dy1 = (int)p[3] - (int)p[1], dx2 = (int)p[4] - (int)p[0], dy2 = (int)p[5] - (int)p[1];
+        if (dx1 * dy2 - dy1 * dx2 < 0) {
+            const uint32_t sx = p[2], sy = p[3];
+            p[2] = p[6]; p[3] = p[7]; p[6] = sx; p[7] = sy;
+        }
+    }
+    uint8_t *dead = dead_scratch + (size_t)f * quad_cap;
+    for (uint32_t i = 0; i < nq; i++) dead[i] = 0;
+    for (uint32_t i = 0; i + 1 < nq; i++) {  // discard_too_near
+        if (dead[i]) continue;
+        const float per_i = perimeter(dst + (size_t)i * 8);
+        for (uint32_t j = i + 1; j < nq; j++) {
+            if (dead[j]) continue;
+            float d = 0.0f;
+            for (int c = 0; c < 4; c++) {
+                const float dx = (float)dst[(size_t)i * 8 + 2 * c] - (float)dst[(size_t)j * 8 + 2 * c];
+                const float dy = (float)dst[(size_t)i * 8 + 2 * c + 1] - (float)dst[(size_t)j * 8 + 2 * c + 1];
+                d += sqrtf((dx * dx) + (dy * dy));
+            }
+            if ((d / 4.0f) < min_corner_separation) {
+                if (dead[i] || dead[j]) continue;
+                if (per_i >= perimeter(dst + (size_t)j * 8)) dead[j] = 1;
+                else dead[i] = 1;  // the reference keeps scanning with this i
+            }
+        }
+    }
+    uint32_t kept = 0;
+    for (uint32_t i = 0; i < nq; i++)
+        if (!dead[i]) {
+            if (kept != i)
+                for (int c = 0; c < 8; c++) dst[(size_t)kept * 8 + c] = dst[(size_t)i * 8 + c];
+            kept++;
+        }
+    out_counts[f] = kept;
+}
+
+}  // namespace
+
+struct K3Workspace::Impl {
+    StepTables *d_tables = nullptr;
+    uint32_t *long_w = nullptr, *long_e = nullptr;
+    unsigned long long *counts = nullptr, *scan = nullptr, *frame_points = nullptr;
+    uint32_t *frame_contours = nullptr;
+    size_t words_cap = 0, frames_cap = 0;
+    void *cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    Contour *contours = nullptr;
+    size_t contours_cap = 0;
+    uint32_t *points = nullptr;
+    size_t points_cap = 0;
+    uint32_t *contour_quads = nullptr;
+    uint8_t *dead = nullptr;
+    size_t dead_cap = 0;
+    unsigned long long *h_last = nullptr;  // pinned: [0] last scan value, [1] last count
+};
+
+K3Workspace::K3Workspace() : impl(new Impl()) {}
+K3Workspace::~K3Workspace() {
+    if (!impl) return;
+    for (void *p : {(void *)impl->d_tables, (void *)impl->long_w, (void *)impl->long_e, (void *)impl->counts, (void *)impl->scan,
+                    (void *)impl->frame_points, (void *)impl->frame_contours, impl->cub_tmp, (void *)impl->contours, (void *)impl->points,
+                    (void *)impl->contour_quads, (void *)impl->dead})
+        if (p) cudaFree(p);
+    if (impl->h_last) cudaFreeHost(impl->h_last);
+    delete impl;
+}
+
+#define K3_CUDA(expr)                              \
+    do {                                           \
+        cudaError_t e__ = (expr);                  \
+        if (e__ != cudaSuccess) return e__;        \
+    } while (0)
+
+template <typename T>
+static cudaError_t grow(T *&p, size_t &cap, size_t need) {
+    if (need <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = need + need / 4 + 1024;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+}
+
+cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
+    K3Workspace::Impl &w = *ws.impl;
+    if (p.n == 0) return cudaSuccess;
+    if (p.w > 65535 || p.h > 65535) return cudaErrorInvalidValue;  // points are packed 16 + 16
+    Geo g;
+    g.planes = p.planes; g.n = p.n; g.w = p.w; g.h = p.h; g.wpr = (p.w + 31) / 32; g.S = g.wpr + 2;
+    g.frame_words = (size_t)(p.h + 2) * g.S;
+    const size_t words_per_frame = (size_t)g.h * g.wpr, nwords = words_per_frame * p.n;
+    if (!w.d_tables) {
+        StepTables *t = new StepTables();
+        build_tables(*t);
+        cudaError_t e = cudaMalloc(&w.d_tables, sizeof(StepTables));
+        if (e == cudaSuccess) e = cudaMemcpy(w.d_tables, t, sizeof(StepTables), cudaMemcpyHostToDevice);
+        delete t;
+        K3_CUDA(e);
+        K3_CUDA(cudaHostAlloc(&w.h_last, 16, cudaHostAllocDefault));
+    }
+    if (nwords > w.words_cap) {
+        for (void *q : {(void *)w.long_w, (void *)w.long_e, (void *)w.counts, (void *)w.scan})
+            if (q) cudaFree(q);
+        w.long_w = w.long_e = nullptr; w.counts = w.scan = nullptr; w.words_cap = 0;
+        K3_CUDA(cudaMalloc(&w.long_w, nwords * 4));
+        K3_CUDA(cudaMalloc(&w.long_e, nwords * 4));
+        K3_CUDA(cudaMalloc(&w.counts, nwords * 8));
+        K3_CUDA(cudaMalloc(&w.scan, nwords * 8));
+        w.words_cap = nwords;
+    }
+    if (p.n > w.frames_cap) {
+        if (w.frame_points) cudaFree(w.frame_points);
+        if (w.frame_contours) cudaFree(w.frame_contours);
+        w.frame_points = nullptr; w.frame_contours = nullptr; w.frames_cap = 0;
+        K3_CUDA(cudaMalloc(&w.frame_points, (size_t)p.n * 8));
+        K3_CUDA(cudaMalloc(&w.frame_contours, (size_t)p.n * 4));
+        w.frames_cap = p.n;
+    }
+    size_t need_tmp = 0;
+    K3_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need_tmp, w.counts, w.scan, nwords, stream));
+    if (need_tmp > w.cub_bytes) {
+        if (w.cub_tmp) cudaFree(w.cub_tmp);
+        w.cub_tmp = nullptr; w.cub_bytes = 0;
+        K3_CUDA(cudaMalloc(&w.cub_tmp, need_tmp));
+        w.cub_bytes = need_tmp;
+    }
+    if ((size_t)p.n * p.quad_cap > w.dead_cap) {
+        if (w.dead) cudaFree(w.dead);
+        w.dead = nullptr; w.dead_cap = 0;
+        K3_CUDA(cudaMalloc(&w.dead, (size_t)p.n * p.quad_cap));
+        w.dead_cap = (size_t)p.n * p.quad_cap;
+    }
+    K3_CUDA(cudaMemsetAsync(w.frame_points, 0, (size_t)p.n * 8, stream));
+    K3_CUDA(cudaMemsetAsync(w.frame_contours, 0, (size_t)p.n * 4, stream));
+    K3_CUDA(cudaMemsetAsync(p.frame_flags, 0, (size_t)p.n * 4, stream));
+
+    SurvOut so;
+    so.long_w = w.long_w; so.long_e = w.long_e; so.counts = w.counts; so.frame_contours = w.frame_contours; so.frame_points = w.frame_points;
+    so.frame_flags = p.frame_flags;
+    const uint32_t blocks = (uint32_t)((nwords + 127) / 128);
+    k3_survivors<<<blocks, 128, 0, stream>>>(g, w.d_tables, p.min_points, so);
+    K3_CUDA(cudaGetLastError());
+    size_t tmp = w.cub_bytes;
+    K3_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.counts, w.scan, nwords, stream));
+    K3_CUDA(cudaMemcpyAsync(&w.h_last[0], w.scan + nwords - 1, 8, cudaMemcpyDeviceToHost, stream));
+    K3_CUDA(cudaMemcpyAsync(&w.h_last[1], w.counts + nwords - 1, 8, cudaMemcpyDeviceToHost, stream));
+    K3_CUDA(cudaStreamSynchronize(stream));
+    const unsigned long long total = w.h_last[0] + w.h_last[1];
+    const unsigned long long n_long = total >> 40, n_points = total & ((1ull << 40) - 1);
+    {
+        size_t old = w.contours_cap;
+        K3_CUDA(grow(w.contours, w.contours_cap, (size_t)n_long + 1));
+        if (w.contours_cap != old) {
+            if (w.contour_quads) cudaFree(w.contour_quads);
+            w.contour_quads = nullptr;
+            K3_CUDA(cudaMalloc(&w.contour_quads, w.contours_cap * 32));
+        }
+        K3_CUDA(grow(w.points, w.points_cap, (size_t)n_points + 1));
+    }
+    if (n_long) {
+        k3_emit<<<blocks, 128, 0, stream>>>(g, w.d_tables, w.long_w, w.long_e, w.scan, w.contours, w.points);
+        K3_CUDA(cudaGetLastError());
+        k3_rdp<<<(uint32_t)((n_long + 3) / 4), 128, 0, stream>>>(w.contours, w.points, (uint32_t)n_long, p.eps_factor, p.min_edge_length,
+                                                               w.contour_quads, p.frame_flags);
+        K3_CUDA(cudaGetLastError());
+    }
+    k3_finalize<<<p.n, 32, 0, stream>>>(w.contour_quads, w.scan, words_per_frame, n_long, p.n, p.min_corner_separation, p.quad_cap, p.quads,
+                                        p.quad_counts, p.before_discard, p.frame_flags, w.dead);
+    K3_CUDA(cudaGetLastError());
+    if (p.frame_contours) K3_CUDA(cudaMemcpyAsync(p.frame_contours, w.frame_contours, (size_t)p.n * 4, cudaMemcpyDeviceToDevice, stream));
+    if (p.frame_points) K3_CUDA(cudaMemcpyAsync(p.frame_points, w.frame_points, (size_t)p.n * 8, cudaMemcpyDeviceToDevice, stream));
+    return cudaSuccess;
+}
+
+}  // namespace a3

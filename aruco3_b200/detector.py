@@ -138,7 +138,7 @@ class Detector:
     """
 
     def __init__(self, config: DetectorConfig | None = None, dictionary: ARDictionary | str = "ARUCO", device: int = 0,
-                 host_threads: int | None = None):
+                 host_threads: int | None = None, contours: str = "device"):
         self.config = config or DetectorConfig()
         self.dictionary = ARDictionary.new_from_named_dict(dictionary) if isinstance(dictionary, str) else dictionary
         self.device = device
@@ -147,6 +147,8 @@ class Detector:
         check(lib().a3_detector_create(C.byref(cfg), C.byref(self.dictionary._c), device, C.byref(self._h)))
         if host_threads:
             check(lib().a3_detector_set_host_threads(self._h, host_threads))
+        # where find_contours + the quad filters run: "device" (kernel K3, host redo of flagged frames) or "host"
+        check(lib().a3_detector_set_contour_mode(self._h, {"host": _ffi.CONTOURS_HOST, "device": _ffi.CONTOURS_DEVICE}[contours]))
         self.last_stats: dict = {}
 
     def close(self):
@@ -245,6 +247,20 @@ class Detector:
         check(lib().a3_gray_threshold_batch(self._h, a.ctypes.data, fmt, _ffi.MEM_HOST, n, w, h, pitch, fstride,
                                             grey.ctypes.data, mask.ctypes.data, bits.ctypes.data if want_bits else None, None))
         return (grey, mask, bits) if want_bits else (grey, mask)
+
+    def quads_from_masks_device(self, masks: np.ndarray, quad_capacity: int = 1024):
+        """find_contours + quad filters on the device (kernel K3) for host masks [n,H,W] -> (list of uint32 [m,8] per frame,
+        flags uint32 [n], contours uint32 [n], points uint64 [n]); a frame with a non-zero flag must be redone by the host stage."""
+        m = np.ascontiguousarray(masks, dtype=np.uint8)
+        if m.ndim == 2:
+            m = m[None]
+        n, h, w = m.shape
+        quads = np.zeros((n, quad_capacity, 8), np.uint32)
+        counts, flags, contours = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        points = np.zeros(n, np.uint64)
+        check(lib().a3_quads_from_masks_device(self._h, m.ctypes.data, n, w, h, quads.ctypes.data, quad_capacity, counts.ctypes.data,
+                                               flags.ctypes.data, contours.ctypes.data, points.ctypes.data))
+        return [quads[f, :counts[f]].copy() for f in range(n)], flags, contours, points
 
     def decode_candidates(self, grey: np.ndarray, quads: np.ndarray, quad_frame: np.ndarray | None = None):
         """extract_homographies + homography_to_code_permutations + match for quads uint32 [m,8] over grey [n,H,W]

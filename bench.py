@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="frames per pipeline chunk (0 = library default)")
+    ap.add_argument("--contours", default="device", choices=["device", "host"], help="where find_contours + quad filters run")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -177,7 +178,7 @@ def main():
     resident = pinned.cuda(non_blocking=False)
     torch.cuda.synchronize()
 
-    det = Detector(dictionary="ARUCO", device=local_rank, host_threads=host_threads)
+    det = Detector(dictionary="ARUCO", device=local_rank, host_threads=host_threads, contours=args.contours)
     L = _ffi.lib()
     if args.chunk:
         tune = _ffi.A3K1Tuning(chunk_frames=args.chunk)
@@ -269,7 +270,8 @@ def main():
                    "parallelism": f"frame-batch sharding x{world}, no collective"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n * h * w * 3, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(acc_dev["pixel_kernel_launches"] + acc_dev["decode_kernel_launches"]),
+        "gpu_launches": int(acc_dev["pixel_kernel_launches"] + acc_dev["decode_kernel_launches"] + 4 * acc_dev["contour_kernel_launches"]),
+        "contour_stage": args.contours, "host_fallback_frames_per_step": acc_dev["host_fallback_frames"] / args.steps,
         "roofline": {"bound": "hbm", "kernel": "k1_strips_kernel<RGB8> (fused into_luma8 + adaptive_threshold, TMA tensor tiles)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                      "frac_of_nominal_8TBps": achieved / 8000.0, "traffic": None,
@@ -279,9 +281,9 @@ def main():
                      "bytes_per_launch": bytes_per_launch, "avg_launch_ms": k1_avg_ms, "launches": launches,
                      "isolated": {"gbs": iso_gbs, "ms": k1_ms, "bytes": iso_bytes, "frac": iso_gbs / peak,
                                   "fps": n / (k1_ms * 1e-3), "note": "K1 alone over the 256 resident frames, grey + 1-bit mask outputs"}},
-        "stages_ms_per_step": {k: acc_dev[k] / args.steps for k in ("ms_h2d", "ms_pixel_kernel", "ms_mask_d2h", "ms_host_quads",
+        "stages_ms_per_step": {k: acc_dev[k] / args.steps for k in ("ms_h2d", "ms_pixel_kernel", "ms_contour_kernels", "ms_mask_d2h", "ms_host_quads",
                                                                      "ms_host_cpu", "ms_decode_kernel", "ms_total")},
-        "stages_ms_per_step_e2e": {k: acc_e2e[k] / args.steps for k in ("ms_h2d", "ms_pixel_kernel", "ms_mask_d2h", "ms_host_quads",
+        "stages_ms_per_step_e2e": {k: acc_e2e[k] / args.steps for k in ("ms_h2d", "ms_pixel_kernel", "ms_contour_kernels", "ms_mask_d2h", "ms_host_quads",
                                                                          "ms_host_cpu", "ms_decode_kernel", "ms_total")},
         "counts_per_step": {k: acc_dev[k] / args.steps for k in ("n_contours", "n_contour_points", "n_candidates", "n_markers")},
         "clocks": clocks, "clocks_e2e": clocks_e2e,

@@ -93,10 +93,13 @@ typedef struct a3_decode {
 /* Counters + device-side stage times of the last call (CUDA events; host stage by steady_clock). */
 typedef struct a3_stats {
     uint64_t n_frames, n_contours, n_contour_points, n_candidates_before_discard, n_candidates, n_markers;
-    /* ms_h2d / ms_pixel_kernel / ms_mask_d2h / ms_decode_kernel: sums of CUDA-event intervals on the stream each runs on;
+    /* ms_h2d / ms_pixel_kernel / ms_contour_kernels / ms_mask_d2h (mask bits, or K3's quads) / ms_decode_kernel: sums of
+     * CUDA-event intervals on the stream each runs on;
      * ms_host_quads: wall time the host stage was active (overlaps the others); ms_host_cpu: CPU time summed over frames */
-    double ms_h2d, ms_pixel_kernel, ms_mask_d2h, ms_host_quads, ms_decode_kernel, ms_host_cpu, ms_total;
-    uint32_t pixel_kernel_launches, decode_kernel_launches, host_threads, reserved;
+    double ms_h2d, ms_pixel_kernel, ms_contour_kernels, ms_mask_d2h, ms_host_quads, ms_decode_kernel, ms_host_cpu, ms_total;
+    uint32_t pixel_kernel_launches, decode_kernel_launches, host_threads, contour_kernel_launches;
+    uint32_t host_fallback_frames; /* device contour stage: frames it handed back to the host stage */
+    uint32_t reserved;
 } a3_stats;
 
 /* Optional per-call outputs of a3_detect_batch (all may be NULL). Host pointers; tightly packed. */
@@ -138,6 +141,13 @@ void a3_detector_destroy(a3_detector *det);
 /* number of host threads used for the contour / quad stage (default: all cores, capped at 64) */
 a3_status a3_detector_set_host_threads(a3_detector *det, uint32_t threads);
 
+/* Where find_contours + the quad filters (src/aruco.rs:64-69) run.  A3_CONTOURS_DEVICE (default): kernel K3; frames
+ * it cannot prove identical to the sequential algorithm (a border whose natural start is barred by the reference's
+ * `x > 0` guard, > 1024 quads, pathological polygon recursion) are redone by the host stage, so results never depend on
+ * the mode.  A3_CONTOURS_HOST: always the host stage (C++ threads), as BASELINE.json's north_star describes it. */
+enum { A3_CONTOURS_HOST = 0, A3_CONTOURS_DEVICE = 1 };
+a3_status a3_detector_set_contour_mode(a3_detector *det, uint32_t mode);
+
 /* Launch-shape knobs of the pixel kernel (benchmark sweeps and tests; results never depend on them). 0 = automatic. */
 typedef struct a3_k1_tuning {
     uint32_t strip_cols;    /* generic kernel: output columns per CTA strip */
@@ -171,6 +181,13 @@ a3_status a3_gray_threshold_batch(a3_detector *det, const void *frames, a3_forma
  * (src/aruco.rs:64-69) on one host mask (0 / non-zero bytes). Host stage of the product. */
 a3_status a3_quads_from_mask(const a3_config *cfg, const uint8_t *mask, uint32_t width, uint32_t height,
                              uint32_t *quads, uint32_t quad_capacity, uint32_t *n_quads, a3_stats *stats);
+
+/* The same stage on the device (kernel K3) for n host masks of w*h bytes each (0 / non-zero), as a parity probe:
+ * quads n*quad_capacity*8, counts n, flags n (non-zero: K3 hands this frame back to the host stage and its quads are
+ * not meaningful), contours n and points n (borders followed and their total points; may be NULL). */
+a3_status a3_quads_from_masks_device(a3_detector *det, const uint8_t *masks, uint32_t n, uint32_t width, uint32_t height,
+                                     uint32_t *quads, uint32_t quad_capacity, uint32_t *counts, uint32_t *flags,
+                                     uint32_t *contours, uint64_t *points);
 
 /* extract_homographies + homography_to_code_permutations + the match loop (src/aruco.rs:72-113) for
  * n_quads candidates over grey frames. HOST pointers; quads n_quads*8, quad_frame n_quads (frame index of

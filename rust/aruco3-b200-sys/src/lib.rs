@@ -78,6 +78,7 @@ pub struct a3_stats {
     pub n_markers: u64,
     pub ms_h2d: f64,
     pub ms_pixel_kernel: f64,
+    pub ms_contour_kernels: f64,
     pub ms_mask_d2h: f64,
     pub ms_host_quads: f64,
     pub ms_decode_kernel: f64,
@@ -86,6 +87,8 @@ pub struct a3_stats {
     pub pixel_kernel_launches: u32,
     pub decode_kernel_launches: u32,
     pub host_threads: u32,
+    pub contour_kernel_launches: u32,
+    pub host_fallback_frames: u32,
     pub reserved: u32,
 }
 
@@ -126,6 +129,7 @@ extern "C" {
     pub fn a3_detector_create(cfg: *const a3_config, dict: *const a3_dictionary, device: i32, out: *mut *mut a3_detector) -> a3_status;
     pub fn a3_detector_destroy(det: *mut a3_detector);
     pub fn a3_detector_set_host_threads(det: *mut a3_detector, threads: u32) -> a3_status;
+    pub fn a3_detector_set_contour_mode(det: *mut a3_detector, mode: u32) -> a3_status;
     pub fn a3_detect_batch(
         det: *mut a3_detector, frames: *const c_void, format: i32, mem: i32, n: u32, width: u32, height: u32, pitch: usize,
         frame_stride: usize, markers: *mut a3_marker, marker_capacity: u32, n_markers: *mut u32, outputs: *mut a3_outputs,

@@ -1,0 +1,118 @@
+"""Kernel K3 (find_contours + quad filters on the device, csrc/k3_contours.cu) against the oracle and the host stage.
+
+K3 decides every border start from the image alone (tools/contour_parallel_proto.py); frames where that formulation
+could differ from the sequential reference are flagged by the kernel and redone by the host stage, so the test checks
+(a) unflagged frames: identical quads, contour count and point count, (b) the flag is raised exactly for the documented
+reason often enough to matter on frame-touching content and never on the benchmark workloads, (c) the end-to-end path
+gives identical results in both contour modes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def a3():
+    import aruco3_b200
+    return aruco3_b200
+
+
+def _oracle_frame(oracle, mask, ocfg):
+    contours, _ = oracle.find_contours(mask)
+    return oracle.candidates_from_mask(mask, ocfg), len(contours), sum(len(c) for c in contours)
+
+
+def _check(a3, oracle, masks, cfg, ocfg, allow_flags=True):
+    with a3.Detector(cfg) as d:
+        quads, flags, contours, points = d.quads_from_masks_device(masks)
+    nflag = 0
+    for f in range(len(masks)):
+        if flags[f]:
+            nflag += 1
+            assert allow_flags, f"frame {f} was flagged ({flags[f]})"
+            continue
+        want, nc, npnt = _oracle_frame(oracle, masks[f], ocfg)
+        assert quads[f].tolist() == want.tolist(), f"frame {f}: quads"
+        assert (int(contours[f]), int(points[f])) == (nc, npnt), f"frame {f}: contour statistics"
+    return nflag
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 3), (31, 7), (32, 32), (33, 17), (64, 48), (97, 131), (200, 120)])
+def test_random_masks(a3, oracle, w, h):
+    rng = np.random.default_rng(w * 977 + h)
+    cfg = a3.DetectorConfig(min_side_length_factor=0.02, min_corner_separation_factor=0.01)
+    ocfg = oracle.default_config(min_side_length_factor=0.02, min_corner_separation_factor=0.01)
+    masks = []
+    for density in (0.05, 0.3, 0.5, 0.7, 0.95):
+        for k in range(8):
+            m = ((rng.random((h, w)) < density) * 255).astype(np.uint8)
+            if k % 2 == 0 and w > 2 and h > 2:  # nothing touches the frame: K3 may not flag these
+                m[0] = m[-1] = 0
+                m[:, 0] = m[:, -1] = 0
+            masks.append(m)
+    for _ in range(10):  # blocky content produces real quads
+        m = np.zeros((h, w), np.uint8)
+        for _ in range(8):
+            x0, y0 = rng.integers(0, w), rng.integers(0, h)
+            m[y0:y0 + rng.integers(1, 40), x0:x0 + rng.integers(1, 40)] = 255
+        for _ in range(4):
+            x0, y0 = rng.integers(0, w), rng.integers(0, h)
+            m[y0:y0 + rng.integers(1, 12), x0:x0 + rng.integers(1, 12)] = 0
+        masks.append(m)
+    masks = np.stack(masks)
+    _check(a3, oracle, masks, cfg, ocfg)
+    inner = np.stack([m for i, m in enumerate(masks[:40]) if i % 2 == 0]) if w > 2 and h > 2 else None
+    if inner is not None:
+        assert _check(a3, oracle, inner, cfg, ocfg, allow_flags=False) == 0
+
+
+@pytest.mark.parametrize("name,frames", [("C1", 4), ("C1n", 2), ("C3", 2), ("C3n", 1), ("C2a", 1), ("C5", 1)])
+def test_benchmark_masks_are_not_flagged(a3, oracle, name, frames):
+    from aruco3_b200 import synth
+    spec = synth.CONFIGS[name]
+    cfg = a3.DetectorConfig(min_corner_separation_factor=spec.min_corner_separation_factor)
+    ocfg = oracle.default_config(min_corner_separation_factor=spec.min_corner_separation_factor)
+    masks = np.stack([oracle.adaptive_threshold(oracle.to_luma8(synth.render_frame(spec, f)[0]), 7) for f in range(frames)])
+    nflag = _check(a3, oracle, masks, cfg, ocfg)
+    if name in ("C1", "C3", "C5"):
+        assert nflag == 0
+
+
+def test_flag_for_barred_start(a3, oracle):
+    """A white area whose top row spans the frame (raster-first pixel in column 0) with a dark blob on the left edge: the
+    reference starts that border from a west crack below its top — the documented reason for a host redo."""
+    m = np.full((60, 80), 255, np.uint8)
+    m[20:30, 0:12] = 0
+    with a3.Detector() as d:
+        _, flags, _, _ = d.quads_from_masks_device(m)
+    assert flags[0] & 1
+
+
+@pytest.mark.parametrize("name,frames", [("C1", 5), ("C1n", 3), ("C3", 2), ("C3n", 1), ("C2a", 1), ("C5", 1)])
+def test_detect_is_identical_in_both_modes(a3, name, frames):
+    from aruco3_b200 import synth
+    spec = synth.CONFIGS[name]
+    imgs, _ = synth.render_batch(spec, frames)
+    cfg = a3.DetectorConfig(min_corner_separation_factor=spec.min_corner_separation_factor)
+    res = {}
+    for mode in ("host", "device"):
+        with a3.Detector(cfg, spec.dictionary, contours=mode) as d:
+            dets = d.detect_batch(imgs, full=True)
+            res[mode] = ([(x.candidates, [(m.id, m.rotation, m.hamming_distance, m.code, m.corners, m.candidate) for m in x.markers]) for x in dets],
+                         {k: d.last_stats[k] for k in ("n_contours", "n_contour_points", "n_candidates_before_discard", "n_candidates", "n_markers")})
+    assert res["host"] == res["device"]
+
+
+def test_flagged_frames_are_redone_by_the_host_stage(a3, oracle):
+    """End to end on frames that K3 flags: a grey-level frame whose mask has the barred-start shape."""
+    img = np.full((3, 96, 128), 200, np.uint8)
+    img[:, 30:50, 0:20] = 20          # dark blob on the left edge
+    img[1, 10:40, 60:100] = 30        # plus a dark rectangle
+    with a3.Detector(contours="device") as d:
+        dev = d.detect_batch(img, full=True)
+        assert d.last_stats["host_fallback_frames"] >= 1
+    with a3.Detector(contours="host") as d:
+        host = d.detect_batch(img, full=True)
+    for f in range(3):
+        assert dev[f].candidates == host[f].candidates
+        assert dev[f].candidates == [[tuple(q[2 * k:2 * k + 2]) for k in range(4)] for q in oracle.detect(img[f]).candidates.tolist()]
