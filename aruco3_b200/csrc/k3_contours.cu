@@ -19,9 +19,13 @@
 // candidate crack of that border.  West candidates walk backwards (the pixel above on a left edge is an earlier
 // candidate: one step), east candidates forwards; only the one survivor of each border walks the full loop.
 //
-// Kernels:  k3_survivors (one thread per 32-pixel word of the 1-bit mask)  ->  prefix sums  ->  k3_emit (survivors of
-// borders long enough to matter write their points)  ->  k3_rdp (one warp per contour: Ramer-Douglas-Peucker, hull,
-// edge test)  ->  k3_finalize (one warp per frame: ordered compaction, clockwise, discard_too_near).
+// Kernels:  k3_candidates (one thread per 32-pixel word of the 1-bit mask; every candidate walks at most kBudget steps:
+// almost all die within a few, short borders finish)  ->  k3_walkers (one thread per undecided candidate: the long
+// borders, all in flight at once)  ->  radix sort of the surviving long borders by raster position (= the reference's
+// discovery order) + prefix sum of their lengths  ->  k3_emit (one thread per border writes its points)  ->  k3_rdp (one
+// warp per border: Ramer-Douglas-Peucker, hull, edge test)  ->  k3_finalize (one warp per frame: ordered compaction,
+// clockwise, discard_too_near).
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "a3_internal.h"
@@ -87,10 +91,14 @@ __device__ __forceinline__ uint32_t ring_of(uint32_t hood) {
     return (m & 1u) | ((t & 1u) << 1) | ((t & 2u) << 1) | ((t & 4u) << 1) | ((m & 4u) << 2) | ((b & 4u) << 3) | ((b & 2u) << 5) | ((b & 1u) << 7);
 }
 
-// The candidate (x, y, kind) walks its border.  Returns true iff it is the raster-first candidate crack of it.
-// n = number of points of the border; first_pixel = it is also the border's raster-first pixel.
-__device__ bool walk_border(const uint32_t *plane, const Geo &g, const uint16_t (*fwd)[512], const uint16_t (*bwd)[512], int sx, int sy, int kind,
-                            uint32_t &n, bool &first_pixel) {
+constexpr uint32_t kBudget = 48;  // steps a candidate may walk inside k3_candidates before it is deferred to k3_walkers
+
+enum { kDead = 0, kSurvivor = 1, kUndecided = 2 };
+
+// The candidate (x, y, kind) walks its border for at most `budget` steps.  kSurvivor: it is the raster-first candidate
+// crack of the border (n = number of points of the border, first_pixel = it is also the border's raster-first pixel).
+__device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (*fwd)[512], const uint16_t (*bwd)[512], int sx, int sy, int kind,
+                           uint32_t budget, uint32_t &n, bool &first_pixel) {
     const uint32_t me = ((uint32_t)(sy * (int)g.w + sx) << 1) | (uint32_t)kind;
     const uint32_t nb0 = ring_of(hood9(plane, g.S, sx, sy));
     const int adj = kind ? 4 : 0;
@@ -101,7 +109,7 @@ __device__ bool walk_border(const uint32_t *plane, const Geo &g, const uint16_t 
     }
     n = 1;
     first_pixel = true;
-    if (pred < 0) return kind == 0 || sx == 0;  // isolated pixel: its west crack (if it is a candidate) comes first
+    if (pred < 0) return (kind == 0 || sx == 0) ? kSurvivor : kDead;  // isolated pixel: its west crack (if a candidate) comes first
     const uint32_t start_pix = (uint32_t)(sy * (int)g.w + sx);
     uint32_t min_pix = start_pix;
     int x, y;
@@ -113,7 +121,7 @@ __device__ bool walk_border(const uint32_t *plane, const Geo &g, const uint16_t 
         x = sx + ddx(pred); y = sy + ddy(pred); state = (uint32_t)((pred + 4) & 7);
     }
     const uint16_t (*lut)[512] = kind ? fwd : bwd;
-    for (;;) {
+    for (uint32_t steps = 0;; steps++) {
         const uint32_t e = lut[state][hood9(plane, g.S, x, y)];
         const uint32_t pix = (uint32_t)(y * (int)g.w + x);
         if (kind) {
@@ -122,8 +130,9 @@ __device__ bool walk_border(const uint32_t *plane, const Geo &g, const uint16_t 
             if (pix == start_pix && (e & 8u)) break;                     // back at the visit that owns the west crack
         }
         // candidate cracks of this visit that come before me in raster order
-        if ((e & 8u) && x > 0 && (pix << 1) < me) return false;
-        if ((e & 16u) && x + 1 < (int)g.w && ((pix << 1) | 1u) < me) return false;
+        if ((e & 8u) && x > 0 && (pix << 1) < me) return kDead;
+        if ((e & 16u) && x + 1 < (int)g.w && ((pix << 1) | 1u) < me) return kDead;
+        if (steps >= budget) return kUndecided;
         min_pix = min(min_pix, pix);
         n++;
         x += (int)((e >> 5) & 3u) - 1;
@@ -131,18 +140,40 @@ __device__ bool walk_border(const uint32_t *plane, const Geo &g, const uint16_t 
         state = e >> 9;
     }
     first_pixel = min_pix == start_pix;
-    return true;
+    return kSurvivor;
 }
 
-struct SurvOut {
-    uint32_t *long_w, *long_e;     // per word: survivors whose border has >= min_points points
-    unsigned long long *counts;    // per word: n_long << 40 | n_long_points
-    uint32_t *frame_contours;      // per frame: borders followed
+// Work lists shared by the kernels of one k3_quads call.
+struct Lists {
+    unsigned long long *walkers;       // undecided candidates: ((word id * 32 + bit) << 1) | kind
+    unsigned long long *long_keys;     // surviving borders with >= min_points points: the same key ...
+    uint32_t *long_n;                  // ... and their number of points
+    uint32_t *counters;                // [0] walkers, [1] long borders, [2] overflow of either list
+    unsigned long long *long_points;   // total points of the long borders
+    uint32_t walkers_cap, long_cap;
+    uint32_t *frame_contours;          // per frame: borders followed
     unsigned long long *frame_points;  // per frame: their points
-    uint32_t *frame_flags;         // per frame: bit 0 barred start (host redo), bit 1 rdp stack overflow, bit 2 quad capacity
+    uint32_t *frame_flags;             // per frame: bit 0 barred start (host redo), bit 1 rdp stack overflow, bit 2 quad capacity
 };
 
-__global__ void __launch_bounds__(128) k3_survivors(const Geo g, const StepTables *tables, const uint32_t min_points, SurvOut o) {
+__device__ __forceinline__ void record_survivor(const Lists &l, uint32_t frame, unsigned long long key, int kind, uint32_t n, bool first_pixel,
+                                                uint32_t min_points) {
+    atomicAdd(&l.frame_contours[frame], 1u);
+    atomicAdd(&l.frame_points[frame], (unsigned long long)n);
+    if (kind == 0 && !first_pixel) atomicOr(&l.frame_flags[frame], 1u);  // a west start below the top of its border: barred natural start
+    if (n >= min_points && n >= 4) {
+        const uint32_t slot = atomicAdd(&l.counters[1], 1u);
+        if (slot < l.long_cap) {
+            l.long_keys[slot] = key;
+            l.long_n[slot] = n;
+            atomicAdd(l.long_points, (unsigned long long)n);
+        } else {
+            atomicOr(&l.counters[2], 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k3_candidates(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
     __shared__ uint16_t fwd[8][512];
     __shared__ uint16_t bwd[8][512];
     for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) {
@@ -159,98 +190,107 @@ __global__ void __launch_bounds__(128) k3_survivors(const Geo g, const StepTable
     const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
     const uint32_t *row = plane + (size_t)(y + 1) * g.S + 1;
     const uint32_t f = row[k];
-    uint32_t lw = 0, le = 0, ncont = 0;
-    unsigned long long npts = 0, nlongpts = 0;
-    uint32_t flags = 0;
-    if (f) {
-        const uint32_t west = (f << 1) | (row[(int)k - 1] >> 31), east = (f >> 1) | (row[k + 1] << 31);
-        uint32_t og = f & ~west, hg = f & ~east;
-        if (k == 0) og &= ~1u;                                           // `x > 0`
-        if (k == (g.w - 1) >> 5) hg &= ~(1u << ((g.w - 1) & 31));        // `x + 1 < w`
-        uint32_t pending = og | hg;
-        while (pending) {
-            const uint32_t b = pending & (0u - pending);
-            pending ^= b;
-            const int x = (int)(k * 32 + __ffs(b) - 1);
-            for (int kind = 0; kind < 2; kind++) {
-                if (!((kind ? hg : og) & b)) continue;
-                uint32_t n;
-                bool first_pixel;
-                if (!walk_border(plane, g, fwd, bwd, x, (int)y, kind, n, first_pixel)) continue;
-                ncont++;
-                npts += n;
-                if (kind == 0 && !first_pixel) flags |= 1u;  // a west start below the top of its border: barred natural start
-                if (n >= min_points && n >= 4) {
-                    (kind ? le : lw) |= b;
-                    nlongpts += n;
-                }
-            }
-        }
-    }
-    o.long_w[gid] = lw;
-    o.long_e[gid] = le;
-    o.counts[gid] = ((unsigned long long)(__popc(lw) + __popc(le)) << 40) | nlongpts;
-    if (ncont) {
-        atomicAdd(&o.frame_contours[frame], ncont);
-        atomicAdd(&o.frame_points[frame], npts);
-    }
-    if (flags) atomicOr(&o.frame_flags[frame], flags);
-}
-
-struct Contour {
-    uint32_t frame, start, n, pad;     // start = x | y << 16
-    unsigned long long point_off;
-};
-
-// survivors of long borders write their points (x | y << 16) in the reference's order: the trace from the start pixel
-__global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *tables, const uint32_t *long_w, const uint32_t *long_e,
-                                               const unsigned long long *scan, Contour *contours, uint32_t *points) {
-    __shared__ uint16_t fwd[8][512];
-    for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) (&fwd[0][0])[i] = (&tables->fwd[0][0])[i];
-    __syncthreads();
-    const size_t words_per_frame = (size_t)g.h * g.wpr;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= words_per_frame * g.n) return;
-    const uint32_t lw = long_w[gid], le = long_e[gid];
-    if (!(lw | le)) return;
-    const uint32_t frame = (uint32_t)(gid / words_per_frame);
-    const uint32_t rem = (uint32_t)(gid % words_per_frame);
-    const int y0 = (int)(rem / g.wpr);
-    const uint32_t k = rem % g.wpr;
-    const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
-    unsigned long long ci = scan[gid] >> 40, po = scan[gid] & ((1ull << 40) - 1);
-    uint32_t pending = lw | le;
+    if (!f) return;
+    const uint32_t west = (f << 1) | (row[(int)k - 1] >> 31), east = (f >> 1) | (row[k + 1] << 31);
+    uint32_t og = f & ~west, hg = f & ~east;
+    if (k == 0) og &= ~1u;                                           // `x > 0`
+    if (k == (g.w - 1) >> 5) hg &= ~(1u << ((g.w - 1) & 31));        // `x + 1 < w`
+    uint32_t pending = og | hg;
     while (pending) {
         const uint32_t b = pending & (0u - pending);
         pending ^= b;
-        const int sx = (int)(k * 32 + __ffs(b) - 1);
+        const int bit = __ffs(b) - 1;
+        const int x = (int)(k * 32) + bit;
         for (int kind = 0; kind < 2; kind++) {
-            if (!((kind ? le : lw) & b)) continue;
-            const uint32_t nb0 = ring_of(hood9(plane, g.S, sx, y0));
-            const int adj = kind ? 4 : 0;
-            int pred = 0;
-            for (int q = 0; q < 8; q++) {
-                const int d = (adj + q) & 7;
-                if ((nb0 >> d) & 1) { pred = d; break; }
+            if (!((kind ? hg : og) & b)) continue;
+            uint32_t n;
+            bool first_pixel;
+            const int r = walk_border(plane, g, fwd, bwd, x, (int)y, kind, kBudget, n, first_pixel);
+            if (r == kDead) continue;
+            const unsigned long long key = ((((unsigned long long)gid << 5) | (unsigned)bit) << 1) | (unsigned)kind;
+            if (r == kSurvivor) {
+                record_survivor(l, frame, key, kind, n, first_pixel, min_points);
+            } else {
+                const uint32_t slot = atomicAdd(&l.counters[0], 1u);
+                if (slot < l.walkers_cap) l.walkers[slot] = key;
+                else atomicOr(&l.counters[2], 1u);
             }
-            int x = sx, y = y0;
-            uint32_t state = (uint32_t)pred, n = 0;
-            uint32_t *out = points + po;
-            for (;;) {
-                if (n && x == sx && y == y0 && state == (uint32_t)pred) break;
-                out[n++] = (uint32_t)x | ((uint32_t)y << 16);
-                const uint32_t e = fwd[state][hood9(plane, g.S, x, y)];
-                x += (int)((e >> 5) & 3u) - 1;
-                y += (int)((e >> 7) & 3u) - 1;
-                state = e >> 9;
-            }
-            Contour c;
-            c.frame = frame; c.start = (uint32_t)sx | ((uint32_t)y0 << 16); c.n = n; c.pad = 0; c.point_off = po;
-            contours[ci] = c;
-            ci++;
-            po += n;
         }
     }
+}
+
+__device__ __forceinline__ void decode_key(const Geo &g, unsigned long long key, uint32_t &frame, int &x, int &y, int &kind) {
+    kind = (int)(key & 1ull);
+    const unsigned long long v = key >> 1;
+    const unsigned long long gid = v >> 5;
+    const size_t words_per_frame = (size_t)g.h * g.wpr;
+    frame = (uint32_t)(gid / words_per_frame);
+    const uint32_t rem = (uint32_t)(gid % words_per_frame);
+    y = (int)(rem / g.wpr);
+    x = (int)((rem % g.wpr) * 32 + (uint32_t)(v & 31ull));
+}
+
+// The undecided candidates — mostly the one survivor of each long border — walk to the end, all at the same time.
+__global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
+    __shared__ uint16_t fwd[8][512];
+    __shared__ uint16_t bwd[8][512];
+    for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) {
+        (&fwd[0][0])[i] = (&tables->fwd[0][0])[i];
+        (&bwd[0][0])[i] = (&tables->bwd[0][0])[i];
+    }
+    __syncthreads();
+    const uint32_t total = min(l.counters[0], l.walkers_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = l.walkers[i];
+        uint32_t frame, n;
+        int x, y, kind;
+        bool first_pixel;
+        decode_key(g, key, frame, x, y, kind);
+        const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+        if (walk_border(plane, g, fwd, bwd, x, y, kind, 0xffffffffu, n, first_pixel) == kSurvivor)
+            record_survivor(l, frame, key, kind, n, first_pixel, min_points);
+    }
+}
+
+struct Contour {
+    uint32_t frame, start, n, kind;     // start = x | y << 16
+    unsigned long long point_off;
+};
+
+// one thread per long border (sorted by raster position of the start): write its points (x | y << 16) in the
+// reference's order, i.e. the forward trace from the start pixel
+__global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *tables, const unsigned long long *keys, const uint32_t *lens,
+                                               const uint32_t *offsets, uint32_t n_contours, Contour *contours, uint32_t *points) {
+    __shared__ uint16_t fwd[8][512];
+    for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) (&fwd[0][0])[i] = (&tables->fwd[0][0])[i];
+    __syncthreads();
+    const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_contours) return;
+    uint32_t frame;
+    int sx, sy, kind;
+    decode_key(g, keys[ci], frame, sx, sy, kind);
+    const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+    const uint32_t nb0 = ring_of(hood9(plane, g.S, sx, sy));
+    const int adj = kind ? 4 : 0;
+    int pred = 0;
+    for (int q = 0; q < 8; q++) {
+        const int d = (adj + q) & 7;
+        if ((nb0 >> d) & 1) { pred = d; break; }
+    }
+    const uint32_t n = lens[ci];
+    uint32_t *out = points + offsets[ci];
+    int x = sx, y = sy;
+    uint32_t state = (uint32_t)pred;
+    for (uint32_t i = 0; i < n; i++) {
+        out[i] = (uint32_t)x | ((uint32_t)y << 16);
+        const uint32_t e = fwd[state][hood9(plane, g.S, x, y)];
+        x += (int)((e >> 5) & 3u) - 1;
+        y += (int)((e >> 7) & 3u) - 1;
+        state = e >> 9;
+    }
+    Contour c;
+    c.frame = frame; c.start = (uint32_t)sx | ((uint32_t)sy << 16); c.n = n; c.kind = (uint32_t)kind; c.point_off = offsets[ci];
+    contours[ci] = c;
 }
 
 struct Pt { int x, y; };
@@ -404,14 +444,26 @@ __device__ __forceinline__ float perimeter(const uint32_t *q) {
 
 // One warp per frame: the frame's quads in contour order, enforce_clockwise_corners, discard_too_near
 // (src/aruco.rs:168-232).  frame_first[f] .. frame_first[f + 1] = the frame's range of contours.
-__global__ void __launch_bounds__(32) k3_finalize(const uint32_t *contour_quads, const unsigned long long *scan, size_t words_per_frame,
-                                                  unsigned long long total_contours, uint32_t n_frames, float min_corner_separation,
+__device__ __forceinline__ uint32_t lower_bound_key(const unsigned long long *keys, uint32_t n, unsigned long long v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (keys[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(32) k3_finalize(const uint32_t *contour_quads, const unsigned long long *keys, size_t words_per_frame,
+                                                  uint32_t total_contours, uint32_t n_frames, float min_corner_separation,
                                                   uint32_t quad_cap, uint32_t *out_quads, uint32_t *out_counts, uint32_t *out_before_discard,
                                                   uint32_t *frame_flags, uint8_t *dead_scratch) {
     const uint32_t f = blockIdx.x;
     const int lane = threadIdx.x;
-    const unsigned long long c0 = scan[(size_t)f * words_per_frame] >> 40;
-    const unsigned long long c1 = f + 1 < n_frames ? scan[(size_t)(f + 1) * words_per_frame] >> 40 : total_contours;
+    // the frame's borders are a contiguous range of the sorted list: keys are (word id, bit, kind) with frame-major word ids
+    const unsigned long long c0 = lower_bound_key(keys, total_contours, ((unsigned long long)f * words_per_frame) << 6);
+    const unsigned long long c1 = lower_bound_key(keys, total_contours, ((unsigned long long)(f + 1) * words_per_frame) << 6);
+    (void)n_frames;
     uint32_t *dst = out_quads + (size_t)f * quad_cap * 8;
     uint32_t nq = 0;
     bool over = false;
@@ -475,30 +527,31 @@ __global__ void __launch_bounds__(32) k3_finalize(const uint32_t *contour_quads,
 
 struct K3Workspace::Impl {
     StepTables *d_tables = nullptr;
-    uint32_t *long_w = nullptr, *long_e = nullptr;
-    unsigned long long *counts = nullptr, *scan = nullptr, *frame_points = nullptr;
-    uint32_t *frame_contours = nullptr;
-    size_t words_cap = 0, frames_cap = 0;
+    // work lists
+    unsigned long long *walkers = nullptr, *long_keys = nullptr, *long_keys_sorted = nullptr, *long_points = nullptr, *frame_points = nullptr;
+    uint32_t *long_n = nullptr, *long_n_sorted = nullptr, *long_off = nullptr, *counters = nullptr, *frame_contours = nullptr;
+    size_t walkers_cap = 0, long_cap = 0, frames_cap = 0;
     void *cub_tmp = nullptr;
     size_t cub_bytes = 0;
     Contour *contours = nullptr;
+    uint32_t *contour_quads = nullptr;
     size_t contours_cap = 0;
     uint32_t *points = nullptr;
     size_t points_cap = 0;
-    uint32_t *contour_quads = nullptr;
     uint8_t *dead = nullptr;
     size_t dead_cap = 0;
-    unsigned long long *h_last = nullptr;  // pinned: [0] last scan value, [1] last count
+    unsigned long long *h_counts = nullptr;  // pinned: [0] counters[0..1], [1] counters[2] (overflow), [2] long_points
 };
 
 K3Workspace::K3Workspace() : impl(new Impl()) {}
 K3Workspace::~K3Workspace() {
     if (!impl) return;
-    for (void *p : {(void *)impl->d_tables, (void *)impl->long_w, (void *)impl->long_e, (void *)impl->counts, (void *)impl->scan,
-                    (void *)impl->frame_points, (void *)impl->frame_contours, impl->cub_tmp, (void *)impl->contours, (void *)impl->points,
-                    (void *)impl->contour_quads, (void *)impl->dead})
+    for (void *p : {(void *)impl->d_tables, (void *)impl->walkers, (void *)impl->long_keys, (void *)impl->long_keys_sorted, (void *)impl->long_points,
+                    (void *)impl->frame_points, (void *)impl->long_n, (void *)impl->long_n_sorted, (void *)impl->long_off, (void *)impl->counters,
+                    (void *)impl->frame_contours, impl->cub_tmp, (void *)impl->contours, (void *)impl->contour_quads, (void *)impl->points,
+                    (void *)impl->dead})
         if (p) cudaFree(p);
-    if (impl->h_last) cudaFreeHost(impl->h_last);
+    if (impl->h_counts) cudaFreeHost(impl->h_counts);
     delete impl;
 }
 
@@ -518,6 +571,17 @@ static cudaError_t grow(T *&p, size_t &cap, size_t need) {
     if (e == cudaSuccess) cap = want;
     return e;
 }
+template <typename T>
+static cudaError_t alloc_exact(T *&p, size_t n) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    return cudaMalloc(&p, n * sizeof(T));
+}
+
+static __global__ void k3_flag_all(uint32_t *frame_flags, uint32_t n, const uint32_t *counters, int force) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (force || counters[2])) frame_flags[i] |= 8u;  // a work list overflowed: every frame of this call goes to the host stage
+}
 
 cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     K3Workspace::Impl &w = *ws.impl;
@@ -534,76 +598,92 @@ cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         if (e == cudaSuccess) e = cudaMemcpy(w.d_tables, t, sizeof(StepTables), cudaMemcpyHostToDevice);
         delete t;
         K3_CUDA(e);
-        K3_CUDA(cudaHostAlloc(&w.h_last, 16, cudaHostAllocDefault));
+        K3_CUDA(cudaHostAlloc(&w.h_counts, 32, cudaHostAllocDefault));
+        K3_CUDA(cudaMalloc(&w.counters, 16));
+        K3_CUDA(cudaMalloc(&w.long_points, 8));
     }
-    if (nwords > w.words_cap) {
-        for (void *q : {(void *)w.long_w, (void *)w.long_e, (void *)w.counts, (void *)w.scan})
-            if (q) cudaFree(q);
-        w.long_w = w.long_e = nullptr; w.counts = w.scan = nullptr; w.words_cap = 0;
-        K3_CUDA(cudaMalloc(&w.long_w, nwords * 4));
-        K3_CUDA(cudaMalloc(&w.long_e, nwords * 4));
-        K3_CUDA(cudaMalloc(&w.counts, nwords * 8));
-        K3_CUDA(cudaMalloc(&w.scan, nwords * 8));
-        w.words_cap = nwords;
+    // list capacities: generous per frame; an overflow sends the whole call to the host stage (flag 8), never a wrong answer
+    const size_t pixels = (size_t)p.w * p.h;
+    const size_t mp = p.min_points < 4 ? 4 : p.min_points;
+    const size_t want_walkers = (size_t)p.n * (pixels / 32 + 4096), want_long = (size_t)p.n * (pixels / (4 * mp) + 1024);
+    if (want_walkers > w.walkers_cap) {
+        K3_CUDA(alloc_exact(w.walkers, want_walkers));
+        w.walkers_cap = want_walkers;
+    }
+    if (want_long > w.long_cap) {
+        K3_CUDA(alloc_exact(w.long_keys, want_long)); K3_CUDA(alloc_exact(w.long_keys_sorted, want_long));
+        K3_CUDA(alloc_exact(w.long_n, want_long)); K3_CUDA(alloc_exact(w.long_n_sorted, want_long)); K3_CUDA(alloc_exact(w.long_off, want_long));
+        w.long_cap = want_long;
+        size_t a = 0, b = 0;
+        K3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, a, w.long_keys, w.long_keys_sorted, w.long_n, w.long_n_sorted, (int)want_long, 0, 64, stream));
+        K3_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b, w.long_n_sorted, w.long_off, (int)want_long, stream));
+        const size_t need = a > b ? a : b;
+        if (need > w.cub_bytes) {
+            if (w.cub_tmp) cudaFree(w.cub_tmp);
+            w.cub_tmp = nullptr; w.cub_bytes = 0;
+            K3_CUDA(cudaMalloc(&w.cub_tmp, need));
+            w.cub_bytes = need;
+        }
     }
     if (p.n > w.frames_cap) {
-        if (w.frame_points) cudaFree(w.frame_points);
-        if (w.frame_contours) cudaFree(w.frame_contours);
-        w.frame_points = nullptr; w.frame_contours = nullptr; w.frames_cap = 0;
-        K3_CUDA(cudaMalloc(&w.frame_points, (size_t)p.n * 8));
-        K3_CUDA(cudaMalloc(&w.frame_contours, (size_t)p.n * 4));
+        K3_CUDA(alloc_exact(w.frame_points, (size_t)p.n));
+        K3_CUDA(alloc_exact(w.frame_contours, (size_t)p.n));
         w.frames_cap = p.n;
     }
-    size_t need_tmp = 0;
-    K3_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need_tmp, w.counts, w.scan, nwords, stream));
-    if (need_tmp > w.cub_bytes) {
-        if (w.cub_tmp) cudaFree(w.cub_tmp);
-        w.cub_tmp = nullptr; w.cub_bytes = 0;
-        K3_CUDA(cudaMalloc(&w.cub_tmp, need_tmp));
-        w.cub_bytes = need_tmp;
-    }
     if ((size_t)p.n * p.quad_cap > w.dead_cap) {
-        if (w.dead) cudaFree(w.dead);
-        w.dead = nullptr; w.dead_cap = 0;
-        K3_CUDA(cudaMalloc(&w.dead, (size_t)p.n * p.quad_cap));
+        K3_CUDA(alloc_exact(w.dead, (size_t)p.n * p.quad_cap));
         w.dead_cap = (size_t)p.n * p.quad_cap;
     }
     K3_CUDA(cudaMemsetAsync(w.frame_points, 0, (size_t)p.n * 8, stream));
     K3_CUDA(cudaMemsetAsync(w.frame_contours, 0, (size_t)p.n * 4, stream));
     K3_CUDA(cudaMemsetAsync(p.frame_flags, 0, (size_t)p.n * 4, stream));
+    K3_CUDA(cudaMemsetAsync(w.counters, 0, 16, stream));
+    K3_CUDA(cudaMemsetAsync(w.long_points, 0, 8, stream));
 
-    SurvOut so;
-    so.long_w = w.long_w; so.long_e = w.long_e; so.counts = w.counts; so.frame_contours = w.frame_contours; so.frame_points = w.frame_points;
-    so.frame_flags = p.frame_flags;
-    const uint32_t blocks = (uint32_t)((nwords + 127) / 128);
-    k3_survivors<<<blocks, 128, 0, stream>>>(g, w.d_tables, p.min_points, so);
+    Lists l;
+    l.walkers = w.walkers; l.long_keys = w.long_keys; l.long_n = w.long_n; l.counters = w.counters; l.long_points = w.long_points;
+    l.walkers_cap = (uint32_t)(w.walkers_cap > 0xffffffffull ? 0xffffffffull : w.walkers_cap);
+    l.long_cap = (uint32_t)(w.long_cap > 0x7fffffffull ? 0x7fffffffull : w.long_cap);
+    l.frame_contours = w.frame_contours; l.frame_points = w.frame_points; l.frame_flags = p.frame_flags;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    k3_candidates<<<(uint32_t)((nwords + 127) / 128), 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
     K3_CUDA(cudaGetLastError());
-    size_t tmp = w.cub_bytes;
-    K3_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.counts, w.scan, nwords, stream));
-    K3_CUDA(cudaMemcpyAsync(&w.h_last[0], w.scan + nwords - 1, 8, cudaMemcpyDeviceToHost, stream));
-    K3_CUDA(cudaMemcpyAsync(&w.h_last[1], w.counts + nwords - 1, 8, cudaMemcpyDeviceToHost, stream));
+    k3_walkers<<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
+    K3_CUDA(cudaGetLastError());
+    k3_flag_all<<<(p.n + 127) / 128, 128, 0, stream>>>(p.frame_flags, p.n, w.counters, 0);
+    K3_CUDA(cudaGetLastError());
+    K3_CUDA(cudaMemcpyAsync(&w.h_counts[0], w.counters, 16, cudaMemcpyDeviceToHost, stream));
+    K3_CUDA(cudaMemcpyAsync(&w.h_counts[2], w.long_points, 8, cudaMemcpyDeviceToHost, stream));
     K3_CUDA(cudaStreamSynchronize(stream));
-    const unsigned long long total = w.h_last[0] + w.h_last[1];
-    const unsigned long long n_long = total >> 40, n_points = total & ((1ull << 40) - 1);
-    {
-        size_t old = w.contours_cap;
-        K3_CUDA(grow(w.contours, w.contours_cap, (size_t)n_long + 1));
-        if (w.contours_cap != old) {
-            if (w.contour_quads) cudaFree(w.contour_quads);
-            w.contour_quads = nullptr;
-            K3_CUDA(cudaMalloc(&w.contour_quads, w.contours_cap * 32));
+    const uint32_t *hc = reinterpret_cast<const uint32_t *>(&w.h_counts[0]);
+    uint32_t n_long = hc[1] < l.long_cap ? hc[1] : l.long_cap;
+    const unsigned long long n_points = w.h_counts[2];
+    if (n_points >= 0xffffffffull && !hc[2]) {  // point offsets are 32-bit: hand the whole call to the host stage
+        k3_flag_all<<<(p.n + 127) / 128, 128, 0, stream>>>(p.frame_flags, p.n, w.counters, 1);
+        K3_CUDA(cudaGetLastError());
+    }
+    if (hc[2] || n_points >= 0xffffffffull) n_long = 0;  // overflow: every frame is flagged for the host stage
+    if (n_long) {
+        if ((size_t)n_long > w.contours_cap) {
+            K3_CUDA(alloc_exact(w.contours, (size_t)n_long + n_long / 4 + 1024));
+            K3_CUDA(alloc_exact(w.contour_quads, ((size_t)n_long + n_long / 4 + 1024) * 8));
+            w.contours_cap = (size_t)n_long + n_long / 4 + 1024;
         }
         K3_CUDA(grow(w.points, w.points_cap, (size_t)n_points + 1));
-    }
-    if (n_long) {
-        k3_emit<<<blocks, 128, 0, stream>>>(g, w.d_tables, w.long_w, w.long_e, w.scan, w.contours, w.points);
+        size_t tmp = w.cub_bytes;
+        const int end_bit = 64 - __builtin_clzll(((unsigned long long)nwords << 6) | 1ull);
+        K3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.long_keys, w.long_keys_sorted, w.long_n, w.long_n_sorted, (int)n_long, 0, end_bit, stream));
+        tmp = w.cub_bytes;
+        K3_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.long_n_sorted, w.long_off, (int)n_long, stream));
+        k3_emit<<<(n_long + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, n_long, w.contours, w.points);
         K3_CUDA(cudaGetLastError());
-        k3_rdp<<<(uint32_t)((n_long + 3) / 4), 128, 0, stream>>>(w.contours, w.points, (uint32_t)n_long, p.eps_factor, p.min_edge_length,
-                                                               w.contour_quads, p.frame_flags);
+        k3_rdp<<<(n_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, n_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags);
         K3_CUDA(cudaGetLastError());
     }
-    k3_finalize<<<p.n, 32, 0, stream>>>(w.contour_quads, w.scan, words_per_frame, n_long, p.n, p.min_corner_separation, p.quad_cap, p.quads,
-                                        p.quad_counts, p.before_discard, p.frame_flags, w.dead);
+    k3_finalize<<<p.n, 32, 0, stream>>>(w.contour_quads, w.long_keys_sorted, words_per_frame, n_long, p.n, p.min_corner_separation, p.quad_cap,
+                                        p.quads, p.quad_counts, p.before_discard, p.frame_flags, w.dead);
     K3_CUDA(cudaGetLastError());
     if (p.frame_contours) K3_CUDA(cudaMemcpyAsync(p.frame_contours, w.frame_contours, (size_t)p.n * 4, cudaMemcpyDeviceToDevice, stream));
     if (p.frame_points) K3_CUDA(cudaMemcpyAsync(p.frame_points, w.frame_points, (size_t)p.n * 8, cudaMemcpyDeviceToDevice, stream));
