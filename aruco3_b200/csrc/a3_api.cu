@@ -408,13 +408,13 @@ a3_status a3_quads_from_masks_device(a3_detector *d, const uint8_t *masks, uint3
     if (n == 0 || w == 0 || h == 0) return A3_OK;
     if (w > 65535 || h > 65535) return fail(A3_ERR_UNSUPPORTED, "a3_quads_from_masks_device: frames larger than 65535 pixels a side");
     A3_CUDA(cudaSetDevice(d->device));
-    const uint32_t wpr = (w + 31) / 32, S = wpr + 2;
-    const size_t plane_words = (size_t)(h + 2) * S;
+    const uint32_t wpr = (w + 31) / 32, Hp = h + 2;
+    const size_t plane_words = (size_t)(wpr + 2) * Hp;
     std::vector<uint32_t> planes((size_t)n * plane_words, 0u);
     for (uint32_t f = 0; f < n; f++)
         for (uint32_t y = 0; y < h; y++)
             for (uint32_t x = 0; x < w; x++)
-                if (masks[((size_t)f * h + y) * w + x]) planes[(size_t)f * plane_words + (size_t)(y + 1) * S + 1 + (x >> 5)] |= 1u << (x & 31);
+                if (masks[((size_t)f * h + y) * w + x]) planes[(size_t)f * plane_words + (size_t)((x >> 5) + 1) * Hp + (y + 1)] |= 1u << (x & 31);
     cudaStream_t s = d->s_pixel;
     d->planes_zeroed_words = 0;  // the pipeline's guard words are overwritten below
     A3_CUDA(d->d_planes.reserve(planes.size()));
@@ -505,12 +505,15 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
     if (fe < 1) fe = 1;
     if (fe > 64) fe = 64;
     if (fe > sb) fe = sb;
-    const uint32_t group = 32;    // frames per decode launch
+    uint32_t group = 32;          // frames per decode launch
     const uint32_t kStaging = 3;  // staging ring depth (host input)
     // contour stage on the device (K3) unless the caller asked for the host stage or the frame is too large for K3's 16-bit points
     const bool gpu_contours = d->contour_mode == A3_CONTOURS_DEVICE && w <= 65535 && h <= 65535;
-    const uint32_t S = (uint32_t)wpr + 2;                    // guarded plane: words per row
-    const size_t plane_words = (size_t)(h + 2) * S;          // words per frame
+    // resident input + device contours: every quad of the super-batch is known at once, so one decode launch keeps the
+    // whole GPU busy (K2 is latency-bound: what counts is candidates in flight)
+    if (gpu_contours && mem == A3_MEM_DEVICE) group = (uint32_t)sb;
+    const uint32_t Hp = h + 2;                               // guarded column-major plane: words per 32-pixel column
+    const size_t plane_words = (size_t)(wpr + 2) * Hp;       // words per frame
     const uint32_t quad_cap = 1024;                          // quads per frame K3 can return (more -> host stage)
     const uint32_t mn = w < h ? w : h;
     const uint32_t min_edge_length = (uint32_t)((float)mn * d->cfg.min_side_length_factor);   // src/aruco.rs:55
@@ -568,8 +571,8 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             p.grey = d->d_grey.p + (size_t)f0 * px; p.mask = want_mask ? d->d_mask.p + (size_t)f0 * px : nullptr;
             p.radius = d->cfg.threshold_window;
             if (gpu_contours) {  // straight into the guarded planes K3 reads
-                p.bits = d->d_planes.p + (size_t)f0 * plane_words + S + 1;
-                p.bits_row_words = S; p.bits_frame_words = plane_words;
+                p.bits = d->d_planes.p + (size_t)f0 * plane_words + Hp + 1;
+                p.bits_col_words = Hp; p.bits_row_words = 1; p.bits_frame_words = plane_words;
             } else {
                 p.bits = d->d_bits.p + (size_t)f0 * bits_words;
             }
@@ -670,7 +673,10 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                 const double t0 = now_ms();
                 A3_CUDA(cudaMemcpyAsync(d->h_plane.p, d->d_planes.p + (size_t)i * plane_words, plane_words * 4, cudaMemcpyDeviceToHost, d->s_decode));
                 A3_CUDA(cudaStreamSynchronize(d->s_decode));
-                quads_from_bits(d->h_plane.p + S + 1, (uint32_t)wpr, w, h, cfg, frame_quads[i], &frame_stats[i], S);
+                std::vector<uint32_t> rows(bits_words);  // back to the row-major mask the host stage reads
+                for (uint32_t k = 0; k < wpr; k++)
+                    for (uint32_t y = 0; y < h; y++) rows[(size_t)y * wpr + k] = d->h_plane.p[(size_t)(k + 1) * Hp + (y + 1)];
+                quads_from_bits(rows.data(), (uint32_t)wpr, w, h, cfg, frame_quads[i], &frame_stats[i]);
                 frame_ms[i] = now_ms() - t0;
                 st.host_fallback_frames++;
             }

@@ -30,10 +30,12 @@ struct K1Params {
     size_t pitch, frame_stride;
     uint8_t *grey;        // device n*h*w or null
     uint8_t *mask;        // device n*h*w or null
-    uint32_t *bits;       // device 1-bit mask or null: word of pixel (x, y) of frame f = bits[f * bits_frame_words + y * bits_row_words + (x >> 5)]
+    uint32_t *bits;       // device 1-bit mask or null: word of pixel (x, y) of frame f =
+                          //   bits[f * bits_frame_words + y * bits_row_words + (x >> 5) * bits_col_words]
     uint32_t radius;      // threshold_window
-    size_t bits_row_words = 0;    // 0 = ceil(w/32) (tightly packed rows)
-    size_t bits_frame_words = 0;  // 0 = h * bits_row_words
+    size_t bits_row_words = 0;    // 0 = ceil(w/32) (row-major, tightly packed rows)
+    size_t bits_col_words = 0;    // 0 = 1
+    size_t bits_frame_words = 0;  // 0 = h * ceil(w/32)
 };
 struct K1Tuning {
     uint32_t strip_cols;  // generic kernel: core columns per strip (multiple of 32); 0 = auto
@@ -81,9 +83,10 @@ struct ResizeTaps {
 ResizeTaps make_resize_taps(uint32_t n_in, uint32_t n_out);
 
 // ---- K3: border following + quad filters on the device (k3_contours.cu) ----------------------------------------
-// Guarded bit planes: per frame (h + 2) rows of S = ceil(w/32) + 2 words, all guard words zero; pixel (x, y) is bit
-// x & 31 of word (y + 1) * S + 1 + (x >> 5).  K1 writes straight into this layout (bits_row_words = S,
-// bits_frame_words = (h + 2) * S, bits = plane + S + 1).
+// Guarded bit planes, COLUMN-major: per frame ceil(w/32) + 2 word columns of Hp = h + 2 words, all guard words zero;
+// pixel (x, y) is bit x & 31 of word ((x >> 5) + 1) * Hp + (y + 1).  Vertically adjacent pixels are adjacent words, so a
+// border walk stays inside a 32-byte sector for 8 rows and inside a word for 32 columns.  K1 writes straight into this
+// layout (bits_col_words = Hp, bits_row_words = 1, bits_frame_words = (ceil(w/32) + 2) * Hp, bits = plane + Hp + 1).
 struct K3Params {
     const uint32_t *planes;       // device, n guarded planes
     uint32_t n, w, h;

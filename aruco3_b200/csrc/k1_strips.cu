@@ -44,6 +44,7 @@ struct StripArgs {
     uint32_t n, w, h;
     uint32_t nstrips, nsegs, seg_rows, njobs;
     uint32_t bits_row_bytes;       // bytes between mask rows (4 * ceil(w / 32) when tightly packed)
+    uint32_t bits_col_bytes;       // bytes between 32-pixel word columns (4 when row-major)
     size_t bits_frame_bytes;       // bytes between frames of the 1-bit mask
     uint32_t stages;               // TMA ring depth per warp (kStages)
     int wide_stores;               // w % 8 == 0 and grey / mask bases 8-byte aligned
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) k1_strips_ke
     const size_t o_px = ((size_t)frame * a.h + m.ys) * a.w + m.x;
     L.grey = a.grey + o_px;
     L.mask = a.mask + o_px;
-    L.bits = a.bits + (size_t)frame * a.bits_frame_bytes + (size_t)m.ys * a.bits_row_bytes + (m.x >> 3);
+    L.bits = a.bits + (size_t)frame * a.bits_frame_bytes + (size_t)m.ys * a.bits_row_bytes + (size_t)(m.x >> 5) * a.bits_col_bytes + ((m.x >> 3) & 3);
     L.row_px = a.w;
     L.row_bits = a.bits_row_bytes;
 
@@ -472,7 +473,8 @@ cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t st
     if (njobs > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     a.njobs = (uint32_t)njobs;
     a.bits_row_bytes = (uint32_t)(4 * (p.bits_row_words ? p.bits_row_words : (p.w + 31) / 32));
-    a.bits_frame_bytes = p.bits_frame_words ? 4 * p.bits_frame_words : (size_t)p.h * a.bits_row_bytes;
+    a.bits_col_bytes = (uint32_t)(4 * (p.bits_col_words ? p.bits_col_words : 1));
+    a.bits_frame_bytes = p.bits_frame_words ? 4 * p.bits_frame_words : (size_t)p.h * 4 * ((p.w + 31) / 32);
     a.stages = kStages;
     a.wide_stores = (p.w % 8 == 0) && ((uintptr_t)p.grey % 8 == 0) && ((uintptr_t)p.mask % 8 == 0);
     const uint32_t grid = (a.njobs + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -480,12 +482,19 @@ cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t st
     // the kernel writes the 1-bit mask by bytes; when w is not a multiple of 32 the tail bytes of each row's last
     // word are never touched by it and must read as zero
     if (p.bits && p.w % 32 != 0) {
-        const size_t tail = 4 * (size_t)((p.w + 31) / 32) - 4;  // last mask word of each row
-        for (uint32_t f = 0; f < (a.bits_frame_bytes == (size_t)p.h * a.bits_row_bytes ? 1u : p.n); f++) {
-            const size_t rows = a.bits_frame_bytes == (size_t)p.h * a.bits_row_bytes ? (size_t)p.n * p.h : p.h;
-            cudaError_t e = cudaMemset2DAsync(reinterpret_cast<uint8_t *>(p.bits) + f * a.bits_frame_bytes + tail, a.bits_row_bytes, 0, 4, rows, stream);
-            if (e != cudaSuccess) return e;
+        // the words of the last 32-pixel column: the kernel only writes their first ceil((w % 32) / 8) bytes
+        uint8_t *last = reinterpret_cast<uint8_t *>(p.bits) + (size_t)((p.w + 31) / 32 - 1) * a.bits_col_bytes;
+        cudaError_t e;
+        if (a.bits_row_bytes == 4)  // column-major: the column is h consecutive words per frame
+            e = cudaMemset2DAsync(last, a.bits_frame_bytes, 0, (size_t)p.h * 4, p.n, stream);
+        else if (a.bits_frame_bytes == (size_t)p.h * a.bits_row_bytes)  // row-major, frames back to back
+            e = cudaMemset2DAsync(last, a.bits_row_bytes, 0, 4, (size_t)p.n * p.h, stream);
+        else {
+            e = cudaSuccess;
+            for (uint32_t f = 0; f < p.n && e == cudaSuccess; f++)
+                e = cudaMemset2DAsync(last + f * a.bits_frame_bytes, a.bits_row_bytes, 0, 4, p.h, stream);
         }
+        if (e != cudaSuccess) return e;
     }
     if (info) {
         info->grid = grid; info->block = kWarpsPerCta * 32; info->smem_bytes = (uint32_t)smem; info->strips = a.nstrips; info->segs = a.nsegs;

@@ -42,7 +42,7 @@ struct K1Args {
     uint32_t radius;
     uint32_t strips, strip_cols, segs, seg_rows;
     uint32_t words_per_row;
-    size_t bits_row_words, bits_frame_words;
+    size_t bits_row_words, bits_col_words, bits_frame_words;
     uint32_t stage_bytes;  // bytes of one RGB row slot (multiple of 16)
     int out_aligned;       // w % 4 == 0 and output bases 4-byte aligned: 32-bit stores allowed
 };
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kMaxThreads) k1_kernel(const K1Args a) {
                 wv |= __shfl_xor_sync(0xffffffffu, wv, 4);
                 const int xw = x & ~31;  // first column of this lane group's word
                 if ((t & 7) == 0 && xw >= cx0 && xw < cx1)
-                    a.bits[(size_t)frame * a.bits_frame_words + (size_t)yo * a.bits_row_words + (xw >> 5)] = wv;
+                    a.bits[(size_t)frame * a.bits_frame_words + (size_t)yo * a.bits_row_words + (size_t)(xw >> 5) * a.bits_col_words] = wv;
             }
         }
         if (++slot_new == win) slot_new = 0;
@@ -379,7 +379,8 @@ cudaError_t k1_gray_threshold(const K1Params &p, const K1Tuning *tuning, cudaStr
     a.strips = strips; a.strip_cols = strip_cols; a.segs = segs; a.seg_rows = seg_rows;
     a.words_per_row = (p.w + 31) / 32;
     a.bits_row_words = p.bits_row_words ? p.bits_row_words : a.words_per_row;
-    a.bits_frame_words = p.bits_frame_words ? p.bits_frame_words : (size_t)p.h * a.bits_row_words;
+    a.bits_col_words = p.bits_col_words ? p.bits_col_words : 1;
+    a.bits_frame_words = p.bits_frame_words ? p.bits_frame_words : (size_t)p.h * a.words_per_row;
     a.stage_bytes = round_up(4 * nt * bpp, 16);
     a.out_aligned = (p.w % 4 == 0) && ((uintptr_t)p.grey % 4 == 0) && ((uintptr_t)p.mask % 4 == 0);
 

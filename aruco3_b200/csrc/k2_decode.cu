@@ -10,9 +10,12 @@
 //   the match loop                  /root/reference/src/aruco.rs:75-96    (ARDictionary::find_nearest
 //                                                                          src/dictionaries.rs:160-196, hamming lib.rs:11-21)
 //
-// One persistent CTA of 256 threads loops over candidates; the dictionary is staged into shared memory once per
-// CTA and matched with __popcll over all four rotations; the winner is a packed-key block min so that both strict-<
-// tie rules of the reference hold (lowest rotation, then lowest index).  Latency/L2-bound and tiny next to K1.
+// One WARP per candidate (8 warps per CTA, no block-wide barrier after the dictionary is staged): lane 0 solves the
+// homography, the warp samples the 49x49 patch and histograms it in its own shared-memory slice, Otsu by warp scans,
+// the separable triangle resize, the border test by a warp vote, the four rotations on four lanes, and the dictionary
+// (staged into shared memory once per CTA) matched with __popcll over all four rotations; the winner is a packed-key
+// warp min so that both strict-< tie rules of the reference hold (lowest rotation, then lowest index).
+// Latency-bound and tiny next to K1: what matters is how many candidates are in flight, hence a warp each.
 #include <math.h>
 
 #include "a3_internal.h"
@@ -21,6 +24,7 @@ namespace a3 {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
 
 struct Proj {
     float inv[9];  // maps patch pixels back into the image (projection.invert())
@@ -133,175 +137,189 @@ __device__ __forceinline__ uint8_t sample(const uint8_t *grey, uint32_t w, uint3
     return clamp_u8_trunc((1.0f - bw) * (float)topv + bw * (float)botv);
 }
 
+// Per-warp scratch in shared memory.
+struct WarpScratch {
+    Proj proj;
+    uint64_t codes[4];
+    uint32_t hist[256];
+};
+__host__ __device__ inline uint32_t k2_warp_bytes(uint32_t ps, uint32_t ms) {
+    const uint32_t b = (uint32_t)sizeof(WarpScratch) + ms * ps * 4 + ((ms * ms + 3) & ~3u) + ps * ps;
+    return (b + 15) & ~15u;
+}
+
 __global__ void __launch_bounds__(kThreads) k2_kernel(const K2Params p, const uint32_t max_taps) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t ps = p.patch_size, ms = p.mark_size, np = ps * ps;
-    // ---- carve ----
+    // ---- carve: per CTA the dictionary and the resize taps, then one slice per warp ----
     uint64_t *dict = reinterpret_cast<uint64_t *>(smem);                       // n_codes
-    float *tmp = reinterpret_cast<float *>(dict + p.n_codes);                 // ms * ps  (vertical pass, f32)
-    float *taps = tmp + ms * ps;                                              // ms * max_taps
+    float *taps = reinterpret_cast<float *>(dict + p.n_codes);                // ms * max_taps
     int *meta = reinterpret_cast<int *>(taps + ms * max_taps);                // 2 * ms
-    uint32_t *hist = reinterpret_cast<uint32_t *>(meta + 2 * ms);             // 256
-    uint32_t *bwv = hist + 256;                                               // 256 background weights
-    uint32_t *bsv = bwv + 256;                                                // 256 background sums
-    double *var = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(bsv + 256) + 7) & ~(uintptr_t)7);  // 256
-    uint32_t *red = reinterpret_cast<uint32_t *>(var + 256);                  // 8 warp partials
-    uint8_t *reduced = reinterpret_cast<uint8_t *>(red + 8);                  // ms * ms (padded to x4)
+    uintptr_t cur = (reinterpret_cast<uintptr_t>(meta + 2 * ms) + 15) & ~(uintptr_t)15;
+    const uint32_t warp_bytes = k2_warp_bytes(ps, ms);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *mine = reinterpret_cast<uint8_t *>(cur) + (size_t)warp * warp_bytes;
+    WarpScratch *ws = reinterpret_cast<WarpScratch *>(mine);
+    float *tmp = reinterpret_cast<float *>(mine + sizeof(WarpScratch));       // ms * ps  (vertical pass, f32)
+    uint8_t *reduced = reinterpret_cast<uint8_t *>(tmp + ms * ps);            // ms * ms (padded to x4)
     uint8_t *patch = reduced + ((ms * ms + 3) & ~3u);                         // ps * ps
-    __shared__ Proj proj;
-    __shared__ uint64_t codes[4];
-    __shared__ int has_codes;
-    __shared__ uint32_t otsu_level;
 
-    const int t = threadIdx.x;
-    for (uint32_t i = t; i < p.n_codes; i += kThreads) dict[i] = p.codes[i];
-    for (uint32_t i = t; i < ms * max_taps; i += kThreads) taps[i] = p.resize_w[i];
-    for (uint32_t i = t; i < 2 * ms; i += kThreads) meta[i] = p.resize_meta[i];
+    for (uint32_t i = threadIdx.x; i < p.n_codes; i += kThreads) dict[i] = p.codes[i];
+    for (uint32_t i = threadIdx.x; i < ms * max_taps; i += kThreads) taps[i] = p.resize_w[i];
+    for (uint32_t i = threadIdx.x; i < 2 * ms; i += kThreads) meta[i] = p.resize_meta[i];
     __syncthreads();
 
-    for (uint32_t q = blockIdx.x; q < p.n_quads; q += gridDim.x) {
+    // one warp per candidate; warps never wait for each other
+    for (uint32_t q = blockIdx.x * kWarps + warp; q < p.n_quads; q += gridDim.x * kWarps) {
         const uint32_t frame = p.quad_frame ? p.quad_frame[q] : 0;
         const uint8_t *grey = p.grey + (size_t)frame * p.w * p.h;
-        if (t == 0) make_projection(p.quads + (size_t)q * 8, (float)ps, &proj);
-        hist[t] = 0;
-        __syncthreads();
-        const int ok = proj.ok;
-        a3_decode out;
-        out.homography_ok = (uint8_t)ok;
+        if (lane == 0) make_projection(p.quads + (size_t)q * 8, (float)ps, &ws->proj);
+        for (int i = lane; i < 256; i += 32) ws->hist[i] = 0;
+        __syncwarp();
+        const int ok = ws->proj.ok;
+        uint32_t otsu_level = 0;
         if (ok) {
             // ---- warp: ps*ps bilinear samples, histogram on the fly ----
-            for (uint32_t i = t; i < np; i += kThreads) {
-                uint8_t v = sample(grey, p.w, p.h, proj.inv, proj.cls, i % ps, i / ps);
+            for (uint32_t i = lane; i < np; i += 32) {
+                const uint8_t v = sample(grey, p.w, p.h, ws->proj.inv, ws->proj.cls, i % ps, i / ps);
                 patch[i] = v;
-                atomicAdd(&hist[v], 1u);
+                atomicAdd(&ws->hist[v], 1u);
             }
-            __syncthreads();
-            // ---- otsu_level: integer prefix sums are exact, the f64 expression keeps the reference's order ----
-            if (t == 0) {
-                uint32_t bw = 0, bs = 0;
-                for (int i = 0; i < 256; i++) { bw += hist[i]; bs += (uint32_t)i * hist[i]; bwv[i] = bw; bsv[i] = bs; }
+            __syncwarp();
+            // ---- otsu_level: integer prefix sums are exact; the f64 expression keeps the reference's order ----
+            uint32_t hb[8], bw = 0, bs = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                hb[j] = ws->hist[lane * 8 + j];
+                bw += hb[j];
+                bs += (uint32_t)(lane * 8 + j) * hb[j];
             }
-            __syncthreads();
-            {
-                const uint32_t total = np;
-                const double total_sum = (double)bsv[255];
-                const uint32_t bw = bwv[t], fw = total - bw;
-                double v = -1.0;
-                if (bw != 0 && fw != 0) {
-                    double bsum = (double)bsv[t];
-                    double fsum = total_sum - bsum;
-                    double bm = bsum / (double)bw;
-                    double fm = fsum / (double)fw;
-                    double diff = bm - fm;
-                    double mds = diff * diff;
-                    v = (double)bw * (double)fw * mds;
+            uint32_t pw = bw, psum = bs;  // inclusive scan over lanes
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t a = __shfl_up_sync(0xffffffffu, pw, off), b = __shfl_up_sync(0xffffffffu, psum, off);
+                if (lane >= off) { pw += a; psum += b; }
+            }
+            const double total_sum = (double)__shfl_sync(0xffffffffu, psum, 31);
+            uint32_t cw = pw - bw, cs = psum - bs;  // exclusive prefix of this lane's first bin
+            double best = -1.0;
+            uint32_t best_t = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                cw += hb[j];
+                cs += (uint32_t)(lane * 8 + j) * hb[j];
+                const uint32_t fw = np - cw;
+                if (cw != 0 && fw != 0) {
+                    const double bsum = (double)cs;
+                    const double fsum = total_sum - bsum;
+                    const double bm = bsum / (double)cw;
+                    const double fm = fsum / (double)fw;
+                    const double diff = bm - fm;
+                    const double mds = diff * diff;
+                    const double v = (double)cw * (double)fw * mds;
+                    if (v > best) { best = v; best_t = (uint32_t)(lane * 8 + j); }
                 }
-                var[t] = v;
             }
-            __syncthreads();
-            if (t == 0) {
-                double largest = 0.0;
-                uint32_t best = 0;
-                for (int i = 0; i < 256; i++)
-                    if (var[i] > largest) { largest = var[i]; best = (uint32_t)i; }
-                otsu_level = best;
+            // first strict maximum over t = 0..255, starting from largest_variance = 0: larger value wins, ties go to the smaller t
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const uint32_t ot = __shfl_xor_sync(0xffffffffu, best_t, off);
+                if (ob > best || (ob == best && ot < best_t)) { best = ob; best_t = ot; }
             }
-            __syncthreads();
-            const uint32_t level = otsu_level;
+            otsu_level = best > 0.0 ? best_t : 0u;
             // ---- threshold(Binary) + resize(Triangle): vertical pass into f32, then horizontal pass ----
-            for (uint32_t i = t; i < ms * ps; i += kThreads) {
+            for (uint32_t i = lane; i < ms * ps; i += 32) {
                 const uint32_t oy = i / ps, x = i % ps;
                 const int left = meta[2 * oy], cnt = meta[2 * oy + 1];
                 const float *wv = taps + oy * max_taps;
                 float acc = 0.0f;
                 for (int k = 0; k < cnt; k++) {
-                    float s = patch[(size_t)(left + k) * ps + x] > level ? 255.0f : 0.0f;
+                    const float s = patch[(size_t)(left + k) * ps + x] > otsu_level ? 255.0f : 0.0f;
                     acc += s * wv[k];
                 }
                 tmp[i] = acc;
             }
-            __syncthreads();
-            for (uint32_t i = t; i < ms * ms; i += kThreads) {
+            __syncwarp();
+            for (uint32_t i = lane; i < ms * ms; i += 32) {
                 const uint32_t y = i / ms, ox = i % ms;
                 const int left = meta[2 * ox], cnt = meta[2 * ox + 1];
                 const float *wv = taps + ox * max_taps;
                 float acc = 0.0f;
                 for (int k = 0; k < cnt; k++) acc += tmp[y * ps + left + k] * wv[k];
-                float c = acc < 0.0f ? 0.0f : (acc > 255.0f ? 255.0f : acc);
+                const float c = acc < 0.0f ? 0.0f : (acc > 255.0f ? 255.0f : acc);
                 reduced[i] = (uint8_t)roundf(c);
             }
-            __syncthreads();
-        } else if (t == 0) {
+        } else {
             // the reference decodes GrayImage::new(1,1): level 0, every cell 0 (src/aruco.rs:256)
-            otsu_level = 0;
-            for (uint32_t i = 0; i < ms * ms; i++) reduced[i] = 0;
+            for (uint32_t i = lane; i < ms * ms; i += 32) reduced[i] = 0;
         }
         if (p.patches) {
             uint8_t *dst = p.patches + (size_t)q * np;
-            for (uint32_t i = t; i < np; i += kThreads) dst[i] = ok ? patch[i] : 0;
+            for (uint32_t i = lane; i < np; i += 32) dst[i] = ok ? patch[i] : 0;
         }
-        __syncthreads();
+        __syncwarp();
         // ---- bits, border test, 4 rotations (src/aruco.rs:276-310) ----
-        if (t == 0) {
-            uint8_t bits[16 * 16], rot[16 * 16];
-            for (uint32_t i = 0; i < ms * ms; i++) bits[i] = reduced[i] > 127;
-            int good = 1;
+        int good = 1;
+        {
             const uint32_t end = ms ? ms - 1 : 0;
-            for (uint32_t i = 0; i < ms; i++)
-                if (bits[i * ms] || bits[i * ms + end] || bits[i] || bits[end * ms + i]) good = 0;
-            if (good) {
-                for (int r = 0; r < 4; r++) {
-                    uint64_t b = 0;
-                    for (uint32_t y = 1; y + 1 < ms; y++)
-                        for (uint32_t x = 1; x + 1 < ms; x++) {
-                            if (bits[y * ms + x]) b |= 1;
-                            b = (b << 1) | (b >> 63);
-                        }
-                    b = (b >> 1) | (b << 63);
-                    codes[r] = b;
-                    uint32_t rr = 0;  // rotate_bit_matrix: new[i][j] = old[j][W-1-i]
-                    for (int x = (int)ms - 1; x >= 0; x--, rr++)
-                        for (uint32_t y = 0; y < ms; y++) rot[rr * ms + y] = bits[y * ms + (uint32_t)x];
-                    for (uint32_t i = 0; i < ms * ms; i++) bits[i] = rot[i];
-                }
-            } else {
-                codes[0] = codes[1] = codes[2] = codes[3] = 0;
-            }
-            has_codes = good;
+            for (uint32_t i = lane; i < ms; i += 32)
+                if (reduced[i * ms] > 127 || reduced[i * ms + end] > 127 || reduced[i] > 127 || reduced[end * ms + i] > 127) good = 0;
+            good = __all_sync(0xffffffffu, good);
         }
-        __syncthreads();
+        if (lane < 4) {
+            // rotation r reads the grid after r applications of rotate_bit_matrix (new[i][j] = old[j][W-1-i]):
+            // r = 1: (i, j) <- (j, W-1-i);  r = 2: (W-1-i, W-1-j);  r = 3: (W-1-j, i)
+            uint64_t b = 0;
+            if (good) {
+                const uint32_t W = ms;
+                for (uint32_t y = 1; y + 1 < ms; y++)
+                    for (uint32_t x = 1; x + 1 < ms; x++) {
+                        uint32_t sy, sx;
+                        switch (lane) {
+                            case 0: sy = y; sx = x; break;
+                            case 1: sy = x; sx = W - 1 - y; break;
+                            case 2: sy = W - 1 - y; sx = W - 1 - x; break;
+                            default: sy = W - 1 - x; sx = y; break;
+                        }
+                        if (reduced[sy * ms + sx] > 127) b |= 1;
+                        b = (b << 1) | (b >> 63);
+                    }
+                b = (b >> 1) | (b << 63);
+            }
+            ws->codes[lane] = b;
+        }
+        __syncwarp();
         // ---- dictionary match: min over (dist, rotation, index) ----
         uint32_t key = 0xffffffffu;
-        if (has_codes) {
-            const uint64_t c0 = codes[0], c1 = codes[1], c2 = codes[2], c3 = codes[3];
-            for (uint32_t i = t; i < p.n_codes; i += kThreads) {
+        if (good) {
+            const uint64_t c0 = ws->codes[0], c1 = ws->codes[1], c2 = ws->codes[2], c3 = ws->codes[3];
+            for (uint32_t i = lane; i < p.n_codes; i += 32) {
                 const uint64_t d = dict[i];
-                uint32_t k0 = ((uint32_t)__popcll(d ^ c0) << 24) | (0u << 22) | i;
-                uint32_t k1 = ((uint32_t)__popcll(d ^ c1) << 24) | (1u << 22) | i;
-                uint32_t k2 = ((uint32_t)__popcll(d ^ c2) << 24) | (2u << 22) | i;
-                uint32_t k3 = ((uint32_t)__popcll(d ^ c3) << 24) | (3u << 22) | i;
+                const uint32_t k0 = ((uint32_t)__popcll(d ^ c0) << 24) | (0u << 22) | i;
+                const uint32_t k1 = ((uint32_t)__popcll(d ^ c1) << 24) | (1u << 22) | i;
+                const uint32_t k2 = ((uint32_t)__popcll(d ^ c2) << 24) | (2u << 22) | i;
+                const uint32_t k3 = ((uint32_t)__popcll(d ^ c3) << 24) | (3u << 22) | i;
                 key = min(key, min(min(k0, k1), min(k2, k3)));
             }
         }
         key = __reduce_min_sync(0xffffffffu, key);
-        if ((t & 31) == 0) red[t >> 5] = key;
-        __syncthreads();
-        if (t == 0) {
-            uint32_t k = red[0];
-            for (int i = 1; i < kThreads / 32; i++) k = min(k, red[i]);
-            out.has_codes = (uint8_t)has_codes;
+        if (lane == 0) {
+            a3_decode out;
+            out.homography_ok = (uint8_t)ok;
+            out.has_codes = (uint8_t)good;
             out.otsu = (uint8_t)otsu_level;
             out.reserved[0] = out.reserved[1] = 0;
-            for (int r = 0; r < 4; r++) out.codes[r] = codes[r];
+            for (int r = 0; r < 4; r++) out.codes[r] = ws->codes[r];
             uint32_t dist = 255, rotation = 0, index = 0;  // find_nearest on an empty list returns (0, 255)
-            if (has_codes && p.n_codes) { dist = k >> 24; rotation = (k >> 22) & 3; index = k & 0x3fffffu; }
+            if (good && p.n_codes) { dist = key >> 24; rotation = (key >> 22) & 3; index = key & 0x3fffffu; }
             out.id = index;
             out.rotation = (uint8_t)rotation;
             out.hamming_distance = (uint8_t)dist;
-            out.accepted = (uint8_t)(has_codes && (!p.filter_high_bit_errors || dist < p.tau));
+            out.accepted = (uint8_t)(good && (!p.filter_high_bit_errors || dist < p.tau));
             p.decodes[q] = out;
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -309,26 +327,24 @@ __global__ void __launch_bounds__(kThreads) k2_kernel(const K2Params p, const ui
 
 size_t k2_smem_bytes(uint32_t ps, uint32_t ms, uint32_t n_codes) {
     ResizeTaps tp = make_resize_taps(ps, ms);
-    size_t b = (size_t)n_codes * 8 + (size_t)ms * ps * 4 + (size_t)ms * tp.max_taps * 4 + (size_t)2 * ms * 4 + 3 * 256 * 4;
-    b = (b + 7) & ~(size_t)7;
-    b += 256 * 8 + 8 * 4 + ((ms * ms + 3) & ~3u) + (size_t)ps * ps;
-    return b + 16;
+    size_t b = (size_t)n_codes * 8 + (size_t)ms * tp.max_taps * 4 + (size_t)2 * ms * 4 + 16;
+    return b + (size_t)kWarps * k2_warp_bytes(ps, ms);
 }
 
 cudaError_t k2_decode(const K2Params &p, cudaStream_t stream) {
     if (p.n_quads == 0) return cudaSuccess;
     if (p.mark_size > 16 || p.mark_size < 3 || p.patch_size == 0 || p.n_codes >= (1u << 22)) return cudaErrorInvalidValue;
     ResizeTaps tp = make_resize_taps(p.patch_size, p.mark_size);
-    // keep `var` 8-byte aligned: pad the float/int region to a multiple of 8 bytes by construction
     size_t smem = k2_smem_bytes(p.patch_size, p.mark_size, p.n_codes);
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 220 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    uint32_t grid = p.n_quads < (uint32_t)(2 * sms) ? p.n_quads : (uint32_t)(2 * sms);
-    k2_kernel<<<grid, kThreads, smem, stream>>>(p, tp.max_taps);
+    const uint32_t want = (p.n_quads + kWarps - 1) / kWarps;
+    const uint32_t resident = (uint32_t)sms * (uint32_t)((227 * 1024) / (smem + 1024) ? (227 * 1024) / (smem + 1024) : 1);
+    k2_kernel<<<want < resident ? want : resident, kThreads, smem, stream>>>(p, tp.max_taps);
     return cudaGetLastError();
 }
 

@@ -71,20 +71,23 @@ __device__ __forceinline__ int ddx(int d) { return (d >= 3 && d <= 5) ? 1 : ((d 
 __device__ __forceinline__ int ddy(int d) { return (d >= 1 && d <= 3) ? -1 : ((d == 0 || d == 4) ? 0 : 1); }
 
 struct Geo {
-    const uint32_t *planes;  // guarded bit planes: frame f at planes + f * frame_words, pixel (x, y) = bit x & 31 of word (y + 1) * S + 1 + (x >> 5)
-    uint32_t n, w, h, wpr, S;
+    const uint32_t *planes;  // guarded column-major bit planes: frame f at planes + f * frame_words, pixel (x, y) = bit x & 31 of
+                             // word ((x >> 5) + 1) * Hp + (y + 1)
+    uint32_t n, w, h, wpr, Hp;
     size_t frame_words;
 };
 
 // 3x3 neighbourhood of (x, y): bits 0-2 row y-1, 3-5 row y, 6-8 row y+1 (bit 0 of each = column x-1)
-__device__ __forceinline__ uint32_t hood9(const uint32_t *plane, uint32_t S, int x, int y) {
-    const int o = x + 31;
-    const uint32_t *p = plane + (size_t)y * S + (o >> 5);  // row y-1 of the guarded plane
+__device__ __forceinline__ uint32_t hood9(const uint32_t *plane, uint32_t Hp, int x, int y) {
+    const int o = x + 31;                                   // column x-1 in guarded coordinates
+    const uint32_t *p = plane + (size_t)(o >> 5) * Hp + y;  // word column of x-1, row y-1 (guarded row index y)
     const int sh = o & 31;
-    const uint32_t t = __funnelshift_r(__ldg(p), __ldg(p + 1), sh) & 7u;
-    const uint32_t m = __funnelshift_r(__ldg(p + S), __ldg(p + S + 1), sh) & 7u;
-    const uint32_t b = __funnelshift_r(__ldg(p + 2 * S), __ldg(p + 2 * S + 1), sh) & 7u;
-    return t | (m << 3) | (b << 6);
+    uint32_t t = __ldg(p) >> sh, m = __ldg(p + 1) >> sh, b = __ldg(p + 2) >> sh;
+    if (sh > 29) {  // the three columns straddle two words
+        const uint32_t *q = p + Hp;
+        t |= __ldg(q) << (32 - sh); m |= __ldg(q + 1) << (32 - sh); b |= __ldg(q + 2) << (32 - sh);
+    }
+    return (t & 7u) | ((m & 7u) << 3) | ((b & 7u) << 6);
 }
 __device__ __forceinline__ uint32_t ring_of(uint32_t hood) {
     const uint32_t t = hood & 7u, m = (hood >> 3) & 7u, b = hood >> 6;
@@ -100,7 +103,7 @@ enum { kDead = 0, kSurvivor = 1, kUndecided = 2 };
 __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (*fwd)[512], const uint16_t (*bwd)[512], int sx, int sy, int kind,
                            uint32_t budget, uint32_t &n, bool &first_pixel) {
     const uint32_t me = ((uint32_t)(sy * (int)g.w + sx) << 1) | (uint32_t)kind;
-    const uint32_t nb0 = ring_of(hood9(plane, g.S, sx, sy));
+    const uint32_t nb0 = ring_of(hood9(plane, g.Hp, sx, sy));
     const int adj = kind ? 4 : 0;
     int pred = -1;
     for (int k = 0; k < 8; k++) {  // clockwise from the zero neighbour: the previous pixel on the border
@@ -122,7 +125,7 @@ __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (
     }
     const uint16_t (*lut)[512] = kind ? fwd : bwd;
     for (uint32_t steps = 0;; steps++) {
-        const uint32_t e = lut[state][hood9(plane, g.S, x, y)];
+        const uint32_t e = lut[state][hood9(plane, g.Hp, x, y)];
         const uint32_t pix = (uint32_t)(y * (int)g.w + x);
         if (kind) {
             if (n && pix == start_pix && state == (uint32_t)pred) break;  // back in the starting state
@@ -173,7 +176,7 @@ __device__ __forceinline__ void record_survivor(const Lists &l, uint32_t frame, 
     }
 }
 
-__global__ void __launch_bounds__(128) k3_candidates(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
+__global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
     __shared__ uint16_t fwd[8][512];
     __shared__ uint16_t bwd[8][512];
     for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) {
@@ -181,39 +184,42 @@ __global__ void __launch_bounds__(128) k3_candidates(const Geo g, const StepTabl
         (&bwd[0][0])[i] = (&tables->bwd[0][0])[i];
     }
     __syncthreads();
-    const size_t words_per_frame = (size_t)g.h * g.wpr;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= words_per_frame * g.n) return;
-    const uint32_t frame = (uint32_t)(gid / words_per_frame);
-    const uint32_t rem = (uint32_t)(gid % words_per_frame);
-    const uint32_t y = rem / g.wpr, k = rem % g.wpr;
-    const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
-    const uint32_t *row = plane + (size_t)(y + 1) * g.S + 1;
-    const uint32_t f = row[k];
-    if (!f) return;
-    const uint32_t west = (f << 1) | (row[(int)k - 1] >> 31), east = (f >> 1) | (row[k + 1] << 31);
-    uint32_t og = f & ~west, hg = f & ~east;
-    if (k == 0) og &= ~1u;                                           // `x > 0`
-    if (k == (g.w - 1) >> 5) hg &= ~(1u << ((g.w - 1) & 31));        // `x + 1 < w`
-    uint32_t pending = og | hg;
-    while (pending) {
-        const uint32_t b = pending & (0u - pending);
-        pending ^= b;
-        const int bit = __ffs(b) - 1;
-        const int x = (int)(k * 32) + bit;
-        for (int kind = 0; kind < 2; kind++) {
-            if (!((kind ? hg : og) & b)) continue;
-            uint32_t n;
-            bool first_pixel;
-            const int r = walk_border(plane, g, fwd, bwd, x, (int)y, kind, kBudget, n, first_pixel);
-            if (r == kDead) continue;
-            const unsigned long long key = ((((unsigned long long)gid << 5) | (unsigned)bit) << 1) | (unsigned)kind;
-            if (r == kSurvivor) {
-                record_survivor(l, frame, key, kind, n, first_pixel, min_points);
-            } else {
-                const uint32_t slot = atomicAdd(&l.counters[0], 1u);
-                if (slot < l.walkers_cap) l.walkers[slot] = key;
-                else atomicOr(&l.counters[2], 1u);
+    const size_t words_per_frame = (size_t)g.h * g.wpr, nwords = words_per_frame * g.n;
+    // persistent blocks (the step tables are loaded once per block), consecutive threads on consecutive words
+    for (size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; tid < nwords; tid += (size_t)gridDim.x * blockDim.x) {
+        // consecutive threads take consecutive rows of one word column: consecutive words of the column-major plane
+        const uint32_t frame = (uint32_t)(tid / words_per_frame);
+        const uint32_t rem = (uint32_t)(tid % words_per_frame);
+        const uint32_t k = rem / g.h, y = rem % g.h;
+        const size_t gid = (size_t)frame * words_per_frame + (size_t)y * g.wpr + k;  // raster word id: the sort key
+        const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+        const uint32_t *col = plane + (size_t)(k + 1) * g.Hp + (y + 1);
+        const uint32_t f = __ldg(col);
+        if (!f) continue;
+        const uint32_t west = (f << 1) | (__ldg(col - g.Hp) >> 31), east = (f >> 1) | (__ldg(col + g.Hp) << 31);
+        uint32_t og = f & ~west, hg = f & ~east;
+        if (k == 0) og &= ~1u;                                           // `x > 0`
+        if (k == (g.w - 1) >> 5) hg &= ~(1u << ((g.w - 1) & 31));        // `x + 1 < w`
+        uint32_t pending = og | hg;
+        while (pending) {
+            const uint32_t b = pending & (0u - pending);
+            pending ^= b;
+            const int bit = __ffs(b) - 1;
+            const int x = (int)(k * 32) + bit;
+            for (int kind = 0; kind < 2; kind++) {
+                if (!((kind ? hg : og) & b)) continue;
+                uint32_t n;
+                bool first_pixel;
+                const int r = walk_border(plane, g, fwd, bwd, x, (int)y, kind, kBudget, n, first_pixel);
+                if (r == kDead) continue;
+                const unsigned long long key = ((((unsigned long long)gid << 5) | (unsigned)bit) << 1) | (unsigned)kind;
+                if (r == kSurvivor) {
+                    record_survivor(l, frame, key, kind, n, first_pixel, min_points);
+                } else {
+                    const uint32_t slot = atomicAdd(&l.counters[0], 1u);
+                    if (slot < l.walkers_cap) l.walkers[slot] = key;
+                    else atomicOr(&l.counters[2], 1u);
+                }
             }
         }
     }
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *ta
     int sx, sy, kind;
     decode_key(g, keys[ci], frame, sx, sy, kind);
     const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
-    const uint32_t nb0 = ring_of(hood9(plane, g.S, sx, sy));
+    const uint32_t nb0 = ring_of(hood9(plane, g.Hp, sx, sy));
     const int adj = kind ? 4 : 0;
     int pred = 0;
     for (int q = 0; q < 8; q++) {
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *ta
     uint32_t state = (uint32_t)pred;
     for (uint32_t i = 0; i < n; i++) {
         out[i] = (uint32_t)x | ((uint32_t)y << 16);
-        const uint32_t e = fwd[state][hood9(plane, g.S, x, y)];
+        const uint32_t e = fwd[state][hood9(plane, g.Hp, x, y)];
         x += (int)((e >> 5) & 3u) - 1;
         y += (int)((e >> 7) & 3u) - 1;
         state = e >> 9;
@@ -458,69 +464,92 @@ __global__ void __launch_bounds__(32) k3_finalize(const uint32_t *contour_quads,
                                                   uint32_t total_contours, uint32_t n_frames, float min_corner_separation,
                                                   uint32_t quad_cap, uint32_t *out_quads, uint32_t *out_counts, uint32_t *out_before_discard,
                                                   uint32_t *frame_flags, uint8_t *dead_scratch) {
+    extern __shared__ uint32_t sq[];  // quad_cap * 8 words of quads, then quad_cap floats of perimeters, then quad_cap dead bytes
+    float *sper = reinterpret_cast<float *>(sq + (size_t)quad_cap * 8);
+    uint8_t *dead = reinterpret_cast<uint8_t *>(sper + quad_cap);
     const uint32_t f = blockIdx.x;
     const int lane = threadIdx.x;
     // the frame's borders are a contiguous range of the sorted list: keys are (word id, bit, kind) with frame-major word ids
-    const unsigned long long c0 = lower_bound_key(keys, total_contours, ((unsigned long long)f * words_per_frame) << 6);
-    const unsigned long long c1 = lower_bound_key(keys, total_contours, ((unsigned long long)(f + 1) * words_per_frame) << 6);
-    (void)n_frames;
-    uint32_t *dst = out_quads + (size_t)f * quad_cap * 8;
+    const uint32_t c0 = lower_bound_key(keys, total_contours, ((unsigned long long)f * words_per_frame) << 6);
+    const uint32_t c1 = lower_bound_key(keys, total_contours, ((unsigned long long)(f + 1) * words_per_frame) << 6);
+    (void)n_frames; (void)dead_scratch;
     uint32_t nq = 0;
     bool over = false;
-    for (unsigned long long base = c0; base < c1; base += 32) {
-        const unsigned long long ci = base + lane;
-        const bool valid = ci < c1 && contour_quads[ci * 8] != 0xffffffffu;
+    for (uint32_t base = c0; base < c1; base += 32) {
+        const uint32_t ci = base + lane;
+        const bool valid = ci < c1 && contour_quads[(size_t)ci * 8] != 0xffffffffu;
         const uint32_t m = __ballot_sync(0xffffffffu, valid);
         if (valid) {
             const uint32_t slot = nq + __popc(m & ((1u << lane) - 1));
-            if (slot < quad_cap)
-                for (int i = 0; i < 8; i++) dst[(size_t)slot * 8 + i] = contour_quads[ci * 8 + i];
-            else
+            if (slot < quad_cap) {
+                const uint4 a = *reinterpret_cast<const uint4 *>(contour_quads + (size_t)ci * 8);
+                const uint4 b = *reinterpret_cast<const uint4 *>(contour_quads + (size_t)ci * 8 + 4);
+                uint32_t *p = sq + (size_t)slot * 8;
+                p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+            } else {
                 over = true;
+            }
         }
         nq += __popc(m);
     }
     over = __any_sync(0xffffffffu, over);
+    if (over) nq = quad_cap;
     __syncwarp();
-    if (lane != 0) return;
-    if (over) { atomicOr(&frame_flags[f], 4u); nq = quad_cap; }
-    out_before_discard[f] = nq;
-    for (uint32_t i = 0; i < nq; i++) {  // enforce_clockwise_corners
-        uint32_t *p = dst + (size_t)i * 8;
+    for (uint32_t i = lane; i < nq; i += 32) {  // enforce_clockwise_corners, perimeters
+        uint32_t *p = sq + (size_t)i * 8;
         const int dx1 = (int)p[2] - (int)p[0], dy1 = (int)p[3] - (int)p[1], dx2 = (int)p[4] - (int)p[0], dy2 = (int)p[5] - (int)p[1];
         if (dx1 * dy2 - dy1 * dx2 < 0) {
             const uint32_t sx = p[2], sy = p[3];
             p[2] = p[6]; p[3] = p[7]; p[6] = sx; p[7] = sy;
         }
+        sper[i] = perimeter(p);
+        dead[i] = 0;
     }
-    uint8_t *dead = dead_scratch + (size_t)f * quad_cap;
-    for (uint32_t i = 0; i < nq; i++) dead[i] = 0;
-    for (uint32_t i = 0; i + 1 < nq; i++) {  // discard_too_near
-        if (dead[i]) continue;
-        const float per_i = perimeter(dst + (size_t)i * 8);
-        for (uint32_t j = i + 1; j < nq; j++) {
-            if (dead[j]) continue;
-            float d = 0.0f;
-            for (int c = 0; c < 4; c++) {
-                const float dx = (float)dst[(size_t)i * 8 + 2 * c] - (float)dst[(size_t)j * 8 + 2 * c];
-                const float dy = (float)dst[(size_t)i * 8 + 2 * c + 1] - (float)dst[(size_t)j * 8 + 2 * c + 1];
-                d += sqrtf((dx * dx) + (dy * dy));
+    __syncwarp();
+    uint32_t *dst = out_quads + (size_t)f * quad_cap * 8;
+    if (lane == 0) {
+        if (over) atomicOr(&frame_flags[f], 4u);
+        out_before_discard[f] = nq;
+    }
+    // discard_too_near: i is sequential as in the reference; for one i the lanes test 32 later quads at a time.  In the
+    // reference's j loop, close quads with a perimeter <= perimeter(i) die until the first close quad with a larger one
+    // kills i, after which nothing else happens for this i.
+    for (uint32_t i = 0; i + 1 < nq; i++) {
+        if (dead[i]) continue;  // warp-uniform (shared memory, synchronised below)
+        const float per_i = sper[i];
+        for (uint32_t j0 = i + 1; j0 < nq; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            bool close = false;
+            if (j < nq && !dead[j]) {
+                float d = 0.0f;
+                for (int c = 0; c < 4; c++) {
+                    const float dx = (float)sq[(size_t)i * 8 + 2 * c] - (float)sq[(size_t)j * 8 + 2 * c];
+                    const float dy = (float)sq[(size_t)i * 8 + 2 * c + 1] - (float)sq[(size_t)j * 8 + 2 * c + 1];
+                    d += sqrtf((dx * dx) + (dy * dy));
+                }
+                close = (d / 4.0f) < min_corner_separation;
             }
-            if ((d / 4.0f) < min_corner_separation) {
-                if (dead[i] || dead[j]) continue;
-                if (per_i >= perimeter(dst + (size_t)j * 8)) dead[j] = 1;
-                else dead[i] = 1;  // the reference keeps scanning with this i
+            const bool killer = close && !(per_i >= sper[j]);
+            const uint32_t mk = __ballot_sync(0xffffffffu, killer);
+            const int first_killer = mk ? __ffs(mk) - 1 : 32;
+            if (close && lane < first_killer) dead[j] = 1;
+            if (mk) {
+                if (lane == 0) dead[i] = 1;
+                break;
             }
         }
+        __syncwarp();
     }
-    uint32_t kept = 0;
-    for (uint32_t i = 0; i < nq; i++)
-        if (!dead[i]) {
-            if (kept != i)
-                for (int c = 0; c < 8; c++) dst[(size_t)kept * 8 + c] = dst[(size_t)i * 8 + c];
-            kept++;
-        }
-    out_counts[f] = kept;
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t kept = 0;
+        for (uint32_t i = 0; i < nq; i++)
+            if (!dead[i]) {
+                for (int c = 0; c < 8; c++) dst[(size_t)kept * 8 + c] = sq[(size_t)i * 8 + c];
+                kept++;
+            }
+        out_counts[f] = kept;
+    }
 }
 
 }  // namespace
@@ -588,8 +617,8 @@ cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
     if (p.w > 65535 || p.h > 65535) return cudaErrorInvalidValue;  // points are packed 16 + 16
     Geo g;
-    g.planes = p.planes; g.n = p.n; g.w = p.w; g.h = p.h; g.wpr = (p.w + 31) / 32; g.S = g.wpr + 2;
-    g.frame_words = (size_t)(p.h + 2) * g.S;
+    g.planes = p.planes; g.n = p.n; g.w = p.w; g.h = p.h; g.wpr = (p.w + 31) / 32; g.Hp = p.h + 2;
+    g.frame_words = (size_t)(g.wpr + 2) * g.Hp;
     const size_t words_per_frame = (size_t)g.h * g.wpr, nwords = words_per_frame * p.n;
     if (!w.d_tables) {
         StepTables *t = new StepTables();
@@ -648,7 +677,10 @@ cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    k3_candidates<<<(uint32_t)((nwords + 127) / 128), 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
+    {
+        const size_t want_blocks = (nwords + 255) / 256, resident = (size_t)sms * 8;
+        k3_candidates<<<(uint32_t)(want_blocks < resident ? want_blocks : resident), 256, 0, stream>>>(g, w.d_tables, p.min_points, l);
+    }
     K3_CUDA(cudaGetLastError());
     k3_walkers<<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
     K3_CUDA(cudaGetLastError());
@@ -682,7 +714,10 @@ cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         k3_rdp<<<(n_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, n_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags);
         K3_CUDA(cudaGetLastError());
     }
-    k3_finalize<<<p.n, 32, 0, stream>>>(w.contour_quads, w.long_keys_sorted, words_per_frame, n_long, p.n, p.min_corner_separation, p.quad_cap,
+    const size_t fin_smem = (size_t)p.quad_cap * (32 + 4 + 1) + 16;
+    if (fin_smem > 200 * 1024) return cudaErrorInvalidValue;
+    K3_CUDA(cudaFuncSetAttribute(k3_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    k3_finalize<<<p.n, 32, fin_smem, stream>>>(w.contour_quads, w.long_keys_sorted, words_per_frame, n_long, p.n, p.min_corner_separation, p.quad_cap,
                                         p.quads, p.quad_counts, p.before_discard, p.frame_flags, w.dead);
     K3_CUDA(cudaGetLastError());
     if (p.frame_contours) K3_CUDA(cudaMemcpyAsync(p.frame_contours, w.frame_contours, (size_t)p.n * 4, cudaMemcpyDeviceToDevice, stream));
