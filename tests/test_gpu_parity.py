@@ -278,3 +278,54 @@ def test_full_size_batch_properties(a3):
     assert false <= 0.01 * found, f"{false} misread ids of {found}"
     assert np.median(errs) <= 5.0 and np.percentile(errs, 99) <= 30.0, f"corner error {np.percentile(errs, [50, 99, 100])}"
     assert [[(m.id, m.corners) for m in x.markers] for x in part] == [[(m.id, m.corners) for m in x.markers] for x in got[37:41]]
+
+
+@pytest.mark.parametrize("contours", ["device", "host"])
+def test_resident_input_equals_host_input(a3, contours):
+    """a3_detect_batch with A3_MEM_DEVICE (frames already in HBM, the flavour bench.py's `value` times) returns the same
+    markers and counters as the host-pointer flavour."""
+    torch = pytest.importorskip("torch")
+    from aruco3_b200 import _ffi, synth
+    frames, _ = synth.render_batch("C1", 7)
+    n, h, w = frames.shape[:3]
+    with a3.Detector(contours=contours) as d:
+        want = d.detect_batch(frames)
+        want_stats = dict(d.last_stats)
+        dev = torch.from_numpy(frames).cuda()
+        markers = (_ffi.A3Marker * 4096)()
+        nm = C.c_uint32()
+        st = _ffi.A3Stats()
+        _ffi.check(_ffi.lib().a3_detect_batch(d._h, dev.data_ptr(), _ffi.FMT_RGB8, _ffi.MEM_DEVICE, n, w, h, w * 3, w * h * 3,
+                                              C.cast(markers, C.c_void_p), 4096, C.byref(nm), None, C.byref(st)))
+    got = [[] for _ in range(n)]
+    for i in range(nm.value):
+        m = markers[i]
+        got[m.frame].append((int(m.id), int(m.rotation), int(m.hamming_distance), [int(v) for v in m.corners]))
+    assert got == [[(m.id, m.rotation, m.hamming_distance, [v for c in m.corners for v in c]) for m in x.markers] for x in want]
+    for k in ("n_contours", "n_contour_points", "n_candidates", "n_markers"):
+        assert getattr(st, k) == want_stats[k], k
+
+
+@pytest.mark.parametrize("channels", [1, 4])
+def test_detect_other_pixel_formats(a3, oracle, channels):
+    """Luma8 passes through into_luma8 unchanged and Rgba8 ignores alpha — through the whole path."""
+    from aruco3_b200 import synth
+    rgb, _ = synth.render_batch("C1", 2)
+    if channels == 1:
+        imgs = np.stack([oracle.to_luma8(f) for f in rgb])
+    else:
+        imgs = np.concatenate([rgb, np.full(rgb.shape[:3] + (1,), 77, np.uint8)], axis=3)
+    with a3.Detector() as d:
+        got = d.detect_batch(imgs, full=True, want_mask=True)
+    for f in range(2):
+        _check_detection(got[f], oracle.detect(imgs[f], "ARUCO"), f"{channels}ch[{f}]")
+
+
+def test_detect_4k_frame(a3, oracle):
+    """BASELINE.json configs[3] frame size (3840 x 2160), one frame, every intermediate against the oracle."""
+    from aruco3_b200 import synth
+    img, _ = synth.render_frame(synth.CONFIGS["C4"], 0)
+    with a3.Detector() as d:
+        got = d.detect_batch(img[None], full=True, want_mask=True)[0]
+    _check_detection(got, oracle.detect(img, "ARUCO"), "C4[0]")
+    assert len(got.markers) >= 18
