@@ -25,13 +25,20 @@
 // discovery order) + prefix sum of their lengths  ->  k3_emit (one thread per border writes its points)  ->  k3_rdp (one
 // warp per border: Ramer-Douglas-Peucker, hull, edge test)  ->  k3_finalize (one warp per frame: ordered compaction,
 // clockwise, discard_too_near).
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "a3_internal.h"
 
 namespace a3 {
 namespace {
+
+namespace cg = cooperative_groups;
 
 constexpr int kDx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};  // ring order w nw n ne e se s sw (screen clockwise)
 constexpr int kDy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
@@ -148,10 +155,12 @@ __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (
 
 // Work lists shared by the kernels of one k3_quads call.
 struct Lists {
-    unsigned long long *walkers;       // undecided candidates: ((word id * 32 + bit) << 1) | kind
+    unsigned long long *cands;         // start candidates left after the word-level filter: ((word id * 32 + bit) << 1) | kind
+    uint32_t cands_cap;
+    unsigned long long *walkers;       // candidates undecided after kBudget steps: the same key
     unsigned long long *long_keys;     // surviving borders with >= min_points points: the same key ...
     uint32_t *long_n;                  // ... and their number of points
-    uint32_t *counters;                // [0] walkers, [1] long borders, [2] overflow of either list
+    uint32_t *counters;                // [0] walkers, [1] long borders, [2] overflow of a list, [3] candidates
     unsigned long long *long_points;   // total points of the long borders
     uint32_t walkers_cap, long_cap;
     uint32_t *frame_contours;          // per frame: borders followed
@@ -177,19 +186,18 @@ __device__ __forceinline__ void record_survivor(const Lists &l, uint32_t frame, 
 }
 
 __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
-    __shared__ uint16_t fwd[8][512];
+    __shared__ uint16_t fwd[8][512];  // only for candidates that do not fit the list (walked right here)
     __shared__ uint16_t bwd[8][512];
     for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) {
         (&fwd[0][0])[i] = (&tables->fwd[0][0])[i];
         (&bwd[0][0])[i] = (&tables->bwd[0][0])[i];
     }
     __syncthreads();
-    const size_t words_per_frame = (size_t)g.h * g.wpr, nwords = words_per_frame * g.n;
-    // persistent blocks (the step tables are loaded once per block), consecutive threads on consecutive words
-    for (size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; tid < nwords; tid += (size_t)gridDim.x * blockDim.x) {
-        // consecutive threads take consecutive rows of one word column: consecutive words of the column-major plane
-        const uint32_t frame = (uint32_t)(tid / words_per_frame);
-        const uint32_t rem = (uint32_t)(tid % words_per_frame);
+    const uint32_t words_per_frame = g.h * g.wpr;
+    // blockIdx.y strides over frames; inside a frame consecutive threads take consecutive rows of one word column:
+    // consecutive words of the column-major plane
+    for (uint32_t frame = blockIdx.y; frame < g.n; frame += gridDim.y)
+    for (uint32_t rem = blockIdx.x * blockDim.x + threadIdx.x; rem < words_per_frame; rem += gridDim.x * blockDim.x) {
         const uint32_t k = rem / g.h, y = rem % g.h;
         const size_t gid = (size_t)frame * words_per_frame + (size_t)y * g.wpr + k;  // raster word id: the sort key
         const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
@@ -200,26 +208,55 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
         uint32_t og = f & ~west, hg = f & ~east;
         if (k == 0) og &= ~1u;                                           // `x > 0`
         if (k == (g.w - 1) >> 5) hg &= ~(1u << ((g.w - 1) & 31));        // `x + 1 < w`
+        if (!(og | hg)) continue;
+        {
+            // Most candidates have a raster-earlier candidate crack of the same border right above them; word arithmetic
+            // on the row above finds those without walking (each rule names a crack that is on the same border because
+            // the background pixels involved are 4-connected and the foreground pixels 8-connected):
+            //   west crack at (x, y):  (x, y-1) also has a west crack                       (straight left edge)
+            //                          N and NW are background, NE is foreground: (x+1, y-1) has a west crack ('/' edge)
+            //   east crack at (x, y):  (x, y-1) also has an east crack                      (straight right edge)
+            //                          N and NE are background, NW is foreground: (x-1, y-1) has an east crack ('\' edge)
+            const uint32_t fa = __ldg(col - 1);                                                   // row y-1 (guard row for y = 0)
+            const uint32_t fa_w = (fa << 1) | (__ldg(col - g.Hp - 1) >> 31);                      // bit x = pixel (x-1, y-1)
+            const uint32_t fa_e = (fa >> 1) | (__ldg(col + g.Hp - 1) << 31);                      // bit x = pixel (x+1, y-1)
+            og &= ~((fa & ~fa_w) | (~fa & ~fa_w & fa_e));
+            hg &= ~((fa & ~fa_e) | (~fa & ~fa_e & fa_w));
+        }
+        // what is left goes to the candidate list (one atomic per warp); k3_walk_short gives every entry a thread
+        const uint32_t mine = __popc(og) + __popc(hg);
+        uint32_t slot;
+        {
+            const cg::coalesced_group cgp = cg::coalesced_threads();  // the lanes that still have candidates in this word
+            const uint32_t before = cg::exclusive_scan(cgp, mine);
+            uint32_t base = 0;
+            if (cgp.thread_rank() == cgp.size() - 1) base = atomicAdd(&l.counters[3], before + mine);
+            base = cgp.shfl(base, cgp.size() - 1);
+            slot = base + before;
+        }
         uint32_t pending = og | hg;
         while (pending) {
             const uint32_t b = pending & (0u - pending);
             pending ^= b;
             const int bit = __ffs(b) - 1;
-            const int x = (int)(k * 32) + bit;
             for (int kind = 0; kind < 2; kind++) {
                 if (!((kind ? hg : og) & b)) continue;
-                uint32_t n;
-                bool first_pixel;
-                const int r = walk_border(plane, g, fwd, bwd, x, (int)y, kind, kBudget, n, first_pixel);
-                if (r == kDead) continue;
                 const unsigned long long key = ((((unsigned long long)gid << 5) | (unsigned)bit) << 1) | (unsigned)kind;
-                if (r == kSurvivor) {
-                    record_survivor(l, frame, key, kind, n, first_pixel, min_points);
-                } else {
-                    const uint32_t slot = atomicAdd(&l.counters[0], 1u);
-                    if (slot < l.walkers_cap) l.walkers[slot] = key;
-                    else atomicOr(&l.counters[2], 1u);
+                if (slot < l.cands_cap) {
+                    l.cands[slot] = key;
+                } else {  // list full (very dense noise): walk it here, same rules as k3_walk_short
+                    uint32_t n;
+                    bool first_pixel;
+                    const int r = walk_border(plane, g, fwd, bwd, (int)(k * 32) + bit, (int)y, kind, kBudget, n, first_pixel);
+                    if (r == kSurvivor) {
+                        record_survivor(l, frame, key, kind, n, first_pixel, min_points);
+                    } else if (r == kUndecided) {
+                        const uint32_t ws = atomicAdd(&l.counters[0], 1u);
+                        if (ws < l.walkers_cap) l.walkers[ws] = key;
+                        else atomicOr(&l.counters[2], 1u);
+                    }
                 }
+                slot++;
             }
         }
     }
@@ -234,6 +271,34 @@ __device__ __forceinline__ void decode_key(const Geo &g, unsigned long long key,
     const uint32_t rem = (uint32_t)(gid % words_per_frame);
     y = (int)(rem / g.wpr);
     x = (int)((rem % g.wpr) * 32 + (uint32_t)(v & 31ull));
+}
+
+// One thread per listed candidate: walk at most kBudget steps.  Nearly all die within a few; short borders finish.
+__global__ void __launch_bounds__(128) k3_walk_short(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
+    __shared__ uint16_t fwd[8][512];
+    __shared__ uint16_t bwd[8][512];
+    for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) {
+        (&fwd[0][0])[i] = (&tables->fwd[0][0])[i];
+        (&bwd[0][0])[i] = (&tables->bwd[0][0])[i];
+    }
+    __syncthreads();
+    const uint32_t total = min(l.counters[3], l.cands_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = l.cands[i];
+        uint32_t frame, n;
+        int x, y, kind;
+        bool first_pixel;
+        decode_key(g, key, frame, x, y, kind);
+        const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+        const int r = walk_border(plane, g, fwd, bwd, x, y, kind, kBudget, n, first_pixel);
+        if (r == kSurvivor) {
+            record_survivor(l, frame, key, kind, n, first_pixel, min_points);
+        } else if (r == kUndecided) {
+            const uint32_t slot = atomicAdd(&l.counters[0], 1u);
+            if (slot < l.walkers_cap) l.walkers[slot] = key;
+            else atomicOr(&l.counters[2], 1u);
+        }
+    }
 }
 
 // The undecided candidates — mostly the one survivor of each long border — walk to the end, all at the same time.
@@ -557,9 +622,9 @@ __global__ void __launch_bounds__(32) k3_finalize(const uint32_t *contour_quads,
 struct K3Workspace::Impl {
     StepTables *d_tables = nullptr;
     // work lists
-    unsigned long long *walkers = nullptr, *long_keys = nullptr, *long_keys_sorted = nullptr, *long_points = nullptr, *frame_points = nullptr;
+    unsigned long long *cands = nullptr, *walkers = nullptr, *long_keys = nullptr, *long_keys_sorted = nullptr, *long_points = nullptr, *frame_points = nullptr;
     uint32_t *long_n = nullptr, *long_n_sorted = nullptr, *long_off = nullptr, *counters = nullptr, *frame_contours = nullptr;
-    size_t walkers_cap = 0, long_cap = 0, frames_cap = 0;
+    size_t cands_cap = 0, walkers_cap = 0, long_cap = 0, frames_cap = 0;
     void *cub_tmp = nullptr;
     size_t cub_bytes = 0;
     Contour *contours = nullptr;
@@ -575,7 +640,7 @@ struct K3Workspace::Impl {
 K3Workspace::K3Workspace() : impl(new Impl()) {}
 K3Workspace::~K3Workspace() {
     if (!impl) return;
-    for (void *p : {(void *)impl->d_tables, (void *)impl->walkers, (void *)impl->long_keys, (void *)impl->long_keys_sorted, (void *)impl->long_points,
+    for (void *p : {(void *)impl->d_tables, (void *)impl->cands, (void *)impl->walkers, (void *)impl->long_keys, (void *)impl->long_keys_sorted, (void *)impl->long_points,
                     (void *)impl->frame_points, (void *)impl->long_n, (void *)impl->long_n_sorted, (void *)impl->long_off, (void *)impl->counters,
                     (void *)impl->frame_contours, impl->cub_tmp, (void *)impl->contours, (void *)impl->contour_quads, (void *)impl->points,
                     (void *)impl->dead})
@@ -612,9 +677,36 @@ static __global__ void k3_flag_all(uint32_t *frame_flags, uint32_t n, const uint
     if (i < n && (force || counters[2])) frame_flags[i] |= 8u;  // a work list overflowed: every frame of this call goes to the host stage
 }
 
+// A3_K3_TIMING=1 in the environment: print the device time of every phase of a k3_quads call (debug aid)
+struct PhaseTimer {
+    bool on;
+    cudaStream_t s;
+    cudaEvent_t ev[16];
+    const char *name[16];
+    int n = 0;
+    PhaseTimer(cudaStream_t stream) : on(getenv("A3_K3_TIMING") != nullptr), s(stream) {}
+    void mark(const char *what) {
+        if (!on || n >= 16) return;
+        cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], s);
+        name[n++] = what;
+    }
+    ~PhaseTimer() {
+        if (!on || n == 0) return;
+        cudaEventSynchronize(ev[n - 1]);
+        for (int i = 1; i < n; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, "k3 %-12s %8.3f ms\n", name[i], ms);
+        }
+        for (int i = 0; i < n; i++) cudaEventDestroy(ev[i]);
+    }
+};
+
 cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     K3Workspace::Impl &w = *ws.impl;
     if (p.n == 0) return cudaSuccess;
+    PhaseTimer timer(stream);
     if (p.w > 65535 || p.h > 65535) return cudaErrorInvalidValue;  // points are packed 16 + 16
     Geo g;
     g.planes = p.planes; g.n = p.n; g.w = p.w; g.h = p.h; g.wpr = (p.w + 31) / 32; g.Hp = p.h + 2;
@@ -635,6 +727,11 @@ cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     const size_t pixels = (size_t)p.w * p.h;
     const size_t mp = p.min_points < 4 ? 4 : p.min_points;
     const size_t want_walkers = (size_t)p.n * (pixels / 32 + 4096), want_long = (size_t)p.n * (pixels / (4 * mp) + 1024);
+    const size_t want_cands = (size_t)p.n * (pixels / 8 + 4096);  // what does not fit is walked inside k3_candidates
+    if (want_cands > w.cands_cap) {
+        K3_CUDA(alloc_exact(w.cands, want_cands));
+        w.cands_cap = want_cands;
+    }
     if (want_walkers > w.walkers_cap) {
         K3_CUDA(alloc_exact(w.walkers, want_walkers));
         w.walkers_cap = want_walkers;
@@ -669,7 +766,9 @@ cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     K3_CUDA(cudaMemsetAsync(w.counters, 0, 16, stream));
     K3_CUDA(cudaMemsetAsync(w.long_points, 0, 8, stream));
 
+    timer.mark("begin");
     Lists l;
+    l.cands = w.cands; l.cands_cap = (uint32_t)(w.cands_cap > 0xffffffffull ? 0xffffffffull : w.cands_cap);
     l.walkers = w.walkers; l.long_keys = w.long_keys; l.long_n = w.long_n; l.counters = w.counters; l.long_points = w.long_points;
     l.walkers_cap = (uint32_t)(w.walkers_cap > 0xffffffffull ? 0xffffffffull : w.walkers_cap);
     l.long_cap = (uint32_t)(w.long_cap > 0x7fffffffull ? 0x7fffffffull : w.long_cap);
@@ -678,17 +777,27 @@ cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     {
-        const size_t want_blocks = (nwords + 255) / 256, resident = (size_t)sms * 8;
-        k3_candidates<<<(uint32_t)(want_blocks < resident ? want_blocks : resident), 256, 0, stream>>>(g, w.d_tables, p.min_points, l);
+        // about 8 resident blocks of 256 threads per SM, split over the frames
+        const uint32_t per_frame = (uint32_t)((words_per_frame + 255) / 256), resident = (uint32_t)sms * 8;
+        const uint32_t gy = p.n < resident ? p.n : resident;
+        uint32_t gx = (resident + gy - 1) / gy;
+        if (gx > per_frame) gx = per_frame;
+        k3_candidates<<<dim3(gx, gy), 256, 0, stream>>>(g, w.d_tables, p.min_points, l);
     }
     K3_CUDA(cudaGetLastError());
+    timer.mark("candidates");
+    k3_walk_short<<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
+    K3_CUDA(cudaGetLastError());
+    timer.mark("walk_short");
     k3_walkers<<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
     K3_CUDA(cudaGetLastError());
+    timer.mark("walkers");
     k3_flag_all<<<(p.n + 127) / 128, 128, 0, stream>>>(p.frame_flags, p.n, w.counters, 0);
     K3_CUDA(cudaGetLastError());
     K3_CUDA(cudaMemcpyAsync(&w.h_counts[0], w.counters, 16, cudaMemcpyDeviceToHost, stream));
     K3_CUDA(cudaMemcpyAsync(&w.h_counts[2], w.long_points, 8, cudaMemcpyDeviceToHost, stream));
     K3_CUDA(cudaStreamSynchronize(stream));
+    timer.mark("sync");
     const uint32_t *hc = reinterpret_cast<const uint32_t *>(&w.h_counts[0]);
     uint32_t n_long = hc[1] < l.long_cap ? hc[1] : l.long_cap;
     const unsigned long long n_points = w.h_counts[2];
@@ -709,17 +818,21 @@ cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         K3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.long_keys, w.long_keys_sorted, w.long_n, w.long_n_sorted, (int)n_long, 0, end_bit, stream));
         tmp = w.cub_bytes;
         K3_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.long_n_sorted, w.long_off, (int)n_long, stream));
+        timer.mark("sort+scan");
         k3_emit<<<(n_long + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, n_long, w.contours, w.points);
         K3_CUDA(cudaGetLastError());
+        timer.mark("emit");
         k3_rdp<<<(n_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, n_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags);
         K3_CUDA(cudaGetLastError());
     }
+    timer.mark("rdp");
     const size_t fin_smem = (size_t)p.quad_cap * (32 + 4 + 1) + 16;
     if (fin_smem > 200 * 1024) return cudaErrorInvalidValue;
     K3_CUDA(cudaFuncSetAttribute(k3_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     k3_finalize<<<p.n, 32, fin_smem, stream>>>(w.contour_quads, w.long_keys_sorted, words_per_frame, n_long, p.n, p.min_corner_separation, p.quad_cap,
                                         p.quads, p.quad_counts, p.before_discard, p.frame_flags, w.dead);
     K3_CUDA(cudaGetLastError());
+    timer.mark("finalize");
     if (p.frame_contours) K3_CUDA(cudaMemcpyAsync(p.frame_contours, w.frame_contours, (size_t)p.n * 4, cudaMemcpyDeviceToDevice, stream));
     if (p.frame_points) K3_CUDA(cudaMemcpyAsync(p.frame_points, w.frame_points, (size_t)p.n * 8, cudaMemcpyDeviceToDevice, stream));
     return cudaSuccess;
