@@ -270,7 +270,7 @@ def main():
                    "parallelism": f"frame-batch sharding x{world}, no collective"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n * h * w * 3, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(acc_dev["pixel_kernel_launches"] + acc_dev["decode_kernel_launches"] + 4 * acc_dev["contour_kernel_launches"]),
+        "gpu_launches": int(acc_dev["pixel_kernel_launches"] + acc_dev["decode_kernel_launches"] + 7 * acc_dev["contour_kernel_launches"]),  # K3 = 7 kernels of ours per call
         "contour_stage": args.contours, "host_fallback_frames_per_step": acc_dev["host_fallback_frames"] / args.steps,
         "roofline": {"bound": "hbm", "kernel": "k1_strips_kernel<RGB8> (fused into_luma8 + adaptive_threshold, TMA tensor tiles)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,

@@ -116,3 +116,26 @@ def test_flagged_frames_are_redone_by_the_host_stage(a3, oracle):
     for f in range(3):
         assert dev[f].candidates == host[f].candidates
         assert dev[f].candidates == [[tuple(q[2 * k:2 * k + 2]) for k in range(4)] for q in oracle.detect(img[f]).candidates.tolist()]
+
+
+def test_many_small_masks_in_one_batch(a3, oracle):
+    """Stress: 1500 random 48x40 masks of every density in ONE K3 call (thin structures, frame contact, nested holes);
+    every unflagged frame must equal the sequential oracle, and the flag rate must stay what the barred-start rule explains
+    (only frames with foreground in column 0 can be flagged)."""
+    rng = np.random.default_rng(2024)
+    n, h, w = 1500, 40, 48
+    dens = rng.choice([0.1, 0.3, 0.45, 0.55, 0.7, 0.9, 0.98], size=n)
+    masks = ((rng.random((n, h, w)) < dens[:, None, None]) * 255).astype(np.uint8)
+    masks[::5, :, 0] = 0  # a fifth of the frames have an empty first column: those can never be flagged
+    cfg = a3.DetectorConfig(min_side_length_factor=0.05, min_corner_separation_factor=0.02)
+    ocfg = oracle.default_config(min_side_length_factor=0.05, min_corner_separation_factor=0.02)
+    with a3.Detector(cfg) as d:
+        quads, flags, contours, points = d.quads_from_masks_device(masks, quad_capacity=256)
+    assert not flags[::5].any()
+    assert flags.astype(bool).mean() < 0.5
+    for f in range(n):
+        if flags[f]:
+            assert flags[f] == 1
+            continue
+        want, nc, npnt = _oracle_frame(oracle, masks[f], ocfg)
+        assert quads[f].tolist() == want.tolist() and (int(contours[f]), int(points[f])) == (nc, npnt), f"frame {f}"
