@@ -32,44 +32,74 @@ struct Proj {
     int ok;
 };
 
-// f64 Gaussian elimination with partial pivoting — the very sequence of operations of oracle/a3ref.c:solve8.
-__device__ bool solve8(double a[8][9]) {
+// f64 Gaussian elimination with partial pivoting on an 8x9 system held in shared memory, by one warp.  Every element
+// goes through the very sequence of operations of oracle/a3ref.c:solve8 (pivot = first row with the largest |a[r][col]|,
+// f = a[r][col] / a[col][col], a[r][k] = a[r][k] - f * a[col][k] for k = col..8, back substitution top-down in k); the
+// warp only spreads independent elements over lanes, which cannot change any rounding.
+__device__ bool solve8_warp(double (*a)[9], int lane) {
     for (int col = 0; col < 8; col++) {
         int piv = col;
         double best = fabs(a[col][col]);
-        for (int r = col + 1; r < 8; r++) {
-            double v = fabs(a[r][col]);
+        for (int r = col + 1; r < 8; r++) {  // 8 shared-memory reads, every lane the same: no divergence, no reduction to get wrong
+            const double v = fabs(a[r][col]);
             if (v > best) { best = v; piv = r; }
         }
         if (best == 0.0) return false;
-        if (piv != col)
-            for (int k = 0; k < 9; k++) { double t = a[col][k]; a[col][k] = a[piv][k]; a[piv][k] = t; }
-        for (int r = col + 1; r < 8; r++) {
-            double f = a[r][col] / a[col][col];
-            for (int k = col; k < 9; k++) a[r][k] = a[r][k] - f * a[col][k];
+        __syncwarp();
+        if (piv != col && lane < 9) { const double t = a[col][lane]; a[col][lane] = a[piv][lane]; a[piv][lane] = t; }
+        __syncwarp();
+        // rows col+1..7, columns col..8: element e -> (row, k); the factor is read before any element of the row changes
+        const int ncols = 9 - col, nelem = (7 - col) * ncols;
+        double f[2], arow[2], acol[2];
+        int rr[2], kk[2];
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+            const int e = lane + 32 * it;
+            rr[it] = -1;
+            if (e < nelem) {
+                rr[it] = col + 1 + e / ncols;
+                kk[it] = col + e % ncols;
+                f[it] = a[rr[it]][col] / a[col][col];
+                arow[it] = a[rr[it]][kk[it]];
+                acol[it] = a[col][kk[it]];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 2; it++)
+            if (rr[it] >= 0) a[rr[it]][kk[it]] = arow[it] - f[it] * acol[it];
+        __syncwarp();
+    }
+    if (lane == 0) {
+        for (int r = 7; r >= 0; r--) {
+            double s = a[r][8];
+            for (int k = r + 1; k < 8; k++) s = s - a[r][k] * a[k][8];
+            a[r][8] = s / a[r][r];
         }
     }
-    for (int r = 7; r >= 0; r--) {
-        double s = a[r][8];
-        for (int k = r + 1; k < 8; k++) s = s - a[r][k] * a[k][8];
-        a[r][8] = s / a[r][r];
-    }
+    __syncwarp();
     return true;
 }
 
-// Projection::from_control_points(quad, [(0,0),(h,0),(h,h),(0,h)]) followed by invert().
-__device__ void make_projection(const uint32_t *quad, float hs, Proj *out) {
-    const float to[8] = {0.0f, 0.0f, hs, 0.0f, hs, hs, 0.0f, hs};
-    double a[8][9];
-    for (int k = 0; k < 4; k++) {
-        double xf = (double)(float)quad[2 * k], yf = (double)(float)quad[2 * k + 1];
-        double x = (double)to[2 * k], y = (double)to[2 * k + 1];
-        double r0[9] = {0.0, 0.0, 0.0, -xf, -yf, -1.0, y * xf, y * yf, -y};
-        double r1[9] = {xf, yf, 1.0, 0.0, 0.0, 0.0, -x * xf, -x * yf, x};
-        for (int i = 0; i < 9; i++) { a[2 * k][i] = r0[i]; a[2 * k + 1][i] = r1[i]; }
+// Projection::from_control_points(quad, [(0,0),(h,0),(h,h),(0,h)]) followed by invert(), by one warp.
+__device__ void make_projection(const uint32_t *quad, float hs, double (*a)[9], Proj *out, int lane) {
+    if (lane < 8) {
+        const int k = lane >> 1;
+        const float to[8] = {0.0f, 0.0f, hs, 0.0f, hs, hs, 0.0f, hs};
+        const double xf = (double)(float)quad[2 * k], yf = (double)(float)quad[2 * k + 1];
+        const double x = (double)to[2 * k], y = (double)to[2 * k + 1];
+        if (lane & 1) {
+            const double r1[9] = {xf, yf, 1.0, 0.0, 0.0, 0.0, -x * xf, -x * yf, x};
+            for (int i = 0; i < 9; i++) a[lane][i] = r1[i];
+        } else {
+            const double r0[9] = {0.0, 0.0, 0.0, -xf, -yf, -1.0, y * xf, y * yf, -y};
+            for (int i = 0; i < 9; i++) a[lane][i] = r0[i];
+        }
     }
-    out->ok = 0;
-    if (!solve8(a)) return;
+    if (lane == 0) out->ok = 0;
+    __syncwarp();
+    const bool solved = solve8_warp(a, lane);
+    if (!solved || lane != 0) return;
     float t[9];
     for (int i = 0; i < 8; i++) t[i] = (float)a[i][8];
     t[8] = 1.0f;
@@ -139,6 +169,7 @@ __device__ __forceinline__ uint8_t sample(const uint8_t *grey, uint32_t w, uint3
 
 // Per-warp scratch in shared memory.
 struct WarpScratch {
+    double a[8][9];      // the 8x8 system of Projection::from_control_points with its right-hand side
     Proj proj;
     uint64_t codes[4];
     uint32_t hist[256];
@@ -148,7 +179,7 @@ __host__ __device__ inline uint32_t k2_warp_bytes(uint32_t ps, uint32_t ms) {
     return (b + 15) & ~15u;
 }
 
-__global__ void __launch_bounds__(kThreads) k2_kernel(const K2Params p, const uint32_t max_taps) {
+__global__ void __launch_bounds__(kThreads, 4) k2_kernel(const K2Params p, const uint32_t max_taps) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t ps = p.patch_size, ms = p.mark_size, np = ps * ps;
     // ---- carve: per CTA the dictionary and the resize taps, then one slice per warp ----
@@ -173,17 +204,29 @@ __global__ void __launch_bounds__(kThreads) k2_kernel(const K2Params p, const ui
     for (uint32_t q = blockIdx.x * kWarps + warp; q < p.n_quads; q += gridDim.x * kWarps) {
         const uint32_t frame = p.quad_frame ? p.quad_frame[q] : 0;
         const uint8_t *grey = p.grey + (size_t)frame * p.w * p.h;
-        if (lane == 0) make_projection(p.quads + (size_t)q * 8, (float)ps, &ws->proj);
+        make_projection(p.quads + (size_t)q * 8, (float)ps, ws->a, &ws->proj, lane);
         for (int i = lane; i < 256; i += 32) ws->hist[i] = 0;
         __syncwarp();
         const int ok = ws->proj.ok;
         uint32_t otsu_level = 0;
         if (ok) {
             // ---- warp: ps*ps bilinear samples, histogram on the fly ----
-            for (uint32_t i = lane; i < np; i += 32) {
-                const uint8_t v = sample(grey, p.w, p.h, ws->proj.inv, ws->proj.cls, i % ps, i / ps);
-                patch[i] = v;
-                atomicAdd(&ws->hist[v], 1u);
+            // four samples per lane in flight: the 16 gathers of a group are independent, so their latencies overlap
+            for (uint32_t base = lane; base < np; base += 128) {
+                uint8_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = base + 32 * u;
+                    v[u] = i < np ? sample(grey, p.w, p.h, ws->proj.inv, ws->proj.cls, i % ps, i / ps) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = base + 32 * u;
+                    if (i < np) {
+                        patch[i] = v[u];
+                        atomicAdd(&ws->hist[v[u]], 1u);
+                    }
+                }
             }
             __syncwarp();
             // ---- otsu_level: integer prefix sums are exact; the f64 expression keeps the reference's order ----
