@@ -515,6 +515,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
     const uint32_t Hp = h + 2;                               // guarded column-major plane: words per 32-pixel column
     const size_t plane_words = (size_t)(wpr + 2) * Hp;       // words per frame
     const uint32_t quad_cap = 1024;                          // quads per frame K3 can return (more -> host stage)
+    const uint32_t quad_head = 64;                           // quads per frame copied back unconditionally
     const uint32_t mn = w < h ? w : h;
     const uint32_t min_edge_length = (uint32_t)((float)mn * d->cfg.min_side_length_factor);   // src/aruco.rs:55
     const float min_corner_separation = (float)mn * d->cfg.min_corner_separation_factor;      // src/aruco.rs:56
@@ -602,8 +603,10 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                     A3_CUDA(cudaMemcpyAsync(d->h_k3flags.p + f0, d->d_k3flags.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
                     A3_CUDA(cudaMemcpyAsync(d->h_k3contours.p + f0, d->d_k3contours.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
                     A3_CUDA(cudaMemcpyAsync(d->h_k3points.p + f0, d->d_k3points.p + f0, (size_t)kn * 8, cudaMemcpyDeviceToHost, d->s_pixel));
-                    A3_CUDA(cudaMemcpyAsync(d->h_k3quads.p + (size_t)f0 * quad_cap * 8, d->d_k3quads.p + (size_t)f0 * quad_cap * 8,
-                                            (size_t)kn * quad_cap * 32, cudaMemcpyDeviceToHost, d->s_pixel));
+                    // the first `quad_head` quads of every frame in one strided copy; a frame with more fetches the rest itself
+                    A3_CUDA(cudaMemcpy2DAsync(d->h_k3quads.p + (size_t)f0 * quad_cap * 8, (size_t)quad_cap * 32,
+                                              d->d_k3quads.p + (size_t)f0 * quad_cap * 8, (size_t)quad_cap * 32, (size_t)quad_head * 32, kn,
+                                              cudaMemcpyDeviceToHost, d->s_pixel));
                 }
             } else {
                 A3_CUDA(cudaMemcpyAsync(d->h_bits.p + (size_t)f0 * bits_words, d->d_bits.p + (size_t)f0 * bits_words, (size_t)cn * bits_words * 4,
@@ -665,6 +668,11 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         auto take_k3_frame = [&](uint32_t i) -> a3_status {
             if (d->h_k3flags.p[i] == 0) {
                 const uint32_t m = d->h_k3counts.p[i];
+                if (m > quad_head) {  // rare (decode-stress scenes): the tail of this frame's quads
+                    A3_CUDA(cudaMemcpyAsync(d->h_k3quads.p + ((size_t)i * quad_cap + quad_head) * 8, d->d_k3quads.p + ((size_t)i * quad_cap + quad_head) * 8,
+                                            (size_t)(m - quad_head) * 32, cudaMemcpyDeviceToHost, d->s_decode));
+                    A3_CUDA(cudaStreamSynchronize(d->s_decode));
+                }
                 frame_quads[i].assign(d->h_k3quads.p + (size_t)i * quad_cap * 8, d->h_k3quads.p + (size_t)i * quad_cap * 8 + (size_t)m * 8);
                 frame_stats[i].n_contours = d->h_k3contours.p[i];
                 frame_stats[i].n_contour_points = d->h_k3points.p[i];
