@@ -110,7 +110,11 @@ struct K3Workspace {
     K3Workspace(const K3Workspace &) = delete;
     K3Workspace &operator=(const K3Workspace &) = delete;
 };
-cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream);  // synchronises the stream once (buffer sizing)
+cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream);  // k3_begin + k3_finish
+// The two halves, so that several batches (each with its own workspace and stream) can be in flight: k3_begin only
+// enqueues; k3_finish synchronises the stream once (buffer sizing) and enqueues the rest.
+cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream);
+cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream);
 
 // ---- host quad stage (host_quads.cpp) ---------------------------------------------------------------
 struct QuadStats {

@@ -635,6 +635,9 @@ struct K3Workspace::Impl {
     uint8_t *dead = nullptr;
     size_t dead_cap = 0;
     unsigned long long *h_counts = nullptr;  // pinned: [0] counters[0..1], [1] counters[2] (overflow), [2] long_points
+    Geo g;                                   // state handed from k3_begin to k3_finish
+    Lists l;
+    int sms = 148;
 };
 
 K3Workspace::K3Workspace() : impl(new Impl()) {}
@@ -704,6 +707,12 @@ struct PhaseTimer {
 };
 
 cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
+    cudaError_t e = k3_begin(ws, p, stream);
+    return e == cudaSuccess ? k3_finish(ws, p, stream) : e;
+}
+
+// First half: candidates and walks; ends with the asynchronous copy of the list counters to the host.
+cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     K3Workspace::Impl &w = *ws.impl;
     if (p.n == 0) return cudaSuccess;
     PhaseTimer timer(stream);
@@ -796,6 +805,20 @@ cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     K3_CUDA(cudaGetLastError());
     K3_CUDA(cudaMemcpyAsync(&w.h_counts[0], w.counters, 16, cudaMemcpyDeviceToHost, stream));
     K3_CUDA(cudaMemcpyAsync(&w.h_counts[2], w.long_points, 8, cudaMemcpyDeviceToHost, stream));
+    w.g = g; w.l = l; w.sms = sms;
+    return cudaSuccess;
+}
+
+// Second half: waits for the counters (the only host synchronisation of the stage), then sort, emission, polygon
+// simplification and the per-frame filters.
+cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
+    K3Workspace::Impl &w = *ws.impl;
+    if (p.n == 0) return cudaSuccess;
+    PhaseTimer timer(stream);
+    timer.mark("begin");
+    const Geo g = w.g;
+    const Lists l = w.l;
+    const size_t words_per_frame = (size_t)g.h * g.wpr, nwords = words_per_frame * p.n;
     K3_CUDA(cudaStreamSynchronize(stream));
     timer.mark("sync");
     const uint32_t *hc = reinterpret_cast<const uint32_t *>(&w.h_counts[0]);
