@@ -235,3 +235,120 @@ def detect_many(frames: np.ndarray, dict_name: str = "ARUCO", cfg: Config | None
     total = lib().a3ref_detect_many(C.byref(cfg), C.byref(d), frames.ctypes.data, fmt, n, w, h, frames.strides[1],
                                     frames.strides[0], threads, C.byref(st))
     return int(total), {f: getattr(st, f) for f, _ in Stats._fields_}
+
+
+# ---- pose step (oracle/a3ref_pose.c; src/pose.rs, src/pinhole.rs) ----------------------------------------------------
+class Pose(C.Structure):
+    _fields_ = [("error", C.c_float), ("rotation", C.c_float * 9), ("translation", C.c_float * 3)]
+
+    def as_tuple(self):
+        return (np.float32(self.error), np.array(self.rotation, np.float32).reshape(3, 3),
+                np.array(self.translation, np.float32))
+
+
+class Intrinsics(C.Structure):
+    _fields_ = [("image_width", C.c_uint32), ("image_height", C.c_uint32), ("focal_x", C.c_float),
+                ("focal_y", C.c_float), ("principal_x", C.c_float), ("principal_y", C.c_float)]
+
+
+_pose_ready = False
+
+
+def _pose_lib():
+    global _pose_ready
+    L = lib()
+    if not _pose_ready:
+        fp, PP = C.POINTER(C.c_float), C.POINTER(Pose)
+        L.a3ref_pose_default.argtypes = [PP]
+        L.a3ref_make_marker_square.argtypes = [C.c_float, fp]
+        L.a3ref_homography_from_marker_square.argtypes = [C.c_float, fp, fp]
+        L.a3ref_find_rotation_to_z.argtypes = [fp, fp]
+        L.a3ref_compute_rotations.argtypes = [fp, C.c_float, C.c_float, fp, fp]
+        L.a3ref_compute_translation.argtypes = [fp, fp, fp, fp]
+        L.a3ref_reprojection_error.restype = C.c_float
+        L.a3ref_reprojection_error.argtypes = [PP, fp, fp]
+        L.a3ref_solve_canonical_form.argtypes = [fp, fp, fp, PP, PP]
+        L.a3ref_solve_with_normalized_points.argtypes = [fp, C.c_float, PP, PP]
+        L.a3ref_solve_with_undistorted_points.argtypes = [C.POINTER(C.c_uint32), C.c_float, C.c_uint32, C.c_uint32, PP, PP]
+        L.a3ref_solve_with_intrinsics.argtypes = [C.POINTER(C.c_uint32), C.c_float, C.POINTER(Intrinsics), PP, PP]
+        L.a3ref_pose_apply.argtypes = [PP, fp, C.c_size_t, C.c_int, fp]
+        L.a3ref_intrinsics_new.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.c_float, fp, fp, C.POINTER(Intrinsics)]
+        L.a3ref_intrinsics_from_fov_horizontal.argtypes = [C.c_float, C.c_float, C.c_uint32, C.c_uint32,
+                                                           C.POINTER(Intrinsics)]
+        L.a3ref_project.argtypes = [C.POINTER(Intrinsics), C.c_float, C.c_float, C.c_float, fp]
+        L.a3ref_project_culled.argtypes = [C.POINTER(Intrinsics), C.c_float, C.c_float, C.c_float, fp]
+        L.a3ref_unproject.argtypes = [C.POINTER(Intrinsics), C.c_float, C.c_float, fp]
+        _pose_ready = True
+    return L
+
+
+def _f(values):
+    a = np.ascontiguousarray(values, np.float32).ravel()
+    return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def marker_square(size: float) -> np.ndarray:
+    out, po = _f(np.zeros(12))
+    _pose_lib().a3ref_make_marker_square(size, po)
+    return out.reshape(4, 3)
+
+
+def homography_from_marker_square(size: float, pts) -> np.ndarray:
+    p, pp = _f(pts)
+    out, po = _f(np.zeros(9))
+    _pose_lib().a3ref_homography_from_marker_square(size, pp, po)
+    return out.reshape(3, 3)
+
+
+def solve_canonical_form(size: float, pts):
+    sq, psq = _f(marker_square(size))
+    p, pp = _f(pts)
+    h, ph = _f(homography_from_marker_square(size, pts))
+    a, b = Pose(), Pose()
+    _pose_lib().a3ref_solve_canonical_form(psq, pp, ph, C.byref(a), C.byref(b))
+    return a, b
+
+
+def solve_with_normalized_points(pts, size: float):
+    p, pp = _f(pts)
+    a, b = Pose(), Pose()
+    _pose_lib().a3ref_solve_with_normalized_points(pp, size, C.byref(a), C.byref(b))
+    return a, b
+
+
+def solve_with_undistorted_points(corners, size: float, image_size):
+    c = np.ascontiguousarray(corners, np.uint32).ravel()
+    a, b = Pose(), Pose()
+    _pose_lib().a3ref_solve_with_undistorted_points(c.ctypes.data_as(C.POINTER(C.c_uint32)), size, image_size[0],
+                                                    image_size[1], C.byref(a), C.byref(b))
+    return a, b
+
+
+def solve_with_intrinsics(corners, size: float, k: Intrinsics):
+    c = np.ascontiguousarray(corners, np.uint32).ravel()
+    a, b = Pose(), Pose()
+    _pose_lib().a3ref_solve_with_intrinsics(c.ctypes.data_as(C.POINTER(C.c_uint32)), size, C.byref(k), C.byref(a),
+                                            C.byref(b))
+    return a, b
+
+
+def pose_apply(pose: Pose, pts, inverse: bool = False) -> np.ndarray:
+    p, pp = _f(pts)
+    out, po = _f(np.zeros(p.size))
+    _pose_lib().a3ref_pose_apply(C.byref(pose), pp, p.size // 3, int(inverse), po)
+    return out.reshape(-1, 3)
+
+
+def intrinsics_new(w, h, fx, fy, px=None, py=None) -> Intrinsics:
+    k = Intrinsics()
+    cx = C.byref(C.c_float(px)) if px is not None else None
+    cy = C.byref(C.c_float(py)) if py is not None else None
+    _pose_lib().a3ref_intrinsics_new(w, h, fx, fy, C.cast(cx, C.POINTER(C.c_float)) if cx else None,
+                                     C.cast(cy, C.POINTER(C.c_float)) if cy else None, C.byref(k))
+    return k
+
+
+def intrinsics_from_fov_horizontal(hfov, sensor_w, rx, ry) -> Intrinsics:
+    k = Intrinsics()
+    _pose_lib().a3ref_intrinsics_from_fov_horizontal(hfov, sensor_w, rx, ry, C.byref(k))
+    return k
