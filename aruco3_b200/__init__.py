@@ -7,5 +7,7 @@ workload generator.  No CPU fallback exists anywhere in this package.
 from .detector import (ARDictionary, Detection, Detector, DetectorConfig, Marker, hamming_distance,  # noqa: F401
                        quads_from_mask)
 from ._ffi import A3Error  # noqa: F401
+from . import pose  # noqa: F401
+from .pose import CameraIntrinsics, MarkerPose  # noqa: F401
 
 __version__ = "0.1.0"

@@ -14,6 +14,7 @@ A3_OK, A3_ERR_INVALID_ARGUMENT, A3_ERR_UNKNOWN_DICTIONARY, A3_ERR_CUDA, A3_ERR_C
 FMT_RGB8, FMT_RGBA8, FMT_LUMA8 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 CONTOURS_HOST, CONTOURS_DEVICE = 0, 1
+POSE_OFF, POSE_UNDISTORTED, POSE_INTRINSICS, POSE_NORMALIZED = 0, 1, 2, 3
 
 
 class A3Config(C.Structure):
@@ -45,16 +46,25 @@ class A3Stats(C.Structure):
                [(n, C.c_double) for n in ("ms_h2d", "ms_pixel_kernel", "ms_contour_kernels", "ms_mask_d2h", "ms_host_quads",
                                           "ms_decode_kernel", "ms_host_cpu", "ms_total")] + \
                [(n, C.c_uint32) for n in ("pixel_kernel_launches", "decode_kernel_launches", "host_threads", "contour_kernel_launches",
-                                          "host_fallback_frames", "reserved")]
+                                          "host_fallback_frames", "pose_kernel_launches")]
 
     def as_dict(self):
-        return {f: getattr(self, f) for f, _ in self._fields_ if f != "reserved"}
+        return {f: getattr(self, f) for f, _ in self._fields_}
 
 
 class A3Outputs(C.Structure):
     _fields_ = [("grey", C.c_void_p), ("mask", C.c_void_p), ("candidates", C.c_void_p), ("candidate_frame", C.c_void_p),
                 ("homographies", C.c_void_p), ("decodes", C.c_void_p), ("cand_capacity", C.c_uint32),
-                ("n_candidates", C.c_uint32), ("frame_marker_offsets", C.c_void_p)]
+                ("n_candidates", C.c_uint32), ("frame_marker_offsets", C.c_void_p), ("marker_poses", C.c_void_p)]
+
+
+class A3Pose(C.Structure):
+    _fields_ = [("error", C.c_float), ("rotation", C.c_float * 9), ("translation", C.c_float * 3)]
+
+
+class A3CameraIntrinsics(C.Structure):
+    _fields_ = [("image_width", C.c_uint32), ("image_height", C.c_uint32), ("focal_x", C.c_float), ("focal_y", C.c_float),
+                ("principal_x", C.c_float), ("principal_y", C.c_float)]
 
 
 class A3K1Tuning(C.Structure):
@@ -123,6 +133,25 @@ def lib():
     L.a3_quads_from_mask.argtypes = [C.POINTER(A3Config), vp, u32, u32, vp, u32, C.POINTER(u32), C.POINTER(A3Stats)]
     L.a3_quads_from_masks_device.argtypes = [vp, vp, u32, u32, u32, vp, u32, vp, vp, vp, vp]
     L.a3_decode_candidates.argtypes = [vp, vp, u32, u32, u32, vp, vp, u32, vp, vp]
+    fp, f32, PK, PP = C.POINTER(C.c_float), C.c_float, C.POINTER(A3CameraIntrinsics), C.POINTER(A3Pose)
+    L.a3_detector_set_pose.argtypes = [vp, u32, f32, PK]
+    L.a3_solve_with_intrinsics.argtypes = [vp, vp, u32, f32, PK, vp, vp]
+    L.a3_solve_with_undistorted_points.argtypes = [vp, vp, u32, f32, u32, u32, vp, vp]
+    L.a3_solve_with_normalized_points.argtypes = [vp, vp, u32, f32, vp, vp]
+    L.a3_pose_default.restype = None
+    L.a3_pose_default.argtypes = [PP]
+    L.a3_pose_apply_transform.restype = None
+    L.a3_pose_apply_transform.argtypes = [PP, vp, u32, C.c_int32, vp]
+    L.a3_camera_intrinsics_new.restype = None
+    L.a3_camera_intrinsics_new.argtypes = [u32, u32, f32, f32, fp, fp, PK]
+    L.a3_camera_intrinsics_from_fov_horizontal.restype = None
+    L.a3_camera_intrinsics_from_fov_horizontal.argtypes = [f32, f32, u32, u32, PK]
+    L.a3_camera_project.restype = None
+    L.a3_camera_project.argtypes = [PK, f32, f32, f32, fp]
+    L.a3_camera_project_culled.restype = C.c_int32
+    L.a3_camera_project_culled.argtypes = [PK, f32, f32, f32, fp]
+    L.a3_camera_unproject.restype = None
+    L.a3_camera_unproject.argtypes = [PK, f32, f32, fp]
     _lib = L
     return L
 

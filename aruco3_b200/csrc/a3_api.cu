@@ -137,10 +137,13 @@ struct DecodeBlock {
     DevBuf<uint32_t> d_quads, d_qframe;
     DevBuf<a3_decode> d_dec;
     DevBuf<uint8_t> d_patches;
+    DevBuf<a3_pose> d_pose;   // K4: two poses per quad (written for accepted candidates only)
+    PinBuf<a3_pose> h_pose;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     uint32_t n_quads = 0;
     void release() {
         h_quads.release(); h_qframe.release(); h_dec.release(); d_quads.release(); d_qframe.release(); d_dec.release(); d_patches.release();
+        d_pose.release(); h_pose.release();
         for (cudaEvent_t *e : {&ev_a, &ev_b}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
     }
 };
@@ -195,6 +198,13 @@ struct a3_detector {
     a3::PinBuf<unsigned long long> h_k3points;
     size_t planes_zeroed_words = 0;
     uint32_t planes_w = 0, planes_h = 0;
+    // pose step (K4)
+    uint32_t pose_mode = A3_POSE_OFF;
+    float pose_marker_size = 0.0f;
+    a3_camera_intrinsics pose_k{};
+    a3::DevBuf<float> d_pose_in;      // standalone solve entry points: 8 x 4 bytes per marker (f32 points or u32 corners)
+    a3::DevBuf<a3_pose> d_pose_out;
+    a3::PinBuf<a3_pose> h_pose_out;
 };
 
 namespace a3 {
@@ -309,6 +319,7 @@ void a3_detector_destroy(a3_detector *d) {
     d->d_planes.release(); d->d_k3quads.release(); d->d_k3counts.release(); d->d_k3before.release(); d->d_k3flags.release();
     d->d_k3contours.release(); d->d_k3points.release(); d->h_k3quads.release(); d->h_k3counts.release(); d->h_k3before.release();
     d->h_k3flags.release(); d->h_k3contours.release(); d->h_k3points.release(); d->h_plane.release();
+    d->d_pose_in.release(); d->d_pose_out.release(); d->h_pose_out.release();
     d->events.release();
     for (auto &b : d->blocks) b->release();
     delete d;
@@ -488,6 +499,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
     const size_t px = (size_t)w * h, wpr = (w + 31) / 32, bits_words = wpr * h;
     const size_t np = (size_t)d->cfg.homography_sample_size * d->cfg.homography_sample_size;
     const bool want_mask = outs && outs->mask, want_grey = outs && outs->grey, want_patches = outs && outs->homographies;
+    const bool want_poses = outs && outs->marker_poses && markers && d->pose_mode != A3_POSE_OFF;
     const K1Tuning *tune = d->has_tuning ? &d->k1_tuning : nullptr;
     const uint8_t *src_all = static_cast<const uint8_t *>(frames);
     a3_stats st;
@@ -721,6 +733,15 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             A3_CUDA(cudaEventRecord(b.ev_b, d->s_decode));
             st.decode_kernel_launches++;
             A3_CUDA(cudaMemcpyAsync(b.h_dec.p, b.d_dec.p, (size_t)nq * sizeof(a3_decode), cudaMemcpyDeviceToHost, d->s_decode));
+            if (want_poses) {  // K4 right behind K2, on K2's records and the quads where they lie
+                A3_CUDA(b.d_pose.reserve((size_t)nq * 2)); A3_CUDA(b.h_pose.reserve((size_t)nq * 2));
+                K4Params kp{};
+                kp.mode = d->pose_mode; kp.corners = b.d_quads.p; kp.decodes = b.d_dec.p; kp.n = nq; kp.marker_size = d->pose_marker_size;
+                kp.image_w = w; kp.image_h = h; kp.k = d->pose_k; kp.poses = b.d_pose.p;
+                A3_CUDA(k4_pose(kp, d->s_decode));
+                st.pose_kernel_launches++;
+                A3_CUDA(cudaMemcpyAsync(b.h_pose.p, b.d_pose.p, (size_t)nq * 2 * sizeof(a3_pose), cudaMemcpyDeviceToHost, d->s_decode));
+            }
             return A3_OK;
         };
         auto drain = [&](a3_status s) {  // an error: let the pool and the streams finish before the buffers go away
@@ -820,6 +841,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                             mk.corners[2 * cidx] = q[2 * sidx];
                             mk.corners[2 * cidx + 1] = q[2 * sidx + 1];
                         }
+                        if (want_poses) memcpy(outs->marker_poses + (size_t)total_markers * 2, b.h_pose.p + (size_t)k * 2, 2 * sizeof(a3_pose));
                     } else {
                         overflow = true;
                     }
@@ -837,6 +859,106 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
     if (stats) *stats = st;
     if (overflow) return fail(A3_ERR_CAPACITY, "a3_detect_batch: output capacity too small (counts are valid)");
     return A3_OK;
+}
+
+// ---- pose step (src/pose.rs, src/pinhole.rs) ----------------------------------------------------------------------
+
+a3_status a3_detector_set_pose(a3_detector *d, uint32_t mode, float marker_size_mm, const a3_camera_intrinsics *k) {
+    if (!d) return fail(A3_ERR_INVALID_ARGUMENT, "a3_detector_set_pose: null detector");
+    if (mode != A3_POSE_OFF && mode != A3_POSE_UNDISTORTED && mode != A3_POSE_INTRINSICS)
+        return fail(A3_ERR_INVALID_ARGUMENT, "a3_detector_set_pose: mode must be OFF, UNDISTORTED or INTRINSICS");
+    if (mode == A3_POSE_INTRINSICS && !k) return fail(A3_ERR_INVALID_ARGUMENT, "a3_detector_set_pose: intrinsics required");
+    d->pose_mode = mode;
+    d->pose_marker_size = marker_size_mm;
+    if (k) d->pose_k = *k;
+    return A3_OK;
+}
+
+static a3_status solve_poses(a3_detector *d, uint32_t mode, const void *in, uint32_t n, float marker_size_mm, uint32_t iw, uint32_t ih,
+                             const a3_camera_intrinsics *k, a3_pose *best, a3_pose *alt) {
+    if (!d || (n && (!in || !best || !alt))) return fail(A3_ERR_INVALID_ARGUMENT, "a3_solve_*: null argument");
+    if (mode == A3_POSE_INTRINSICS && !k) return fail(A3_ERR_INVALID_ARGUMENT, "a3_solve_with_intrinsics: null intrinsics");
+    if (n == 0) return A3_OK;
+    A3_CUDA(cudaSetDevice(d->device));
+    cudaStream_t s = d->s_decode;
+    A3_CUDA(d->d_pose_in.reserve((size_t)n * 8)); A3_CUDA(d->d_pose_out.reserve((size_t)n * 2)); A3_CUDA(d->h_pose_out.reserve((size_t)n * 2));
+    A3_CUDA(cudaMemcpyAsync(d->d_pose_in.p, in, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    K4Params kp{};
+    kp.mode = mode; kp.n = n; kp.marker_size = marker_size_mm; kp.image_w = iw; kp.image_h = ih; kp.poses = d->d_pose_out.p;
+    if (mode == A3_POSE_NORMALIZED) kp.points = d->d_pose_in.p;
+    else kp.corners = reinterpret_cast<const uint32_t *>(d->d_pose_in.p);
+    if (k) kp.k = *k;
+    A3_CUDA(k4_pose(kp, s));
+    A3_CUDA(cudaMemcpyAsync(d->h_pose_out.p, d->d_pose_out.p, (size_t)n * 2 * sizeof(a3_pose), cudaMemcpyDeviceToHost, s));
+    A3_CUDA(cudaStreamSynchronize(s));
+    for (uint32_t i = 0; i < n; i++) { best[i] = d->h_pose_out.p[2 * (size_t)i]; alt[i] = d->h_pose_out.p[2 * (size_t)i + 1]; }
+    return A3_OK;
+}
+
+a3_status a3_solve_with_intrinsics(a3_detector *d, const uint32_t *corners, uint32_t n, float marker_size_mm, const a3_camera_intrinsics *k,
+                                   a3_pose *best, a3_pose *alt) {
+    return solve_poses(d, A3_POSE_INTRINSICS, corners, n, marker_size_mm, 0, 0, k, best, alt);
+}
+a3_status a3_solve_with_undistorted_points(a3_detector *d, const uint32_t *corners, uint32_t n, float marker_size_mm, uint32_t image_width,
+                                           uint32_t image_height, a3_pose *best, a3_pose *alt) {
+    return solve_poses(d, A3_POSE_UNDISTORTED, corners, n, marker_size_mm, image_width, image_height, nullptr, best, alt);
+}
+a3_status a3_solve_with_normalized_points(a3_detector *d, const float *points, uint32_t n, float marker_size_mm, a3_pose *best, a3_pose *alt) {
+    return solve_poses(d, A3_POSE_NORMALIZED, points, n, marker_size_mm, 0, 0, nullptr, best, alt);
+}
+
+void a3_pose_default(a3_pose *p) {
+    if (!p) return;
+    p->error = 1e31f;
+    for (int i = 0; i < 9; i++) p->rotation[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+    p->translation[0] = p->translation[1] = p->translation[2] = 0.0f;
+}
+
+// R*p + t, or R^T*(p - t); products accumulate column by column as nalgebra's gemv does
+void a3_pose_apply_transform(const a3_pose *p, const float *pts, uint32_t n, int32_t inverse, float *out) {
+    if (!p || !pts || !out) return;
+    const float *R = p->rotation, *t = p->translation;
+    for (uint32_t i = 0; i < n; i++) {
+        const float *v = pts + 3 * (size_t)i;
+        float *o = out + 3 * (size_t)i;
+        if (!inverse) {
+            for (int r = 0; r < 3; r++) o[r] = (R[r * 3 + 2] * v[2] + (R[r * 3 + 1] * v[1] + R[r * 3] * v[0])) + t[r];
+        } else {
+            const float dv[3] = {v[0] - t[0], v[1] - t[1], v[2] - t[2]};
+            for (int r = 0; r < 3; r++) o[r] = R[6 + r] * dv[2] + (R[3 + r] * dv[1] + R[r] * dv[0]);
+        }
+    }
+}
+
+void a3_camera_intrinsics_new(uint32_t iw, uint32_t ih, float fx, float fy, const float *px, const float *py, a3_camera_intrinsics *out) {
+    if (!out) return;
+    *out = a3_camera_intrinsics{iw, ih, fx, fy, px ? *px : (float)iw / 2.0f, py ? *py : (float)ih / 2.0f};
+}
+
+void a3_camera_intrinsics_from_fov_horizontal(float hfov, float sensor_w, uint32_t rx, uint32_t ry, a3_camera_intrinsics *out) {
+    if (!out) return;
+    const float aspect = (float)rx / (float)ry;
+    const float vfov = hfov / aspect, sensor_h = sensor_w / aspect;
+    *out = a3_camera_intrinsics{rx, ry, (sensor_w * 0.5f) / tanf(hfov * 0.5f), (sensor_h * 0.5f) / tanf(vfov * 0.5f), (float)rx * 0.5f,
+                                (float)ry * 0.5f};
+}
+
+void a3_camera_project(const a3_camera_intrinsics *k, float x, float y, float z, float out[3]) {
+    out[0] = (x * k->focal_x) + (z * k->principal_x);
+    out[1] = (y * k->focal_y) + (z * k->principal_y);
+    out[2] = z;
+}
+
+int32_t a3_camera_project_culled(const a3_camera_intrinsics *k, float x, float y, float z, float out[2]) {
+    if (z <= 0.0f) return 0;
+    out[0] = (x * k->focal_x) / z + k->principal_x;
+    out[1] = (y * k->focal_y) / z + k->principal_y;
+    return 1;
+}
+
+void a3_camera_unproject(const a3_camera_intrinsics *k, float x, float y, float out[2]) {
+    out[0] = (x - k->principal_x) / k->focal_x;
+    out[1] = (y - k->principal_y) / k->focal_y;
 }
 
 }  // extern "C"

@@ -116,6 +116,20 @@ cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream);  
 cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream);
 cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream);
 
+// ---- K4: marker pose from four corners (k4_pose.cu) --------------------------------------------------------------
+struct K4Params {
+    uint32_t mode;               // A3_POSE_UNDISTORTED / A3_POSE_INTRINSICS (corners) or A3_POSE_NORMALIZED (points)
+    const float *points;         // device n*8 (NORMALIZED)
+    const uint32_t *corners;     // device n*8 (other modes)
+    const a3_decode *decodes;    // device n or null; when set: only accepted items, corners.rotate_left(rotation)
+    uint32_t n;
+    float marker_size;
+    uint32_t image_w, image_h;   // UNDISTORTED
+    a3_camera_intrinsics k;      // INTRINSICS
+    a3_pose *poses;              // device n*2: [2i] best, [2i+1] alternative
+};
+cudaError_t k4_pose(const K4Params &p, cudaStream_t stream);
+
 // ---- host quad stage (host_quads.cpp) ---------------------------------------------------------------
 struct QuadStats {
     uint64_t n_contours = 0, n_contour_points = 0, n_before_discard = 0;

@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _ffi
-from ._ffi import A3Config, A3Decode, A3Dictionary, A3Error, A3Marker, A3Outputs, A3Stats, check, lib
+from ._ffi import A3Config, A3Decode, A3Dictionary, A3Error, A3Marker, A3Outputs, A3Pose, A3Stats, check, lib
 
 
 @dataclass
@@ -97,6 +97,7 @@ class Marker:
     hamming_distance: int
     rotation: int = 0
     candidate: int = 0
+    poses: tuple | None = None   # (best, alt) MarkerPose when the detector has a pose mode (Detector.set_pose)
 
 
 @dataclass
@@ -150,6 +151,20 @@ class Detector:
         # where find_contours + the quad filters run: "device" (kernel K3, host redo of flagged frames) or "host"
         check(lib().a3_detector_set_contour_mode(self._h, {"host": _ffi.CONTOURS_HOST, "device": _ffi.CONTOURS_DEVICE}[contours]))
         self.last_stats: dict = {}
+        self._pose_mode = _ffi.POSE_OFF
+
+    def set_pose(self, marker_size_mm: float | None, camera_intrinsics=None):
+        """Also solve every marker's pose pair inside `detect` / `detect_batch` (kernel K4 behind the decode kernel):
+        `pose::solve_with_intrinsics(&m.corners, size, &k)` when `camera_intrinsics` is given
+        (examples/macroquad_detect.rs:150), else `pose::solve_with_undistorted_points(&m.corners, size, (w, h))`
+        (examples/webcam_kamera.rs:68).  `marker_size_mm=None` switches it off."""
+        if marker_size_mm is None:
+            mode = _ffi.POSE_OFF
+        else:
+            mode = _ffi.POSE_INTRINSICS if camera_intrinsics is not None else _ffi.POSE_UNDISTORTED
+        check(lib().a3_detector_set_pose(self._h, mode, marker_size_mm or 0.0,
+                                         C.byref(camera_intrinsics._c) if camera_intrinsics is not None else None))
+        self._pose_mode = mode
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -189,6 +204,10 @@ class Detector:
             offsets = np.zeros(n + 1, np.uint32)
             outs.frame_marker_offsets = offsets.ctypes.data
             keep = []
+            poses = None
+            if self._pose_mode != _ffi.POSE_OFF:
+                poses = (A3Pose * (2 * cap_m))()
+                outs.marker_poses = C.cast(poses, C.c_void_p).value
             if full:
                 grey = np.empty((n, h, w), np.uint8)
                 cands = np.zeros((cap_c, 8), np.uint32)
@@ -220,6 +239,9 @@ class Detector:
             m = markers[i]
             dets[m.frame].markers.append(Marker(int(m.id), int(m.code), [(int(m.corners[2 * k]), int(m.corners[2 * k + 1])) for k in range(4)],
                                                 int(m.hamming_distance), int(m.rotation), int(m.candidate)))
+            if poses is not None:
+                from .pose import MarkerPose
+                dets[m.frame].markers[-1].poses = (MarkerPose.from_c(poses[2 * i]), MarkerPose.from_c(poses[2 * i + 1]))
         if full:
             for f in range(n):
                 dets[f].grey = grey[f]

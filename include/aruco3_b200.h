@@ -99,8 +99,30 @@ typedef struct a3_stats {
     double ms_h2d, ms_pixel_kernel, ms_contour_kernels, ms_mask_d2h, ms_host_quads, ms_decode_kernel, ms_host_cpu, ms_total;
     uint32_t pixel_kernel_launches, decode_kernel_launches, host_threads, contour_kernel_launches;
     uint32_t host_fallback_frames; /* device contour stage: frames it handed back to the host stage */
-    uint32_t reserved;
+    uint32_t pose_kernel_launches; /* K4 launches (a3_detector_set_pose) */
 } a3_stats;
+
+/* MarkerPose (src/pose.rs:8-12): scene-from-marker transform in OpenCV chirality (+Z forward, +Y down, +X right).
+ * rotation is row-major (m11 m12 m13 m21 ...).  Default (src/pose.rs:42-50): error 1e31, identity, zero. */
+typedef struct a3_pose {
+    float error;
+    float rotation[9];
+    float translation[3];
+} a3_pose;
+
+/* CameraIntrinsics, field for field (src/pinhole.rs:11-18). */
+typedef struct a3_camera_intrinsics {
+    uint32_t image_width, image_height;
+    float focal_x, focal_y, principal_x, principal_y;
+} a3_camera_intrinsics;
+
+/* How image corners become the normalised points the pose solver works on. */
+enum {
+    A3_POSE_OFF = 0,
+    A3_POSE_UNDISTORTED = 1, /* solve_with_undistorted_points: (x / image_w, y / image_h), src/pose.rs:59-62 */
+    A3_POSE_INTRINSICS = 2,  /* solve_with_intrinsics: CameraIntrinsics::unproject, src/pose.rs:52-55           */
+    A3_POSE_NORMALIZED = 3   /* solve_with_normalized_points: f32 points used as they are, src/pose.rs:64-81   */
+};
 
 /* Optional per-call outputs of a3_detect_batch (all may be NULL). Host pointers; tightly packed. */
 typedef struct a3_outputs {
@@ -113,6 +135,8 @@ typedef struct a3_outputs {
     uint32_t cand_capacity;
     uint32_t n_candidates;      /* out */
     uint32_t *frame_marker_offsets; /* n+1: markers of frame f are [off[f], off[f+1]) (may be NULL) */
+    a3_pose *marker_poses;      /* marker_capacity*2: [2i] best and [2i+1] alternative pose of markers[i]; filled when
+                                 * the detector has a pose mode (a3_detector_set_pose), may be NULL */
 } a3_outputs;
 
 typedef struct a3_detector a3_detector;
@@ -195,6 +219,37 @@ a3_status a3_quads_from_masks_device(a3_detector *det, const uint8_t *masks, uin
 a3_status a3_decode_candidates(a3_detector *det, const uint8_t *grey, uint32_t n_frames, uint32_t width,
                                uint32_t height, const uint32_t *quads, const uint32_t *quad_frame, uint32_t n_quads,
                                a3_decode *decodes, uint8_t *patches);
+
+/* ---- pose (src/pose.rs, src/pinhole.rs): the step after detect in the reference's examples ---- */
+
+/* Make a3_detect_batch also solve the pose pair of every marker on the device (kernel K4, queued behind K2) into
+ * a3_outputs.marker_poses.  mode: A3_POSE_OFF, A3_POSE_UNDISTORTED (image size = the frame size, as
+ * examples/webcam_kamera.rs:68 calls it) or A3_POSE_INTRINSICS (k required, examples/macroquad_detect.rs:150). */
+a3_status a3_detector_set_pose(a3_detector *det, uint32_t mode, float marker_size_mm, const a3_camera_intrinsics *k);
+
+/* pose::solve_with_intrinsics / solve_with_undistorted_points / solve_with_normalized_points over n markers at once
+ * (src/pose.rs:52-81).  HOST pointers; corners n*8 u32 (x0,y0..x3,y3, clockwise from the marker's top-left, i.e.
+ * a3_marker.corners), points n*8 f32; best / alt: n poses each, best has the smaller reprojection error. */
+a3_status a3_solve_with_intrinsics(a3_detector *det, const uint32_t *corners, uint32_t n, float marker_size_mm,
+                                   const a3_camera_intrinsics *k, a3_pose *best, a3_pose *alt);
+a3_status a3_solve_with_undistorted_points(a3_detector *det, const uint32_t *corners, uint32_t n, float marker_size_mm,
+                                           uint32_t image_width, uint32_t image_height, a3_pose *best, a3_pose *alt);
+a3_status a3_solve_with_normalized_points(a3_detector *det, const float *points, uint32_t n, float marker_size_mm,
+                                          a3_pose *best, a3_pose *alt);
+
+/* Plain host helpers (constructors and one-point conversions; nothing here is on the hot path). */
+void a3_pose_default(a3_pose *p);                                                   /* src/pose.rs:42-50        */
+/* apply_transform_to_points / apply_inverse_transform_to_points (src/pose.rs:17-39); points and out: n*3 f32 */
+void a3_pose_apply_transform(const a3_pose *p, const float *points, uint32_t n, int32_t inverse, float *out);
+/* CameraIntrinsics::new (src/pinhole.rs:26-35); principal_x / principal_y may be NULL (= image centre) */
+void a3_camera_intrinsics_new(uint32_t image_width, uint32_t image_height, float focal_x, float focal_y,
+                              const float *principal_x, const float *principal_y, a3_camera_intrinsics *out);
+/* CameraIntrinsics::new_from_fov_horizontal (src/pinhole.rs:37-60) */
+void a3_camera_intrinsics_from_fov_horizontal(float horizontal_fov_radians, float sensor_width_mm, uint32_t resolution_x,
+                                              uint32_t resolution_y, a3_camera_intrinsics *out);
+void a3_camera_project(const a3_camera_intrinsics *k, float x, float y, float z, float out[3]);        /* :65-71 */
+int32_t a3_camera_project_culled(const a3_camera_intrinsics *k, float x, float y, float z, float out[2]); /* :76-84 */
+void a3_camera_unproject(const a3_camera_intrinsics *k, float x, float y, float out[2]);               /* :88-93 */
 
 #ifdef __cplusplus
 }

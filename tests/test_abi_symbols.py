@@ -47,15 +47,16 @@ def test_struct_layouts_match_header(tmp_path):
     from aruco3_b200 import _ffi
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "aruco3_b200.h"\nint main(void){'
-                   'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(a3_config), sizeof(a3_dictionary), sizeof(a3_marker), sizeof(a3_decode),'
-                   ' sizeof(a3_stats), sizeof(a3_outputs), sizeof(a3_k1_tuning));'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(a3_config), sizeof(a3_dictionary), sizeof(a3_marker), sizeof(a3_decode),'
+                   ' sizeof(a3_stats), sizeof(a3_outputs), sizeof(a3_k1_tuning), sizeof(a3_pose), sizeof(a3_camera_intrinsics));'
                    'printf("%zu %zu %zu %zu\\n", offsetof(a3_marker, frame), offsetof(a3_decode, has_codes), offsetof(a3_stats, ms_h2d),'
                    ' offsetof(a3_outputs, frame_marker_offsets)); return 0; }\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     sizes = [int(v) for v in out]
-    want = [C.sizeof(t) for t in (_ffi.A3Config, _ffi.A3Dictionary, _ffi.A3Marker, _ffi.A3Decode, _ffi.A3Stats, _ffi.A3Outputs, _ffi.A3K1Tuning)]
+    want = [C.sizeof(t) for t in (_ffi.A3Config, _ffi.A3Dictionary, _ffi.A3Marker, _ffi.A3Decode, _ffi.A3Stats, _ffi.A3Outputs, _ffi.A3K1Tuning,
+                                  _ffi.A3Pose, _ffi.A3CameraIntrinsics)]
     want += [_ffi.A3Marker.frame.offset, _ffi.A3Decode.has_codes.offset, _ffi.A3Stats.ms_h2d.offset, _ffi.A3Outputs.frame_marker_offsets.offset]
     assert sizes == want
 
