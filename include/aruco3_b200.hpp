@@ -5,11 +5,13 @@
 //   DetectorConfig   /root/reference/src/aruco.rs:23-43        Detector    /root/reference/src/aruco.rs:46-52
 //   Detection        /root/reference/src/aruco.rs:16-21        Marker      /root/reference/src/aruco.rs:8-13
 //   ARDictionary     /root/reference/src/dictionaries.rs:22-28, 115-232
+//   MarkerPose, pose::solve_with_*   /root/reference/src/pose.rs:8-81     CameraIntrinsics  /root/reference/src/pinhole.rs:11-94
 // Where the reference panics (unknown dictionary name, threshold_window == 0, epsilon <= 0) this mirror throws
 // aruco3::Error.  Link with -laruco3_b200.  No CPU fallback: constructing a Detector without a CUDA device throws.
 #ifndef ARUCO3_B200_HPP
 #define ARUCO3_B200_HPP
 
+#include <array>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -207,6 +209,115 @@ private:
     int device_ = 0;
     a3_detector *h_ = nullptr;
 };
+
+// src/pinhole.rs:11-18
+struct CameraIntrinsics {
+    uint32_t image_width = 0, image_height = 0;
+    float focal_x = 0, focal_y = 0, principal_x = 0, principal_y = 0;
+
+    CameraIntrinsics() = default;
+    // CameraIntrinsics::new (src/pinhole.rs:26-35); a null principal point is the image centre (Option::None)
+    CameraIntrinsics(uint32_t w, uint32_t h, float fx, float fy, const float *px = nullptr, const float *py = nullptr) {
+        a3_camera_intrinsics k;
+        a3_camera_intrinsics_new(w, h, fx, fy, px, py, &k);
+        *this = from_c(k);
+    }
+    // src/pinhole.rs:37-60
+    static CameraIntrinsics new_from_fov_horizontal(float horizontal_fov_radians, float sensor_width_mm, uint32_t resolution_x, uint32_t resolution_y) {
+        a3_camera_intrinsics k;
+        a3_camera_intrinsics_from_fov_horizontal(horizontal_fov_radians, sensor_width_mm, resolution_x, resolution_y, &k);
+        return from_c(k);
+    }
+    std::array<float, 3> project(float x, float y, float z) const {  // :65-71
+        std::array<float, 3> o{};
+        const a3_camera_intrinsics k = c();
+        a3_camera_project(&k, x, y, z, o.data());
+        return o;
+    }
+    bool project_culled(float x, float y, float z, std::pair<float, float> *out) const {  // :76-84 (Option -> bool)
+        float o[2];
+        const a3_camera_intrinsics k = c();
+        if (!a3_camera_project_culled(&k, x, y, z, o)) return false;
+        if (out) *out = {o[0], o[1]};
+        return true;
+    }
+    std::pair<float, float> unproject(float x, float y) const {  // :88-93
+        float o[2];
+        const a3_camera_intrinsics k = c();
+        a3_camera_unproject(&k, x, y, o);
+        return {o[0], o[1]};
+    }
+    a3_camera_intrinsics c() const { return a3_camera_intrinsics{image_width, image_height, focal_x, focal_y, principal_x, principal_y}; }
+    static CameraIntrinsics from_c(const a3_camera_intrinsics &k) {
+        CameraIntrinsics r;
+        r.image_width = k.image_width; r.image_height = k.image_height; r.focal_x = k.focal_x; r.focal_y = k.focal_y;
+        r.principal_x = k.principal_x; r.principal_y = k.principal_y;
+        return r;
+    }
+};
+
+// src/pose.rs:8-12; Default src/pose.rs:42-50.  rotation is row-major.
+struct MarkerPose {
+    float error = 1e31f;
+    std::array<float, 9> rotation{{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+    std::array<float, 3> translation{{0, 0, 0}};
+
+    using Point3 = std::array<float, 3>;
+    std::vector<Point3> apply_transform_to_points(const std::vector<Point3> &points) const { return apply(points, 0); }          // :17-28
+    std::vector<Point3> apply_inverse_transform_to_points(const std::vector<Point3> &points) const { return apply(points, 1); }  // :30-39
+    static MarkerPose from_c(const a3_pose &p) {
+        MarkerPose m;
+        m.error = p.error;
+        for (int i = 0; i < 9; i++) m.rotation[i] = p.rotation[i];
+        for (int i = 0; i < 3; i++) m.translation[i] = p.translation[i];
+        return m;
+    }
+
+private:
+    std::vector<Point3> apply(const std::vector<Point3> &points, int inverse) const {
+        a3_pose p;
+        p.error = error;
+        for (int i = 0; i < 9; i++) p.rotation[i] = rotation[i];
+        for (int i = 0; i < 3; i++) p.translation[i] = translation[i];
+        std::vector<Point3> out(points.size());
+        if (!points.empty()) a3_pose_apply_transform(&p, points[0].data(), (uint32_t)points.size(), inverse, out[0].data());
+        return out;
+    }
+};
+
+// src/pose.rs:52-81.  The solvers run on the detector's device (kernel K4); (best, alt) as in the reference.
+namespace pose {
+using Corners = std::vector<std::pair<uint32_t, uint32_t>>;  // Marker::corners
+
+inline std::pair<MarkerPose, MarkerPose> solve_with_intrinsics(const Detector &det, const Corners &image_points, float marker_size_mm,
+                                                               const CameraIntrinsics &camera_intrinsics) {
+    if (image_points.size() != 4) throw Error(A3_ERR_INVALID_ARGUMENT, "solve_with_intrinsics: four corners expected");
+    uint32_t c[8];
+    for (int i = 0; i < 4; i++) { c[2 * i] = image_points[i].first; c[2 * i + 1] = image_points[i].second; }
+    const a3_camera_intrinsics k = camera_intrinsics.c();
+    a3_pose best, alt;
+    check(a3_solve_with_intrinsics(det.handle(), c, 1, marker_size_mm, &k, &best, &alt));
+    return {MarkerPose::from_c(best), MarkerPose::from_c(alt)};
+}
+inline std::pair<MarkerPose, MarkerPose> solve_with_undistorted_points(const Detector &det, const Corners &image_points, float marker_size_mm,
+                                                                       std::pair<uint32_t, uint32_t> image_size) {
+    if (image_points.size() != 4) throw Error(A3_ERR_INVALID_ARGUMENT, "solve_with_undistorted_points: four corners expected");
+    uint32_t c[8];
+    for (int i = 0; i < 4; i++) { c[2 * i] = image_points[i].first; c[2 * i + 1] = image_points[i].second; }
+    a3_pose best, alt;
+    check(a3_solve_with_undistorted_points(det.handle(), c, 1, marker_size_mm, image_size.first, image_size.second, &best, &alt));
+    return {MarkerPose::from_c(best), MarkerPose::from_c(alt)};
+}
+inline std::pair<MarkerPose, MarkerPose> solve_with_normalized_points(const Detector &det, const std::vector<std::pair<float, float>> &points,
+                                                                      float marker_size_mm) {
+    if (points.size() != 4) throw Error(A3_ERR_INVALID_ARGUMENT, "solve_with_normalized_points: four points expected");
+    float c[8];
+    for (int i = 0; i < 4; i++) { c[2 * i] = points[i].first; c[2 * i + 1] = points[i].second; }
+    a3_pose best, alt;
+    check(a3_solve_with_normalized_points(det.handle(), c, 1, marker_size_mm, &best, &alt));
+    return {MarkerPose::from_c(best), MarkerPose::from_c(alt)};
+}
+}  // namespace pose
 
 }  // namespace aruco3
 #endif  // ARUCO3_B200_HPP

@@ -89,8 +89,34 @@ pub struct a3_stats {
     pub host_threads: u32,
     pub contour_kernel_launches: u32,
     pub host_fallback_frames: u32,
-    pub reserved: u32,
+    pub pose_kernel_launches: u32,
 }
+
+/// MarkerPose, reference `src/pose.rs:8-12`; rotation row-major
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct a3_pose {
+    pub error: f32,
+    pub rotation: [f32; 9],
+    pub translation: [f32; 3],
+}
+
+/// CameraIntrinsics, reference `src/pinhole.rs:11-18`
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct a3_camera_intrinsics {
+    pub image_width: u32,
+    pub image_height: u32,
+    pub focal_x: f32,
+    pub focal_y: f32,
+    pub principal_x: f32,
+    pub principal_y: f32,
+}
+
+pub const A3_POSE_OFF: u32 = 0;
+pub const A3_POSE_UNDISTORTED: u32 = 1;
+pub const A3_POSE_INTRINSICS: u32 = 2;
+pub const A3_POSE_NORMALIZED: u32 = 3;
 
 #[repr(C)]
 pub struct a3_outputs {
@@ -103,6 +129,7 @@ pub struct a3_outputs {
     pub cand_capacity: u32,
     pub n_candidates: u32,
     pub frame_marker_offsets: *mut u32,
+    pub marker_poses: *mut a3_pose,
 }
 
 #[repr(C)]
@@ -147,4 +174,30 @@ extern "C" {
         det: *mut a3_detector, grey: *const u8, n_frames: u32, width: u32, height: u32, quads: *const u32, quad_frame: *const u32,
         n_quads: u32, decodes: *mut a3_decode, patches: *mut u8,
     ) -> a3_status;
+
+    // pose step (reference src/pose.rs, src/pinhole.rs)
+    pub fn a3_detector_set_pose(det: *mut a3_detector, mode: u32, marker_size_mm: f32, k: *const a3_camera_intrinsics) -> a3_status;
+    pub fn a3_solve_with_intrinsics(
+        det: *mut a3_detector, corners: *const u32, n: u32, marker_size_mm: f32, k: *const a3_camera_intrinsics, best: *mut a3_pose,
+        alt: *mut a3_pose,
+    ) -> a3_status;
+    pub fn a3_solve_with_undistorted_points(
+        det: *mut a3_detector, corners: *const u32, n: u32, marker_size_mm: f32, image_width: u32, image_height: u32,
+        best: *mut a3_pose, alt: *mut a3_pose,
+    ) -> a3_status;
+    pub fn a3_solve_with_normalized_points(
+        det: *mut a3_detector, points: *const f32, n: u32, marker_size_mm: f32, best: *mut a3_pose, alt: *mut a3_pose,
+    ) -> a3_status;
+    pub fn a3_pose_default(p: *mut a3_pose);
+    pub fn a3_pose_apply_transform(p: *const a3_pose, points: *const f32, n: u32, inverse: i32, out: *mut f32);
+    pub fn a3_camera_intrinsics_new(
+        image_width: u32, image_height: u32, focal_x: f32, focal_y: f32, principal_x: *const f32, principal_y: *const f32,
+        out: *mut a3_camera_intrinsics,
+    );
+    pub fn a3_camera_intrinsics_from_fov_horizontal(
+        horizontal_fov_radians: f32, sensor_width_mm: f32, resolution_x: u32, resolution_y: u32, out: *mut a3_camera_intrinsics,
+    );
+    pub fn a3_camera_project(k: *const a3_camera_intrinsics, x: f32, y: f32, z: f32, out: *mut f32);
+    pub fn a3_camera_project_culled(k: *const a3_camera_intrinsics, x: f32, y: f32, z: f32, out: *mut f32) -> i32;
+    pub fn a3_camera_unproject(k: *const a3_camera_intrinsics, x: f32, y: f32, out: *mut f32);
 }

@@ -149,7 +149,7 @@ impl Detector {
             let mut out = sys::a3_outputs {
                 grey: grey.as_mut_ptr(), mask: ptr::null_mut(), candidates: cands.as_mut_ptr(), candidate_frame: cframe.as_mut_ptr(),
                 homographies: patches.as_mut_ptr(), decodes: decs.as_mut_ptr(), cand_capacity: cap_c as u32, n_candidates: 0,
-                frame_marker_offsets: ptr::null_mut(),
+                frame_marker_offsets: ptr::null_mut(), marker_poses: ptr::null_mut(),
             };
             let mut nm = 0u32;
             let st = unsafe {
@@ -191,5 +191,111 @@ impl Detector {
             }
             return dets;
         }
+    }
+}
+
+/// Drop-in for the reference's `pose` module (`src/pose.rs:52-81`): same function names, argument order and return
+/// shape, plus the `Detector` whose device runs the solve (kernel K4).
+pub mod pose {
+    use super::{last_error, sys, Detector};
+
+    /// reference `src/pose.rs:8-12`; `rotation` row-major (the reference's `na::Matrix3::new` argument order)
+    #[derive(Clone, Debug)]
+    pub struct MarkerPose {
+        pub error: f32,
+        pub rotation: [f32; 9],
+        pub translation: [f32; 3],
+    }
+
+    impl Default for MarkerPose {
+        /// reference `src/pose.rs:42-50`
+        fn default() -> Self {
+            Self { error: 1e31, rotation: [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0], translation: [0.0; 3] }
+        }
+    }
+
+    impl MarkerPose {
+        fn raw(&self) -> sys::a3_pose {
+            sys::a3_pose { error: self.error, rotation: self.rotation, translation: self.translation }
+        }
+        fn apply(&self, points: &Vec<(f32, f32, f32)>, inverse: i32) -> Vec<(f32, f32, f32)> {
+            let flat: Vec<f32> = points.iter().flat_map(|p| [p.0, p.1, p.2]).collect();
+            let mut out = vec![0f32; flat.len()];
+            unsafe { sys::a3_pose_apply_transform(&self.raw(), flat.as_ptr(), points.len() as u32, inverse, out.as_mut_ptr()) };
+            out.chunks(3).map(|c| (c[0], c[1], c[2])).collect()
+        }
+        /// reference `src/pose.rs:17-20`
+        pub fn apply_transform_to_points(&self, points: &Vec<(f32, f32, f32)>) -> Vec<(f32, f32, f32)> {
+            self.apply(points, 0)
+        }
+        /// reference `src/pose.rs:30-33`
+        pub fn apply_inverse_transform_to_points(&self, points: &Vec<(f32, f32, f32)>) -> Vec<(f32, f32, f32)> {
+            self.apply(points, 1)
+        }
+    }
+
+    /// reference `src/pinhole.rs:11-18`
+    pub type CameraIntrinsics = sys::a3_camera_intrinsics;
+
+    /// `CameraIntrinsics::new`, reference `src/pinhole.rs:26-35`
+    pub fn camera_intrinsics_new(w: u32, h: u32, fx: f32, fy: f32, px: Option<f32>, py: Option<f32>) -> CameraIntrinsics {
+        let mut k = CameraIntrinsics::default();
+        let (pxp, pyp) = (px.as_ref().map_or(std::ptr::null(), |v| v as *const f32), py.as_ref().map_or(std::ptr::null(), |v| v as *const f32));
+        unsafe { sys::a3_camera_intrinsics_new(w, h, fx, fy, pxp, pyp, &mut k) };
+        k
+    }
+
+    /// `CameraIntrinsics::new_from_fov_horizontal`, reference `src/pinhole.rs:37-60`
+    pub fn camera_intrinsics_new_from_fov_horizontal(hfov: f32, sensor_width_mm: f32, rx: u32, ry: u32) -> CameraIntrinsics {
+        let mut k = CameraIntrinsics::default();
+        unsafe { sys::a3_camera_intrinsics_from_fov_horizontal(hfov, sensor_width_mm, rx, ry, &mut k) };
+        k
+    }
+
+    fn pair(best: sys::a3_pose, alt: sys::a3_pose) -> (MarkerPose, MarkerPose) {
+        let f = |p: sys::a3_pose| MarkerPose { error: p.error, rotation: p.rotation, translation: p.translation };
+        (f(best), f(alt))
+    }
+    fn flat(points: &Vec<(u32, u32)>) -> [u32; 8] {
+        assert_eq!(points.len(), 4);
+        let mut c = [0u32; 8];
+        for (i, p) in points.iter().enumerate() {
+            c[2 * i] = p.0;
+            c[2 * i + 1] = p.1;
+        }
+        c
+    }
+    const ZERO: sys::a3_pose = sys::a3_pose { error: 0.0, rotation: [0.0; 9], translation: [0.0; 3] };
+
+    /// reference `src/pose.rs:52-55`
+    pub fn solve_with_intrinsics(det: &Detector, image_points: &Vec<(u32, u32)>, marker_size_mm: f32, k: &CameraIntrinsics) -> (MarkerPose, MarkerPose) {
+        let (c, mut b, mut a) = (flat(image_points), ZERO, ZERO);
+        let st = unsafe { sys::a3_solve_with_intrinsics(det.handle().0, c.as_ptr(), 1, marker_size_mm, k, &mut b, &mut a) };
+        if st != sys::A3_OK {
+            panic!("{}", last_error());
+        }
+        pair(b, a)
+    }
+
+    /// reference `src/pose.rs:59-62`
+    pub fn solve_with_undistorted_points(det: &Detector, image_points: &Vec<(u32, u32)>, marker_size_mm: f32, image_size: (u32, u32)) -> (MarkerPose, MarkerPose) {
+        let (c, mut b, mut a) = (flat(image_points), ZERO, ZERO);
+        let st = unsafe { sys::a3_solve_with_undistorted_points(det.handle().0, c.as_ptr(), 1, marker_size_mm, image_size.0, image_size.1, &mut b, &mut a) };
+        if st != sys::A3_OK {
+            panic!("{}", last_error());
+        }
+        pair(b, a)
+    }
+
+    /// reference `src/pose.rs:64-81`
+    pub fn solve_with_normalized_points(det: &Detector, points: &Vec<(f32, f32)>, marker_size_mm: f32) -> (MarkerPose, MarkerPose) {
+        assert_eq!(points.len(), 4);
+        let c: Vec<f32> = points.iter().flat_map(|p| [p.0, p.1]).collect();
+        let (mut b, mut a) = (ZERO, ZERO);
+        let st = unsafe { sys::a3_solve_with_normalized_points(det.handle().0, c.as_ptr(), 1, marker_size_mm, &mut b, &mut a) };
+        if st != sys::A3_OK {
+            panic!("{}", last_error());
+        }
+        pair(b, a)
     }
 }

@@ -31,6 +31,17 @@ int main(int argc, char **argv) {
     printf("grey %u %u %llu\n", d.grey.width, d.grey.height, sum);
     for (auto &c : d.candidates) printf("cand %u %u %u %u %u %u %u %u\n", c[0].first, c[0].second, c[1].first, c[1].second, c[2].first, c[2].second, c[3].first, c[3].second);
     for (auto &p : d.homographies) printf("patch %u\n", p.width);
+    for (auto &m : d.markers) {  // examples/webcam_kamera.rs:68
+        auto poses = aruco3::pose::solve_with_undistorted_points(detector, m.corners, 40.0f, {w, h});
+        printf("pose %.9g %.9g %.9g %.9g %.9g\n", poses.first.error, poses.first.translation[0], poses.first.translation[1],
+               poses.first.translation[2], poses.second.translation[2]);
+    }
+    aruco3::MarkerPose mp;
+    mp.translation = {1.0f, 2.0f, 3.0f};
+    mp.rotation = {0, 0, 1, 0, 1, 0, 1, 0, 0};
+    auto moved = mp.apply_transform_to_points({{7.0f, 11.0f, 13.0f}});  // src/pose.rs:379-392
+    if (moved[0][0] != 14.0f || moved[0][1] != 13.0f || moved[0][2] != 10.0f) return 5;
+    if (aruco3::CameraIntrinsics(640, 480, 1.0f, 1.0f).principal_x != 320.0f) return 6;
     for (auto &m : d.markers)
         printf("marker %zu %llu %u %u %u %u %u %u %u %u %u\n", m.id, (unsigned long long)m.code, m.hamming_distance, m.corners[0].first, m.corners[0].second,
                m.corners[1].first, m.corners[1].second, m.corners[2].first, m.corners[2].second, m.corners[3].first, m.corners[3].second);
@@ -64,3 +75,8 @@ def test_cpp_detector_matches_oracle(oracle, tmp_path):
     assert [int(ln.split()[1]) for ln in out if ln.startswith("patch")] == [49 if ok else 1 for ok in ref.homography_ok]
     markers = [[int(v) for v in ln.split()[1:]] for ln in out if ln.startswith("marker")]
     assert markers == [[m["id"], m["code"], m["hamming_distance"]] + m["corners"] for m in ref.markers]
+    poses = [[np.float32(v) for v in ln.split()[1:]] for ln in out if ln.startswith("pose")]
+    assert len(poses) == len(ref.markers) > 0
+    for got, m in zip(poses, ref.markers):
+        best, alt = oracle.solve_with_undistorted_points(m["corners"], 40.0, (640, 480))
+        assert got == [np.float32(best.error)] + [np.float32(v) for v in best.translation] + [np.float32(alt.translation[2])]
