@@ -11,7 +11,7 @@ LIB_PATH = PKG / "libaruco3_b200.so"
 
 A3_OK, A3_ERR_INVALID_ARGUMENT, A3_ERR_UNKNOWN_DICTIONARY, A3_ERR_CUDA, A3_ERR_CAPACITY, A3_ERR_UNSUPPORTED, \
     A3_ERR_OUT_OF_MEMORY = range(7)
-FMT_RGB8, FMT_RGBA8, FMT_LUMA8 = 0, 1, 2
+FMT_RGB8, FMT_RGBA8, FMT_LUMA8, FMT_BGR8, FMT_BGRA8 = 0, 1, 2, 3, 4
 MEM_HOST, MEM_DEVICE = 0, 1
 CONTOURS_HOST, CONTOURS_DEVICE = 0, 1
 POSE_OFF, POSE_UNDISTORTED, POSE_INTRINSICS, POSE_NORMALIZED = 0, 1, 2, 3

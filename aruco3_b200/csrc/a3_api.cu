@@ -220,7 +220,7 @@ a3_status check_config(const a3_config &c) {
     return A3_OK;
 }
 
-uint32_t bytes_per_pixel(a3_format f) { return f == A3_FMT_RGB8 ? 3 : (f == A3_FMT_RGBA8 ? 4 : 1); }
+uint32_t bytes_per_pixel(a3_format f) { return (uint32_t)fmt_bpp((int)f); }
 
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -354,7 +354,7 @@ a3_status a3_gray_threshold_batch(a3_detector *d, const void *frames, a3_format 
                                   uint32_t w, uint32_t h, size_t pitch, size_t frame_stride, uint8_t *grey, uint8_t *mask,
                                   uint32_t *mask_bits, void *cuda_stream) {
     if (!d || !frames) return fail(A3_ERR_INVALID_ARGUMENT, "a3_gray_threshold_batch: null argument");
-    if ((int)format < 0 || (int)format > 2) return fail(A3_ERR_INVALID_ARGUMENT, "bad format");
+    if (!fmt_valid((int)format)) return fail(A3_ERR_INVALID_ARGUMENT, "bad format");
     if (n == 0 || w == 0 || h == 0) return A3_OK;
     const uint32_t bpp = bytes_per_pixel(format);
     if (pitch < (size_t)w * bpp || frame_stride < pitch * h) return fail(A3_ERR_INVALID_ARGUMENT, "pitch / frame_stride too small");
@@ -484,7 +484,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                           uint32_t h, size_t pitch, size_t frame_stride, a3_marker *markers, uint32_t marker_capacity,
                           uint32_t *n_markers, a3_outputs *outs, a3_stats *stats) {
     if (!d || !frames || !n_markers) return fail(A3_ERR_INVALID_ARGUMENT, "a3_detect_batch: null argument");
-    if ((int)format < 0 || (int)format > 2) return fail(A3_ERR_INVALID_ARGUMENT, "bad format");
+    if (!fmt_valid((int)format)) return fail(A3_ERR_INVALID_ARGUMENT, "bad format");
     *n_markers = 0;
     if (outs) outs->n_candidates = 0;
     if (stats) memset(stats, 0, sizeof(*stats));

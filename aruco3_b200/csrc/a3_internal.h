@@ -12,6 +12,11 @@
 
 namespace a3 {
 
+// ---- pixel formats (a3_format) ----------------------------------------------------------------------------
+__host__ __device__ constexpr int fmt_bpp(int f) { return (f == A3_FMT_RGB8 || f == A3_FMT_BGR8) ? 3 : ((f == A3_FMT_RGBA8 || f == A3_FMT_BGRA8) ? 4 : 1); }
+__host__ __device__ constexpr bool fmt_bgr(int f) { return f == A3_FMT_BGR8 || f == A3_FMT_BGRA8; }  // byte 0 is blue
+__host__ __device__ constexpr bool fmt_valid(int f) { return f >= 0 && f <= A3_FMT_BGRA8; }
+
 // ---- error plumbing -------------------------------------------------------------------------
 void set_error(const std::string &msg);
 a3_status fail(a3_status s, const std::string &msg);

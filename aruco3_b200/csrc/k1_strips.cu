@@ -85,18 +85,19 @@ __device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *map, 
 // 8 px are not 16 bytes (RGB8, LUMA8).
 template <int FMT>
 struct Fmt {
-    static constexpr int bpp = FMT == A3_FMT_RGB8 ? 3 : (FMT == A3_FMT_RGBA8 ? 4 : 1);
-    static constexpr int lead_px = FMT == A3_FMT_RGBA8 ? 0 : 8;          // columns staged before x0
+    static constexpr int bpp = fmt_bpp(FMT);
+    static constexpr int lead_px = bpp == 4 ? 0 : 8;                      // columns staged before x0
     static constexpr int lead_bytes = lead_px * bpp;                      // 24 / 0 / 8: keeps 8-byte alignment of lane loads
     static constexpr int row_bytes = (256 + 2 * lead_px) * bpp;           // 816 / 1024 / 272 (multiples of 16)
     static constexpr int box_x = row_bytes / 4;                           // box width in u32 elements (<= 256)
 };
 
-// grey of one [R,G,B,x] word, left in byte 1 of the result (bytes 2 and 3 are zero)
+// grey of one [R,G,B,x] word ([B,G,R,x] when BGR), left in byte 1 of the result (bytes 2 and 3 are zero)
+template <bool BGR>
 __device__ __forceinline__ uint32_t luma_h(uint32_t px) {
-    const uint32_t hi = __dp4a(px, 0x00021b08u, 0u);              // 8 R + 27 G + 2 B
-    const uint32_t v = __dp4a(px, 0x00d2f04eu, hi << 8);          // + 78 R + 240 G + 210 B  = 2126 R + 7152 G + 722 B
-    return __umulhi(v, kMagic);                                    // floor(v / 10000) << 8 | fraction byte
+    const uint32_t hi = __dp4a(px, BGR ? 0x00081b02u : 0x00021b08u, 0u);      // 8 R + 27 G + 2 B
+    const uint32_t v = __dp4a(px, BGR ? 0x004ef0d2u : 0x00d2f04eu, hi << 8);  // + 78 R + 240 G + 210 B  = 2126 R + 7152 G + 722 B
+    return __umulhi(v, kMagic);                                                // floor(v / 10000) << 8 | fraction byte
 }
 
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
@@ -123,21 +124,22 @@ __device__ __forceinline__ void load_grey8(uint32_t row, uint32_t &p01, uint32_t
         p45 = __byte_perm(g.y, 0u, 0x4140); p67 = __byte_perm(g.y, 0u, 0x4342);
     } else {
         uint32_t h[8];
-        if constexpr (FMT == A3_FMT_RGB8) {
+        constexpr bool BGR = fmt_bgr(FMT);
+        if constexpr (fmt_bpp(FMT) == 3) {
             const uint2 a = lds64(row), b = lds64(row + 8), c = lds64(row + 16);
             // 12 bytes -> 4 pixel words; the 4th byte of each word has weight 0
-            h[0] = luma_h(a.x);
-            h[1] = luma_h(__byte_perm(a.x, a.y, 0x6543));
-            h[2] = luma_h(__byte_perm(a.y, b.x, 0x5432));
-            h[3] = luma_h(b.x >> 8);
-            h[4] = luma_h(b.y);
-            h[5] = luma_h(__byte_perm(b.y, c.x, 0x6543));
-            h[6] = luma_h(__byte_perm(c.x, c.y, 0x5432));
-            h[7] = luma_h(c.y >> 8);
+            h[0] = luma_h<BGR>(a.x);
+            h[1] = luma_h<BGR>(__byte_perm(a.x, a.y, 0x6543));
+            h[2] = luma_h<BGR>(__byte_perm(a.y, b.x, 0x5432));
+            h[3] = luma_h<BGR>(b.x >> 8);
+            h[4] = luma_h<BGR>(b.y);
+            h[5] = luma_h<BGR>(__byte_perm(b.y, c.x, 0x6543));
+            h[6] = luma_h<BGR>(__byte_perm(c.x, c.y, 0x5432));
+            h[7] = luma_h<BGR>(c.y >> 8);
         } else {
             const uint4 a = lds128(row), b = lds128(row + 16);
-            h[0] = luma_h(a.x); h[1] = luma_h(a.y); h[2] = luma_h(a.z); h[3] = luma_h(a.w);
-            h[4] = luma_h(b.x); h[5] = luma_h(b.y); h[6] = luma_h(b.z); h[7] = luma_h(b.w);
+            h[0] = luma_h<BGR>(a.x); h[1] = luma_h<BGR>(a.y); h[2] = luma_h<BGR>(a.z); h[3] = luma_h<BGR>(a.w);
+            h[4] = luma_h<BGR>(b.x); h[5] = luma_h<BGR>(b.y); h[6] = luma_h<BGR>(b.z); h[7] = luma_h<BGR>(b.w);
         }
         p01 = __byte_perm(h[0], h[1], 0x6521); p23 = __byte_perm(h[2], h[3], 0x6521);
         p45 = __byte_perm(h[4], h[5], 0x6521); p67 = __byte_perm(h[6], h[7], 0x6521);
@@ -421,20 +423,20 @@ cudaError_t launch_strips(const CUtensorMap &map, const StripArgs &a, bool mask,
 }  // namespace
 
 bool k1_strips_eligible(const K1Params &p) {
-    const uint32_t bpp = p.format == A3_FMT_RGB8 ? 3 : (p.format == A3_FMT_RGBA8 ? 4 : 1);
+    const uint32_t bpp = fmt_bpp(p.format);
     return p.radius == 7 && p.grey != nullptr && p.w % 4 == 0 && p.w >= 4 && p.pitch % 16 == 0 && p.frame_stride % 16 == 0 &&
            p.frame_stride % p.pitch == 0 && (uintptr_t)p.src % 16 == 0 && (uintptr_t)p.grey % 4 == 0 && (uintptr_t)p.mask % 4 == 0 &&
            (uint64_t)p.w * bpp <= p.pitch && p.n <= 0x7fffffffu && encode_tiled_fn() != nullptr;
 }
 
 cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t stream, K1LaunchInfo *info) {
-    const uint32_t bpp = p.format == A3_FMT_RGB8 ? 3 : (p.format == A3_FMT_RGBA8 ? 4 : 1);
+    const uint32_t bpp = fmt_bpp(p.format);
 
     // ---- tensor map over the frames viewed as u32 [n][h][pitch / 4]; dim 0 stops at the last pixel's bytes ----
     CUtensorMap map;
     const cuuint64_t gdim[3] = {(cuuint64_t)p.w * bpp / 4, p.h, p.n};
     const cuuint64_t gstride[2] = {p.pitch, p.frame_stride};
-    const uint32_t row_bytes = (256u + (p.format == A3_FMT_RGBA8 ? 0u : 16u)) * bpp;  // Fmt<>::row_bytes
+    const uint32_t row_bytes = (256u + (bpp == 4 ? 0u : 16u)) * bpp;  // Fmt<>::row_bytes
     const cuuint32_t box[3] = {row_bytes / 4, (cuuint32_t)kBoxRows, 1};
     const cuuint32_t estride[3] = {1, 1, 1};
     const CUresult cr = encode_tiled_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(p.src), gdim, gstride, box, estride,
@@ -445,8 +447,7 @@ cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t st
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t per_warp = p.format == A3_FMT_RGB8 ? Stage<A3_FMT_RGB8>::per_warp
-                              : (p.format == A3_FMT_RGBA8 ? Stage<A3_FMT_RGBA8>::per_warp : Stage<A3_FMT_LUMA8>::per_warp);
+    const uint32_t per_warp = bpp == 3 ? Stage<A3_FMT_RGB8>::per_warp : (bpp == 4 ? Stage<A3_FMT_RGBA8>::per_warp : Stage<A3_FMT_LUMA8>::per_warp);
     const size_t smem = (size_t)per_warp * kWarpsPerCta;
     // resident CTAs per SM: bounded by shared memory (~30 KB per CTA) and by the register cap of __launch_bounds__
     uint32_t ctas_per_sm = (uint32_t)((227 * 1024) / (smem + 1024));
@@ -505,6 +506,8 @@ cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t st
         case A3_FMT_RGB8: return launch_strips<A3_FMT_RGB8>(map, a, mask, bits, grid, smem, stream);
         case A3_FMT_RGBA8: return launch_strips<A3_FMT_RGBA8>(map, a, mask, bits, grid, smem, stream);
         case A3_FMT_LUMA8: return launch_strips<A3_FMT_LUMA8>(map, a, mask, bits, grid, smem, stream);
+        case A3_FMT_BGR8: return launch_strips<A3_FMT_BGR8>(map, a, mask, bits, grid, smem, stream);
+        case A3_FMT_BGRA8: return launch_strips<A3_FMT_BGRA8>(map, a, mask, bits, grid, smem, stream);
         default: return cudaErrorInvalidValue;
     }
 }

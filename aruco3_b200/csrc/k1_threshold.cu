@@ -80,25 +80,28 @@ __device__ __forceinline__ uint32_t luma(uint32_t r, uint32_t g, uint32_t b) {
 }
 
 template <int FMT>
-struct Bpp { static constexpr int v = FMT == A3_FMT_RGB8 ? 3 : (FMT == A3_FMT_RGBA8 ? 4 : 1); };
+struct Bpp { static constexpr int v = fmt_bpp(FMT); };
+// luma of the pixel bytes b0 b1 b2 as they lie in memory (R,G,B or B,G,R)
+template <int FMT>
+__device__ __forceinline__ uint32_t luma_px(uint32_t b0, uint32_t b1, uint32_t b2) { return fmt_bgr(FMT) ? luma(b2, b1, b0) : luma(b0, b1, b2); }
 
 // 4 grey bytes (little endian: pixel j in byte j) of the thread's 4 columns from the staged row.
 template <int FMT>
 __device__ __forceinline__ uint32_t grey4_from_stage(const uint8_t *stage, int t) {
-    if constexpr (FMT == A3_FMT_RGB8) {
+    if constexpr (Bpp<FMT>::v == 3) {
         const uint32_t *s = reinterpret_cast<const uint32_t *>(stage) + 3 * t;
         uint32_t w0 = s[0], w1 = s[1], w2 = s[2];
-        uint32_t g0 = luma(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
-        uint32_t g1 = luma(w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff);
-        uint32_t g2 = luma((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
-        uint32_t g3 = luma((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
+        uint32_t g0 = luma_px<FMT>(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
+        uint32_t g1 = luma_px<FMT>(w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff);
+        uint32_t g2 = luma_px<FMT>((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
+        uint32_t g3 = luma_px<FMT>((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
         return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
-    } else if constexpr (FMT == A3_FMT_RGBA8) {
+    } else if constexpr (Bpp<FMT>::v == 4) {
         uint4 v = reinterpret_cast<const uint4 *>(stage)[t];
-        uint32_t g0 = luma(v.x & 0xff, (v.x >> 8) & 0xff, (v.x >> 16) & 0xff);
-        uint32_t g1 = luma(v.y & 0xff, (v.y >> 8) & 0xff, (v.y >> 16) & 0xff);
-        uint32_t g2 = luma(v.z & 0xff, (v.z >> 8) & 0xff, (v.z >> 16) & 0xff);
-        uint32_t g3 = luma(v.w & 0xff, (v.w >> 8) & 0xff, (v.w >> 16) & 0xff);
+        uint32_t g0 = luma_px<FMT>(v.x & 0xff, (v.x >> 8) & 0xff, (v.x >> 16) & 0xff);
+        uint32_t g1 = luma_px<FMT>(v.y & 0xff, (v.y >> 8) & 0xff, (v.y >> 16) & 0xff);
+        uint32_t g2 = luma_px<FMT>(v.z & 0xff, (v.z >> 8) & 0xff, (v.z >> 16) & 0xff);
+        uint32_t g3 = luma_px<FMT>(v.w & 0xff, (v.w >> 8) & 0xff, (v.w >> 16) & 0xff);
         return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
     } else {
         return reinterpret_cast<const uint32_t *>(stage)[t];
@@ -115,7 +118,7 @@ __device__ __forceinline__ uint32_t grey4_from_global(const uint8_t *row, uint32
             const uint8_t *p = row + (size_t)(x + j) * Bpp<FMT>::v;
             uint32_t g;
             if constexpr (FMT == A3_FMT_LUMA8) g = p[0];
-            else g = luma(p[0], p[1], p[2]);
+            else g = luma_px<FMT>(p[0], p[1], p[2]);
             out |= g << (8 * j);
         }
     }
@@ -324,7 +327,7 @@ cudaError_t k1_gray_threshold(const K1Params &p, const K1Tuning *tuning, cudaStr
     if (p.radius == 0 || p.radius > (uint32_t)kMaxRadius) return cudaErrorInvalidValue;
     if (!(tuning && tuning->force_generic) && k1_strips_eligible(p)) return k1_strips(p, tuning, stream, info);
     const uint32_t r = p.radius;
-    const uint32_t bpp = p.format == A3_FMT_RGB8 ? 3 : (p.format == A3_FMT_RGBA8 ? 4 : 1);
+    const uint32_t bpp = fmt_bpp(p.format);
     const uint32_t max_core = 4 * kMaxThreads - 64;  // leave room for the 32-aligned left halo and the right halo
 
     // ---- tiling ----
@@ -397,6 +400,8 @@ cudaError_t k1_gray_threshold(const K1Params &p, const K1Tuning *tuning, cudaStr
         case A3_FMT_RGB8: return dispatch<A3_FMT_RGB8>(a, r == 7, tma, grid, block, smem, stream);
         case A3_FMT_RGBA8: return dispatch<A3_FMT_RGBA8>(a, r == 7, tma, grid, block, smem, stream);
         case A3_FMT_LUMA8: return dispatch<A3_FMT_LUMA8>(a, r == 7, tma, grid, block, smem, stream);
+        case A3_FMT_BGR8: return dispatch<A3_FMT_BGR8>(a, r == 7, tma, grid, block, smem, stream);
+        case A3_FMT_BGRA8: return dispatch<A3_FMT_BGRA8>(a, r == 7, tma, grid, block, smem, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -112,18 +112,19 @@ class Detection:
     decodes: list = field(default_factory=list)
 
 
-_FMT = {3: _ffi.FMT_RGB8, 4: _ffi.FMT_RGBA8}
+_FMT = {("rgb", 3): _ffi.FMT_RGB8, ("rgb", 4): _ffi.FMT_RGBA8, ("bgr", 3): _ffi.FMT_BGR8, ("bgr", 4): _ffi.FMT_BGRA8}
 
 
-def _frames_view(frames: np.ndarray):
-    """-> (contiguous uint8 array, format, n, h, w, pitch, frame_stride) for [n,H,W,3|4] or [n,H,W]."""
+def _frames_view(frames: np.ndarray, order: str = "rgb"):
+    """-> (contiguous uint8 array, format, n, h, w, pitch, frame_stride) for [n,H,W,3|4] or [n,H,W]; `order` "bgr" =
+    camera byte order B,G,R[,A] (A3_FMT_BGR8 / A3_FMT_BGRA8)."""
     a = np.asarray(frames)
     if a.dtype != np.uint8:
         raise A3Error(_ffi.A3_ERR_UNSUPPORTED, "only 8-bit images are supported (Rgb8 / Rgba8 / Luma8)")
     if a.ndim == 3:
         fmt = _ffi.FMT_LUMA8
-    elif a.ndim == 4 and a.shape[3] in _FMT:
-        fmt = _FMT[a.shape[3]]
+    elif a.ndim == 4 and (order, a.shape[3]) in _FMT:
+        fmt = _FMT[(order, a.shape[3])]
     else:
         raise A3Error(_ffi.A3_ERR_INVALID_ARGUMENT, f"bad frame array shape {a.shape}")
     a = np.ascontiguousarray(a)
@@ -184,15 +185,16 @@ class Detector:
         self.close()
 
     # ---- the reference's entry point -------------------------------------------------------------------
-    def detect(self, image: np.ndarray) -> Detection:
+    def detect(self, image: np.ndarray, order: str = "rgb") -> Detection:
         """`Detector::detect(&self, image: DynamicImage) -> Detection` (src/aruco.rs:52-121): one image [H,W,3|4] or [H,W]."""
-        return self.detect_batch(np.asarray(image)[None], full=True)[0]
+        return self.detect_batch(np.asarray(image)[None], full=True, order=order)[0]
 
     def detect_batch(self, frames: np.ndarray, full: bool = False, want_mask: bool = False, cand_capacity: int = 0,
-                     marker_capacity: int = 0) -> list:
+                     marker_capacity: int = 0, order: str = "rgb") -> list:
         """`detect` over n equally sized frames -> [Detection].  `full` also returns grey, candidates, homographies
-        and the per-candidate decode records (what `Detection` holds in the reference); without it only markers."""
-        a, fmt, n, h, w, pitch, fstride = _frames_view(frames)
+        and the per-candidate decode records (what `Detection` holds in the reference); without it only markers.
+        `order="bgr"`: frames are B,G,R[,A] as cameras deliver them; the result is that of the swizzled image."""
+        a, fmt, n, h, w, pitch, fstride = _frames_view(frames, order)
         hs = self.config.homography_sample_size
         cap_m = marker_capacity or max(64 * n, 1024)
         cap_c = cand_capacity or max(128 * n, 2048)
@@ -260,9 +262,9 @@ class Detector:
         return dets
 
     # ---- stage probes (the same kernels) -----------------------------------------------------------------
-    def gray_threshold(self, frames: np.ndarray, want_bits: bool = False):
+    def gray_threshold(self, frames: np.ndarray, want_bits: bool = False, order: str = "rgb"):
         """into_luma8 + adaptive_threshold over [n,H,W,C] host frames -> (grey [n,H,W], mask [n,H,W][, bits [n,H,ceil(W/32)]])."""
-        a, fmt, n, h, w, pitch, fstride = _frames_view(frames)
+        a, fmt, n, h, w, pitch, fstride = _frames_view(frames, order)
         grey = np.empty((n, h, w), np.uint8)
         mask = np.empty((n, h, w), np.uint8)
         bits = np.empty((n, h, (w + 31) // 32), np.uint32) if want_bits else None

@@ -256,6 +256,15 @@ def main():
     iso_bytes = (3 + 1 + 0.125) * w * h * n
     iso_gbs = iso_bytes / (k1_ms * 1e-3) / 1e9
 
+    # DRAM bytes per K1 launch from the committed ncu --set full capture (profiles/k1_traffic.json), scaled to this
+    # launch's frame count; null when the file is absent
+    traffic, traffic_src = None, None
+    tf = ROOT / "profiles" / "k1_traffic.json"
+    if tf.exists():
+        t = json.loads(tf.read_text())
+        traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) * (bytes_per_launch / (5.0 * w * h)) / t["frames_per_launch"]
+        traffic_src = t["source"]
+
     total_frames = n * world * args.steps
     value = total_frames / (ms_dev * 1e-3)
     e2e_value = total_frames / (ms_e2e * 1e-3)
@@ -274,7 +283,7 @@ def main():
         "contour_stage": args.contours, "host_fallback_frames_per_step": acc_dev["host_fallback_frames"] / args.steps,
         "roofline": {"bound": "hbm", "kernel": "k1_strips_kernel<RGB8> (fused into_luma8 + adaptive_threshold, TMA tensor tiles)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                     "frac_of_nominal_8TBps": achieved / 8000.0, "traffic": None,
+                     "frac_of_nominal_8TBps": achieved / 8000.0, "traffic": traffic, "traffic_source": traffic_src,
                      "achieved_moved": moved, "frac_moved": moved / peak,
                      "note": "achieved = SURVEY 8d algorithmic 5 B/px (3 RGB + 1 grey + 1 mask) / K1 time; the pipeline writes the mask "
                              "1 bit/px, so it moves 4.125 B/px: achieved_moved",

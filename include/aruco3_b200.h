@@ -42,7 +42,16 @@ enum {
 
 /* DynamicImage variants accepted at the boundary (callers pass RgbImage.into() / RgbaImage.into(),
  * benches/detect_markers.rs:49, examples/webcam_kamera.rs:56); Luma8 passes through into_luma8. */
-typedef enum { A3_FMT_RGB8 = 0, A3_FMT_RGBA8 = 1, A3_FMT_LUMA8 = 2 } a3_format;
+typedef enum {
+    A3_FMT_RGB8 = 0,
+    A3_FMT_RGBA8 = 1,
+    A3_FMT_LUMA8 = 2,
+    /* camera byte orders: the kernel reads B,G,R[,A] and applies the luma weights accordingly, which is
+     * pixel for pixel the host swizzle into an RgbImage / RgbaImage that examples/webcam_kamera.rs:38-52 does before
+     * detect.  `Detection.grey` etc. are those of the swizzled image. */
+    A3_FMT_BGR8 = 3,
+    A3_FMT_BGRA8 = 4
+} a3_format;
 typedef enum { A3_MEM_HOST = 0, A3_MEM_DEVICE = 1 } a3_mem_kind;
 
 /* DetectorConfig, field for field (src/aruco.rs:23-30); defaults src/aruco.rs:32-43. */

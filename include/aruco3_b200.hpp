@@ -109,7 +109,7 @@ struct Detection {
     std::vector<Marker> markers;
 };
 
-enum class PixelFormat { Rgb8 = A3_FMT_RGB8, Rgba8 = A3_FMT_RGBA8, Luma8 = A3_FMT_LUMA8 };
+enum class PixelFormat { Rgb8 = A3_FMT_RGB8, Rgba8 = A3_FMT_RGBA8, Luma8 = A3_FMT_LUMA8, Bgr8 = A3_FMT_BGR8, Bgra8 = A3_FMT_BGRA8 };
 
 // `Detector { config, dictionary }` (src/aruco.rs:46-49) bound to one CUDA device.  Thread-compatible: one per
 // (host thread, device).  Public fields are read at construction; call rebuild() after changing them.
@@ -145,7 +145,7 @@ public:
     // The same over n equally sized frames; `full` fills grey / candidates / homographies, otherwise only markers.
     std::vector<Detection> detect_batch(const uint8_t *frames, uint32_t n, uint32_t width, uint32_t height,
                                         PixelFormat fmt = PixelFormat::Rgb8, bool full = false, a3_stats *stats = nullptr) const {
-        const uint32_t bpp = fmt == PixelFormat::Rgb8 ? 3 : (fmt == PixelFormat::Rgba8 ? 4 : 1);
+        const uint32_t bpp = (fmt == PixelFormat::Rgb8 || fmt == PixelFormat::Bgr8) ? 3 : (fmt == PixelFormat::Luma8 ? 1 : 4);
         const size_t pitch = (size_t)width * bpp, stride = pitch * height, px = (size_t)width * height;
         const size_t hs = config.homography_sample_size, np = hs * hs;
         std::vector<Detection> out(n);

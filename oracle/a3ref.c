@@ -142,9 +142,10 @@ void a3ref_to_luma8(const uint8_t *src, int format, uint32_t w, uint32_t h, size
             memcpy(o, row, w);
             continue;
         }
-        uint32_t bpp = format == A3REF_FMT_RGBA8 ? 4 : 3;
+        uint32_t bpp = (format == A3REF_FMT_RGBA8 || format == A3REF_FMT_BGRA8) ? 4 : 3;
+        int bgr = format == A3REF_FMT_BGR8 || format == A3REF_FMT_BGRA8; /* examples/webcam_kamera.rs:38-52: r = buffer[idx+2], b = buffer[idx+0] */
         for (uint32_t x = 0; x < w; x++) {
-            uint32_t r = row[x * bpp], g = row[x * bpp + 1], b = row[x * bpp + 2];
+            uint32_t r = row[x * bpp + (bgr ? 2 : 0)], g = row[x * bpp + 1], b = row[x * bpp + (bgr ? 0 : 2)];
             uint32_t l = 2126u * r + 7152u * g + 722u * b; /* SRGB_LUMA */
             o[x] = (uint8_t)(l / 10000u);                  /* SRGB_LUMA_DIV, truncating */
         }

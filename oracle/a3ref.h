@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-enum { A3REF_FMT_RGB8 = 0, A3REF_FMT_RGBA8 = 1, A3REF_FMT_LUMA8 = 2 };
+/* BGR8 / BGRA8: the host swizzle of examples/webcam_kamera.rs:38-52 followed by into_luma8 */
+enum { A3REF_FMT_RGB8 = 0, A3REF_FMT_RGBA8 = 1, A3REF_FMT_LUMA8 = 2, A3REF_FMT_BGR8 = 3, A3REF_FMT_BGRA8 = 4 };
 
 /* src/aruco.rs:23-30 (DetectorConfig), same field order. */
 typedef struct a3ref_config {

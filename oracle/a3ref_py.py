@@ -11,7 +11,7 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-FMT_RGB8, FMT_RGBA8, FMT_LUMA8 = 0, 1, 2
+FMT_RGB8, FMT_RGBA8, FMT_LUMA8, FMT_BGR8, FMT_BGRA8 = 0, 1, 2, 3, 4
 
 
 class Config(C.Structure):
@@ -140,17 +140,17 @@ def try_find_nearest(d: Dictionary, bits: int):
     return (idx.value, dist.value) if ok else None
 
 
-def _fmt_of(img: np.ndarray) -> int:
+def _fmt_of(img: np.ndarray, order: str = "rgb") -> int:
     if img.ndim == 2:
         return FMT_LUMA8
-    return {3: FMT_RGB8, 4: FMT_RGBA8}[img.shape[2]]
+    return {("rgb", 3): FMT_RGB8, ("rgb", 4): FMT_RGBA8, ("bgr", 3): FMT_BGR8, ("bgr", 4): FMT_BGRA8}[(order, img.shape[2])]
 
 
-def to_luma8(img: np.ndarray) -> np.ndarray:
+def to_luma8(img: np.ndarray, order: str = "rgb") -> np.ndarray:
     img = np.ascontiguousarray(img)
     h, w = img.shape[:2]
     out = np.empty((h, w), np.uint8)
-    lib().a3ref_to_luma8(img.ctypes.data, _fmt_of(img), w, h, img.strides[0], out.ctypes.data)
+    lib().a3ref_to_luma8(img.ctypes.data, _fmt_of(img, order), w, h, img.strides[0], out.ctypes.data)
     return out
 
 

@@ -14,6 +14,8 @@ pub const A3_ERR_OUT_OF_MEMORY: a3_status = 6;
 pub const A3_FMT_RGB8: i32 = 0;
 pub const A3_FMT_RGBA8: i32 = 1;
 pub const A3_FMT_LUMA8: i32 = 2;
+pub const A3_FMT_BGR8: i32 = 3; // camera byte order: what examples/webcam_kamera.rs:38-52 swizzles on the host
+pub const A3_FMT_BGRA8: i32 = 4;
 pub const A3_MEM_HOST: i32 = 0;
 pub const A3_MEM_DEVICE: i32 = 1;
 

@@ -76,6 +76,33 @@ def test_k1_formats(det, oracle, c):
         _check_k1(det, oracle, s[..., 0] if c == 1 else s)
 
 
+@pytest.mark.parametrize("c", [3, 4])
+@pytest.mark.parametrize("w,h", [(640, 480), (1920, 1080), (33, 17), (250, 31)])
+def test_k1_bgr_formats(a3, det, oracle, c, w, h):
+    """A3_FMT_BGR8 / A3_FMT_BGRA8: camera byte order read directly == the host swizzle of
+    examples/webcam_kamera.rs:38-52 followed by into_luma8, on the fast (TMA strips) and the generic kernel."""
+    frames = _noise(100 + c + w, (3, h, w, c))
+    grey, mask = det.gray_threshold(frames, order="bgr")
+    swz = frames.copy()
+    swz[..., 0], swz[..., 2] = frames[..., 2], frames[..., 0]
+    grey2, mask2 = det.gray_threshold(swz)
+    assert np.array_equal(grey, grey2) and np.array_equal(mask, mask2)
+    for i in range(frames.shape[0]):
+        assert np.array_equal(grey[i], oracle.to_luma8(frames[i], order="bgr"))
+        assert np.array_equal(grey[i], oracle.to_luma8(swz[i]))
+
+
+def test_detect_bgra_equals_swizzled_rgba(a3):
+    from aruco3_b200 import synth
+    rgb, _ = synth.render_batch("C1", 3)
+    bgra = np.concatenate([rgb[..., ::-1], np.full(rgb.shape[:3] + (1,), 255, np.uint8)], axis=3)
+    with a3.Detector(dictionary="ARUCO") as d:
+        want = d.detect_batch(rgb)
+        got = d.detect_batch(bgra, order="bgr")
+    assert [[(m.id, m.corners, m.rotation) for m in x.markers] for x in got] == [[(m.id, m.corners, m.rotation) for m in x.markers] for x in want]
+    assert sum(len(x.markers) for x in got) > 5
+
+
 @pytest.mark.parametrize("radius", [1, 2, 3, 5, 7, 8, 12, 16])
 def test_k1_radius(a3, oracle, radius):
     """threshold_window is a public config field (src/aruco.rs:24)."""

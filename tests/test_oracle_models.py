@@ -19,6 +19,10 @@ def test_luma_matches_integer_formula(oracle):
     assert np.array_equal(oracle.to_luma8(want), want)            # Luma8 passes through
     px = np.array([[[255, 255, 255], [0, 255, 0], [255, 0, 0], [0, 0, 255]]], np.uint8)
     assert oracle.to_luma8(px).tolist() == [[255, 182, 54, 18]]
+    # camera byte order (examples/webcam_kamera.rs:38-52 swizzle, then into_luma8)
+    assert np.array_equal(oracle.to_luma8(np.ascontiguousarray(rgb[..., ::-1]), order="bgr"), want)
+    bgra = np.dstack([rgb[..., ::-1], rgba[..., 3:]])
+    assert np.array_equal(oracle.to_luma8(np.ascontiguousarray(bgra), order="bgr"), want)
 
 
 @pytest.mark.parametrize("w,h,r", [(40, 30, 7), (9, 5, 7), (15, 15, 7), (64, 3, 3), (1, 1, 7), (33, 47, 1), (50, 20, 12)])
