@@ -297,6 +297,13 @@ def main():
         "counts_per_step": {k: acc_dev[k] / args.steps for k in ("n_contours", "n_contour_points", "n_candidates", "n_markers")},
         "clocks": clocks, "clocks_e2e": clocks_e2e,
     }
+    # the latency-bound stages are reported as units per second of their own kernel time, not as roofline fractions
+    if acc_dev["ms_decode_kernel"] > 0:
+        line["k2_decode"] = {"candidates_per_s": acc_dev["n_candidates"] / (acc_dev["ms_decode_kernel"] * 1e-3), "unit": "candidates/s",
+                             "ms_per_step": acc_dev["ms_decode_kernel"] / args.steps, "candidates_per_step": acc_dev["n_candidates"] / args.steps}
+    if acc_dev["ms_contour_kernels"] > 0:
+        line["k3_contours"] = {"border_points_per_s": acc_dev["n_contour_points"] / (acc_dev["ms_contour_kernels"] * 1e-3), "unit": "border points/s",
+                               "ms_per_step": acc_dev["ms_contour_kernels"] / args.steps}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = min(n, max(32, 2 * cores))
         fps, s_per_step, mk, st = cpu_reference_run(pinned.numpy()[:sample], cores, 1, 1)
