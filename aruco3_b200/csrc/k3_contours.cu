@@ -102,13 +102,39 @@ __device__ __forceinline__ uint32_t ring_of(uint32_t hood) {
 }
 
 constexpr uint32_t kBudget = 48;  // steps a candidate may walk inside k3_candidates before it is deferred to k3_walkers
+// A walk is a chain of dependent loads: its time is its length.  The first walk of a border cannot be split (the
+// candidate must see the whole loop), but while it walks it drops a checkpoint every kSeg points, and k3_emit then
+// writes the points with one thread per checkpoint: chains of kSeg steps instead of the longest border.
+constexpr uint32_t kSeg = 64;
+static_assert(kBudget < kSeg, "borders finished inside the budget must fit one emit segment");
+struct Ckpt { uint32_t walker, pos, xy, state; };  // pos: points walked when it was dropped (forward index, or backward count for west starts)
 
 enum { kDead = 0, kSurvivor = 1, kUndecided = 2 };
+
+// Work lists shared by the kernels of one k3_quads call.
+struct Lists {
+    unsigned long long *cands;         // start candidates left after the word-level filter: ((word id * 32 + bit) << 1) | kind
+    uint32_t cands_cap;
+    unsigned long long *walkers;       // candidates undecided after kBudget steps: the same key
+    unsigned long long *long_keys;     // surviving borders with >= min_points points: the same key ...
+    uint32_t *long_n;                  // ... and their number of points
+    uint32_t *counters;                // [0] walkers, [1] long borders, [2] overflow of a list, [3] candidates, [4] checkpoints
+    uint32_t *long_slot;               // value array of the sort: the border's slot in long_keys / long_n
+    uint32_t *walker_slot;             // per entry of `walkers`: slot of the border it survived as, or 0xffffffff
+    Ckpt *ckpts;                       // checkpoints dropped by k3_walkers
+    uint32_t ckpt_cap;
+    unsigned long long *long_points;   // total points of the long borders
+    uint32_t walkers_cap, long_cap;
+    uint32_t *frame_contours;          // per frame: borders followed
+    unsigned long long *frame_points;  // per frame: their points
+    uint32_t *frame_flags;             // per frame: bit 0 barred start (host redo), bit 1 rdp stack overflow, bit 2 quad capacity
+};
+
 
 // The candidate (x, y, kind) walks its border for at most `budget` steps.  kSurvivor: it is the raster-first candidate
 // crack of the border (n = number of points of the border, first_pixel = it is also the border's raster-first pixel).
 __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (*fwd)[512], const uint16_t (*bwd)[512], int sx, int sy, int kind,
-                           uint32_t budget, uint32_t &n, bool &first_pixel) {
+                           uint32_t budget, uint32_t &n, bool &first_pixel, const Lists *ck = nullptr, uint32_t walker = 0) {
     const uint32_t me = ((uint32_t)(sy * (int)g.w + sx) << 1) | (uint32_t)kind;
     const uint32_t nb0 = ring_of(hood9(plane, g.Hp, sx, sy));
     const int adj = kind ? 4 : 0;
@@ -143,6 +169,11 @@ __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (
         if ((e & 8u) && x > 0 && (pix << 1) < me) return kDead;
         if ((e & 16u) && x + 1 < (int)g.w && ((pix << 1) | 1u) < me) return kDead;
         if (steps >= budget) return kUndecided;
+        if (ck && n && n % kSeg == 0) {  // the pixel under the walk is point n (forwards) / the n-th point from the end (backwards)
+            const uint32_t c = atomicAdd(&ck->counters[4], 1u);
+            if (c < ck->ckpt_cap) ck->ckpts[c] = Ckpt{walker, n, (uint32_t)x | ((uint32_t)y << 16), kind ? state : (e & 7u)};
+            else atomicOr(&ck->counters[2], 1u);
+        }
         min_pix = min(min_pix, pix);
         n++;
         x += (int)((e >> 5) & 3u) - 1;
@@ -153,23 +184,8 @@ __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (
     return kSurvivor;
 }
 
-// Work lists shared by the kernels of one k3_quads call.
-struct Lists {
-    unsigned long long *cands;         // start candidates left after the word-level filter: ((word id * 32 + bit) << 1) | kind
-    uint32_t cands_cap;
-    unsigned long long *walkers;       // candidates undecided after kBudget steps: the same key
-    unsigned long long *long_keys;     // surviving borders with >= min_points points: the same key ...
-    uint32_t *long_n;                  // ... and their number of points
-    uint32_t *counters;                // [0] walkers, [1] long borders, [2] overflow of a list, [3] candidates
-    unsigned long long *long_points;   // total points of the long borders
-    uint32_t walkers_cap, long_cap;
-    uint32_t *frame_contours;          // per frame: borders followed
-    unsigned long long *frame_points;  // per frame: their points
-    uint32_t *frame_flags;             // per frame: bit 0 barred start (host redo), bit 1 rdp stack overflow, bit 2 quad capacity
-};
-
-__device__ __forceinline__ void record_survivor(const Lists &l, uint32_t frame, unsigned long long key, int kind, uint32_t n, bool first_pixel,
-                                                uint32_t min_points) {
+__device__ __forceinline__ uint32_t record_survivor(const Lists &l, uint32_t frame, unsigned long long key, int kind, uint32_t n, bool first_pixel,
+                                                    uint32_t min_points) {
     atomicAdd(&l.frame_contours[frame], 1u);
     atomicAdd(&l.frame_points[frame], (unsigned long long)n);
     if (kind == 0 && !first_pixel) atomicOr(&l.frame_flags[frame], 1u);  // a west start below the top of its border: barred natural start
@@ -178,11 +194,13 @@ __device__ __forceinline__ void record_survivor(const Lists &l, uint32_t frame, 
         if (slot < l.long_cap) {
             l.long_keys[slot] = key;
             l.long_n[slot] = n;
+            l.long_slot[slot] = slot;
             atomicAdd(l.long_points, (unsigned long long)n);
-        } else {
-            atomicOr(&l.counters[2], 1u);
+            return slot;
         }
+        atomicOr(&l.counters[2], 1u);
     }
+    return 0xffffffffu;
 }
 
 __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
@@ -222,6 +240,22 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
             const uint32_t fa_e = (fa >> 1) | (__ldg(col + g.Hp - 1) << 31);                      // bit x = pixel (x+1, y-1)
             og &= ~((fa & ~fa_w) | (~fa & ~fa_w & fa_e));
             hg &= ~((fa & ~fa_e) | (~fa & ~fa_e & fa_w));
+            // The same two ideas over runs instead of single pixels (stair steps of shallow edges), inside this word; a run
+            // that leaves the word is simply not used.  runs(P, S): all bits of the runs of ones of P whose lowest bit is in S
+            // (the carry of P + S sweeps each such run).
+            //   background run below foreground:  P  = above F, here B;  it ends (on one side) at a pixel that is B in both
+            //     rows (T): the foreground pixel of the row above next to T has a west / east crack, and both background
+            //     chains are 4-connected through the run.
+            //   foreground run below background:  P2 = above B, here F;  it ends at a pixel whose upper neighbour is F: that
+            //     pixel has a west / east crack towards the run (needs NW / NE background for the connection).
+            auto runs = [](uint32_t P, uint32_t S) { return ((P + (S & P)) ^ P) & P; };
+            const uint32_t valid = (k == (g.w - 1) >> 5) ? (0xffffffffu >> (31 - ((g.w - 1) & 31))) : 0xffffffffu;  // real pixels of this word
+            const uint32_t P = fa & ~f, T = ~fa & ~f & valid, P2 = ~fa & f;
+            const uint32_t rP = __brev(P), rP2 = __brev(P2);
+            og &= ~(runs(P, T << 1) << 1);                                  // west crack right of a P run that starts right of a T
+            og &= ~(__brev(runs(rP2, __brev(fa) << 1)) & ~fa_w);            // west crack at the low end of a P2 run that ends below an F
+            hg &= ~(__brev(runs(rP, __brev(T) << 1)) >> 1);                 // east crack left of a P run that ends left of a T
+            hg &= ~(runs(P2, fa << 1) & ~fa_e);                             // east crack at the high end of a P2 run that starts below an F
         }
         // what is left goes to the candidate list (one atomic per warp); k3_walk_short gives every entry a thread
         const uint32_t mine = __popc(og) + __popc(hg);
@@ -318,9 +352,20 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
         bool first_pixel;
         decode_key(g, key, frame, x, y, kind);
         const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
-        if (walk_border(plane, g, fwd, bwd, x, y, kind, 0xffffffffu, n, first_pixel) == kSurvivor)
-            record_survivor(l, frame, key, kind, n, first_pixel, min_points);
+        uint32_t slot = 0xffffffffu;
+        if (walk_border(plane, g, fwd, bwd, x, y, kind, 0xffffffffu, n, first_pixel, &l, i) == kSurvivor)
+            slot = record_survivor(l, frame, key, kind, n, first_pixel, min_points);
+        l.walker_slot[i] = slot;
     }
+}
+
+// after the sort: lengths in sorted order (input of the prefix sum) and the sorted position of every slot
+__global__ void __launch_bounds__(256) k3_rank(const uint32_t *slot_sorted, const uint32_t *long_n, uint32_t n_long, uint32_t *n_sorted, uint32_t *rank) {
+    const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_long) return;
+    const uint32_t s = slot_sorted[ci];
+    n_sorted[ci] = long_n[s];
+    rank[s] = ci;
 }
 
 struct Contour {
@@ -328,40 +373,57 @@ struct Contour {
     unsigned long long point_off;
 };
 
-// one thread per long border (sorted by raster position of the start): write its points (x | y << 16) in the
-// reference's order, i.e. the forward trace from the start pixel
+// Writes the points (x | y << 16) of the long borders (sorted by raster position of the start) in the reference's order,
+// i.e. the forward trace from the start pixel, kSeg points per thread: thread ci < n_contours starts at the border's
+// start pixel, the others at a checkpoint dropped by the border's walker.
 __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *tables, const unsigned long long *keys, const uint32_t *lens,
-                                               const uint32_t *offsets, uint32_t n_contours, Contour *contours, uint32_t *points) {
+                                               const uint32_t *offsets, uint32_t n_contours, const uint32_t *rank, const uint32_t *walker_slot,
+                                               const Ckpt *ckpts, uint32_t n_ckpts, Contour *contours, uint32_t *points) {
     __shared__ uint16_t fwd[8][512];
     for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) (&fwd[0][0])[i] = (&tables->fwd[0][0])[i];
     __syncthreads();
-    const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ci >= n_contours) return;
-    uint32_t frame;
-    int sx, sy, kind;
-    decode_key(g, keys[ci], frame, sx, sy, kind);
-    const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
-    const uint32_t nb0 = ring_of(hood9(plane, g.Hp, sx, sy));
-    const int adj = kind ? 4 : 0;
-    int pred = 0;
-    for (int q = 0; q < 8; q++) {
-        const int d = (adj + q) & 7;
-        if ((nb0 >> d) & 1) { pred = d; break; }
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_contours + n_ckpts) return;
+    uint32_t frame, ci, first, count, state;
+    int x, y, sx, sy, kind;
+    if (t < n_contours) {
+        ci = t;
+        decode_key(g, keys[ci], frame, sx, sy, kind);
+        const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+        const uint32_t nb0 = ring_of(hood9(plane, g.Hp, sx, sy));
+        const int adj = kind ? 4 : 0;
+        int pred = 0;
+        for (int q = 0; q < 8; q++) {
+            const int d = (adj + q) & 7;
+            if ((nb0 >> d) & 1) { pred = d; break; }
+        }
+        const uint32_t n = lens[ci];
+        // forward walkers drop checkpoints at points kSeg, 2 kSeg, ...; backward walkers kSeg, 2 kSeg, ... points before the end
+        first = 0; count = kind ? min(kSeg, n) : n - kSeg * ((n - 1) / kSeg);
+        x = sx; y = sy; state = (uint32_t)pred;
+        Contour c;
+        c.frame = frame; c.start = (uint32_t)sx | ((uint32_t)sy << 16); c.n = n; c.kind = (uint32_t)kind; c.point_off = offsets[ci];
+        contours[ci] = c;
+    } else {
+        const Ckpt c = ckpts[t - n_contours];
+        const uint32_t slot = walker_slot[c.walker];
+        if (slot == 0xffffffffu) return;  // that walker did not survive (or its border is too short to matter)
+        ci = rank[slot];
+        decode_key(g, keys[ci], frame, sx, sy, kind);
+        const uint32_t n = lens[ci];
+        first = kind ? c.pos : n - c.pos;
+        count = kind ? min(kSeg, n - c.pos) : kSeg;
+        x = (int)(c.xy & 0xffffu); y = (int)(c.xy >> 16); state = c.state;
     }
-    const uint32_t n = lens[ci];
-    uint32_t *out = points + offsets[ci];
-    int x = sx, y = sy;
-    uint32_t state = (uint32_t)pred;
-    for (uint32_t i = 0; i < n; i++) {
+    const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+    uint32_t *out = points + offsets[ci] + first;
+    for (uint32_t i = 0; i < count; i++) {
         out[i] = (uint32_t)x | ((uint32_t)y << 16);
         const uint32_t e = fwd[state][hood9(plane, g.Hp, x, y)];
         x += (int)((e >> 5) & 3u) - 1;
         y += (int)((e >> 7) & 3u) - 1;
         state = e >> 9;
     }
-    Contour c;
-    c.frame = frame; c.start = (uint32_t)sx | ((uint32_t)sy << 16); c.n = n; c.kind = (uint32_t)kind; c.point_off = offsets[ci];
-    contours[ci] = c;
 }
 
 struct Pt { int x, y; };
@@ -624,7 +686,9 @@ struct K3Workspace::Impl {
     // work lists
     unsigned long long *cands = nullptr, *walkers = nullptr, *long_keys = nullptr, *long_keys_sorted = nullptr, *long_points = nullptr, *frame_points = nullptr;
     uint32_t *long_n = nullptr, *long_n_sorted = nullptr, *long_off = nullptr, *counters = nullptr, *frame_contours = nullptr;
-    size_t cands_cap = 0, walkers_cap = 0, long_cap = 0, frames_cap = 0;
+    uint32_t *long_slot = nullptr, *long_slot_sorted = nullptr, *long_rank = nullptr, *walker_slot = nullptr;
+    Ckpt *ckpts = nullptr;
+    size_t cands_cap = 0, walkers_cap = 0, long_cap = 0, frames_cap = 0, ckpt_cap = 0;
     void *cub_tmp = nullptr;
     size_t cub_bytes = 0;
     Contour *contours = nullptr;
@@ -634,7 +698,7 @@ struct K3Workspace::Impl {
     size_t points_cap = 0;
     uint8_t *dead = nullptr;
     size_t dead_cap = 0;
-    unsigned long long *h_counts = nullptr;  // pinned: [0] counters[0..1], [1] counters[2] (overflow), [2] long_points
+    unsigned long long *h_counts = nullptr;  // pinned: [0..3] the eight 32-bit counters, [4] long_points
     Geo g;                                   // state handed from k3_begin to k3_finish
     Lists l;
     int sms = 148;
@@ -646,7 +710,8 @@ K3Workspace::~K3Workspace() {
     for (void *p : {(void *)impl->d_tables, (void *)impl->cands, (void *)impl->walkers, (void *)impl->long_keys, (void *)impl->long_keys_sorted, (void *)impl->long_points,
                     (void *)impl->frame_points, (void *)impl->long_n, (void *)impl->long_n_sorted, (void *)impl->long_off, (void *)impl->counters,
                     (void *)impl->frame_contours, impl->cub_tmp, (void *)impl->contours, (void *)impl->contour_quads, (void *)impl->points,
-                    (void *)impl->dead})
+                    (void *)impl->dead, (void *)impl->long_slot, (void *)impl->long_slot_sorted, (void *)impl->long_rank, (void *)impl->walker_slot,
+                    (void *)impl->ckpts})
         if (p) cudaFree(p);
     if (impl->h_counts) cudaFreeHost(impl->h_counts);
     delete impl;
@@ -728,8 +793,8 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         if (e == cudaSuccess) e = cudaMemcpy(w.d_tables, t, sizeof(StepTables), cudaMemcpyHostToDevice);
         delete t;
         K3_CUDA(e);
-        K3_CUDA(cudaHostAlloc(&w.h_counts, 32, cudaHostAllocDefault));
-        K3_CUDA(cudaMalloc(&w.counters, 16));
+        K3_CUDA(cudaHostAlloc(&w.h_counts, 64, cudaHostAllocDefault));
+        K3_CUDA(cudaMalloc(&w.counters, 32));
         K3_CUDA(cudaMalloc(&w.long_points, 8));
     }
     // list capacities: generous per frame; an overflow sends the whole call to the host stage (flag 8), never a wrong answer
@@ -743,14 +808,21 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     }
     if (want_walkers > w.walkers_cap) {
         K3_CUDA(alloc_exact(w.walkers, want_walkers));
+        K3_CUDA(alloc_exact(w.walker_slot, want_walkers));
         w.walkers_cap = want_walkers;
+    }
+    const size_t want_ckpts = (size_t)p.n * (pixels / kSeg + 4096);  // one per kSeg walked points; an overflow flags the call (host stage)
+    if (want_ckpts > w.ckpt_cap) {
+        K3_CUDA(alloc_exact(w.ckpts, want_ckpts));
+        w.ckpt_cap = want_ckpts;
     }
     if (want_long > w.long_cap) {
         K3_CUDA(alloc_exact(w.long_keys, want_long)); K3_CUDA(alloc_exact(w.long_keys_sorted, want_long));
         K3_CUDA(alloc_exact(w.long_n, want_long)); K3_CUDA(alloc_exact(w.long_n_sorted, want_long)); K3_CUDA(alloc_exact(w.long_off, want_long));
+        K3_CUDA(alloc_exact(w.long_slot, want_long)); K3_CUDA(alloc_exact(w.long_slot_sorted, want_long)); K3_CUDA(alloc_exact(w.long_rank, want_long));
         w.long_cap = want_long;
         size_t a = 0, b = 0;
-        K3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, a, w.long_keys, w.long_keys_sorted, w.long_n, w.long_n_sorted, (int)want_long, 0, 64, stream));
+        K3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, a, w.long_keys, w.long_keys_sorted, w.long_slot, w.long_slot_sorted, (int)want_long, 0, 64, stream));
         K3_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b, w.long_n_sorted, w.long_off, (int)want_long, stream));
         const size_t need = a > b ? a : b;
         if (need > w.cub_bytes) {
@@ -772,7 +844,7 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     K3_CUDA(cudaMemsetAsync(w.frame_points, 0, (size_t)p.n * 8, stream));
     K3_CUDA(cudaMemsetAsync(w.frame_contours, 0, (size_t)p.n * 4, stream));
     K3_CUDA(cudaMemsetAsync(p.frame_flags, 0, (size_t)p.n * 4, stream));
-    K3_CUDA(cudaMemsetAsync(w.counters, 0, 16, stream));
+    K3_CUDA(cudaMemsetAsync(w.counters, 0, 32, stream));
     K3_CUDA(cudaMemsetAsync(w.long_points, 0, 8, stream));
 
     timer.mark("begin");
@@ -782,6 +854,8 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     l.walkers_cap = (uint32_t)(w.walkers_cap > 0xffffffffull ? 0xffffffffull : w.walkers_cap);
     l.long_cap = (uint32_t)(w.long_cap > 0x7fffffffull ? 0x7fffffffull : w.long_cap);
     l.frame_contours = w.frame_contours; l.frame_points = w.frame_points; l.frame_flags = p.frame_flags;
+    l.long_slot = w.long_slot; l.walker_slot = w.walker_slot; l.ckpts = w.ckpts;
+    l.ckpt_cap = (uint32_t)(w.ckpt_cap > 0x7fffffffull ? 0x7fffffffull : w.ckpt_cap);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -803,8 +877,8 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     timer.mark("walkers");
     k3_flag_all<<<(p.n + 127) / 128, 128, 0, stream>>>(p.frame_flags, p.n, w.counters, 0);
     K3_CUDA(cudaGetLastError());
-    K3_CUDA(cudaMemcpyAsync(&w.h_counts[0], w.counters, 16, cudaMemcpyDeviceToHost, stream));
-    K3_CUDA(cudaMemcpyAsync(&w.h_counts[2], w.long_points, 8, cudaMemcpyDeviceToHost, stream));
+    K3_CUDA(cudaMemcpyAsync(&w.h_counts[0], w.counters, 32, cudaMemcpyDeviceToHost, stream));
+    K3_CUDA(cudaMemcpyAsync(&w.h_counts[4], w.long_points, 8, cudaMemcpyDeviceToHost, stream));
     w.g = g; w.l = l; w.sms = sms;
     return cudaSuccess;
 }
@@ -823,7 +897,9 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     timer.mark("sync");
     const uint32_t *hc = reinterpret_cast<const uint32_t *>(&w.h_counts[0]);
     uint32_t n_long = hc[1] < l.long_cap ? hc[1] : l.long_cap;
-    const unsigned long long n_points = w.h_counts[2];
+    const unsigned long long n_points = w.h_counts[4];
+    const uint32_t n_ckpts = hc[4] < l.ckpt_cap ? hc[4] : l.ckpt_cap;
+    if (timer.on) fprintf(stderr, "k3 lists: %u candidates, %u walkers, %u long borders, %llu points, %u checkpoints\n", hc[3], hc[0], hc[1], n_points, hc[4]);
     if (n_points >= 0xffffffffull && !hc[2]) {  // point offsets are 32-bit: hand the whole call to the host stage
         k3_flag_all<<<(p.n + 127) / 128, 128, 0, stream>>>(p.frame_flags, p.n, w.counters, 1);
         K3_CUDA(cudaGetLastError());
@@ -838,11 +914,14 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         K3_CUDA(grow(w.points, w.points_cap, (size_t)n_points + 1));
         size_t tmp = w.cub_bytes;
         const int end_bit = 64 - __builtin_clzll(((unsigned long long)nwords << 6) | 1ull);
-        K3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.long_keys, w.long_keys_sorted, w.long_n, w.long_n_sorted, (int)n_long, 0, end_bit, stream));
+        K3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.long_keys, w.long_keys_sorted, w.long_slot, w.long_slot_sorted, (int)n_long, 0, end_bit, stream));
+        k3_rank<<<(n_long + 255) / 256, 256, 0, stream>>>(w.long_slot_sorted, w.long_n, n_long, w.long_n_sorted, w.long_rank);
+        K3_CUDA(cudaGetLastError());
         tmp = w.cub_bytes;
         K3_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.long_n_sorted, w.long_off, (int)n_long, stream));
         timer.mark("sort+scan");
-        k3_emit<<<(n_long + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, n_long, w.contours, w.points);
+        k3_emit<<<(n_long + n_ckpts + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, n_long, w.long_rank,
+                                                                   w.walker_slot, w.ckpts, n_ckpts, w.contours, w.points);
         K3_CUDA(cudaGetLastError());
         timer.mark("emit");
         k3_rdp<<<(n_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, n_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags);
