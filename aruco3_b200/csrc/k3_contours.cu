@@ -101,6 +101,64 @@ __device__ __forceinline__ uint32_t ring_of(uint32_t hood) {
     return (m & 1u) | ((t & 1u) << 1) | ((t & 2u) << 1) | ((t & 4u) << 1) | ((m & 4u) << 2) | ((b & 4u) << 3) | ((b & 2u) << 5) | ((b & 1u) << 7);
 }
 
+// The same neighbourhood for k3_emit: a border moves one pixel per step, so the three words of the current word column
+// (and, next to a 32-pixel boundary, of the following one) stay in registers; a step that keeps its row loads nothing,
+// a step that changes row loads one word (two at a boundary).  A warp's lanes walk 32 different borders, so every load
+// is 32 separate L1 wavefronts, and with one thread per segment k3_emit is bound by exactly those (measured: the first
+// walks, which are bound by the latency of the longest chain instead, get slower with the extra branches).
+struct Window {
+    const uint32_t *plane;
+    uint32_t Hp;
+    int kc, yg;            // guarded word column of pixel x-1; guarded row of y-1 (== y)
+    uint32_t t, m, b;      // column kc, rows y-1, y, y+1
+    uint32_t t2, m2, b2;   // column kc+1, valid where v2 has bit 0 / 1 / 2
+    uint32_t v2;
+};
+__device__ __forceinline__ void win_load(Window &w, int x, int y) {
+    w.kc = (x + 31) >> 5; w.yg = y;
+    const uint32_t *p = w.plane + (size_t)w.kc * w.Hp + y;
+    w.t = __ldg(p); w.m = __ldg(p + 1); w.b = __ldg(p + 2);
+    w.v2 = 0;
+}
+__device__ __forceinline__ uint32_t win_hood(Window &w, int x) {
+    const int sh = (x + 31) & 31;
+    uint32_t t = w.t >> sh, m = w.m >> sh, b = w.b >> sh;
+    if (sh > 29) {
+        if (w.v2 != 7u) {
+            const uint32_t *q = w.plane + (size_t)(w.kc + 1) * w.Hp + w.yg;
+            if (!(w.v2 & 1u)) w.t2 = __ldg(q);
+            if (!(w.v2 & 2u)) w.m2 = __ldg(q + 1);
+            if (!(w.v2 & 4u)) w.b2 = __ldg(q + 2);
+            w.v2 = 7u;
+        }
+        t |= w.t2 << (32 - sh); m |= w.m2 << (32 - sh); b |= w.b2 << (32 - sh);
+    }
+    return (t & 7u) | ((m & 7u) << 3) | ((b & 7u) << 6);
+}
+// the walk moved to (x, y), at most one pixel away in each direction
+__device__ __forceinline__ void win_move(Window &w, int x, int y) {
+    const int kc = (x + 31) >> 5, dy = y - w.yg;
+    if (kc != w.kc) {
+        if (dy == 0 && kc == w.kc + 1 && w.v2 == 7u) {         // the following column becomes the current one
+            w.t = w.t2; w.m = w.m2; w.b = w.b2; w.v2 = 0; w.kc = kc;
+        } else if (dy == 0 && kc == w.kc - 1) {                // the current column becomes the following one
+            w.t2 = w.t; w.m2 = w.m; w.b2 = w.b; w.v2 = 7u; w.kc = kc;
+            const uint32_t *p = w.plane + (size_t)kc * w.Hp + y;
+            w.t = __ldg(p); w.m = __ldg(p + 1); w.b = __ldg(p + 2);
+        } else {
+            win_load(w, x, y);
+        }
+    } else if (dy > 0) {
+        w.t = w.m; w.m = w.b; w.b = __ldg(w.plane + (size_t)kc * w.Hp + y + 2);
+        w.t2 = w.m2; w.m2 = w.b2; w.v2 >>= 1;
+        w.yg = y;
+    } else if (dy < 0) {
+        w.b = w.m; w.m = w.t; w.t = __ldg(w.plane + (size_t)kc * w.Hp + y);
+        w.b2 = w.m2; w.m2 = w.t2; w.v2 = (w.v2 << 1) & 7u;
+        w.yg = y;
+    }
+}
+
 constexpr uint32_t kBudget = 48;  // steps a candidate may walk inside k3_candidates before it is deferred to k3_walkers
 // A walk is a chain of dependent loads: its time is its length.  The first walk of a border cannot be split (the
 // candidate must see the whole loop), but while it walks it drops a checkpoint every kSeg points, and k3_emit then
@@ -214,15 +272,32 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
     const uint32_t words_per_frame = g.h * g.wpr;
     // blockIdx.y strides over frames; inside a frame consecutive threads take consecutive rows of one word column:
     // consecutive words of the column-major plane
+    // The scan is a stream of dependent loads with almost no work behind them (most words have no crack at all), so each
+    // thread first issues the loads of kBatch words (the word and its two horizontal neighbours) and only then looks at them.
+    constexpr int kBatch = 4;
+    const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t frame = blockIdx.y; frame < g.n; frame += gridDim.y)
-    for (uint32_t rem = blockIdx.x * blockDim.x + threadIdx.x; rem < words_per_frame; rem += gridDim.x * blockDim.x) {
+    for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < words_per_frame; base += stride * kBatch) {
+      const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+      uint32_t fv[kBatch], lv[kBatch], rv[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; u++) {
+          const uint32_t rem = base + (uint32_t)u * stride;
+          fv[u] = 0; lv[u] = 0; rv[u] = 0;
+          if (rem < words_per_frame) {
+              const uint32_t *col = plane + (size_t)(rem / g.h + 1) * g.Hp + (rem % g.h + 1);
+              fv[u] = __ldg(col); lv[u] = __ldg(col - g.Hp); rv[u] = __ldg(col + g.Hp);
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; u++) {
+        const uint32_t f = fv[u];
+        if (!f) continue;
+        const uint32_t rem = base + (uint32_t)u * stride;
         const uint32_t k = rem / g.h, y = rem % g.h;
         const size_t gid = (size_t)frame * words_per_frame + (size_t)y * g.wpr + k;  // raster word id: the sort key
-        const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
         const uint32_t *col = plane + (size_t)(k + 1) * g.Hp + (y + 1);
-        const uint32_t f = __ldg(col);
-        if (!f) continue;
-        const uint32_t west = (f << 1) | (__ldg(col - g.Hp) >> 31), east = (f >> 1) | (__ldg(col + g.Hp) << 31);
+        const uint32_t west = (f << 1) | (lv[u] >> 31), east = (f >> 1) | (rv[u] << 31);
         uint32_t og = f & ~west, hg = f & ~east;
         if (k == 0) og &= ~1u;                                           // `x > 0`
         if (k == (g.w - 1) >> 5) hg &= ~(1u << ((g.w - 1) & 31));        // `x + 1 < w`
@@ -293,6 +368,7 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
                 slot++;
             }
         }
+      }
     }
 }
 
@@ -415,15 +491,28 @@ __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *ta
         count = kind ? min(kSeg, n - c.pos) : kSeg;
         x = (int)(c.xy & 0xffffu); y = (int)(c.xy >> 16); state = c.state;
     }
-    const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+    Window win;
+    win.plane = g.planes + (size_t)frame * g.frame_words; win.Hp = g.Hp;
+    win_load(win, x, y);
     uint32_t *out = points + offsets[ci] + first;
-    for (uint32_t i = 0; i < count; i++) {
-        out[i] = (uint32_t)x | ((uint32_t)y << 16);
-        const uint32_t e = fwd[state][hood9(plane, g.Hp, x, y)];
+    // four points per 16-byte store where the destination allows it (points + offset is only 4-byte aligned in general)
+    uint32_t i = 0;
+    auto step = [&]() {
+        const uint32_t v = (uint32_t)x | ((uint32_t)y << 16);
+        const uint32_t e = fwd[state][win_hood(win, x)];
         x += (int)((e >> 5) & 3u) - 1;
         y += (int)((e >> 7) & 3u) - 1;
         state = e >> 9;
+        win_move(win, x, y);
+        return v;
+    };
+    while (i < count && ((uintptr_t)(out + i) & 15u)) out[i++] = step();
+    for (; i + 4 <= count; i += 4) {
+        uint4 v;
+        v.x = step(); v.y = step(); v.z = step(); v.w = step();
+        *reinterpret_cast<uint4 *>(out + i) = v;
     }
+    while (i < count) out[i++] = step();
 }
 
 struct Pt { int x, y; };
@@ -494,7 +583,7 @@ __global__ void __launch_bounds__(128) k3_rdp(const Contour *contours, const uin
     int sp = 0;
     if (lane == 0) stack[0] = make_uint2(0u, c.n - 1);
     sp = 1;
-    uint32_t nout = 0;
+    uint32_t nout = 0, nsplit = 0;
     Pt out[4];
     bool overflow = false;
     while (sp > 0) {
@@ -504,17 +593,19 @@ __global__ void __launch_bounds__(128) k3_rdp(const Contour *contours, const uin
         const Pt ps = unpack(pts[s.x]), pe = unpack(pts[s.y]);
         const long long a = (long long)ps.y - pe.y, b = (long long)pe.x - ps.x, cc = (long long)ps.x * pe.y - (long long)pe.x * ps.y;
         const double den = sqrt((double)a * (double)a + (double)b * (double)b);
-        // pass 1: largest numerator
+        // pass 1: largest numerator and the first index that reaches it (per lane in index order, then across lanes)
         long long best = 0;
+        uint32_t best_i = 0xffffffffu;
         for (uint32_t i = s.x + 1 + lane; i <= s.y; i += 32) {
             const Pt p = unpack(pts[i]);
             long long v = a * p.x + b * p.y + cc;
             v = v < 0 ? -v : v;
-            best = v > best ? v : best;
+            if (v > best) { best = v; best_i = i; }
         }
         for (int off = 16; off; off >>= 1) {
             const long long other = __shfl_xor_sync(0xffffffffu, best, off);
-            best = other > best ? other : best;
+            const uint32_t other_i = __shfl_xor_sync(0xffffffffu, best_i, off);
+            if (other > best || (other == best && other_i < best_i)) { best = other; best_i = other_i; }
         }
         double dmax = 0.0;
         uint32_t index = 0;
@@ -524,18 +615,23 @@ __global__ void __launch_bounds__(128) k3_rdp(const Contour *contours, const uin
                 long long t = best;  // smallest numerator whose quotient equals the maximum's
                 while (t > 1 && (double)(t - 1) / den == q) t--;
                 dmax = q;
-                uint32_t first = 0xffffffffu;
-                for (uint32_t i = s.x + 1 + lane; i <= s.y && first == 0xffffffffu; i += 32) {
-                    const Pt p = unpack(pts[i]);
-                    long long v = a * p.x + b * p.y + cc;
-                    v = v < 0 ? -v : v;
-                    if (v >= t) first = i;
+                uint32_t first = best_i;
+                if (t != best) {  // rare: a smaller numerator rounds to the same distance, and one of those may come earlier
+                    first = 0xffffffffu;
+                    for (uint32_t i = s.x + 1 + lane; i <= s.y && first == 0xffffffffu; i += 32) {
+                        const Pt p = unpack(pts[i]);
+                        long long v = a * p.x + b * p.y + cc;
+                        v = v < 0 ? -v : v;
+                        if (v >= t) first = i;
+                    }
+                    for (int off = 16; off; off >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
                 }
-                for (int off = 16; off; off >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
                 index = first;
             }
         }
         if (dmax > eps) {
+            // every split adds one vertex to the final polygon (vertices = splits + 1): the fourth split settles "not a quad"
+            if (++nsplit >= 4) { nout = 5; break; }
             if (sp + 2 > kRdpStack) { overflow = true; break; }
             __syncwarp();
             if (lane == 0) {
