@@ -276,33 +276,46 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
     // thread first issues the loads of kBatch words (the word and its two horizontal neighbours) and only then looks at them.
     constexpr int kBatch = 4;
     const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t last_k = (g.w - 1) >> 5, last_bit = (g.w - 1) & 31;
     for (uint32_t frame = blockIdx.y; frame < g.n; frame += gridDim.y)
     for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < words_per_frame; base += stride * kBatch) {
-      const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
-      uint32_t fv[kBatch], lv[kBatch], rv[kBatch];
-#pragma unroll
-      for (int u = 0; u < kBatch; u++) {
-          const uint32_t rem = base + (uint32_t)u * stride;
-          fv[u] = 0; lv[u] = 0; rv[u] = 0;
-          if (rem < words_per_frame) {
-              const uint32_t *col = plane + (size_t)(rem / g.h + 1) * g.Hp + (rem % g.h + 1);
-              fv[u] = __ldg(col); lv[u] = __ldg(col - g.Hp); rv[u] = __ldg(col + g.Hp);
-          }
-      }
-#pragma unroll
-      for (int u = 0; u < kBatch; u++) {
-        const uint32_t f = fv[u];
-        if (!f) continue;
-        const uint32_t rem = base + (uint32_t)u * stride;
-        const uint32_t k = rem / g.h, y = rem % g.h;
-        const size_t gid = (size_t)frame * words_per_frame + (size_t)y * g.wpr + k;  // raster word id: the sort key
-        const uint32_t *col = plane + (size_t)(k + 1) * g.Hp + (y + 1);
-        const uint32_t west = (f << 1) | (lv[u] >> 31), east = (f >> 1) | (rv[u] << 31);
-        uint32_t og = f & ~west, hg = f & ~east;
-        if (k == 0) og &= ~1u;                                           // `x > 0`
-        if (k == (g.w - 1) >> 5) hg &= ~(1u << ((g.w - 1) & 31));        // `x + 1 < w`
-        if (!(og | hg)) continue;
+        const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+        uint32_t fv[kBatch], og[kBatch], hg[kBatch], av[kBatch], awv[kBatch], aev[kBatch];
+        // phase 1: the word and its two horizontal neighbours -> west / east cracks that may start a border
         {
+            uint32_t lv[kBatch], rv[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; u++) {
+                const uint32_t rem = base + (uint32_t)u * stride;
+                fv[u] = 0; lv[u] = 0; rv[u] = 0;
+                if (rem < words_per_frame) {
+                    const uint32_t *col = plane + (size_t)(rem / g.h + 1) * g.Hp + (rem % g.h + 1);
+                    fv[u] = __ldg(col); lv[u] = __ldg(col - g.Hp); rv[u] = __ldg(col + g.Hp);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; u++) {
+                const uint32_t f = fv[u], k = (base + (uint32_t)u * stride) / g.h;
+                og[u] = f & ~((f << 1) | (lv[u] >> 31));
+                hg[u] = f & ~((f >> 1) | (rv[u] << 31));
+                if (k == 0) og[u] &= ~1u;                        // `x > 0`
+                if (k == last_k) hg[u] &= ~(1u << last_bit);     // `x + 1 < w`
+            }
+        }
+        // phase 2: the row above (three words) of the words that have such cracks, all loads first
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {
+            av[u] = 0; awv[u] = 0; aev[u] = 0;
+            if (og[u] | hg[u]) {
+                const uint32_t rem = base + (uint32_t)u * stride;
+                const uint32_t *col = plane + (size_t)(rem / g.h + 1) * g.Hp + (rem % g.h + 1);
+                av[u] = __ldg(col - 1); awv[u] = __ldg(col - g.Hp - 1); aev[u] = __ldg(col + g.Hp - 1);   // row y-1 (guard row for y = 0)
+            }
+        }
+        uint32_t mine = 0;
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {
+            if (!(og[u] | hg[u])) continue;
             // Most candidates have a raster-earlier candidate crack of the same border right above them; word arithmetic
             // on the row above finds those without walking (each rule names a crack that is on the same border because
             // the background pixels involved are 4-connected and the foreground pixels 8-connected):
@@ -310,11 +323,11 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
             //                          N and NW are background, NE is foreground: (x+1, y-1) has a west crack ('/' edge)
             //   east crack at (x, y):  (x, y-1) also has an east crack                      (straight right edge)
             //                          N and NE are background, NW is foreground: (x-1, y-1) has an east crack ('\' edge)
-            const uint32_t fa = __ldg(col - 1);                                                   // row y-1 (guard row for y = 0)
-            const uint32_t fa_w = (fa << 1) | (__ldg(col - g.Hp - 1) >> 31);                      // bit x = pixel (x-1, y-1)
-            const uint32_t fa_e = (fa >> 1) | (__ldg(col + g.Hp - 1) << 31);                      // bit x = pixel (x+1, y-1)
-            og &= ~((fa & ~fa_w) | (~fa & ~fa_w & fa_e));
-            hg &= ~((fa & ~fa_e) | (~fa & ~fa_e & fa_w));
+            const uint32_t f = fv[u], fa = av[u], k = (base + (uint32_t)u * stride) / g.h;
+            const uint32_t fa_w = (fa << 1) | (awv[u] >> 31);                      // bit x = pixel (x-1, y-1)
+            const uint32_t fa_e = (fa >> 1) | (aev[u] << 31);                      // bit x = pixel (x+1, y-1)
+            og[u] &= ~((fa & ~fa_w) | (~fa & ~fa_w & fa_e));
+            hg[u] &= ~((fa & ~fa_e) | (~fa & ~fa_e & fa_w));
             // The same two ideas over runs instead of single pixels (stair steps of shallow edges), inside this word; a run
             // that leaves the word is simply not used.  runs(P, S): all bits of the runs of ones of P whose lowest bit is in S
             // (the carry of P + S sweeps each such run).
@@ -324,51 +337,58 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
             //   foreground run below background:  P2 = above B, here F;  it ends at a pixel whose upper neighbour is F: that
             //     pixel has a west / east crack towards the run (needs NW / NE background for the connection).
             auto runs = [](uint32_t P, uint32_t S) { return ((P + (S & P)) ^ P) & P; };
-            const uint32_t valid = (k == (g.w - 1) >> 5) ? (0xffffffffu >> (31 - ((g.w - 1) & 31))) : 0xffffffffu;  // real pixels of this word
+            const uint32_t valid = (k == last_k) ? (0xffffffffu >> (31 - last_bit)) : 0xffffffffu;  // real pixels of this word
             const uint32_t P = fa & ~f, T = ~fa & ~f & valid, P2 = ~fa & f;
             const uint32_t rP = __brev(P), rP2 = __brev(P2);
-            og &= ~(runs(P, T << 1) << 1);                                  // west crack right of a P run that starts right of a T
-            og &= ~(__brev(runs(rP2, __brev(fa) << 1)) & ~fa_w);            // west crack at the low end of a P2 run that ends below an F
-            hg &= ~(__brev(runs(rP, __brev(T) << 1)) >> 1);                 // east crack left of a P run that ends left of a T
-            hg &= ~(runs(P2, fa << 1) & ~fa_e);                             // east crack at the high end of a P2 run that starts below an F
+            og[u] &= ~(runs(P, T << 1) << 1);                                  // west crack right of a P run that starts right of a T
+            og[u] &= ~(__brev(runs(rP2, __brev(fa) << 1)) & ~fa_w);            // west crack at the low end of a P2 run that ends below an F
+            hg[u] &= ~(__brev(runs(rP, __brev(T) << 1)) >> 1);                 // east crack left of a P run that ends left of a T
+            hg[u] &= ~(runs(P2, fa << 1) & ~fa_e);                             // east crack at the high end of a P2 run that starts below an F
+            mine += __popc(og[u]) + __popc(hg[u]);
         }
-        // what is left goes to the candidate list (one atomic per warp); k3_walk_short gives every entry a thread
-        const uint32_t mine = __popc(og) + __popc(hg);
+        if (!mine) continue;
+        // what is left goes to the candidate list (one atomic per warp and batch); k3_walk_short gives every entry a thread
         uint32_t slot;
         {
-            const cg::coalesced_group cgp = cg::coalesced_threads();  // the lanes that still have candidates in this word
+            const cg::coalesced_group cgp = cg::coalesced_threads();  // the lanes that still have candidates
             const uint32_t before = cg::exclusive_scan(cgp, mine);
-            uint32_t base = 0;
-            if (cgp.thread_rank() == cgp.size() - 1) base = atomicAdd(&l.counters[3], before + mine);
-            base = cgp.shfl(base, cgp.size() - 1);
-            slot = base + before;
+            uint32_t first = 0;
+            if (cgp.thread_rank() == cgp.size() - 1) first = atomicAdd(&l.counters[3], before + mine);
+            first = cgp.shfl(first, cgp.size() - 1);
+            slot = first + before;
         }
-        uint32_t pending = og | hg;
-        while (pending) {
-            const uint32_t b = pending & (0u - pending);
-            pending ^= b;
-            const int bit = __ffs(b) - 1;
-            for (int kind = 0; kind < 2; kind++) {
-                if (!((kind ? hg : og) & b)) continue;
-                const unsigned long long key = ((((unsigned long long)gid << 5) | (unsigned)bit) << 1) | (unsigned)kind;
-                if (slot < l.cands_cap) {
-                    l.cands[slot] = key;
-                } else {  // list full (very dense noise): walk it here, same rules as k3_walk_short
-                    uint32_t n;
-                    bool first_pixel;
-                    const int r = walk_border(plane, g, fwd, bwd, (int)(k * 32) + bit, (int)y, kind, kBudget, n, first_pixel);
-                    if (r == kSurvivor) {
-                        record_survivor(l, frame, key, kind, n, first_pixel, min_points);
-                    } else if (r == kUndecided) {
-                        const uint32_t ws = atomicAdd(&l.counters[0], 1u);
-                        if (ws < l.walkers_cap) l.walkers[ws] = key;
-                        else atomicOr(&l.counters[2], 1u);
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {
+            uint32_t pending = og[u] | hg[u];
+            if (!pending) continue;
+            const uint32_t rem = base + (uint32_t)u * stride;
+            const uint32_t k = rem / g.h, y = rem % g.h;
+            const size_t gid = (size_t)frame * words_per_frame + (size_t)y * g.wpr + k;  // raster word id: the sort key
+            while (pending) {
+                const uint32_t b = pending & (0u - pending);
+                pending ^= b;
+                const int bit = __ffs(b) - 1;
+                for (int kind = 0; kind < 2; kind++) {
+                    if (!((kind ? hg[u] : og[u]) & b)) continue;
+                    const unsigned long long key = ((((unsigned long long)gid << 5) | (unsigned)bit) << 1) | (unsigned)kind;
+                    if (slot < l.cands_cap) {
+                        l.cands[slot] = key;
+                    } else {  // list full (very dense noise): walk it here, same rules as k3_walk_short
+                        uint32_t n;
+                        bool first_pixel;
+                        const int r = walk_border(plane, g, fwd, bwd, (int)(k * 32) + bit, (int)y, kind, kBudget, n, first_pixel);
+                        if (r == kSurvivor) {
+                            record_survivor(l, frame, key, kind, n, first_pixel, min_points);
+                        } else if (r == kUndecided) {
+                            const uint32_t ws = atomicAdd(&l.counters[0], 1u);
+                            if (ws < l.walkers_cap) l.walkers[ws] = key;
+                            else atomicOr(&l.counters[2], 1u);
+                        }
                     }
+                    slot++;
                 }
-                slot++;
             }
         }
-      }
     }
 }
 
@@ -421,6 +441,8 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
     }
     __syncthreads();
     const uint32_t total = min(l.counters[0], l.walkers_cap);
+    // (measured: fewer walkers per warp, software prefetch of the sector ahead and a register window all make this kernel
+    // slower: its time is the dependent chain of the longest border, about 750 cycles per step with 32 borders per warp)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const unsigned long long key = l.walkers[i];
         uint32_t frame, n;
@@ -956,7 +978,7 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     {
-        // about 8 resident blocks of 256 threads per SM, split over the frames
+        // about 8 blocks of 256 threads per SM (measured best: more, smaller shares than one resident wave), split over the frames
         const uint32_t per_frame = (uint32_t)((words_per_frame + 255) / 256), resident = (uint32_t)sms * 8;
         const uint32_t gy = p.n < resident ? p.n : resident;
         uint32_t gx = (resident + gy - 1) / gy;

@@ -268,7 +268,10 @@ def main():
     total_frames = n * world * args.steps
     value = total_frames / (ms_dev * 1e-3)
     e2e_value = total_frames / (ms_e2e * 1e-3)
-    d2h = int(n * h * wpr * 4 + acc_e2e["n_candidates"] / args.steps * C.sizeof(_ffi.A3Decode))
+    # device -> host per step: the decode records, plus the mask bits (host contour stage) or K3's quads (first 64 per frame)
+    # and five per-frame counters (device contour stage)
+    d2h_front = n * h * wpr * 4 if args.contours == "host" else n * (64 * 32 + 4 * 4 + 8)
+    d2h = int(d2h_front + acc_e2e["n_candidates"] / args.steps * C.sizeof(_ffi.A3Decode))
     line = {
         "metric": "frames_per_sec_1080p_batch256", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -279,7 +282,7 @@ def main():
                    "parallelism": f"frame-batch sharding x{world}, no collective"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n * h * w * 3, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(acc_dev["pixel_kernel_launches"] + acc_dev["decode_kernel_launches"] + 7 * acc_dev["contour_kernel_launches"]),  # K3 = 7 kernels of ours per call
+        "gpu_launches": int(acc_dev["pixel_kernel_launches"] + acc_dev["decode_kernel_launches"] + 8 * acc_dev["contour_kernel_launches"]),  # K3 = 8 kernels of ours per call (+ cub sort / scan)
         "contour_stage": args.contours, "host_fallback_frames_per_step": acc_dev["host_fallback_frames"] / args.steps,
         "roofline": {"bound": "hbm", "kernel": "k1_strips_kernel<RGB8> (fused into_luma8 + adaptive_threshold, TMA tensor tiles)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
