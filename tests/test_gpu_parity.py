@@ -307,23 +307,38 @@ def test_full_size_batch_properties(a3):
     assert [[(m.id, m.corners) for m in x.markers] for x in part] == [[(m.id, m.corners) for m in x.markers] for x in got[37:41]]
 
 
-@pytest.mark.parametrize("contours", ["device", "host"])
-def test_resident_input_equals_host_input(a3, contours):
+@pytest.mark.parametrize("contours,nframes", [("device", 7), ("host", 7), ("device", 64), ("device", 131)])
+def test_resident_input_equals_host_input(a3, contours, nframes):
     """a3_detect_batch with A3_MEM_DEVICE (frames already in HBM, the flavour bench.py's `value` times) returns the same
-    markers and counters as the host-pointer flavour."""
+    markers and counters as the host-pointer flavour (which runs K1 / K3 / K2 per chunk of frames, while resident input
+    runs each once over the batch); the 131-frame case also carries pose output."""
     torch = pytest.importorskip("torch")
     from aruco3_b200 import _ffi, synth
-    frames, _ = synth.render_batch("C1", 7)
+    frames, _ = synth.render_batch("C1" if nframes != 64 else "C1n", nframes)
     n, h, w = frames.shape[:3]
+    cap = 64 * n + 4096
     with a3.Detector(contours=contours) as d:
+        if nframes == 131:
+            d.set_pose(40.0)
         want = d.detect_batch(frames)
         want_stats = dict(d.last_stats)
         dev = torch.from_numpy(frames).cuda()
-        markers = (_ffi.A3Marker * 4096)()
+        markers = (_ffi.A3Marker * cap)()
         nm = C.c_uint32()
         st = _ffi.A3Stats()
-        _ffi.check(_ffi.lib().a3_detect_batch(d._h, dev.data_ptr(), _ffi.FMT_RGB8, _ffi.MEM_DEVICE, n, w, h, w * 3, w * h * 3,
-                                              C.cast(markers, C.c_void_p), 4096, C.byref(nm), None, C.byref(st)))
+        outs = _ffi.A3Outputs()
+        poses = (_ffi.A3Pose * (2 * cap))()
+        outs.marker_poses = C.cast(poses, C.c_void_p).value
+        for _ in range(2):  # twice: the second call reuses every buffer of the first
+            _ffi.check(_ffi.lib().a3_detect_batch(d._h, dev.data_ptr(), _ffi.FMT_RGB8, _ffi.MEM_DEVICE, n, w, h, w * 3, w * h * 3,
+                                                  C.cast(markers, C.c_void_p), cap, C.byref(nm), C.byref(outs), C.byref(st)))
+    if nframes == 131:
+        k = 0
+        for x in want:
+            for m in x.markers:
+                assert bytes(poses[2 * k]) == bytes(m.poses[0].to_c()) and bytes(poses[2 * k + 1]) == bytes(m.poses[1].to_c())
+                k += 1
+        assert k == nm.value
     got = [[] for _ in range(n)]
     for i in range(nm.value):
         m = markers[i]
