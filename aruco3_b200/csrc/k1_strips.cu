@@ -33,7 +33,10 @@ namespace a3 {
 namespace {
 
 constexpr int kWarpsPerCta = 4;
-constexpr int kMinCtasPerSm = 7;   // register cap: 65536 / (128 * 7) -> 72 per thread, matches the 7 CTAs the shared memory allows
+#ifndef A3_K1_MIN_CTAS
+#define A3_K1_MIN_CTAS 7
+#endif
+constexpr int kMinCtasPerSm = A3_K1_MIN_CTAS;   // register cap: 65536 / (128 * 7) -> 72 per thread, matches the 7 CTAs the shared memory allows
 constexpr int kRing = 16;          // >= 2 * 7 + 1 grey rows; a power of two so ring slots are `row & 15`
 constexpr int kCore = 240;         // output columns per warp
 constexpr int kHalo = 8;           // >= radius, keeps every lane's 8 columns 8-px aligned

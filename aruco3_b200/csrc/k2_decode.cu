@@ -167,6 +167,8 @@ __device__ __forceinline__ uint8_t sample(const uint8_t *grey, uint32_t w, uint3
     return clamp_u8_trunc((1.0f - bw) * (float)topv + bw * (float)botv);
 }
 
+constexpr int kInFlight = 4;  // samples per lane whose gathers are issued before any is consumed
+
 // Per-warp scratch in shared memory.
 struct WarpScratch {
     double a[8][9];      // the 8x8 system of Projection::from_control_points with its right-hand side
@@ -179,7 +181,7 @@ __host__ __device__ inline uint32_t k2_warp_bytes(uint32_t ps, uint32_t ms) {
     return (b + 15) & ~15u;
 }
 
-__global__ void __launch_bounds__(kThreads, 4) k2_kernel(const K2Params p, const uint32_t max_taps) {
+__global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const uint32_t max_taps) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t ps = p.patch_size, ms = p.mark_size, np = ps * ps;
     // ---- carve: per CTA the dictionary and the resize taps, then one slice per warp ----
@@ -211,16 +213,25 @@ __global__ void __launch_bounds__(kThreads, 4) k2_kernel(const K2Params p, const
         uint32_t otsu_level = 0;
         if (ok) {
             // ---- warp: ps*ps bilinear samples, histogram on the fly ----
-            // four samples per lane in flight: the 16 gathers of a group are independent, so their latencies overlap
-            for (uint32_t base = lane; base < np; base += 128) {
-                uint8_t v[4];
+            // The inverse map goes into registers first: it lives in shared memory next to the histogram the loop updates
+            // with atomics, so the compiler would otherwise reload all nine coefficients (generic loads) for every sample.
+            float inv[9];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+            for (int k = 0; k < 9; k++) inv[k] = ws->proj.inv[k];
+            const int cls = ws->proj.cls;
+            const uint32_t fw = p.w, fh = p.h;
+            // four samples per lane in flight: the 16 gathers of a group are independent, so their latencies overlap (eight
+            // measured no faster).  The kernel is built for 3 CTAs per SM (80 registers): at 4 CTAs (64 registers) this
+            // loop spills, and the spill traffic made the whole kernel 1.8x slower.
+            for (uint32_t base = lane; base < np; base += 32 * kInFlight) {
+                uint8_t v[kInFlight];
+#pragma unroll
+                for (int u = 0; u < kInFlight; u++) {
                     const uint32_t i = base + 32 * u;
-                    v[u] = i < np ? sample(grey, p.w, p.h, ws->proj.inv, ws->proj.cls, i % ps, i / ps) : 0;
+                    v[u] = i < np ? sample(grey, fw, fh, inv, cls, i % ps, i / ps) : 0;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < kInFlight; u++) {
                     const uint32_t i = base + 32 * u;
                     if (i < np) {
                         patch[i] = v[u];
