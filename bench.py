@@ -38,6 +38,23 @@ BATCH = 256
 ALGO_BYTES_PER_PIXEL = 5   # 3 B RGB read + 1 B grey written + 1 B mask written
 
 
+def bind_near_gpu(index):
+    """One process per GPU: run this rank (and so first-touch its pinned frames) on the cores NVML reports as local to the
+    GPU, so that the H2D stream of every rank reads host memory of its own socket.  Returns the number of cores, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index), (ncpu + 63) // 64)
+        cpus = {i * 64 + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1} & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def rank_info():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -163,6 +180,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_near_gpu(local_rank) if world > 1 else None  # before the pinned buffers are allocated and touched
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cores = os.cpu_count() or 1
@@ -278,6 +296,7 @@ def main():
         "vs_baseline": None, "dtype": "u8/u32 integer pixels, f32/f64 decode", "data": "synthetic",
         "config": {"workload": f"{WORKLOAD}: 1920x1080 RGB8 x {n} frames per GPU, 20 ARUCO markers/frame, noise 0 (BASELINE.json configs[2])",
                    "frames_per_gpu_per_step": n, "host_threads_per_rank": host_threads, "host_cores": cores,
+                   "rank_cpu_affinity_cores": numa,
                    "l2": f"inputs larger than L2 ({n * h * w * 3 / 1e6:.0f} MB of RGB per step per GPU, never re-read)",
                    "parallelism": f"frame-batch sharding x{world}, no collective"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n * h * w * 3, "d2h_bytes_per_step": d2h,

@@ -371,3 +371,37 @@ def test_detect_4k_frame(a3, oracle):
         got = d.detect_batch(img[None], full=True, want_mask=True)[0]
     _check_detection(got, oracle.detect(img, "ARUCO"), "C4[0]")
     assert len(got.markers) >= 18
+
+
+def test_detect_4k_batch_in_chunks(a3, oracle):
+    """BASELINE.json configs[3] frames (3840 x 2160) as a batch: host input is staged 3 frames (~96 MB) per front-end
+    chunk, so 5 frames cross chunk boundaries; markers of every frame equal the oracle's and do not depend on the batch."""
+    from aruco3_b200 import synth
+    frames, _ = synth.render_batch("C4", 5)
+    with a3.Detector() as d:
+        got = d.detect_batch(frames)
+        assert d.last_stats["pixel_kernel_launches"] >= 2
+        alone = d.detect_batch(frames[3:4])
+    for f in (0, 2, 4):
+        ref = oracle.detect(frames[f], "ARUCO")
+        gm = [(m.candidate, m.id, m.rotation, m.hamming_distance, m.code, [v for c in m.corners for v in c]) for m in got[f].markers]
+        rm = [(m["candidate"], m["id"], m["rotation"], m["hamming_distance"], m["code"], m["corners"]) for m in ref.markers]
+        assert gm == rm, f"C4[{f}]"
+    assert [(m.id, m.corners) for m in alone[0].markers] == [(m.id, m.corners) for m in got[3].markers]
+
+
+def test_decode_stress_batch(a3, oracle):
+    """BASELINE.json configs[4]: AprilTag 36h11 frames with 200+ small markers each (more than the 64 quads per frame the
+    pipeline copies back unconditionally), several frames per batch."""
+    from aruco3_b200 import synth
+    spec = synth.CONFIGS["C5"]
+    frames, _ = synth.render_batch(spec, 3)
+    cfg = a3.DetectorConfig(min_corner_separation_factor=spec.min_corner_separation_factor)
+    ocfg = oracle.default_config(min_corner_separation_factor=spec.min_corner_separation_factor)
+    with a3.Detector(cfg, spec.dictionary) as d:
+        got = d.detect_batch(frames)
+    for f in range(3):
+        ref = oracle.detect(frames[f], spec.dictionary, ocfg)
+        gm = [(m.candidate, m.id, m.rotation, m.hamming_distance, m.code, [v for c in m.corners for v in c]) for m in got[f].markers]
+        rm = [(m["candidate"], m["id"], m["rotation"], m["hamming_distance"], m["code"], m["corners"]) for m in ref.markers]
+        assert gm == rm and len(gm) >= 150, f"C5[{f}]: {len(gm)} markers"
