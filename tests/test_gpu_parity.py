@@ -405,3 +405,86 @@ def test_decode_stress_batch(a3, oracle):
         gm = [(m.candidate, m.id, m.rotation, m.hamming_distance, m.code, [v for c in m.corners for v in c]) for m in got[f].markers]
         rm = [(m["candidate"], m["id"], m["rotation"], m["hamming_distance"], m["code"], m["corners"]) for m in ref.markers]
         assert gm == rm and len(gm) >= 150, f"C5[{f}]: {len(gm)} markers"
+
+
+@pytest.mark.parametrize("dict_name,hs", [("ARUCO", 49), ("APRILTAG_16H5", 49), ("CHILITAGS", 49), ("APRILTAG_36H11", 32), ("ARUCO_MIP_36H12", 77)])
+def test_decode_fuzz(a3, oracle, dict_name, hs):
+    """K2 against the oracle on 1500 arbitrary quads (any four points: rotated, concave, tiny, huge, partly outside) over a
+    smooth and a noisy frame, for mark sizes 6 / 7 / 8 / 10 and other homography_sample_size values: projection class and
+    failure, every patch byte, Otsu level, the four codes, the match (id, rotation, distance) and acceptance."""
+    rng = np.random.default_rng(hash((dict_name, hs)) & 0xffff)
+    w, h = 352, 288
+    grey = np.stack([_smooth(5, 1, h, w, 1)[0, :, :, 0], _noise(6, (h, w))])
+    n = 1500
+    kind = rng.integers(0, 4, n)
+    quads = np.zeros((n, 8), np.int64)
+    for k in range(n):
+        if kind[k] == 0:    # any four points
+            q = np.stack([rng.integers(0, w, 4), rng.integers(0, h, 4)], 1)
+        elif kind[k] == 1:  # rotated square with jitter
+            c, sd, a = rng.uniform([20, 20], [w - 20, h - 20]), rng.uniform(3, 120), rng.uniform(0, 2 * np.pi)
+            base = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]]) * sd
+            rot = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+            q = c + base @ rot.T + rng.uniform(-0.2, 0.2, (4, 2)) * sd
+        elif kind[k] == 2:  # thin sliver
+            x0, y0 = rng.integers(0, w - 2), rng.integers(0, h - 2)
+            q = np.array([[x0, y0], [x0 + rng.integers(1, w), y0 + 1], [x0 + rng.integers(1, w), y0 + 2], [x0, y0 + 1]])
+        else:               # axis-aligned rectangle touching the frame edges
+            x1, y1 = rng.integers(1, w), rng.integers(1, h)
+            q = np.array([[0, 0], [x1, 0], [x1, y1], [0, y1]]) + rng.integers(0, 2, 2) * [w - 1 - x1, h - 1 - y1]
+        quads[k] = np.clip(np.rint(q), 0, [w - 1, h - 1]).astype(np.int64).ravel()
+    quads = quads.astype(np.uint32)
+    qf = rng.integers(0, 2, n).astype(np.uint32)
+    dic = oracle.dictionary(dict_name)
+    ms = oracle.lib().a3ref_mark_size(C.byref(dic))
+    with a3.Detector(a3.DetectorConfig(homography_sample_size=hs), dict_name) as d:
+        decs, patches = d.decode_candidates(grey, quads, qf)
+    L = oracle.lib()
+    accepted = 0
+    for k in range(n):
+        patch = np.zeros((hs, hs), np.uint8)
+        g = np.ascontiguousarray(grey[qf[k]])
+        qk = np.ascontiguousarray(quads[k])
+        ok = L.a3ref_extract_homography(g.ctypes.data, w, h, qk.ctypes.data, hs, patch.ctypes.data)
+        assert bool(ok) == decs[k]["homography_ok"], f"quad {k} {quads[k].tolist()}: homography_ok"
+        assert np.array_equal(patches[k], patch), f"quad {k} {quads[k].tolist()}: patch"
+        codes, otsu = (C.c_uint64 * 4)(), C.c_uint8()
+        src = patch if ok else np.zeros((1, 1), np.uint8)
+        some = L.a3ref_homography_to_code_permutations(src.ctypes.data, src.shape[1], src.shape[0], ms, codes, C.byref(otsu), None)
+        assert decs[k]["otsu"] == otsu.value and decs[k]["has_codes"] == bool(some), f"quad {k}: otsu / has_codes"
+        if not some:
+            assert not decs[k]["accepted"]
+            continue
+        assert decs[k]["codes"] == list(codes), f"quad {k}: codes"
+        best, best_r, best_i = 255, 0, 0  # the match loop of src/aruco.rs:75-96
+        for r in range(4):
+            i, dist = oracle.find_nearest(dic, codes[r])
+            if dist < best:
+                best, best_r, best_i = dist, r, i
+        assert (decs[k]["hamming_distance"], decs[k]["rotation"], decs[k]["id"]) == (best, best_r, best_i), f"quad {k}: match"
+        assert decs[k]["accepted"] == (best < dic.tau)
+        accepted += decs[k]["accepted"]
+    assert sum(d_["homography_ok"] for d_ in decs) > n // 2
+
+
+@pytest.mark.parametrize("w,h,side,noise,dict_name", [(333, 251, (24, 60), 0, "ARUCO"), (97, 131, (20, 40), 3, "ARUCO"),
+                                                      (1282, 722, (40, 150), 6, "APRILTAG_25H9"), (1000, 37, (16, 30), 0, "ARUCO"),
+                                                      (501, 499, (30, 90), 12, "ARUCO_MIP_25H7"), (2049, 65, (20, 50), 2, "ARTOOLKITPLUS")])
+def test_detect_fuzz_sizes(a3, oracle, w, h, side, noise, dict_name):
+    """Whole path on frame sizes that take the generic pixel kernel (widths that are not multiples of 4, strips narrower
+    than a warp, one-strip-high frames), several noise levels and dictionaries, RGB and RGBA: every intermediate equals
+    the oracle's."""
+    from aruco3_b200 import synth
+    spec = synth.FrameSpec(f"fuzz{w}x{h}", 7, w, h, dictionary=dict_name, markers=(1, 6), side=side, noise=noise)
+    frames, _ = synth.render_batch(spec, 4)
+    with a3.Detector(dictionary=dict_name) as d:
+        got = d.detect_batch(frames, full=True, want_mask=True)
+        rgba = np.concatenate([frames, np.full(frames.shape[:3] + (1,), 7, np.uint8)], axis=3)
+        got4 = d.detect_batch(rgba)
+    total = 0
+    for f in range(frames.shape[0]):
+        ref = oracle.detect(frames[f], dict_name)
+        _check_detection(got[f], ref, f"{w}x{h}[{f}]")
+        assert [(m.id, m.corners, m.rotation) for m in got4[f].markers] == [(m.id, m.corners, m.rotation) for m in got[f].markers]
+        total += len(ref.candidates)
+    assert total > 0
