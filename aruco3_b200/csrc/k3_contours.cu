@@ -87,7 +87,7 @@ struct Geo {
 // 3x3 neighbourhood of (x, y): bits 0-2 row y-1, 3-5 row y, 6-8 row y+1 (bit 0 of each = column x-1)
 __device__ __forceinline__ uint32_t hood9(const uint32_t *plane, uint32_t Hp, int x, int y) {
     const int o = x + 31;                                   // column x-1 in guarded coordinates
-    const uint32_t *p = plane + (size_t)(o >> 5) * Hp + y;  // word column of x-1, row y-1 (guarded row index y)
+    const uint32_t *p = plane + ((uint32_t)(o >> 5) * Hp + (uint32_t)y);  // word column of x-1, row y-1 (guarded row index y); < 2^28 words
     const int sh = o & 31;
     uint32_t t = __ldg(p) >> sh, m = __ldg(p + 1) >> sh, b = __ldg(p + 2) >> sh;
     if (sh > 29) {  // the three columns straddle two words
