@@ -270,32 +270,34 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
     }
     __syncthreads();
     const uint32_t words_per_frame = g.h * g.wpr;
-    // blockIdx.y strides over frames; inside a frame consecutive threads take consecutive rows of one word column:
-    // consecutive words of the column-major plane
     // The scan is a stream of dependent loads with almost no work behind them (most words have no crack at all), so each
     // thread first issues the loads of kBatch words (the word and its two horizontal neighbours) and only then looks at them.
+    // Index space without divisions: a block takes whole word columns k (blockIdx.x strides over them), its threads take
+    // consecutive rows y of the column (consecutive words of the column-major plane), kBatch rows per thread and pass.
     constexpr int kBatch = 4;
-    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t stride = blockDim.x;
     const uint32_t last_k = (g.w - 1) >> 5, last_bit = (g.w - 1) & 31;
     for (uint32_t frame = blockIdx.y; frame < g.n; frame += gridDim.y)
-    for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < words_per_frame; base += stride * kBatch) {
+    for (uint32_t k = blockIdx.x; k < g.wpr; k += gridDim.x)
+    for (uint32_t base = threadIdx.x; base < g.h; base += stride * kBatch) {
         const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+        const uint32_t *colk = plane + (size_t)(k + 1) * g.Hp + 1;  // row 0 of word column k
         uint32_t fv[kBatch], og[kBatch], hg[kBatch], av[kBatch], awv[kBatch], aev[kBatch];
         // phase 1: the word and its two horizontal neighbours -> west / east cracks that may start a border
         {
             uint32_t lv[kBatch], rv[kBatch];
 #pragma unroll
             for (int u = 0; u < kBatch; u++) {
-                const uint32_t rem = base + (uint32_t)u * stride;
+                const uint32_t y = base + (uint32_t)u * stride;
                 fv[u] = 0; lv[u] = 0; rv[u] = 0;
-                if (rem < words_per_frame) {
-                    const uint32_t *col = plane + (size_t)(rem / g.h + 1) * g.Hp + (rem % g.h + 1);
+                if (y < g.h) {
+                    const uint32_t *col = colk + y;
                     fv[u] = __ldg(col); lv[u] = __ldg(col - g.Hp); rv[u] = __ldg(col + g.Hp);
                 }
             }
 #pragma unroll
             for (int u = 0; u < kBatch; u++) {
-                const uint32_t f = fv[u], k = (base + (uint32_t)u * stride) / g.h;
+                const uint32_t f = fv[u];
                 og[u] = f & ~((f << 1) | (lv[u] >> 31));
                 hg[u] = f & ~((f >> 1) | (rv[u] << 31));
                 if (k == 0) og[u] &= ~1u;                        // `x > 0`
@@ -307,8 +309,7 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
         for (int u = 0; u < kBatch; u++) {
             av[u] = 0; awv[u] = 0; aev[u] = 0;
             if (og[u] | hg[u]) {
-                const uint32_t rem = base + (uint32_t)u * stride;
-                const uint32_t *col = plane + (size_t)(rem / g.h + 1) * g.Hp + (rem % g.h + 1);
+                const uint32_t *col = colk + (base + (uint32_t)u * stride);
                 av[u] = __ldg(col - 1); awv[u] = __ldg(col - g.Hp - 1); aev[u] = __ldg(col + g.Hp - 1);   // row y-1 (guard row for y = 0)
             }
         }
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
             //                          N and NW are background, NE is foreground: (x+1, y-1) has a west crack ('/' edge)
             //   east crack at (x, y):  (x, y-1) also has an east crack                      (straight right edge)
             //                          N and NE are background, NW is foreground: (x-1, y-1) has an east crack ('\' edge)
-            const uint32_t f = fv[u], fa = av[u], k = (base + (uint32_t)u * stride) / g.h;
+            const uint32_t f = fv[u], fa = av[u];
             const uint32_t fa_w = (fa << 1) | (awv[u] >> 31);                      // bit x = pixel (x-1, y-1)
             const uint32_t fa_e = (fa >> 1) | (aev[u] << 31);                      // bit x = pixel (x+1, y-1)
             og[u] &= ~((fa & ~fa_w) | (~fa & ~fa_w & fa_e));
@@ -361,8 +362,7 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
         for (int u = 0; u < kBatch; u++) {
             uint32_t pending = og[u] | hg[u];
             if (!pending) continue;
-            const uint32_t rem = base + (uint32_t)u * stride;
-            const uint32_t k = rem / g.h, y = rem % g.h;
+            const uint32_t y = base + (uint32_t)u * stride;
             const size_t gid = (size_t)frame * words_per_frame + (size_t)y * g.wpr + k;  // raster word id: the sort key
             while (pending) {
                 const uint32_t b = pending & (0u - pending);
@@ -979,11 +979,17 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     {
         // about 8 blocks of 256 threads per SM (measured best: more, smaller shares than one resident wave), split over the frames
-        const uint32_t per_frame = (uint32_t)((words_per_frame + 255) / 256), resident = (uint32_t)sms * 8;
+        // (blockIdx.x strides over the word columns of a frame, blockIdx.y over frames)
+        const uint32_t resident = (uint32_t)sms * 8;
         const uint32_t gy = p.n < resident ? p.n : resident;
         uint32_t gx = (resident + gy - 1) / gy;
-        if (gx > per_frame) gx = per_frame;
-        k3_candidates<<<dim3(gx, gy), 256, 0, stream>>>(g, w.d_tables, p.min_points, l);
+        if (gx > g.wpr) gx = g.wpr;
+        // threads per block so that whole passes over a column (4 rows per thread and pass) leave few idle lanes
+        const uint32_t passes = (p.h + 1023) / 1024;
+        uint32_t bd = ((p.h + 4 * passes - 1) / (4 * passes) + 31) & ~31u;
+        if (bd < 64) bd = 64;
+        if (bd > 256) bd = 256;
+        k3_candidates<<<dim3(gx, gy), bd, 0, stream>>>(g, w.d_tables, p.min_points, l);
     }
     K3_CUDA(cudaGetLastError());
     timer.mark("candidates");
