@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
     const uint32_t last_k = (g.w - 1) >> 5, last_bit = (g.w - 1) & 31;
     for (uint32_t frame = blockIdx.y; frame < g.n; frame += gridDim.y)
     for (uint32_t k = blockIdx.x; k < g.wpr; k += gridDim.x)
-    for (uint32_t base = threadIdx.x; base < g.h; base += stride * kBatch) {
+    for (uint32_t base0 = 0; base0 < g.h; base0 += stride * kBatch) {  // warp-uniform trip count: rows beyond h read as empty words
+        const uint32_t base = base0 + threadIdx.x;
         const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
         const uint32_t *colk = plane + (size_t)(k + 1) * g.Hp + 1;  // row 0 of word column k
         uint32_t fv[kBatch], og[kBatch], hg[kBatch], av[kBatch], awv[kBatch], aev[kBatch];
@@ -347,38 +348,41 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
             hg[u] &= ~(runs(P2, fa << 1) & ~fa_e);                             // east crack at the high end of a P2 run that starts below an F
             mine += __popc(og[u]) + __popc(hg[u]);
         }
-        if (!mine) continue;
-        // what is left goes to the candidate list (one atomic per warp and batch); k3_walk_short gives every entry a thread
-        uint32_t slot;
-        {
-            const cg::coalesced_group cgp = cg::coalesced_threads();  // the lanes that still have candidates
-            const uint32_t before = cg::exclusive_scan(cgp, mine);
-            uint32_t first = 0;
-            if (cgp.thread_rank() == cgp.size() - 1) first = atomicAdd(&l.counters[3], before + mine);
-            first = cgp.shfl(first, cgp.size() - 1);
-            slot = first + before;
+        // what is left goes to the candidate list (one atomic per warp and batch); k3_walk_short gives every entry a thread.
+        // Every lane of the warp is here (uniform trip counts, whole warps), so the prefix is a plain shuffle scan.
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, mine != 0)) continue;
+        const int lane = threadIdx.x & 31;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += up;
         }
+        uint32_t first = 0;
+        if (lane == 31) first = atomicAdd(&l.counters[3], incl);
+        first = __shfl_sync(0xffffffffu, first, 31);
+        uint32_t slot = first + incl - mine;
+        if (!mine) continue;
 #pragma unroll
         for (int u = 0; u < kBatch; u++) {
-            uint32_t pending = og[u] | hg[u];
-            if (!pending) continue;
+            if (!(og[u] | hg[u])) continue;
             const uint32_t y = base + (uint32_t)u * stride;
-            const size_t gid = (size_t)frame * words_per_frame + (size_t)y * g.wpr + k;  // raster word id: the sort key
-            while (pending) {
-                const uint32_t b = pending & (0u - pending);
-                pending ^= b;
-                const int bit = __ffs(b) - 1;
-                for (int kind = 0; kind < 2; kind++) {
-                    if (!((kind ? hg[u] : og[u]) & b)) continue;
-                    const unsigned long long key = ((((unsigned long long)gid << 5) | (unsigned)bit) << 1) | (unsigned)kind;
+            const unsigned long long gid = (unsigned long long)frame * words_per_frame + (unsigned long long)y * g.wpr + k;  // raster word id: the sort key
+            // raster order inside the word: by bit, west before east
+            for (uint32_t pending = og[u] | hg[u]; pending; pending &= pending - 1) {
+                const uint32_t bit = (uint32_t)__ffs(pending) - 1u;
+                for (uint32_t kind = 0; kind < 2; kind++) {
+                    if (!(((kind ? hg[u] : og[u]) >> bit) & 1u)) continue;
+                    const unsigned long long key = (((gid << 5) | bit) << 1) | kind;
                     if (slot < l.cands_cap) {
                         l.cands[slot] = key;
                     } else {  // list full (very dense noise): walk it here, same rules as k3_walk_short
                         uint32_t n;
                         bool first_pixel;
-                        const int r = walk_border(plane, g, fwd, bwd, (int)(k * 32) + bit, (int)y, kind, kBudget, n, first_pixel);
+                        const int r = walk_border(plane, g, fwd, bwd, (int)(k * 32 + bit), (int)y, (int)kind, kBudget, n, first_pixel);
                         if (r == kSurvivor) {
-                            record_survivor(l, frame, key, kind, n, first_pixel, min_points);
+                            record_survivor(l, frame, key, (int)kind, n, first_pixel, min_points);
                         } else if (r == kUndecided) {
                             const uint32_t ws = atomicAdd(&l.counters[0], 1u);
                             if (ws < l.walkers_cap) l.walkers[ws] = key;
