@@ -417,7 +417,8 @@ a3_status a3_quads_from_masks_device(a3_detector *d, const uint8_t *masks, uint3
     if (!d || !masks || !quads || !counts || !flags || quad_capacity == 0)
         return fail(A3_ERR_INVALID_ARGUMENT, "a3_quads_from_masks_device: null argument");
     if (n == 0 || w == 0 || h == 0) return A3_OK;
-    if (w > 65535 || h > 65535) return fail(A3_ERR_UNSUPPORTED, "a3_quads_from_masks_device: frames larger than 65535 pixels a side");
+    if (w > 65535 || h > 65535 || (uint64_t)w * h >= (1ull << 29))
+        return fail(A3_ERR_UNSUPPORTED, "a3_quads_from_masks_device: frames larger than 65535 pixels a side or 2^29 pixels");
     A3_CUDA(cudaSetDevice(d->device));
     const uint32_t wpr = (w + 31) / 32, Hp = h + 2;
     const size_t plane_words = (size_t)(wpr + 2) * Hp;
@@ -520,7 +521,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
     uint32_t group = 32;          // frames per decode launch
     const uint32_t kStaging = 3;  // staging ring depth (host input)
     // contour stage on the device (K3) unless the caller asked for the host stage or the frame is too large for K3's 16-bit points
-    const bool gpu_contours = d->contour_mode == A3_CONTOURS_DEVICE && w <= 65535 && h <= 65535;
+    const bool gpu_contours = d->contour_mode == A3_CONTOURS_DEVICE && w <= 65535 && h <= 65535 && (uint64_t)w * h < (1ull << 29);
     // resident input + device contours: every quad of the super-batch is known at once, so one decode launch keeps the
     // whole GPU busy (K2 is latency-bound: what counts is candidates in flight)
     if (gpu_contours && mem == A3_MEM_DEVICE) group = (uint32_t)sb;

@@ -160,12 +160,16 @@ __device__ __forceinline__ void win_move(Window &w, int x, int y) {
 }
 
 constexpr uint32_t kBudget = 48;  // steps a candidate may walk inside k3_candidates before it is deferred to k3_walkers
-// A walk is a chain of dependent loads: its time is its length.  The first walk of a border cannot be split (the
-// candidate must see the whole loop), but while it walks it drops a checkpoint every kSeg points, and k3_emit then
-// writes the points with one thread per checkpoint: chains of kSeg steps instead of the longest border.
+// A walk is a chain of dependent loads: its time is its length.  The long walks (k3_walkers) are done by a PAIR of lanes
+// that leave the start pixel in opposite directions and stop where they meet, which halves the chain; while they walk
+// they drop a checkpoint every kSeg points, and k3_emit then writes the points with one thread per checkpoint: chains of
+// kSeg steps instead of the longest border.
 constexpr uint32_t kSeg = 64;
 static_assert(kBudget < kSeg, "borders finished inside the budget must fit one emit segment");
-struct Ckpt { uint32_t walker, pos, xy, state; };  // pos: points walked when it was dropped (forward index, or backward count for west starts)
+// pos: forward index of the checkpoint's pixel, or (kCkptBackward set in `state`) its distance from the END of the border;
+// state: the forward state there (direction of the previous border pixel)
+struct Ckpt { uint32_t walker, pos, xy, state; };
+constexpr uint32_t kCkptBackward = 0x80000000u;
 
 enum { kDead = 0, kSurvivor = 1, kUndecided = 2 };
 
@@ -192,7 +196,7 @@ struct Lists {
 // The candidate (x, y, kind) walks its border for at most `budget` steps.  kSurvivor: it is the raster-first candidate
 // crack of the border (n = number of points of the border, first_pixel = it is also the border's raster-first pixel).
 __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (*fwd)[512], const uint16_t (*bwd)[512], int sx, int sy, int kind,
-                           uint32_t budget, uint32_t &n, bool &first_pixel, const Lists *ck = nullptr, uint32_t walker = 0) {
+                           uint32_t budget, uint32_t &n, bool &first_pixel) {
     const uint32_t me = ((uint32_t)(sy * (int)g.w + sx) << 1) | (uint32_t)kind;
     const uint32_t nb0 = ring_of(hood9(plane, g.Hp, sx, sy));
     const int adj = kind ? 4 : 0;
@@ -227,11 +231,6 @@ __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (
         if ((e & 8u) && x > 0 && (pix << 1) < me) return kDead;
         if ((e & 16u) && x + 1 < (int)g.w && ((pix << 1) | 1u) < me) return kDead;
         if (steps >= budget) return kUndecided;
-        if (ck && n && n % kSeg == 0) {  // the pixel under the walk is point n (forwards) / the n-th point from the end (backwards)
-            const uint32_t c = atomicAdd(&ck->counters[4], 1u);
-            if (c < ck->ckpt_cap) ck->ckpts[c] = Ckpt{walker, n, (uint32_t)x | ((uint32_t)y << 16), kind ? state : (e & 7u)};
-            else atomicOr(&ck->counters[2], 1u);
-        }
         min_pix = min(min_pix, pix);
         n++;
         x += (int)((e >> 5) & 3u) - 1;
@@ -435,7 +434,14 @@ __global__ void __launch_bounds__(128) k3_walk_short(const Geo g, const StepTabl
     }
 }
 
-// The undecided candidates — mostly the one survivor of each long border — walk to the end, all at the same time.
+// The undecided candidates — mostly the one survivor of each long border — walk to the end, all at the same time, each
+// as a pair of adjacent lanes: the even lane follows the border forwards from the start visit (index 0, 1, 2, ...), the odd
+// lane backwards (index n-1, n-2, ...), in lockstep, and after every step they compare visits (pixel + direction of the
+// previous border pixel identify a visit uniquely within the loop).  When the forward lane stands on the backward lane's
+// current visit the border has 2s + 1 points, when it stands on the backward lane's previous visit it has 2s.  Every visit
+// is examined by one of the two for raster-earlier candidate cracks (either finding one kills the candidate).
+// (Measured before the pairing: fewer walkers per warp, software prefetch of the sector ahead and a register window all
+// made this kernel slower: its time is the dependent chain of the longest border, about 750 cycles per step.)
 __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
     __shared__ uint16_t fwd[8][512];
     __shared__ uint16_t bwd[8][512];
@@ -445,18 +451,79 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
     }
     __syncthreads();
     const uint32_t total = min(l.counters[0], l.walkers_cap);
-    // (measured: fewer walkers per warp, software prefetch of the sector ahead and a register window all make this kernel
-    // slower: its time is the dependent chain of the longest border, about 750 cycles per step with 32 borders per warp)
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, back = tid & 1u;
+    const uint32_t pair_mask = 3u << (threadIdx.x & 30u);   // the two lanes of this pair: they never diverge from each other
+    const uint16_t (*lut)[512] = back ? bwd : fwd;
+    for (uint32_t i = tid >> 1; i < total; i += (gridDim.x * blockDim.x) >> 1) {
         const unsigned long long key = l.walkers[i];
-        uint32_t frame, n;
-        int x, y, kind;
-        bool first_pixel;
-        decode_key(g, key, frame, x, y, kind);
+        uint32_t frame;
+        int sx, sy, kind;
+        decode_key(g, key, frame, sx, sy, kind);
         const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+        const uint32_t me = ((uint32_t)(sy * (int)g.w + sx) << 1) | (uint32_t)kind;
+        const uint32_t start_pix = (uint32_t)(sy * (int)g.w + sx);
+        const uint32_t nb0 = ring_of(hood9(plane, g.Hp, sx, sy));
+        const int adj = kind ? 4 : 0;
+        int pred = -1;
+        for (int k = 0; k < 8; k++) {  // clockwise from the zero neighbour: the previous pixel on the border
+            const int d = (adj + k) & 7;
+            if ((nb0 >> d) & 1) { pred = d; break; }
+        }
+        if (pred < 0) {  // isolated pixel (decided in k3_walk_short already; kept for completeness)
+            if (!back) {
+                uint32_t slot = 0xffffffffu;
+                if (kind == 0 || sx == 0) slot = record_survivor(l, frame, key, kind, 1, true, min_points);
+                l.walker_slot[i] = slot;
+            }
+            continue;
+        }
+        int x = sx, y = sy;
+        uint32_t state = (uint32_t)pred;  // forwards: the start visit
+        if (back) { x = sx + ddx(pred); y = sy + ddy(pred); state = (uint32_t)((pred + 4) & 7); }  // backwards: the visit before it
+        uint32_t min_pix = start_pix, n = 0, prev_back_id = 0xffffffffu, my_prev_id = 0xffffffffu;
+        bool dead = false;
+        for (uint32_t s = 0;; s++) {
+            const uint32_t e = lut[state][hood9(plane, g.Hp, x, y)];
+            const uint32_t pix = (uint32_t)(y * (int)g.w + x);
+            const uint32_t fstate = back ? (e & 7u) : state;                  // direction of the previous border pixel at this visit
+            const uint32_t id = (pix << 3) | fstate;
+            // candidate cracks of this visit that come before me in raster order
+            const bool mine_dead = ((e & 8u) && x > 0 && (pix << 1) < me) || ((e & 16u) && x + 1 < (int)g.w && ((pix << 1) | 1u) < me);
+            const uint32_t other_id = __shfl_xor_sync(pair_mask, id, 1);
+            dead = __shfl_xor_sync(pair_mask, (int)mine_dead, 1) || mine_dead;
+            if (dead) break;
+            // the forward lane compares with the backward lane's current and previous visit; the backward lane mirrors it
+            const uint32_t fwd_id = back ? other_id : id, back_id = back ? id : other_id;
+            const uint32_t back_prev = back ? my_prev_id : prev_back_id;
+            min_pix = min(min_pix, pix);
+            if (fwd_id == back_id) { n = 2 * s + 1; break; }
+            if (s > 0 && fwd_id == back_prev) { n = 2 * s; break; }
+            // checkpoints for k3_emit: forwards at index kSeg, 2 kSeg, ...; backwards kSeg, 2 kSeg, ... points before the end
+            const uint32_t walked = back ? s + 1 : s;
+            if (walked && walked % kSeg == 0) {
+                const uint32_t c = atomicAdd(&l.counters[4], 1u);
+                if (c < l.ckpt_cap) l.ckpts[c] = Ckpt{i, walked, (uint32_t)x | ((uint32_t)y << 16), fstate | (back ? kCkptBackward : 0u)};
+                else atomicOr(&l.counters[2], 1u);
+            }
+            my_prev_id = id;
+            prev_back_id = other_id;
+            x += (int)((e >> 5) & 3u) - 1;
+            y += (int)((e >> 7) & 3u) - 1;
+            state = e >> 9;
+        }
+        min_pix = min(min_pix, __shfl_xor_sync(pair_mask, min_pix, 1));
+        if (back) continue;
         uint32_t slot = 0xffffffffu;
-        if (walk_border(plane, g, fwd, bwd, x, y, kind, 0xffffffffu, n, first_pixel, &l, i) == kSurvivor)
-            slot = record_survivor(l, frame, key, kind, n, first_pixel, min_points);
+        if (!dead) {
+            // the meeting point is where the forward lane stands: one more checkpoint there closes the gap between the last
+            // forward and the first backward segment (they may overlap: every segment writes the same values)
+            if (n > kSeg) {
+                const uint32_t c = atomicAdd(&l.counters[4], 1u);
+                if (c < l.ckpt_cap) l.ckpts[c] = Ckpt{i, n / 2, (uint32_t)x | ((uint32_t)y << 16), state};
+                else atomicOr(&l.counters[2], 1u);
+            }
+            slot = record_survivor(l, frame, key, kind, n, min_pix == start_pix, min_points);
+        }
         l.walker_slot[i] = slot;
     }
 }
@@ -500,8 +567,7 @@ __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *ta
             if ((nb0 >> d) & 1) { pred = d; break; }
         }
         const uint32_t n = lens[ci];
-        // forward walkers drop checkpoints at points kSeg, 2 kSeg, ...; backward walkers kSeg, 2 kSeg, ... points before the end
-        first = 0; count = kind ? min(kSeg, n) : n - kSeg * ((n - 1) / kSeg);
+        first = 0; count = min(kSeg, n);  // the rest is covered from the checkpoints (none for borders of at most kSeg points)
         x = sx; y = sy; state = (uint32_t)pred;
         Contour c;
         c.frame = frame; c.start = (uint32_t)sx | ((uint32_t)sy << 16); c.n = n; c.kind = (uint32_t)kind; c.point_off = offsets[ci];
@@ -513,9 +579,9 @@ __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *ta
         ci = rank[slot];
         decode_key(g, keys[ci], frame, sx, sy, kind);
         const uint32_t n = lens[ci];
-        first = kind ? c.pos : n - c.pos;
-        count = kind ? min(kSeg, n - c.pos) : kSeg;
-        x = (int)(c.xy & 0xffffu); y = (int)(c.xy >> 16); state = c.state;
+        first = (c.state & kCkptBackward) ? n - c.pos : c.pos;
+        count = min(kSeg, n - first);
+        x = (int)(c.xy & 0xffffu); y = (int)(c.xy >> 16); state = c.state & 7u;
     }
     Window win;
     win.plane = g.planes + (size_t)frame * g.frame_words; win.Hp = g.Hp;
@@ -904,6 +970,7 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
     PhaseTimer timer(stream);
     if (p.w > 65535 || p.h > 65535) return cudaErrorInvalidValue;  // points are packed 16 + 16
+    if ((unsigned long long)p.w * p.h >= (1ull << 29)) return cudaErrorInvalidValue;  // pixel index << 3 | state must fit 32 bits
     Geo g;
     g.planes = p.planes; g.n = p.n; g.w = p.w; g.h = p.h; g.wpr = (p.w + 31) / 32; g.Hp = p.h + 2;
     g.frame_words = (size_t)(g.wpr + 2) * g.Hp;
