@@ -242,6 +242,26 @@ def main():
     ms_dev, acc_dev, clocks = timed(resident.data_ptr(), _ffi.MEM_DEVICE, args.steps, args.warmup)
     ms_e2e, acc_e2e, clocks_e2e = timed(pinned.data_ptr(), _ffi.MEM_HOST, args.steps, 1)
 
+    # ---- BASELINE.json configs[1] beside the headline: one 1080p frame from host memory per call, wall-clock latency ----
+    def single_frame_latency(frame_tensor, reps=40):
+        one = (_ffi.A3Marker * 4096)()
+        lat = []
+        for it in range(reps + 5):
+            t0 = time.perf_counter()
+            _ffi.check(L.a3_detect_batch(det._h, frame_tensor.data_ptr(), _ffi.FMT_RGB8, _ffi.MEM_HOST, 1, w, h, w * 3, w * h * 3,
+                                         C.cast(one, C.c_void_p), 4096, C.byref(n_markers), None, None))
+            if it >= 5:
+                lat.append((time.perf_counter() - t0) * 1e3)
+        return float(np.median(lat))
+
+    latency = None
+    if rank == 0:
+        noise = torch.empty((1, h, w, 3), dtype=torch.uint8, pin_memory=True)
+        noise.numpy()[:] = np.random.default_rng(0xA3C0DE00 + 2000).integers(0, 256, size=(1, h, w, 3), dtype=np.uint8)
+        latency = {"unit": "ms per detect() call, host frame in, markers out (median of 40)",
+                   "marker_frame_1080p": single_frame_latency(pinned[:1]),
+                   "noise_frame_1080p_reference_bench_workload": single_frame_latency(noise)}
+
     # ---- K1 alone on the resident frames (isolated figure; the roofline entry uses the in-pipeline time) ----
     wpr = (w + 31) // 32
     d_grey = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
@@ -318,6 +338,7 @@ def main():
                                                                          "ms_host_cpu", "ms_decode_kernel", "ms_total")},
         "counts_per_step": {k: acc_dev[k] / args.steps for k in ("n_contours", "n_contour_points", "n_candidates", "n_markers")},
         "clocks": clocks, "clocks_e2e": clocks_e2e,
+        "single_frame_latency": latency,
     }
     # the latency-bound stages are reported as units per second of their own kernel time, not as roofline fractions
     if acc_dev["ms_decode_kernel"] > 0:
