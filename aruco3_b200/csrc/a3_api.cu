@@ -198,6 +198,7 @@ struct a3_detector {
     a3::PinBuf<unsigned long long> h_k3points;
     size_t planes_zeroed_words = 0;
     uint32_t planes_w = 0, planes_h = 0;
+    std::vector<std::vector<uint32_t>> frame_quads;  // per-frame quads of the batch in flight (capacity reused across calls)
     // pose step (K4)
     uint32_t pose_mode = A3_POSE_OFF;
     float pose_marker_size = 0.0f;
@@ -535,7 +536,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
 
     uint32_t total_markers = 0, total_cands = 0;
     bool overflow = false;
-    std::vector<std::vector<uint32_t>> frame_quads;
+    std::vector<std::vector<uint32_t>> &frame_quads = d->frame_quads;  // kept in the handle: no allocation per call once warm
     std::vector<QuadStats> frame_stats;
     std::vector<double> frame_ms;
 
@@ -571,7 +572,8 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             A3_CUDA(d->events.get(&ev_fe[j])); A3_CUDA(d->events.get(&ev_k1a[j])); A3_CUDA(d->events.get(&ev_k1b[j]));
             A3_CUDA(d->events.get(&ev_h2da[j])); A3_CUDA(d->events.get(&ev_h2db[j])); A3_CUDA(d->events.get(&ev_k3[j]));
         }
-        frame_quads.assign(sn, {});
+        if (frame_quads.size() < sn) frame_quads.resize(sn);
+        for (uint32_t i = 0; i < sn; i++) frame_quads[i].clear();
         frame_stats.assign(sn, QuadStats());
         frame_ms.assign(sn, 0.0);
         std::unique_ptr<std::atomic<uint32_t>[]> group_done(new std::atomic<uint32_t>[ngroups]);

@@ -400,8 +400,14 @@ __device__ __forceinline__ void decode_key(const Geo &g, unsigned long long key,
     const unsigned long long v = key >> 1;
     const unsigned long long gid = v >> 5;
     const size_t words_per_frame = (size_t)g.h * g.wpr;
-    frame = (uint32_t)(gid / words_per_frame);
-    const uint32_t rem = (uint32_t)(gid % words_per_frame);
+    uint32_t rem;
+    if ((gid >> 32) == 0 && (words_per_frame >> 32) == 0) {  // the usual case: a 32-bit division instead of the 64-bit routine
+        frame = (uint32_t)gid / (uint32_t)words_per_frame;
+        rem = (uint32_t)gid - frame * (uint32_t)words_per_frame;
+    } else {
+        frame = (uint32_t)(gid / words_per_frame);
+        rem = (uint32_t)(gid % words_per_frame);
+    }
     y = (int)(rem / g.wpr);
     x = (int)((rem % g.wpr) * 32 + (uint32_t)(v & 31ull));
 }
