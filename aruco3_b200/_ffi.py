@@ -46,7 +46,7 @@ class A3Stats(C.Structure):
                [(n, C.c_double) for n in ("ms_h2d", "ms_pixel_kernel", "ms_contour_kernels", "ms_mask_d2h", "ms_host_quads",
                                           "ms_decode_kernel", "ms_host_cpu", "ms_total")] + \
                [(n, C.c_uint32) for n in ("pixel_kernel_launches", "decode_kernel_launches", "host_threads", "contour_kernel_launches",
-                                          "host_fallback_frames", "pose_kernel_launches")]
+                                          "host_fallback_frames", "pose_kernel_launches", "one_shot", "one_shot_retry")]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

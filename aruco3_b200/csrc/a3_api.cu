@@ -199,6 +199,10 @@ struct a3_detector {
     size_t planes_zeroed_words = 0;
     uint32_t planes_w = 0, planes_h = 0;
     std::vector<std::vector<uint32_t>> frame_quads;  // per-frame quads of the batch in flight (capacity reused across calls)
+    // one-shot route (pack_quads): K3's quads go to K2 on the device; launch and copy sizes come from the previous call
+    a3::DevBuf<uint32_t> d_qoff, d_packinfo;
+    a3::PinBuf<uint32_t> h_packinfo;
+    uint32_t hist_nq = 0, hist_nq_n = 0, hist_nq_w = 0, hist_nq_h = 0;  // quads of the previous call with this geometry (0 = none)
     // pose step (K4)
     uint32_t pose_mode = A3_POSE_OFF;
     float pose_marker_size = 0.0f;
@@ -225,6 +229,71 @@ uint32_t bytes_per_pixel(a3_format f) { return (uint32_t)fmt_bpp((int)f); }
 
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- K3 -> K2 on the device -----------------------------------------------------------------------------------------
+// K3 leaves each frame's quads in its own block of quad_cap slots.  These two kernels gather them into the dense list in
+// frame / candidate order that K2, K4 and the marker assembly use, so the quads need not visit the host between the
+// contour stage and the decode.  info[0] = quads in total, info[1] = 1 when that route cannot be used for this call (the
+// speculative K3 finish gave up, a frame is flagged for the host stage, or the list does not fit `cap`): the host then takes
+// the ordinary route.
+__global__ void __launch_bounds__(1024) pack_offsets_kernel(const uint32_t *counts, const uint32_t *flags, uint32_t n_frames, uint32_t quad_cap,
+                                                            uint32_t cap, const uint32_t *k3_failed, uint32_t *offsets, uint32_t *info) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t base_s, bad_s;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (k3_failed && *k3_failed) {
+        if (threadIdx.x == 0) { info[0] = 0; info[1] = 1; }
+        return;
+    }
+    if (threadIdx.x == 0) { base_s = 0; bad_s = 0; }
+    __syncthreads();
+    for (uint32_t f0 = 0; f0 < n_frames; f0 += 1024) {
+        const uint32_t f = f0 + threadIdx.x;
+        uint32_t m = 0;
+        if (f < n_frames) {
+            m = counts[f] < quad_cap ? counts[f] : quad_cap;
+            if (flags[f]) { m = 0; bad_s = 1; }
+        }
+        uint32_t incl = m;
+        for (uint32_t o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t ws = warp_sums[lane];
+            uint32_t wi = ws;
+            for (uint32_t o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += v;
+            }
+            warp_sums[lane] = wi - ws;
+        }
+        __syncthreads();
+        const uint32_t off = base_s + warp_sums[warp] + incl - m;
+        if (f < n_frames) offsets[f] = off;
+        __syncthreads();
+        if (threadIdx.x == 1023) base_s = off + m;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        offsets[n_frames] = base_s;
+        const bool bad = bad_s || base_s > cap;
+        info[0] = bad ? 0u : base_s;
+        info[1] = bad ? 1u : 0u;
+    }
+}
+__global__ void __launch_bounds__(128) pack_quads_kernel(const uint32_t *quads, const uint32_t *offsets, uint32_t quad_cap, uint32_t cap,
+                                                         const uint32_t *info, uint32_t *out_quads, uint32_t *out_frame) {
+    if (info[1]) return;
+    const uint32_t f = blockIdx.x, o0 = offsets[f], m = offsets[f + 1] - o0;
+    const uint32_t *src = quads + (size_t)f * quad_cap * 8;
+    for (uint32_t i = threadIdx.x; i < m * 8; i += blockDim.x)
+        if (o0 + (i >> 3) < cap) out_quads[(size_t)o0 * 8 + i] = src[i];
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+        if (o0 + i < cap) out_frame[o0 + i] = f;
 }
 
 K2Params k2_params(const a3_detector *d, const uint8_t *grey, uint32_t w, uint32_t h) {
@@ -320,6 +389,7 @@ void a3_detector_destroy(a3_detector *d) {
     d->d_planes.release(); d->d_k3quads.release(); d->d_k3counts.release(); d->d_k3before.release(); d->d_k3flags.release();
     d->d_k3contours.release(); d->d_k3points.release(); d->h_k3quads.release(); d->h_k3counts.release(); d->h_k3before.release();
     d->h_k3flags.release(); d->h_k3contours.release(); d->h_k3points.release(); d->h_plane.release();
+    d->d_qoff.release(); d->d_packinfo.release(); d->h_packinfo.release();
     d->d_pose_in.release(); d->d_pose_out.release(); d->h_pose_out.release();
     d->events.release();
     for (auto &b : d->blocks) b->release();
@@ -526,6 +596,12 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
     // resident input + device contours: every quad of the super-batch is known at once, so one decode launch keeps the
     // whole GPU busy (K2 is latency-bound: what counts is candidates in flight)
     if (gpu_contours && mem == A3_MEM_DEVICE) group = (uint32_t)sb;
+    // One-shot route: when one K3 launch covers the whole (super-)batch — resident input, or host input that fits one
+    // front-end chunk, e.g. a single frame — the second half of K3, the gather of its quads, K2 and K4 are all queued behind
+    // K1 without a host synchronisation, sized from the previous call of the same geometry; the host synchronises once at the
+    // end, checks that the sizes held and otherwise takes the ordinary route from where the speculation stopped.
+    const bool one_shot = gpu_contours && (mem == A3_MEM_DEVICE || n <= fe) && !getenv("A3_NO_ONE_SHOT");
+    if (one_shot) group = (uint32_t)sb;
     const uint32_t Hp = h + 2;                               // guarded column-major plane: words per 32-pixel column
     const size_t plane_words = (size_t)(wpr + 2) * Hp;       // words per frame
     const uint32_t quad_cap = 1024;                          // quads per frame K3 can return (more -> host stage)
@@ -598,6 +674,94 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             st.pixel_kernel_launches++;
             return A3_OK;
         };
+        // ---- device contour stage: copies of K3's results, and the one-shot route behind a speculative K3 finish ----
+        K3Params k3_last{};
+        bool k3_spec_inflight = false, one_shot_enqueued = false, one_shot_done = false;
+        uint32_t one_shot_cap = 0;
+        auto k3_stats_d2h = [&](uint32_t f0, uint32_t kn) -> a3_status {
+            A3_CUDA(cudaMemcpyAsync(d->h_k3counts.p + f0, d->d_k3counts.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+            A3_CUDA(cudaMemcpyAsync(d->h_k3before.p + f0, d->d_k3before.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+            A3_CUDA(cudaMemcpyAsync(d->h_k3flags.p + f0, d->d_k3flags.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+            A3_CUDA(cudaMemcpyAsync(d->h_k3contours.p + f0, d->d_k3contours.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+            A3_CUDA(cudaMemcpyAsync(d->h_k3points.p + f0, d->d_k3points.p + f0, (size_t)kn * 8, cudaMemcpyDeviceToHost, d->s_pixel));
+            return A3_OK;
+        };
+        auto k3_head_d2h = [&](uint32_t f0, uint32_t kn) -> a3_status {
+            // the first `quad_head` quads of every frame in one strided copy; a frame with more fetches the rest itself
+            A3_CUDA(cudaMemcpy2DAsync(d->h_k3quads.p + (size_t)f0 * quad_cap * 8, (size_t)quad_cap * 32,
+                                      d->d_k3quads.p + (size_t)f0 * quad_cap * 8, (size_t)quad_cap * 32, (size_t)quad_head * 32, kn,
+                                      cudaMemcpyDeviceToHost, d->s_pixel));
+            return A3_OK;
+        };
+        // gather K3's quads on the device, decode them (K2, K4) and copy everything back, all on the pixel stream
+        auto enqueue_one_shot = [&]() -> a3_status {
+            DecodeBlock &b = *d->blocks[0];
+            const uint32_t cap = d->hist_nq + d->hist_nq / 8 + 256;
+            A3_CUDA(d->d_qoff.reserve((size_t)sn + 1)); A3_CUDA(d->d_packinfo.reserve(2)); A3_CUDA(d->h_packinfo.reserve(2));
+            A3_CUDA(b.h_quads.reserve((size_t)cap * 8)); A3_CUDA(b.h_qframe.reserve(cap)); A3_CUDA(b.h_dec.reserve(cap));
+            A3_CUDA(b.d_quads.reserve((size_t)cap * 8)); A3_CUDA(b.d_qframe.reserve(cap)); A3_CUDA(b.d_dec.reserve(cap));
+            if (want_patches) A3_CUDA(b.d_patches.reserve(cap * np));
+            if (!b.ev_a) { A3_CUDA(cudaEventCreate(&b.ev_a)); A3_CUDA(cudaEventCreate(&b.ev_b)); }
+            pack_offsets_kernel<<<1, 1024, 0, d->s_pixel>>>(d->d_k3counts.p, d->d_k3flags.p, sn, quad_cap, cap, k3_speculation_failed_flag(d->k3),
+                                                            d->d_qoff.p, d->d_packinfo.p);
+            A3_CUDA(cudaGetLastError());
+            pack_quads_kernel<<<sn, 128, 0, d->s_pixel>>>(d->d_k3quads.p, d->d_qoff.p, quad_cap, cap, d->d_packinfo.p, b.d_quads.p, b.d_qframe.p);
+            A3_CUDA(cudaGetLastError());
+            K2Params p = k2_params(d, d->d_grey.p, w, h);
+            p.quads = b.d_quads.p; p.quad_frame = b.d_qframe.p; p.n_quads = cap; p.n_quads_dev = d->d_packinfo.p; p.decodes = b.d_dec.p;
+            p.patches = want_patches ? b.d_patches.p : nullptr;
+            A3_CUDA(cudaEventRecord(b.ev_a, d->s_pixel));
+            A3_CUDA(k2_decode(p, d->s_pixel));
+            A3_CUDA(cudaEventRecord(b.ev_b, d->s_pixel));
+            A3_CUDA(cudaMemcpyAsync(d->h_packinfo.p, d->d_packinfo.p, 8, cudaMemcpyDeviceToHost, d->s_pixel));
+            A3_CUDA(cudaMemcpyAsync(b.h_quads.p, b.d_quads.p, (size_t)cap * 32, cudaMemcpyDeviceToHost, d->s_pixel));
+            A3_CUDA(cudaMemcpyAsync(b.h_dec.p, b.d_dec.p, (size_t)cap * sizeof(a3_decode), cudaMemcpyDeviceToHost, d->s_pixel));
+            if (want_poses) {
+                A3_CUDA(b.d_pose.reserve((size_t)cap * 2)); A3_CUDA(b.h_pose.reserve((size_t)cap * 2));
+                K4Params kp{};
+                kp.mode = d->pose_mode; kp.corners = b.d_quads.p; kp.decodes = b.d_dec.p; kp.n = cap; kp.n_dev = d->d_packinfo.p;
+                kp.marker_size = d->pose_marker_size; kp.image_w = w; kp.image_h = h; kp.k = d->pose_k; kp.poses = b.d_pose.p;
+                A3_CUDA(k4_pose(kp, d->s_pixel));
+                A3_CUDA(cudaMemcpyAsync(b.h_pose.p, b.d_pose.p, (size_t)cap * 2 * sizeof(a3_pose), cudaMemcpyDeviceToHost, d->s_pixel));
+            }
+            one_shot_enqueued = true; one_shot_cap = cap;
+            return A3_OK;
+        };
+        // after the synchronisation: did every speculated size hold?  Then the frames' quads and the decode records are already
+        // on the host.  Otherwise finish K3 exactly (if that was what failed) and fetch its quads the ordinary way.
+        auto settle_one_shot = [&]() -> a3_status {
+            const bool held = k3_speculation_held(d->k3, k3_last);
+            k3_spec_inflight = false;
+            if (held && one_shot_enqueued && d->h_packinfo.p[1] == 0 && d->h_packinfo.p[0] <= one_shot_cap) {
+                DecodeBlock &b = *d->blocks[0];
+                b.n_quads = d->h_packinfo.p[0];
+                uint32_t k = 0;
+                for (uint32_t i = 0; i < sn; i++) {
+                    const uint32_t m = d->h_k3counts.p[i] < quad_cap ? d->h_k3counts.p[i] : quad_cap;
+                    frame_quads[i].assign(b.h_quads.p + (size_t)k * 8, b.h_quads.p + (size_t)(k + m) * 8);
+                    frame_stats[i].n_contours = d->h_k3contours.p[i];
+                    frame_stats[i].n_contour_points = d->h_k3points.p[i];
+                    frame_stats[i].n_before_discard = d->h_k3before.p[i];
+                    k += m;
+                }
+                group_done[0].store(sn);
+                d->hist_nq = b.n_quads ? b.n_quads : 1;
+                st.decode_kernel_launches++;
+                if (want_poses) st.pose_kernel_launches++;
+                st.one_shot = 1;
+                one_shot_done = true;
+                return A3_OK;
+            }
+            if (!held || one_shot_enqueued) st.one_shot_retry = 1;
+            one_shot_enqueued = false;
+            if (!held) {
+                A3_CUDA(k3_finish(d->k3, k3_last, d->s_pixel));
+                if (a3_status s = k3_stats_d2h(0, sn)) return s;
+            }
+            if (a3_status s = k3_head_d2h(0, sn)) return s;
+            A3_CUDA(cudaStreamSynchronize(d->s_pixel));
+            return A3_OK;
+        };
         auto bits_d2h = [&](uint32_t f0, uint32_t cn, uint32_t j) -> a3_status {
             if (gpu_contours) {
                 if (mem == A3_MEM_HOST || j == 0) {  // K3 over the frames K1 just produced (everything for resident input)
@@ -610,18 +774,20 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                     kp.quad_cap = quad_cap; kp.quads = d->d_k3quads.p + (size_t)f0 * quad_cap * 8; kp.quad_counts = d->d_k3counts.p + f0;
                     kp.before_discard = d->d_k3before.p + f0; kp.frame_flags = d->d_k3flags.p + f0;
                     kp.frame_contours = d->d_k3contours.p + f0; kp.frame_points = d->d_k3points.p + f0;
-                    A3_CUDA(k3_quads(d->k3, kp, d->s_pixel));
+                    A3_CUDA(k3_begin(d->k3, kp, d->s_pixel));
+                    bool spec = false;
+                    if (one_shot && s0 == 0 && sn == n) A3_CUDA(k3_finish_speculative(d->k3, kp, d->s_pixel, &spec));
+                    if (!spec) A3_CUDA(k3_finish(d->k3, kp, d->s_pixel));
                     A3_CUDA(cudaEventRecord(ev_k3[j], d->s_pixel));
                     st.contour_kernel_launches++;
-                    A3_CUDA(cudaMemcpyAsync(d->h_k3counts.p + f0, d->d_k3counts.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
-                    A3_CUDA(cudaMemcpyAsync(d->h_k3before.p + f0, d->d_k3before.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
-                    A3_CUDA(cudaMemcpyAsync(d->h_k3flags.p + f0, d->d_k3flags.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
-                    A3_CUDA(cudaMemcpyAsync(d->h_k3contours.p + f0, d->d_k3contours.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
-                    A3_CUDA(cudaMemcpyAsync(d->h_k3points.p + f0, d->d_k3points.p + f0, (size_t)kn * 8, cudaMemcpyDeviceToHost, d->s_pixel));
-                    // the first `quad_head` quads of every frame in one strided copy; a frame with more fetches the rest itself
-                    A3_CUDA(cudaMemcpy2DAsync(d->h_k3quads.p + (size_t)f0 * quad_cap * 8, (size_t)quad_cap * 32,
-                                              d->d_k3quads.p + (size_t)f0 * quad_cap * 8, (size_t)quad_cap * 32, (size_t)quad_head * 32, kn,
-                                              cudaMemcpyDeviceToHost, d->s_pixel));
+                    k3_last = kp; k3_spec_inflight = spec;
+                    if (a3_status s = k3_stats_d2h(f0, kn)) return s;
+                    const bool geometry = d->hist_nq_n == n && d->hist_nq_w == w && d->hist_nq_h == h;
+                    if (spec && d->hist_nq && geometry) {
+                        if (a3_status s = enqueue_one_shot()) return s;
+                    } else if (!spec) {
+                        if (a3_status s = k3_head_d2h(f0, kn)) return s;
+                    }
                 }
             } else {
                 A3_CUDA(cudaMemcpyAsync(d->h_bits.p + (size_t)f0 * bits_words, d->d_bits.p + (size_t)f0 * bits_words, (size_t)cn * bits_words * 4,
@@ -710,10 +876,12 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         // ---- decode of group g (asynchronous) ----
         auto launch_group = [&](uint32_t g) -> a3_status {
             DecodeBlock &b = *d->blocks[g];
+            if (one_shot_done && g == 0) return A3_OK;  // decoded on the device behind K3 already
             const uint32_t f0 = g * group, f1 = f0 + group_size(g);
             uint32_t nq = 0;
             for (uint32_t i = f0; i < f1; i++) nq += (uint32_t)(frame_quads[i].size() / 8);
             b.n_quads = nq;
+            if (one_shot && ngroups == 1) { d->hist_nq = nq ? nq : 1; d->hist_nq_n = n; d->hist_nq_w = w; d->hist_nq_h = h; }
             if (!b.ev_a) { A3_CUDA(cudaEventCreate(&b.ev_a)); A3_CUDA(cudaEventCreate(&b.ev_b)); }
             if (nq == 0) return A3_OK;
             A3_CUDA(b.h_quads.reserve((size_t)nq * 8)); A3_CUDA(b.h_qframe.reserve(nq)); A3_CUDA(b.h_dec.reserve(nq));
@@ -767,7 +935,8 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             if (e != cudaSuccess) { err = cuda_fail(e, "cudaEventSynchronize(front end)"); break; }
             const uint32_t upto = (j + 1) * (uint32_t)fe < sn ? (j + 1) * (uint32_t)fe : sn;
             if (gpu_contours) {
-                if (mem == A3_MEM_HOST || j == 0)  // resident input: K3 ran once over everything
+                if (k3_spec_inflight && (err = settle_one_shot())) break;
+                if ((mem == A3_MEM_HOST || j == 0) && !one_shot_done)  // resident input: K3 ran once over everything
                     for (uint32_t i = (mem == A3_MEM_HOST ? j * (uint32_t)fe : 0); i < (mem == A3_MEM_HOST ? upto : sn) && !err; i++) err = take_k3_frame(i);
             } else {
                 d->pool.publish(upto);
@@ -794,6 +963,9 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                 if (mem == A3_MEM_HOST || j == 0) {
                     cudaEventElapsedTime(&ms, ev_k1b[j], ev_k3[j]); st.ms_contour_kernels += ms;
                     cudaEventElapsedTime(&ms, ev_k3[j], ev_fe[j]); st.ms_mask_d2h += ms;
+                    if (one_shot_done && d->blocks[0]->n_quads) {  // the decode sits between those two events on this route
+                        cudaEventElapsedTime(&ms, d->blocks[0]->ev_a, d->blocks[0]->ev_b); st.ms_mask_d2h -= ms;
+                    }
                 }
             } else {
                 cudaEventElapsedTime(&ms, (mem == A3_MEM_HOST || j == 0) ? ev_k1b[j] : ev_fe[j - 1], ev_fe[j]);

@@ -64,6 +64,7 @@ struct K2Params {
     const uint32_t *quads;      // device n_quads*8
     const uint32_t *quad_frame; // device n_quads or null (all frame 0)
     uint32_t n_quads;
+    const uint32_t *n_quads_dev = nullptr;  // device, optional: the real number of quads (<= n_quads, which then only sizes the launch)
     uint32_t patch_size;        // homography_sample_size
     uint32_t mark_size;         // get_mark_size()
     const uint64_t *codes;      // device dictionary
@@ -120,6 +121,12 @@ cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream);  
 // enqueues; k3_finish synchronises the stream once (buffer sizing) and enqueues the rest.
 cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream);
 cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream);
+// k3_finish without the synchronisation: launches sized from the previous call of this geometry, real sizes read on the
+// device.  After the caller's own synchronisation of the stream k3_speculation_held() says whether the sizes fitted; if
+// not (or if *speculated came back false), k3_finish does the second half exactly.
+cudaError_t k3_finish_speculative(K3Workspace &ws, const K3Params &p, cudaStream_t stream, bool *speculated);
+bool k3_speculation_held(K3Workspace &ws, const K3Params &p);
+const uint32_t *k3_speculation_failed_flag(K3Workspace &ws);  // device word, non-zero = the speculative finish in flight gave up
 
 // ---- K4: marker pose from four corners (k4_pose.cu) --------------------------------------------------------------
 struct K4Params {
@@ -128,6 +135,7 @@ struct K4Params {
     const uint32_t *corners;     // device n*8 (other modes)
     const a3_decode *decodes;    // device n or null; when set: only accepted items, corners.rotate_left(rotation)
     uint32_t n;
+    const uint32_t *n_dev = nullptr;  // device, optional: the real number of items (<= n, which then only sizes the launch)
     float marker_size;
     uint32_t image_w, image_h;   // UNDISTORTED
     a3_camera_intrinsics k;      // INTRINSICS

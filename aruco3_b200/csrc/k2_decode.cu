@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const
     __syncthreads();
 
     // one warp per candidate; warps never wait for each other
-    for (uint32_t q = blockIdx.x * kWarps + warp; q < p.n_quads; q += gridDim.x * kWarps) {
+    const uint32_t n_quads = p.n_quads_dev ? min(*p.n_quads_dev, p.n_quads) : p.n_quads;
+    for (uint32_t q = blockIdx.x * kWarps + warp; q < n_quads; q += gridDim.x * kWarps) {
         const uint32_t frame = p.quad_frame ? p.quad_frame[q] : 0;
         const uint8_t *grey = p.grey + (size_t)frame * p.w * p.h;
         make_projection(p.quads + (size_t)q * 8, (float)ps, ws->a, &ws->proj, lane);

@@ -539,8 +539,29 @@ __global__ void __launch_bounds__(256) k3_rank(const uint32_t *slot_sorted, cons
     const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= n_long) return;
     const uint32_t s = slot_sorted[ci];
+    if (s == 0xffffffffu) {  // padding of a speculatively sized sort (k3_spec_prepare): sorts last, has no points
+        n_sorted[ci] = 0;
+        return;
+    }
     n_sorted[ci] = long_n[s];
     rank[s] = ci;
+}
+
+// Speculative finish (k3_finish_speculative): the second half of the stage is enqueued before the list sizes are known on
+// the host, sized from the previous call.  counters[5] = 1 when the real sizes do not fit (every later kernel of the chain
+// then returns at once and the host, which sees the same counters after its next synchronisation, redoes the second half
+// exactly); the sort input is padded to its speculated size with keys that sort last.
+constexpr uint32_t kSpecFail = 5;
+__global__ void __launch_bounds__(256) k3_spec_prepare(unsigned long long *long_keys, uint32_t *long_slot, uint32_t *counters,
+                                                       const unsigned long long *long_points, uint32_t cap_long, uint32_t cap_ckpts,
+                                                       unsigned long long cap_points) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_long = counters[1];
+    if (i == 0) counters[kSpecFail] = (counters[2] || n_long > cap_long || counters[4] > cap_ckpts || *long_points > cap_points) ? 1u : 0u;
+    if (i >= n_long && i < cap_long) {
+        long_keys[i] = ~0ull;
+        long_slot[i] = 0xffffffffu;
+    }
 }
 
 struct Contour {
@@ -553,8 +574,13 @@ struct Contour {
 // start pixel, the others at a checkpoint dropped by the border's walker.
 __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *tables, const unsigned long long *keys, const uint32_t *lens,
                                                const uint32_t *offsets, uint32_t n_contours, const uint32_t *rank, const uint32_t *walker_slot,
-                                               const Ckpt *ckpts, uint32_t n_ckpts, Contour *contours, uint32_t *points) {
+                                               const Ckpt *ckpts, uint32_t n_ckpts, Contour *contours, uint32_t *points, const uint32_t *dyn) {
     __shared__ uint16_t fwd[8][512];
+    if (dyn) {  // speculative finish: the real sizes are on the device only
+        if (dyn[kSpecFail]) return;
+        n_contours = dyn[1]; n_ckpts = dyn[4];
+        if (blockIdx.x * blockDim.x >= n_contours + n_ckpts) return;
+    }
     for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) (&fwd[0][0])[i] = (&tables->fwd[0][0])[i];
     __syncthreads();
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -669,10 +695,14 @@ constexpr int kRdpStack = 64;
 // One warp per contour: approximate_polygon_dp(points, n * eps, closed) -> exactly 4 vertices? -> hull -> edge test
 // (src/aruco.rs:133-159).  Same span order and the same "first strict maximum" rule as host_quads.cpp:simplify_closed.
 __global__ void __launch_bounds__(128) k3_rdp(const Contour *contours, const uint32_t *points, uint32_t n_contours, double eps_factor,
-                                              uint32_t min_edge_length, uint32_t *quads, uint32_t *frame_flags) {
+                                              uint32_t min_edge_length, uint32_t *quads, uint32_t *frame_flags, const uint32_t *dyn) {
     __shared__ uint2 stacks[4][kRdpStack];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t ci = blockIdx.x * 4 + wid;
+    if (dyn) {
+        if (dyn[kSpecFail]) return;
+        n_contours = dyn[1];
+    }
     if (ci >= n_contours) return;
     const Contour c = contours[ci];
     const uint32_t *pts = points + c.point_off;
@@ -784,7 +814,11 @@ __device__ __forceinline__ uint32_t lower_bound_key(const unsigned long long *ke
 __global__ void __launch_bounds__(32) k3_finalize(const uint32_t *contour_quads, const unsigned long long *keys, size_t words_per_frame,
                                                   uint32_t total_contours, uint32_t n_frames, float min_corner_separation,
                                                   uint32_t quad_cap, uint32_t *out_quads, uint32_t *out_counts, uint32_t *out_before_discard,
-                                                  uint32_t *frame_flags, uint8_t *dead_scratch) {
+                                                  uint32_t *frame_flags, uint8_t *dead_scratch, const uint32_t *dyn) {
+    if (dyn) {
+        if (dyn[kSpecFail]) return;
+        total_contours = dyn[1];
+    }
     extern __shared__ uint32_t sq[];  // quad_cap * 8 words of quads, then quad_cap floats of perimeters, then quad_cap dead bytes
     float *sper = reinterpret_cast<float *>(sq + (size_t)quad_cap * 8);
     uint8_t *dead = reinterpret_cast<uint8_t *>(sper + quad_cap);
@@ -896,6 +930,13 @@ struct K3Workspace::Impl {
     Geo g;                                   // state handed from k3_begin to k3_finish
     Lists l;
     int sms = 148;
+    // list sizes of the previous call with this geometry: what k3_finish_speculative sizes its launches from
+    bool hist_valid = false;
+    uint32_t hist_n = 0, hist_w = 0, hist_h = 0, hist_long = 0, hist_ckpts = 0;
+    unsigned long long hist_points = 0;
+    // capacities the speculative finish in flight was enqueued with (0 = none in flight)
+    uint32_t spec_long = 0, spec_ckpts = 0;
+    unsigned long long spec_points = 0;
 };
 
 K3Workspace::K3Workspace() : impl(new Impl()) {}
@@ -1101,6 +1142,9 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     const unsigned long long n_points = w.h_counts[4];
     const uint32_t n_ckpts = hc[4] < l.ckpt_cap ? hc[4] : l.ckpt_cap;
     if (timer.on) fprintf(stderr, "k3 lists: %u candidates, %u walkers, %u long borders, %llu points, %u checkpoints\n", hc[3], hc[0], hc[1], n_points, hc[4]);
+    w.hist_valid = !hc[2] && n_points < 0xffffffffull;
+    w.hist_n = p.n; w.hist_w = p.w; w.hist_h = p.h; w.hist_long = hc[1]; w.hist_ckpts = hc[4]; w.hist_points = n_points;
+    w.spec_long = 0;
     if (n_points >= 0xffffffffull && !hc[2]) {  // point offsets are 32-bit: hand the whole call to the host stage
         k3_flag_all<<<(p.n + 127) / 128, 128, 0, stream>>>(p.frame_flags, p.n, w.counters, 1);
         K3_CUDA(cudaGetLastError());
@@ -1122,10 +1166,10 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         K3_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.long_n_sorted, w.long_off, (int)n_long, stream));
         timer.mark("sort+scan");
         k3_emit<<<(n_long + n_ckpts + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, n_long, w.long_rank,
-                                                                   w.walker_slot, w.ckpts, n_ckpts, w.contours, w.points);
+                                                                   w.walker_slot, w.ckpts, n_ckpts, w.contours, w.points, nullptr);
         K3_CUDA(cudaGetLastError());
         timer.mark("emit");
-        k3_rdp<<<(n_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, n_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags);
+        k3_rdp<<<(n_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, n_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags, nullptr);
         K3_CUDA(cudaGetLastError());
     }
     timer.mark("rdp");
@@ -1133,12 +1177,87 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     if (fin_smem > 200 * 1024) return cudaErrorInvalidValue;
     K3_CUDA(cudaFuncSetAttribute(k3_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     k3_finalize<<<p.n, 32, fin_smem, stream>>>(w.contour_quads, w.long_keys_sorted, words_per_frame, n_long, p.n, p.min_corner_separation, p.quad_cap,
-                                        p.quads, p.quad_counts, p.before_discard, p.frame_flags, w.dead);
+                                        p.quads, p.quad_counts, p.before_discard, p.frame_flags, w.dead, nullptr);
     K3_CUDA(cudaGetLastError());
     timer.mark("finalize");
     if (p.frame_contours) K3_CUDA(cudaMemcpyAsync(p.frame_contours, w.frame_contours, (size_t)p.n * 4, cudaMemcpyDeviceToDevice, stream));
     if (p.frame_points) K3_CUDA(cudaMemcpyAsync(p.frame_points, w.frame_points, (size_t)p.n * 8, cudaMemcpyDeviceToDevice, stream));
     return cudaSuccess;
+}
+
+// Second half without the host synchronisation: the same kernels, launched with the list sizes of the previous call of
+// this geometry plus headroom; the real sizes stay on the device (`counters`).  *speculated = false (nothing enqueued)
+// when there is no such history.  The caller synchronises the stream later and asks k3_speculation_held(); when it did
+// not hold, k3_finish redoes the second half exactly (k3_begin's lists are untouched by a failed speculation).
+cudaError_t k3_finish_speculative(K3Workspace &ws, const K3Params &p, cudaStream_t stream, bool *speculated) {
+    K3Workspace::Impl &w = *ws.impl;
+    *speculated = false;
+    w.spec_long = 0;
+    if (p.n == 0 || !w.hist_valid || w.hist_n != p.n || w.hist_w != p.w || w.hist_h != p.h) return cudaSuccess;
+    const Geo g = w.g;
+    const Lists l = w.l;
+    const size_t words_per_frame = (size_t)g.h * g.wpr, nwords = words_per_frame * p.n;
+    const size_t fin_smem = (size_t)p.quad_cap * (32 + 4 + 1) + 16;
+    if (fin_smem > 200 * 1024) return cudaSuccess;
+    unsigned long long cap_long64 = (unsigned long long)w.hist_long + w.hist_long / 8 + 256;
+    if (cap_long64 > l.long_cap) cap_long64 = l.long_cap;
+    unsigned long long cap_ckpts64 = (unsigned long long)w.hist_ckpts + w.hist_ckpts / 8 + 1024;
+    if (cap_ckpts64 > l.ckpt_cap) cap_ckpts64 = l.ckpt_cap;
+    unsigned long long cap_points = w.hist_points + w.hist_points / 8 + 65536;
+    if (cap_points > 0xfffffffeull) cap_points = 0xfffffffeull;
+    const uint32_t cap_long = (uint32_t)cap_long64, cap_ckpts = (uint32_t)cap_ckpts64;
+    if ((size_t)cap_long > w.contours_cap) {
+        K3_CUDA(alloc_exact(w.contours, (size_t)cap_long + cap_long / 4 + 1024));
+        K3_CUDA(alloc_exact(w.contour_quads, ((size_t)cap_long + cap_long / 4 + 1024) * 8));
+        w.contours_cap = (size_t)cap_long + cap_long / 4 + 1024;
+    }
+    K3_CUDA(grow(w.points, w.points_cap, (size_t)cap_points + 1));
+    PhaseTimer timer(stream);
+    timer.mark("begin");
+    k3_spec_prepare<<<(cap_long + 255) / 256, 256, 0, stream>>>(w.long_keys, w.long_slot, w.counters, w.long_points, cap_long, cap_ckpts, cap_points);
+    K3_CUDA(cudaGetLastError());
+    size_t tmp = w.cub_bytes;
+    const int end_bit = 64 - __builtin_clzll(((unsigned long long)nwords << 6) | 1ull);
+    K3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.long_keys, w.long_keys_sorted, w.long_slot, w.long_slot_sorted, (int)cap_long, 0, end_bit, stream));
+    k3_rank<<<(cap_long + 255) / 256, 256, 0, stream>>>(w.long_slot_sorted, w.long_n, cap_long, w.long_n_sorted, w.long_rank);
+    K3_CUDA(cudaGetLastError());
+    tmp = w.cub_bytes;
+    K3_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.long_n_sorted, w.long_off, (int)cap_long, stream));
+    timer.mark("sort+scan");
+    k3_emit<<<(cap_long + cap_ckpts + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, cap_long, w.long_rank,
+                                                                   w.walker_slot, w.ckpts, cap_ckpts, w.contours, w.points, w.counters);
+    K3_CUDA(cudaGetLastError());
+    timer.mark("emit");
+    k3_rdp<<<(cap_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, cap_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags, w.counters);
+    K3_CUDA(cudaGetLastError());
+    timer.mark("rdp");
+    K3_CUDA(cudaFuncSetAttribute(k3_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    k3_finalize<<<p.n, 32, fin_smem, stream>>>(w.contour_quads, w.long_keys_sorted, words_per_frame, cap_long, p.n, p.min_corner_separation, p.quad_cap,
+                                        p.quads, p.quad_counts, p.before_discard, p.frame_flags, w.dead, w.counters);
+    K3_CUDA(cudaGetLastError());
+    timer.mark("finalize");
+    if (p.frame_contours) K3_CUDA(cudaMemcpyAsync(p.frame_contours, w.frame_contours, (size_t)p.n * 4, cudaMemcpyDeviceToDevice, stream));
+    if (p.frame_points) K3_CUDA(cudaMemcpyAsync(p.frame_points, w.frame_points, (size_t)p.n * 8, cudaMemcpyDeviceToDevice, stream));
+    w.spec_long = cap_long ? cap_long : 1; w.spec_ckpts = cap_ckpts; w.spec_points = cap_points;
+    *speculated = true;
+    return cudaSuccess;
+}
+
+// Device word that is non-zero when the speculative finish in flight gave up (for kernels queued behind it).
+const uint32_t *k3_speculation_failed_flag(K3Workspace &ws) { return ws.impl->counters ? ws.impl->counters + kSpecFail : nullptr; }
+
+// After the stream of a speculative finish has been synchronised: did the real list sizes fit?  (The same test
+// k3_spec_prepare made on the device.)  Records the sizes for the next call either way.
+bool k3_speculation_held(K3Workspace &ws, const K3Params &p) {
+    K3Workspace::Impl &w = *ws.impl;
+    if (!w.spec_long) return false;
+    const uint32_t *hc = reinterpret_cast<const uint32_t *>(&w.h_counts[0]);
+    const unsigned long long n_points = w.h_counts[4];
+    const bool held = !hc[2] && hc[1] <= w.spec_long && hc[4] <= w.spec_ckpts && n_points <= w.spec_points;
+    w.hist_valid = !hc[2] && n_points < 0xffffffffull;
+    w.hist_n = p.n; w.hist_w = p.w; w.hist_h = p.h; w.hist_long = hc[1]; w.hist_ckpts = hc[4]; w.hist_points = n_points;
+    w.spec_long = 0;
+    return held;
 }
 
 }  // namespace a3

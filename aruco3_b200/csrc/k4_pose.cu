@@ -159,7 +159,7 @@ __device__ void solve_square(const float (&px)[4], const float (&py)[4], float m
 
 __global__ void __launch_bounds__(128) k4_pose_kernel(K4Params p) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
+    if (i >= p.n || (p.n_dev && i >= *p.n_dev)) return;
     uint32_t rot = 0;
     if (p.decodes) {  // pipeline use: only accepted candidates become markers; corners.rotate_left(rotation), aruco.rs:97-103
         const a3_decode &dc = p.decodes[i];

@@ -109,6 +109,10 @@ typedef struct a3_stats {
     uint32_t pixel_kernel_launches, decode_kernel_launches, host_threads, contour_kernel_launches;
     uint32_t host_fallback_frames; /* device contour stage: frames it handed back to the host stage */
     uint32_t pose_kernel_launches; /* K4 launches (a3_detector_set_pose) */
+    /* one-shot route (device contour stage, one K3 launch per call): K3's second half, K2 and K4 queued without a host
+     * synchronisation, sized from the previous call of the same geometry.  one_shot = 1 when this call's results came
+     * from it; one_shot_retry = 1 when its sizes did not hold and the ordinary route finished the call instead. */
+    uint32_t one_shot, one_shot_retry;
 } a3_stats;
 
 /* MarkerPose (src/pose.rs:8-12): scene-from-marker transform in OpenCV chirality (+Z forward, +Y down, +X right).

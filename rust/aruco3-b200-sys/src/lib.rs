@@ -92,6 +92,8 @@ pub struct a3_stats {
     pub contour_kernel_launches: u32,
     pub host_fallback_frames: u32,
     pub pose_kernel_launches: u32,
+    pub one_shot: u32,
+    pub one_shot_retry: u32,
 }
 
 /// MarkerPose, reference `src/pose.rs:8-12`; rotation row-major

@@ -127,8 +127,9 @@ impl Detector {
             DynamicImage::ImageLuma8(g) => (g.into_raw(), sys::A3_FMT_LUMA8, 1),
             DynamicImage::ImageRgba8(i) => (i.into_raw(), sys::A3_FMT_RGBA8, 4),
             DynamicImage::ImageRgb8(i) => (i.into_raw(), sys::A3_FMT_RGB8, 3),
-            // documented deviation: other variants go through Rgb8 first (the reference converts them directly to Luma8)
-            other => (other.into_rgb8().into_raw(), sys::A3_FMT_RGB8, 3),
+            // 16-bit, float and LumaA variants: the reference's own host conversion (`image`'s into_luma8, src/aruco.rs:60),
+            // so grey is identical by construction; the device then takes the Luma8 pass-through
+            other => (other.into_luma8().into_raw(), sys::A3_FMT_LUMA8, 1),
         };
         self.detect_batch(&buf, fmt, 1, w, h, bpp).pop().unwrap()
     }

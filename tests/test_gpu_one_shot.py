@@ -1,0 +1,120 @@
+"""The one-shot route of a3_detect_batch (device contour stage, one K3 launch per call): from the second call of a geometry
+on, K3's second half, the gather of its quads, K2 and K4 are queued without a host synchronisation and sized from the
+previous call.  Results must be identical whichever route a call takes — sizes held, K3's lists outgrew the speculation,
+the quad list outgrew it, or a frame was flagged for the host stage."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def a3():
+    import aruco3_b200
+    from aruco3_b200 import _ffi
+    if _ffi.lib().a3_device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu tests have no fallback")
+    return aruco3_b200
+
+
+def _summary(dets):
+    return [([list(sum(c, ())) for c in x.candidates],
+             [(m.candidate, m.id, m.rotation, m.hamming_distance, m.code, m.corners) for m in x.markers],
+             [None if h is None else h.tobytes() for h in (x.homographies or [])]) for x in dets]
+
+
+def _fresh(a3, frames, **kw):
+    with a3.Detector(**kw) as d:
+        out = _summary(d.detect_batch(frames, full=True))
+        assert d.last_stats["one_shot"] == 0  # no history yet
+    return out
+
+
+def test_repeat_calls_take_the_one_shot_route(a3, oracle):
+    from aruco3_b200 import synth
+    frames, _ = synth.render_batch("C1", 6)
+    want = _fresh(a3, frames)
+    for f in range(len(frames)):  # and that is the oracle's answer
+        ref = oracle.detect(frames[f], "ARUCO")
+        assert want[f][0] == ref.candidates.tolist()
+        assert [m[1:5] for m in want[f][1]] == [(m["id"], m["rotation"], m["hamming_distance"], m["code"]) for m in ref.markers]
+    with a3.Detector() as d:
+        d.set_pose(40.0)
+        first = d.detect_batch(frames, full=True)
+        assert (d.last_stats["one_shot"], d.last_stats["one_shot_retry"]) == (0, 0)
+        for _ in range(3):
+            again = d.detect_batch(frames, full=True)
+            assert (d.last_stats["one_shot"], d.last_stats["one_shot_retry"]) == (1, 0)
+            assert _summary(again) == want
+            assert [[(p.error, p.rotation.tobytes(), p.translation.tobytes()) for m in x.markers for p in m.poses] for x in again] == \
+                   [[(p.error, p.rotation.tobytes(), p.translation.tobytes()) for m in x.markers for p in m.poses] for x in first]
+        assert d.last_stats["decode_kernel_launches"] == 1 and d.last_stats["pose_kernel_launches"] == 1
+        assert d.last_stats["n_candidates"] == sum(len(x[0]) for x in want)
+
+
+def test_k3_lists_outgrow_the_speculation(a3):
+    """Flat frames (no border at all), marker frames and pure-noise frames (tens of thousands of long borders) alternate
+    in one detector: going up the speculation fails and the call is finished the ordinary way, going down it holds."""
+    from aruco3_b200 import synth
+    clean, _ = synth.render_batch("C1", 5)
+    noise = np.random.default_rng(9).integers(0, 256, size=clean.shape, dtype=np.uint8)
+    flat = np.full_like(clean, 200)
+    want = {"clean": _fresh(a3, clean), "noise": _fresh(a3, noise), "flat": [([], [], [])] * 5}
+    inputs = {"clean": clean, "noise": noise, "flat": flat}
+    routes = []
+    with a3.Detector() as d:
+        for name in ("flat", "flat", "noise", "clean", "noise", "noise", "flat", "clean"):
+            assert _summary(d.detect_batch(inputs[name], full=True)) == want[name], name
+            routes.append((name, d.last_stats["one_shot"], d.last_stats["one_shot_retry"]))
+    assert routes[0][1:] == (0, 0) and all(r[1] + r[2] == 1 for r in routes[1:]), routes
+    assert routes[1][1:] == (1, 0), routes   # flat after flat
+    assert routes[2][1:] == (0, 1), routes   # noise after flat cannot fit
+    assert routes[3][1:] == (1, 0), routes   # clean after noise does
+    assert routes[4][1:] == (0, 1), routes   # noise after clean cannot
+    assert routes[5][1:] == (1, 0), routes   # noise after noise
+    assert routes[6][1:] == (1, 0), routes   # flat after noise
+
+
+def test_quad_list_outgrows_the_speculation(a3):
+    """Many borders but few quads first (noise), then the decode-stress scene with 200+ quads in the same geometry."""
+    from aruco3_b200 import synth
+    spec = synth.CONFIGS["C5"]
+    stress, _ = synth.render_batch(spec, 1)
+    noise = np.random.default_rng(5).integers(0, 256, size=stress.shape, dtype=np.uint8)
+    cfg = a3.DetectorConfig(min_corner_separation_factor=spec.min_corner_separation_factor)
+    want = _fresh(a3, stress, config=cfg, dictionary=spec.dictionary)
+    assert len(want[0][0]) > 64
+    with a3.Detector(cfg, spec.dictionary) as d:
+        d.detect_batch(noise)
+        d.detect_batch(noise)
+        assert d.last_stats["one_shot"] == 1
+        assert _summary(d.detect_batch(stress, full=True)) == want
+        assert (d.last_stats["one_shot"], d.last_stats["one_shot_retry"]) == (0, 1)
+        assert _summary(d.detect_batch(stress, full=True)) == want
+        assert (d.last_stats["one_shot"], d.last_stats["one_shot_retry"]) == (1, 0)
+
+
+def test_flagged_frames_leave_the_one_shot_route(a3):
+    img = np.full((3, 96, 128), 200, np.uint8)
+    img[:, 30:50, 0:20] = 20          # dark blob on the left edge: K3 flags the frame (barred start)
+    img[1, 10:40, 60:100] = 30
+    want = _fresh(a3, img)
+    with a3.Detector() as d:
+        for call in range(3):
+            assert _summary(d.detect_batch(img, full=True)) == want
+            assert d.last_stats["host_fallback_frames"] >= 1 and d.last_stats["one_shot"] == 0
+            if call:
+                assert d.last_stats["one_shot_retry"] == 1
+
+
+def test_batches_of_changing_size(a3):
+    """A change of batch size drops the history: the first call of a geometry is never one-shot, the second is."""
+    from aruco3_b200 import synth
+    frames, _ = synth.render_batch("C1", 9)
+    want = _fresh(a3, frames)
+    routes = []
+    with a3.Detector() as d:
+        for n in (9, 9, 4, 4, 9, 9):
+            assert _summary(d.detect_batch(frames[:n], full=True)) == want[:n]
+            routes.append(d.last_stats["one_shot"])
+    assert routes == [0, 1, 0, 1, 0, 1]
