@@ -595,7 +595,10 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
     const bool gpu_contours = d->contour_mode == A3_CONTOURS_DEVICE && w <= 65535 && h <= 65535 && (uint64_t)w * h < (1ull << 29);
     // resident input + device contours: every quad of the super-batch is known at once, so one decode launch keeps the
     // whole GPU busy (K2 is latency-bound: what counts is candidates in flight)
-    if (gpu_contours && mem == A3_MEM_DEVICE) group = (uint32_t)sb;
+    if (gpu_contours && mem == A3_MEM_DEVICE) {
+        group = (uint32_t)sb;
+        fe = sb;  // nothing to stage and one K3 launch: one front-end unit per super-batch
+    }
     // One-shot route: when one K3 launch covers the whole (super-)batch — resident input, or host input that fits one
     // front-end chunk, e.g. a single frame — the second half of K3, the gather of its quads, K2 and K4 are all queued behind
     // K1 without a host synchronisation, sized from the previous call of the same geometry; the host synchronises once at the

@@ -79,11 +79,11 @@ def test_quad_list_outgrows_the_speculation(a3):
     """Many borders but few quads first (noise), then the decode-stress scene with 200+ quads in the same geometry."""
     from aruco3_b200 import synth
     spec = synth.CONFIGS["C5"]
-    stress, _ = synth.render_batch(spec, 1)
+    stress, _ = synth.render_batch(spec, 2)  # two frames: more quads than the 256 of headroom over the noise frames' few
     noise = np.random.default_rng(5).integers(0, 256, size=stress.shape, dtype=np.uint8)
     cfg = a3.DetectorConfig(min_corner_separation_factor=spec.min_corner_separation_factor)
     want = _fresh(a3, stress, config=cfg, dictionary=spec.dictionary)
-    assert len(want[0][0]) > 64
+    assert len(want[0][0]) + len(want[1][0]) > 300
     with a3.Detector(cfg, spec.dictionary) as d:
         d.detect_batch(noise)
         d.detect_batch(noise)
