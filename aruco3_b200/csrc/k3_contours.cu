@@ -21,14 +21,14 @@
 //
 // Kernels:  k3_candidates (one thread per 32-pixel word of the 1-bit mask; every candidate walks at most kBudget steps:
 // almost all die within a few, short borders finish)  ->  k3_walkers (one thread per undecided candidate: the long
-// borders, all in flight at once)  ->  radix sort of the surviving long borders by raster position (= the reference's
-// discovery order) + prefix sum of their lengths  ->  k3_emit (one thread per border writes its points)  ->  k3_rdp (one
+// borders, all in flight at once)  ->  the surviving long borders put in raster order of their starts (= the reference's
+// discovery order): k3_order ranks them frame by frame, a radix sort takes over when a frame has more than its list holds
+// ->  k3_emit (one thread per border writes its points)  ->  k3_rdp (one
 // warp per border: Ramer-Douglas-Peucker, hull, edge test)  ->  k3_finalize (one warp per frame: ordered compaction,
 // clockwise, discard_too_near).
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -172,6 +172,7 @@ struct Ckpt { uint32_t walker, pos, xy, state; };
 constexpr uint32_t kCkptBackward = 0x80000000u;
 
 enum { kDead = 0, kSurvivor = 1, kUndecided = 2 };
+constexpr uint32_t kSpecFail = 5;  // index into Lists::counters: the speculative finish gave up (k3_spec_prepare)
 
 // Work lists shared by the kernels of one k3_quads call.
 struct Lists {
@@ -180,7 +181,8 @@ struct Lists {
     unsigned long long *walkers;       // candidates undecided after kBudget steps: the same key
     unsigned long long *long_keys;     // surviving borders with >= min_points points: the same key ...
     uint32_t *long_n;                  // ... and their number of points
-    uint32_t *counters;                // [0] walkers, [1] long borders, [2] overflow of a list, [3] candidates, [4] checkpoints
+    uint32_t *counters;                // [0] walkers, [1] long borders, [2] overflow of a list, [3] candidates, [4] checkpoints,
+                                       // [5] speculative finish gave up, [7] most long borders in one frame
     uint32_t *long_slot;               // value array of the sort: the border's slot in long_keys / long_n
     uint32_t *walker_slot;             // per entry of `walkers`: slot of the border it survived as, or 0xffffffff
     Ckpt *ckpts;                       // checkpoints dropped by k3_walkers
@@ -190,6 +192,13 @@ struct Lists {
     uint32_t *frame_contours;          // per frame: borders followed
     unsigned long long *frame_points;  // per frame: their points
     uint32_t *frame_flags;             // per frame: bit 0 barred start (host redo), bit 1 rdp stack overflow, bit 2 quad capacity
+    uint32_t *long_off_slot;           // per slot of long_keys: where the border's points go (allocated with one atomic add)
+    // the same long borders listed per frame, frame_cap entries each (0 = not kept): what k3_order ranks; counters[7] = the
+    // largest number of long borders any frame has
+    uint32_t frame_cap;
+    uint32_t *frame_long_count;
+    unsigned long long *frame_keys;
+    uint32_t *frame_slots;
 };
 
 
@@ -252,7 +261,15 @@ __device__ __forceinline__ uint32_t record_survivor(const Lists &l, uint32_t fra
             l.long_keys[slot] = key;
             l.long_n[slot] = n;
             l.long_slot[slot] = slot;
-            atomicAdd(l.long_points, (unsigned long long)n);
+            l.long_off_slot[slot] = (uint32_t)atomicAdd(l.long_points, (unsigned long long)n);  // totals beyond 32 bits flag the whole call
+            if (l.frame_cap) {
+                const uint32_t j = atomicAdd(&l.frame_long_count[frame], 1u);
+                if (j < l.frame_cap) {
+                    l.frame_keys[(size_t)frame * l.frame_cap + j] = key;
+                    l.frame_slots[(size_t)frame * l.frame_cap + j] = slot;
+                }
+                atomicMax(&l.counters[7], j + 1);
+            }
             return slot;
         }
         atomicOr(&l.counters[2], 1u);
@@ -534,30 +551,67 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
     }
 }
 
-// after the sort: lengths in sorted order (input of the prefix sum) and the sorted position of every slot
-__global__ void __launch_bounds__(256) k3_rank(const uint32_t *slot_sorted, const uint32_t *long_n, uint32_t n_long, uint32_t *n_sorted, uint32_t *rank) {
+// after the radix sort: lengths and point offsets in sorted order and the sorted position of every slot
+__global__ void __launch_bounds__(256) k3_rank(const uint32_t *slot_sorted, const uint32_t *long_n, const uint32_t *off_slot, uint32_t n_long,
+                                               uint32_t *n_sorted, uint32_t *off_sorted, uint32_t *rank) {
     const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= n_long) return;
     const uint32_t s = slot_sorted[ci];
     if (s == 0xffffffffu) {  // padding of a speculatively sized sort (k3_spec_prepare): sorts last, has no points
         n_sorted[ci] = 0;
+        off_sorted[ci] = 0;
         return;
     }
     n_sorted[ci] = long_n[s];
+    off_sorted[ci] = off_slot[s];
     rank[s] = ci;
+}
+
+// The order of the long borders without a global sort: the keys are frame-major, so a border's position is the number
+// of long borders in earlier frames plus its rank among those of its own frame.  One CTA per frame: sums the counts of
+// the frames before it, loads the frame's keys (at most frame_cap; the host takes the radix sort when a frame has more)
+// into shared memory and ranks each by counting the smaller ones.  Replaces radix sort + k3_rank (seven launches).
+constexpr uint32_t kOrderCap = 1024;
+__global__ void __launch_bounds__(256) k3_order(const Lists l, uint32_t n_frames, unsigned long long *keys_sorted, uint32_t *n_sorted,
+                                                uint32_t *off_sorted, uint32_t *rank, const uint32_t *dyn) {
+    __shared__ unsigned long long keys[kOrderCap];
+    __shared__ uint32_t partial[8];
+    if (dyn && dyn[kSpecFail]) return;
+    const uint32_t f = blockIdx.x, cap = l.frame_cap;
+    uint32_t before = 0;
+    for (uint32_t i = threadIdx.x; i < f; i += blockDim.x) before += min(l.frame_long_count[i], cap);
+    for (int o = 16; o; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if ((threadIdx.x & 31) == 0) partial[threadIdx.x >> 5] = before;
+    const uint32_t m = min(l.frame_long_count[f], cap);
+    const unsigned long long *fk = l.frame_keys + (size_t)f * cap;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) keys[i] = fk[i];
+    __syncthreads();
+    uint32_t base = 0;
+    for (uint32_t i = 0; i < blockDim.x / 32; i++) base += partial[i];
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        const unsigned long long k = keys[i];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < m; j++) r += keys[j] < k ? 1u : 0u;
+        const uint32_t ci = base + r, slot = l.frame_slots[(size_t)f * cap + i];
+        keys_sorted[ci] = k;
+        n_sorted[ci] = l.long_n[slot];
+        off_sorted[ci] = l.long_off_slot[slot];
+        rank[slot] = ci;
+    }
 }
 
 // Speculative finish (k3_finish_speculative): the second half of the stage is enqueued before the list sizes are known on
 // the host, sized from the previous call.  counters[5] = 1 when the real sizes do not fit (every later kernel of the chain
 // then returns at once and the host, which sees the same counters after its next synchronisation, redoes the second half
 // exactly); the sort input is padded to its speculated size with keys that sort last.
-constexpr uint32_t kSpecFail = 5;
 __global__ void __launch_bounds__(256) k3_spec_prepare(unsigned long long *long_keys, uint32_t *long_slot, uint32_t *counters,
                                                        const unsigned long long *long_points, uint32_t cap_long, uint32_t cap_ckpts,
-                                                       unsigned long long cap_points) {
+                                                       unsigned long long cap_points, uint32_t cap_frame_long) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_long = counters[1];
-    if (i == 0) counters[kSpecFail] = (counters[2] || n_long > cap_long || counters[4] > cap_ckpts || *long_points > cap_points) ? 1u : 0u;
+    if (i == 0)
+        counters[kSpecFail] = (counters[2] || n_long > cap_long || counters[4] > cap_ckpts || *long_points > cap_points ||
+                               counters[7] > cap_frame_long) ? 1u : 0u;
     if (i >= n_long && i < cap_long) {
         long_keys[i] = ~0ull;
         long_slot[i] = 0xffffffffu;
@@ -915,6 +969,9 @@ struct K3Workspace::Impl {
     unsigned long long *cands = nullptr, *walkers = nullptr, *long_keys = nullptr, *long_keys_sorted = nullptr, *long_points = nullptr, *frame_points = nullptr;
     uint32_t *long_n = nullptr, *long_n_sorted = nullptr, *long_off = nullptr, *counters = nullptr, *frame_contours = nullptr;
     uint32_t *long_slot = nullptr, *long_slot_sorted = nullptr, *long_rank = nullptr, *walker_slot = nullptr;
+    uint32_t *long_off_slot = nullptr, *frame_long_count = nullptr, *frame_slots = nullptr;
+    unsigned long long *frame_keys = nullptr;
+    size_t frame_lists_cap = 0;              // frames the per-frame lists are allocated for
     Ckpt *ckpts = nullptr;
     size_t cands_cap = 0, walkers_cap = 0, long_cap = 0, frames_cap = 0, ckpt_cap = 0;
     void *cub_tmp = nullptr;
@@ -935,8 +992,9 @@ struct K3Workspace::Impl {
     uint32_t hist_n = 0, hist_w = 0, hist_h = 0, hist_long = 0, hist_ckpts = 0;
     unsigned long long hist_points = 0;
     // capacities the speculative finish in flight was enqueued with (0 = none in flight)
-    uint32_t spec_long = 0, spec_ckpts = 0;
+    uint32_t spec_long = 0, spec_ckpts = 0, spec_frame_long = 0;
     unsigned long long spec_points = 0;
+    uint32_t hist_frame_long = 0;            // most long borders in one frame, previous call
 };
 
 K3Workspace::K3Workspace() : impl(new Impl()) {}
@@ -946,7 +1004,7 @@ K3Workspace::~K3Workspace() {
                     (void *)impl->frame_points, (void *)impl->long_n, (void *)impl->long_n_sorted, (void *)impl->long_off, (void *)impl->counters,
                     (void *)impl->frame_contours, impl->cub_tmp, (void *)impl->contours, (void *)impl->contour_quads, (void *)impl->points,
                     (void *)impl->dead, (void *)impl->long_slot, (void *)impl->long_slot_sorted, (void *)impl->long_rank, (void *)impl->walker_slot,
-                    (void *)impl->ckpts})
+                    (void *)impl->ckpts, (void *)impl->long_off_slot, (void *)impl->frame_long_count, (void *)impl->frame_slots, (void *)impl->frame_keys})
         if (p) cudaFree(p);
     if (impl->h_counts) cudaFreeHost(impl->h_counts);
     delete impl;
@@ -1056,11 +1114,10 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         K3_CUDA(alloc_exact(w.long_keys, want_long)); K3_CUDA(alloc_exact(w.long_keys_sorted, want_long));
         K3_CUDA(alloc_exact(w.long_n, want_long)); K3_CUDA(alloc_exact(w.long_n_sorted, want_long)); K3_CUDA(alloc_exact(w.long_off, want_long));
         K3_CUDA(alloc_exact(w.long_slot, want_long)); K3_CUDA(alloc_exact(w.long_slot_sorted, want_long)); K3_CUDA(alloc_exact(w.long_rank, want_long));
+        K3_CUDA(alloc_exact(w.long_off_slot, want_long));
         w.long_cap = want_long;
-        size_t a = 0, b = 0;
-        K3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, a, w.long_keys, w.long_keys_sorted, w.long_slot, w.long_slot_sorted, (int)want_long, 0, 64, stream));
-        K3_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b, w.long_n_sorted, w.long_off, (int)want_long, stream));
-        const size_t need = a > b ? a : b;
+        size_t need = 0;
+        K3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, w.long_keys, w.long_keys_sorted, w.long_slot, w.long_slot_sorted, (int)want_long, 0, 64, stream));
         if (need > w.cub_bytes) {
             if (w.cub_tmp) cudaFree(w.cub_tmp);
             w.cub_tmp = nullptr; w.cub_bytes = 0;
@@ -1071,7 +1128,15 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     if (p.n > w.frames_cap) {
         K3_CUDA(alloc_exact(w.frame_points, (size_t)p.n));
         K3_CUDA(alloc_exact(w.frame_contours, (size_t)p.n));
+        K3_CUDA(alloc_exact(w.frame_long_count, (size_t)p.n));
         w.frames_cap = p.n;
+    }
+    // per-frame lists of the long borders for k3_order: kOrderCap entries per frame while that stays below 256 MB
+    const bool frame_lists = (size_t)p.n * kOrderCap * 12 <= ((size_t)256 << 20) && !getenv("A3_K3_RADIX_SORT");
+    if (frame_lists && p.n > w.frame_lists_cap) {
+        K3_CUDA(alloc_exact(w.frame_keys, (size_t)p.n * kOrderCap));
+        K3_CUDA(alloc_exact(w.frame_slots, (size_t)p.n * kOrderCap));
+        w.frame_lists_cap = p.n;
     }
     if ((size_t)p.n * p.quad_cap > w.dead_cap) {
         K3_CUDA(alloc_exact(w.dead, (size_t)p.n * p.quad_cap));
@@ -1079,6 +1144,7 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     }
     K3_CUDA(cudaMemsetAsync(w.frame_points, 0, (size_t)p.n * 8, stream));
     K3_CUDA(cudaMemsetAsync(w.frame_contours, 0, (size_t)p.n * 4, stream));
+    K3_CUDA(cudaMemsetAsync(w.frame_long_count, 0, (size_t)p.n * 4, stream));
     K3_CUDA(cudaMemsetAsync(p.frame_flags, 0, (size_t)p.n * 4, stream));
     K3_CUDA(cudaMemsetAsync(w.counters, 0, 32, stream));
     K3_CUDA(cudaMemsetAsync(w.long_points, 0, 8, stream));
@@ -1091,6 +1157,8 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     l.long_cap = (uint32_t)(w.long_cap > 0x7fffffffull ? 0x7fffffffull : w.long_cap);
     l.frame_contours = w.frame_contours; l.frame_points = w.frame_points; l.frame_flags = p.frame_flags;
     l.long_slot = w.long_slot; l.walker_slot = w.walker_slot; l.ckpts = w.ckpts;
+    l.long_off_slot = w.long_off_slot; l.frame_cap = frame_lists ? kOrderCap : 0u; l.frame_long_count = w.frame_long_count;
+    l.frame_keys = w.frame_keys; l.frame_slots = w.frame_slots;
     l.ckpt_cap = (uint32_t)(w.ckpt_cap > 0x7fffffffull ? 0x7fffffffull : w.ckpt_cap);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1144,6 +1212,7 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     if (timer.on) fprintf(stderr, "k3 lists: %u candidates, %u walkers, %u long borders, %llu points, %u checkpoints\n", hc[3], hc[0], hc[1], n_points, hc[4]);
     w.hist_valid = !hc[2] && n_points < 0xffffffffull;
     w.hist_n = p.n; w.hist_w = p.w; w.hist_h = p.h; w.hist_long = hc[1]; w.hist_ckpts = hc[4]; w.hist_points = n_points;
+    w.hist_frame_long = hc[7];
     w.spec_long = 0;
     if (n_points >= 0xffffffffull && !hc[2]) {  // point offsets are 32-bit: hand the whole call to the host stage
         k3_flag_all<<<(p.n + 127) / 128, 128, 0, stream>>>(p.frame_flags, p.n, w.counters, 1);
@@ -1157,14 +1226,17 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
             w.contours_cap = (size_t)n_long + n_long / 4 + 1024;
         }
         K3_CUDA(grow(w.points, w.points_cap, (size_t)n_points + 1));
-        size_t tmp = w.cub_bytes;
-        const int end_bit = 64 - __builtin_clzll(((unsigned long long)nwords << 6) | 1ull);
-        K3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.long_keys, w.long_keys_sorted, w.long_slot, w.long_slot_sorted, (int)n_long, 0, end_bit, stream));
-        k3_rank<<<(n_long + 255) / 256, 256, 0, stream>>>(w.long_slot_sorted, w.long_n, n_long, w.long_n_sorted, w.long_rank);
-        K3_CUDA(cudaGetLastError());
-        tmp = w.cub_bytes;
-        K3_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.long_n_sorted, w.long_off, (int)n_long, stream));
-        timer.mark("sort+scan");
+        if (l.frame_cap && hc[7] <= l.frame_cap) {
+            k3_order<<<p.n, 256, 0, stream>>>(l, p.n, w.long_keys_sorted, w.long_n_sorted, w.long_off, w.long_rank, nullptr);
+            K3_CUDA(cudaGetLastError());
+        } else {
+            size_t tmp = w.cub_bytes;
+            const int end_bit = 64 - __builtin_clzll(((unsigned long long)nwords << 6) | 1ull);
+            K3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.long_keys, w.long_keys_sorted, w.long_slot, w.long_slot_sorted, (int)n_long, 0, end_bit, stream));
+            k3_rank<<<(n_long + 255) / 256, 256, 0, stream>>>(w.long_slot_sorted, w.long_n, w.long_off_slot, n_long, w.long_n_sorted, w.long_off, w.long_rank);
+            K3_CUDA(cudaGetLastError());
+        }
+        timer.mark("order");
         k3_emit<<<(n_long + n_ckpts + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, n_long, w.long_rank,
                                                                    w.walker_slot, w.ckpts, n_ckpts, w.contours, w.points, nullptr);
         K3_CUDA(cudaGetLastError());
@@ -1214,16 +1286,23 @@ cudaError_t k3_finish_speculative(K3Workspace &ws, const K3Params &p, cudaStream
     K3_CUDA(grow(w.points, w.points_cap, (size_t)cap_points + 1));
     PhaseTimer timer(stream);
     timer.mark("begin");
-    k3_spec_prepare<<<(cap_long + 255) / 256, 256, 0, stream>>>(w.long_keys, w.long_slot, w.counters, w.long_points, cap_long, cap_ckpts, cap_points);
+    // which ordering: the per-frame ranking when the previous call's fullest frame fits its lists with room to spare
+    const bool per_frame = l.frame_cap && w.hist_frame_long + w.hist_frame_long / 4 + 16 <= l.frame_cap;
+    const uint32_t cap_frame_long = per_frame ? l.frame_cap : 0xffffffffu;
+    k3_spec_prepare<<<(cap_long + 255) / 256, 256, 0, stream>>>(w.long_keys, w.long_slot, w.counters, w.long_points, cap_long, cap_ckpts, cap_points,
+                                                                cap_frame_long);
     K3_CUDA(cudaGetLastError());
-    size_t tmp = w.cub_bytes;
-    const int end_bit = 64 - __builtin_clzll(((unsigned long long)nwords << 6) | 1ull);
-    K3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.long_keys, w.long_keys_sorted, w.long_slot, w.long_slot_sorted, (int)cap_long, 0, end_bit, stream));
-    k3_rank<<<(cap_long + 255) / 256, 256, 0, stream>>>(w.long_slot_sorted, w.long_n, cap_long, w.long_n_sorted, w.long_rank);
-    K3_CUDA(cudaGetLastError());
-    tmp = w.cub_bytes;
-    K3_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.long_n_sorted, w.long_off, (int)cap_long, stream));
-    timer.mark("sort+scan");
+    if (per_frame) {
+        k3_order<<<p.n, 256, 0, stream>>>(l, p.n, w.long_keys_sorted, w.long_n_sorted, w.long_off, w.long_rank, w.counters);
+        K3_CUDA(cudaGetLastError());
+    } else {
+        size_t tmp = w.cub_bytes;
+        const int end_bit = 64 - __builtin_clzll(((unsigned long long)nwords << 6) | 1ull);
+        K3_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.long_keys, w.long_keys_sorted, w.long_slot, w.long_slot_sorted, (int)cap_long, 0, end_bit, stream));
+        k3_rank<<<(cap_long + 255) / 256, 256, 0, stream>>>(w.long_slot_sorted, w.long_n, w.long_off_slot, cap_long, w.long_n_sorted, w.long_off, w.long_rank);
+        K3_CUDA(cudaGetLastError());
+    }
+    timer.mark("order");
     k3_emit<<<(cap_long + cap_ckpts + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, cap_long, w.long_rank,
                                                                    w.walker_slot, w.ckpts, cap_ckpts, w.contours, w.points, w.counters);
     K3_CUDA(cudaGetLastError());
@@ -1238,7 +1317,7 @@ cudaError_t k3_finish_speculative(K3Workspace &ws, const K3Params &p, cudaStream
     timer.mark("finalize");
     if (p.frame_contours) K3_CUDA(cudaMemcpyAsync(p.frame_contours, w.frame_contours, (size_t)p.n * 4, cudaMemcpyDeviceToDevice, stream));
     if (p.frame_points) K3_CUDA(cudaMemcpyAsync(p.frame_points, w.frame_points, (size_t)p.n * 8, cudaMemcpyDeviceToDevice, stream));
-    w.spec_long = cap_long ? cap_long : 1; w.spec_ckpts = cap_ckpts; w.spec_points = cap_points;
+    w.spec_long = cap_long ? cap_long : 1; w.spec_ckpts = cap_ckpts; w.spec_points = cap_points; w.spec_frame_long = cap_frame_long;
     *speculated = true;
     return cudaSuccess;
 }
@@ -1253,9 +1332,10 @@ bool k3_speculation_held(K3Workspace &ws, const K3Params &p) {
     if (!w.spec_long) return false;
     const uint32_t *hc = reinterpret_cast<const uint32_t *>(&w.h_counts[0]);
     const unsigned long long n_points = w.h_counts[4];
-    const bool held = !hc[2] && hc[1] <= w.spec_long && hc[4] <= w.spec_ckpts && n_points <= w.spec_points;
+    const bool held = !hc[2] && hc[1] <= w.spec_long && hc[4] <= w.spec_ckpts && n_points <= w.spec_points && hc[7] <= w.spec_frame_long;
     w.hist_valid = !hc[2] && n_points < 0xffffffffull;
     w.hist_n = p.n; w.hist_w = p.w; w.hist_h = p.h; w.hist_long = hc[1]; w.hist_ckpts = hc[4]; w.hist_points = n_points;
+    w.hist_frame_long = hc[7];
     w.spec_long = 0;
     return held;
 }
