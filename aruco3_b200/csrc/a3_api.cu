@@ -141,6 +141,9 @@ struct DecodeBlock {
     PinBuf<a3_pose> h_pose;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     uint32_t n_quads = 0;
+    // where the host reads this group's records: h_dec / h_pose, or the one-shot arena
+    const a3_decode *dec_view = nullptr;
+    const a3_pose *pose_view = nullptr;
     void release() {
         h_quads.release(); h_qframe.release(); h_dec.release(); d_quads.release(); d_qframe.release(); d_dec.release(); d_patches.release();
         d_pose.release(); h_pose.release();
@@ -200,8 +203,11 @@ struct a3_detector {
     uint32_t planes_w = 0, planes_h = 0;
     std::vector<std::vector<uint32_t>> frame_quads;  // per-frame quads of the batch in flight (capacity reused across calls)
     // one-shot route (pack_quads): K3's quads go to K2 on the device; launch and copy sizes come from the previous call
-    a3::DevBuf<uint32_t> d_qoff, d_packinfo;
-    a3::PinBuf<uint32_t> h_packinfo;
+    a3::DevBuf<uint32_t> d_qoff;
+    // arena of the one-shot route, one device-to-host copy per call: [0] quads in total, [1] route unusable; K3's per-frame
+    // counters; the gathered quads; K2's records; K4's poses
+    a3::DevBuf<uint8_t> d_shot;
+    a3::PinBuf<uint8_t> h_shot;
     uint32_t hist_nq = 0, hist_nq_n = 0, hist_nq_w = 0, hist_nq_h = 0;  // quads of the previous call with this geometry (0 = none)
     // pose step (K4)
     uint32_t pose_mode = A3_POSE_OFF;
@@ -389,7 +395,7 @@ void a3_detector_destroy(a3_detector *d) {
     d->d_planes.release(); d->d_k3quads.release(); d->d_k3counts.release(); d->d_k3before.release(); d->d_k3flags.release();
     d->d_k3contours.release(); d->d_k3points.release(); d->h_k3quads.release(); d->h_k3counts.release(); d->h_k3before.release();
     d->h_k3flags.release(); d->h_k3contours.release(); d->h_k3points.release(); d->h_plane.release();
-    d->d_qoff.release(); d->d_packinfo.release(); d->h_packinfo.release();
+    d->d_qoff.release(); d->d_shot.release(); d->h_shot.release();
     d->d_pose_in.release(); d->d_pose_out.release(); d->h_pose_out.release();
     d->events.release();
     for (auto &b : d->blocks) b->release();
@@ -645,6 +651,29 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         if (want_mask) A3_CUDA(d->d_mask.reserve(sn * px));
         if (mem == A3_MEM_HOST) A3_CUDA(d->d_src.reserve((size_t)kStaging * fe * frame_stride));
         while (d->blocks.size() < ngroups) d->blocks.emplace_back(new DecodeBlock());
+        // K3's per-frame counters: separate buffers, or (one-shot route) sections of the arena that goes back in one copy
+        uint32_t *ds_counts = d->d_k3counts.p, *ds_before = d->d_k3before.p, *ds_flags = d->d_k3flags.p, *ds_contours = d->d_k3contours.p;
+        unsigned long long *ds_points = d->d_k3points.p;
+        uint32_t *hs_counts = d->h_k3counts.p, *hs_before = d->h_k3before.p, *hs_flags = d->h_k3flags.p, *hs_contours = d->h_k3contours.p;
+        unsigned long long *hs_points = d->h_k3points.p;
+        const bool shot = one_shot && s0 == 0 && sn == n;
+        const bool shot_hist = shot && d->hist_nq && d->hist_nq_n == n && d->hist_nq_w == w && d->hist_nq_h == h;
+        const uint32_t shot_cap = shot_hist ? d->hist_nq + d->hist_nq / 8 + 256 : 0;  // quads the arena holds
+        const size_t shot_c = ((size_t)sn + 1) & ~(size_t)1;
+        const size_t off_stats = 16, off_quads = (off_stats + 24 * shot_c + 15) & ~(size_t)15, off_dec = off_quads + (size_t)shot_cap * 32;
+        const size_t off_pose = off_dec + (size_t)shot_cap * sizeof(a3_decode);
+        const size_t shot_bytes = off_pose + (want_poses ? (size_t)shot_cap * 2 * sizeof(a3_pose) : 0);
+        if (shot) {
+            A3_CUDA(d->d_shot.reserve(shot_bytes)); A3_CUDA(d->h_shot.reserve(shot_bytes));
+            auto carve = [&](uint8_t *base, uint32_t *&c, uint32_t *&b, uint32_t *&f, uint32_t *&k, unsigned long long *&pt) {
+                uint32_t *q = reinterpret_cast<uint32_t *>(base + off_stats);
+                c = q; b = q + shot_c; f = q + 2 * shot_c; k = q + 3 * shot_c; pt = reinterpret_cast<unsigned long long *>(q + 4 * shot_c);
+            };
+            carve(d->d_shot.p, ds_counts, ds_before, ds_flags, ds_contours, ds_points);
+            carve(d->h_shot.p, hs_counts, hs_before, hs_flags, hs_contours, hs_points);
+        }
+        uint32_t *const d_info = reinterpret_cast<uint32_t *>(d->d_shot.p);
+        const uint32_t *const h_info = reinterpret_cast<const uint32_t *>(d->h_shot.p);
         d->events.reset();
         std::vector<cudaEvent_t> ev_fe(nfe), ev_k1a(nfe), ev_k1b(nfe), ev_h2da(nfe), ev_h2db(nfe), ev_k3(nfe);
         for (uint32_t j = 0; j < nfe; j++) {
@@ -682,11 +711,15 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         bool k3_spec_inflight = false, one_shot_enqueued = false, one_shot_done = false;
         uint32_t one_shot_cap = 0;
         auto k3_stats_d2h = [&](uint32_t f0, uint32_t kn) -> a3_status {
-            A3_CUDA(cudaMemcpyAsync(d->h_k3counts.p + f0, d->d_k3counts.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
-            A3_CUDA(cudaMemcpyAsync(d->h_k3before.p + f0, d->d_k3before.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
-            A3_CUDA(cudaMemcpyAsync(d->h_k3flags.p + f0, d->d_k3flags.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
-            A3_CUDA(cudaMemcpyAsync(d->h_k3contours.p + f0, d->d_k3contours.p + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
-            A3_CUDA(cudaMemcpyAsync(d->h_k3points.p + f0, d->d_k3points.p + f0, (size_t)kn * 8, cudaMemcpyDeviceToHost, d->s_pixel));
+            if (shot) {  // the counters are one block of the arena
+                A3_CUDA(cudaMemcpyAsync(d->h_shot.p + off_stats, d->d_shot.p + off_stats, 24 * shot_c, cudaMemcpyDeviceToHost, d->s_pixel));
+                return A3_OK;
+            }
+            A3_CUDA(cudaMemcpyAsync(hs_counts + f0, ds_counts + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+            A3_CUDA(cudaMemcpyAsync(hs_before + f0, ds_before + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+            A3_CUDA(cudaMemcpyAsync(hs_flags + f0, ds_flags + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+            A3_CUDA(cudaMemcpyAsync(hs_contours + f0, ds_contours + f0, (size_t)kn * 4, cudaMemcpyDeviceToHost, d->s_pixel));
+            A3_CUDA(cudaMemcpyAsync(hs_points + f0, ds_points + f0, (size_t)kn * 8, cudaMemcpyDeviceToHost, d->s_pixel));
             return A3_OK;
         };
         auto k3_head_d2h = [&](uint32_t f0, uint32_t kn) -> a3_status {
@@ -699,34 +732,32 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         // gather K3's quads on the device, decode them (K2, K4) and copy everything back, all on the pixel stream
         auto enqueue_one_shot = [&]() -> a3_status {
             DecodeBlock &b = *d->blocks[0];
-            const uint32_t cap = d->hist_nq + d->hist_nq / 8 + 256;
-            A3_CUDA(d->d_qoff.reserve((size_t)sn + 1)); A3_CUDA(d->d_packinfo.reserve(2)); A3_CUDA(d->h_packinfo.reserve(2));
-            A3_CUDA(b.h_quads.reserve((size_t)cap * 8)); A3_CUDA(b.h_qframe.reserve(cap)); A3_CUDA(b.h_dec.reserve(cap));
-            A3_CUDA(b.d_quads.reserve((size_t)cap * 8)); A3_CUDA(b.d_qframe.reserve(cap)); A3_CUDA(b.d_dec.reserve(cap));
+            const uint32_t cap = shot_cap;
+            uint32_t *d_quads = reinterpret_cast<uint32_t *>(d->d_shot.p + off_quads);
+            a3_decode *d_dec = reinterpret_cast<a3_decode *>(d->d_shot.p + off_dec);
+            a3_pose *d_pose = reinterpret_cast<a3_pose *>(d->d_shot.p + off_pose);
+            A3_CUDA(d->d_qoff.reserve((size_t)sn + 1));
+            A3_CUDA(b.d_qframe.reserve(cap));
             if (want_patches) A3_CUDA(b.d_patches.reserve(cap * np));
             if (!b.ev_a) { A3_CUDA(cudaEventCreate(&b.ev_a)); A3_CUDA(cudaEventCreate(&b.ev_b)); }
-            pack_offsets_kernel<<<1, 1024, 0, d->s_pixel>>>(d->d_k3counts.p, d->d_k3flags.p, sn, quad_cap, cap, k3_speculation_failed_flag(d->k3),
-                                                            d->d_qoff.p, d->d_packinfo.p);
+            pack_offsets_kernel<<<1, 1024, 0, d->s_pixel>>>(ds_counts, ds_flags, sn, quad_cap, cap, k3_speculation_failed_flag(d->k3), d->d_qoff.p, d_info);
             A3_CUDA(cudaGetLastError());
-            pack_quads_kernel<<<sn, 128, 0, d->s_pixel>>>(d->d_k3quads.p, d->d_qoff.p, quad_cap, cap, d->d_packinfo.p, b.d_quads.p, b.d_qframe.p);
+            pack_quads_kernel<<<sn, 128, 0, d->s_pixel>>>(d->d_k3quads.p, d->d_qoff.p, quad_cap, cap, d_info, d_quads, b.d_qframe.p);
             A3_CUDA(cudaGetLastError());
             K2Params p = k2_params(d, d->d_grey.p, w, h);
-            p.quads = b.d_quads.p; p.quad_frame = b.d_qframe.p; p.n_quads = cap; p.n_quads_dev = d->d_packinfo.p; p.decodes = b.d_dec.p;
+            p.quads = d_quads; p.quad_frame = b.d_qframe.p; p.n_quads = cap; p.n_quads_dev = d_info; p.decodes = d_dec;
             p.patches = want_patches ? b.d_patches.p : nullptr;
             A3_CUDA(cudaEventRecord(b.ev_a, d->s_pixel));
             A3_CUDA(k2_decode(p, d->s_pixel));
             A3_CUDA(cudaEventRecord(b.ev_b, d->s_pixel));
-            A3_CUDA(cudaMemcpyAsync(d->h_packinfo.p, d->d_packinfo.p, 8, cudaMemcpyDeviceToHost, d->s_pixel));
-            A3_CUDA(cudaMemcpyAsync(b.h_quads.p, b.d_quads.p, (size_t)cap * 32, cudaMemcpyDeviceToHost, d->s_pixel));
-            A3_CUDA(cudaMemcpyAsync(b.h_dec.p, b.d_dec.p, (size_t)cap * sizeof(a3_decode), cudaMemcpyDeviceToHost, d->s_pixel));
             if (want_poses) {
-                A3_CUDA(b.d_pose.reserve((size_t)cap * 2)); A3_CUDA(b.h_pose.reserve((size_t)cap * 2));
                 K4Params kp{};
-                kp.mode = d->pose_mode; kp.corners = b.d_quads.p; kp.decodes = b.d_dec.p; kp.n = cap; kp.n_dev = d->d_packinfo.p;
-                kp.marker_size = d->pose_marker_size; kp.image_w = w; kp.image_h = h; kp.k = d->pose_k; kp.poses = b.d_pose.p;
+                kp.mode = d->pose_mode; kp.corners = d_quads; kp.decodes = d_dec; kp.n = cap; kp.n_dev = d_info;
+                kp.marker_size = d->pose_marker_size; kp.image_w = w; kp.image_h = h; kp.k = d->pose_k; kp.poses = d_pose;
                 A3_CUDA(k4_pose(kp, d->s_pixel));
-                A3_CUDA(cudaMemcpyAsync(b.h_pose.p, b.d_pose.p, (size_t)cap * 2 * sizeof(a3_pose), cudaMemcpyDeviceToHost, d->s_pixel));
             }
+            // everything the host needs in one copy: route info, K3's counters, the quads, K2's records, K4's poses
+            A3_CUDA(cudaMemcpyAsync(d->h_shot.p, d->d_shot.p, shot_bytes, cudaMemcpyDeviceToHost, d->s_pixel));
             one_shot_enqueued = true; one_shot_cap = cap;
             return A3_OK;
         };
@@ -735,16 +766,19 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         auto settle_one_shot = [&]() -> a3_status {
             const bool held = k3_speculation_held(d->k3, k3_last);
             k3_spec_inflight = false;
-            if (held && one_shot_enqueued && d->h_packinfo.p[1] == 0 && d->h_packinfo.p[0] <= one_shot_cap) {
+            if (held && one_shot_enqueued && h_info[1] == 0 && h_info[0] <= one_shot_cap) {
                 DecodeBlock &b = *d->blocks[0];
-                b.n_quads = d->h_packinfo.p[0];
+                b.n_quads = h_info[0];
+                b.dec_view = reinterpret_cast<const a3_decode *>(d->h_shot.p + off_dec);
+                b.pose_view = reinterpret_cast<const a3_pose *>(d->h_shot.p + off_pose);
+                const uint32_t *h_quads = reinterpret_cast<const uint32_t *>(d->h_shot.p + off_quads);
                 uint32_t k = 0;
                 for (uint32_t i = 0; i < sn; i++) {
-                    const uint32_t m = d->h_k3counts.p[i] < quad_cap ? d->h_k3counts.p[i] : quad_cap;
-                    frame_quads[i].assign(b.h_quads.p + (size_t)k * 8, b.h_quads.p + (size_t)(k + m) * 8);
-                    frame_stats[i].n_contours = d->h_k3contours.p[i];
-                    frame_stats[i].n_contour_points = d->h_k3points.p[i];
-                    frame_stats[i].n_before_discard = d->h_k3before.p[i];
+                    const uint32_t m = hs_counts[i] < quad_cap ? hs_counts[i] : quad_cap;
+                    frame_quads[i].assign(h_quads + (size_t)k * 8, h_quads + (size_t)(k + m) * 8);
+                    frame_stats[i].n_contours = hs_contours[i];
+                    frame_stats[i].n_contour_points = hs_points[i];
+                    frame_stats[i].n_before_discard = hs_before[i];
                     k += m;
                 }
                 group_done[0].store(sn);
@@ -774,22 +808,22 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                     kp.eps_factor = d->cfg.contour_simplification_epsilon; kp.min_edge_length = min_edge_length;
                     kp.min_corner_separation = min_corner_separation;
                     kp.min_points = (uint32_t)floor(sqrt(2.0 * (double)min_edge_length));
-                    kp.quad_cap = quad_cap; kp.quads = d->d_k3quads.p + (size_t)f0 * quad_cap * 8; kp.quad_counts = d->d_k3counts.p + f0;
-                    kp.before_discard = d->d_k3before.p + f0; kp.frame_flags = d->d_k3flags.p + f0;
-                    kp.frame_contours = d->d_k3contours.p + f0; kp.frame_points = d->d_k3points.p + f0;
+                    kp.quad_cap = quad_cap; kp.quads = d->d_k3quads.p + (size_t)f0 * quad_cap * 8; kp.quad_counts = ds_counts + f0;
+                    kp.before_discard = ds_before + f0; kp.frame_flags = ds_flags + f0;
+                    kp.frame_contours = ds_contours + f0; kp.frame_points = ds_points + f0;
                     A3_CUDA(k3_begin(d->k3, kp, d->s_pixel));
                     bool spec = false;
-                    if (one_shot && s0 == 0 && sn == n) A3_CUDA(k3_finish_speculative(d->k3, kp, d->s_pixel, &spec));
+                    if (shot) A3_CUDA(k3_finish_speculative(d->k3, kp, d->s_pixel, &spec));
                     if (!spec) A3_CUDA(k3_finish(d->k3, kp, d->s_pixel));
                     A3_CUDA(cudaEventRecord(ev_k3[j], d->s_pixel));
                     st.contour_kernel_launches++;
                     k3_last = kp; k3_spec_inflight = spec;
-                    if (a3_status s = k3_stats_d2h(f0, kn)) return s;
-                    const bool geometry = d->hist_nq_n == n && d->hist_nq_w == w && d->hist_nq_h == h;
-                    if (spec && d->hist_nq && geometry) {
-                        if (a3_status s = enqueue_one_shot()) return s;
-                    } else if (!spec) {
-                        if (a3_status s = k3_head_d2h(f0, kn)) return s;
+                    if (spec && shot_cap) {
+                        if (a3_status s = enqueue_one_shot()) return s;  // its single copy carries the counters too
+                    } else {
+                        if (a3_status s = k3_stats_d2h(f0, kn)) return s;
+                        if (!spec)
+                            if (a3_status s = k3_head_d2h(f0, kn)) return s;
                     }
                 }
             } else {
@@ -850,17 +884,17 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         }
         // device-contour mode: take frame i's quads from K3's output, or redo the frame on the host when K3 flagged it
         auto take_k3_frame = [&](uint32_t i) -> a3_status {
-            if (d->h_k3flags.p[i] == 0) {
-                const uint32_t m = d->h_k3counts.p[i];
+            if (hs_flags[i] == 0) {
+                const uint32_t m = hs_counts[i];
                 if (m > quad_head) {  // rare (decode-stress scenes): the tail of this frame's quads
                     A3_CUDA(cudaMemcpyAsync(d->h_k3quads.p + ((size_t)i * quad_cap + quad_head) * 8, d->d_k3quads.p + ((size_t)i * quad_cap + quad_head) * 8,
                                             (size_t)(m - quad_head) * 32, cudaMemcpyDeviceToHost, d->s_decode));
                     A3_CUDA(cudaStreamSynchronize(d->s_decode));
                 }
                 frame_quads[i].assign(d->h_k3quads.p + (size_t)i * quad_cap * 8, d->h_k3quads.p + (size_t)i * quad_cap * 8 + (size_t)m * 8);
-                frame_stats[i].n_contours = d->h_k3contours.p[i];
-                frame_stats[i].n_contour_points = d->h_k3points.p[i];
-                frame_stats[i].n_before_discard = d->h_k3before.p[i];
+                frame_stats[i].n_contours = hs_contours[i];
+                frame_stats[i].n_contour_points = hs_points[i];
+                frame_stats[i].n_before_discard = hs_before[i];
             } else {
                 const double t0 = now_ms();
                 A3_CUDA(cudaMemcpyAsync(d->h_plane.p, d->d_planes.p + (size_t)i * plane_words, plane_words * 4, cudaMemcpyDeviceToHost, d->s_decode));
@@ -907,6 +941,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             A3_CUDA(cudaEventRecord(b.ev_b, d->s_decode));
             st.decode_kernel_launches++;
             A3_CUDA(cudaMemcpyAsync(b.h_dec.p, b.d_dec.p, (size_t)nq * sizeof(a3_decode), cudaMemcpyDeviceToHost, d->s_decode));
+            b.dec_view = b.h_dec.p; b.pose_view = nullptr;
             if (want_poses) {  // K4 right behind K2, on K2's records and the quads where they lie
                 A3_CUDA(b.d_pose.reserve((size_t)nq * 2)); A3_CUDA(b.h_pose.reserve((size_t)nq * 2));
                 K4Params kp{};
@@ -915,6 +950,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                 A3_CUDA(k4_pose(kp, d->s_decode));
                 st.pose_kernel_launches++;
                 A3_CUDA(cudaMemcpyAsync(b.h_pose.p, b.d_pose.p, (size_t)nq * 2 * sizeof(a3_pose), cudaMemcpyDeviceToHost, d->s_decode));
+                b.pose_view = b.h_pose.p;
             }
             return A3_OK;
         };
@@ -994,7 +1030,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                 if (outs && outs->frame_marker_offsets) outs->frame_marker_offsets[s0 + i] = total_markers;
                 const uint32_t m = (uint32_t)(frame_quads[i].size() / 8);
                 for (uint32_t j = 0; j < m; j++, k++) {
-                    const a3_decode &dc = b.h_dec.p[k];
+                    const a3_decode &dc = b.dec_view[k];
                     const uint32_t *q = &frame_quads[i][(size_t)j * 8];
                     if (outs && total_cands < outs->cand_capacity) {
                         if (outs->candidates) memcpy(outs->candidates + (size_t)total_cands * 8, q, 32);
@@ -1019,7 +1055,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                             mk.corners[2 * cidx] = q[2 * sidx];
                             mk.corners[2 * cidx + 1] = q[2 * sidx + 1];
                         }
-                        if (want_poses) memcpy(outs->marker_poses + (size_t)total_markers * 2, b.h_pose.p + (size_t)k * 2, 2 * sizeof(a3_pose));
+                        if (want_poses) memcpy(outs->marker_poses + (size_t)total_markers * 2, b.pose_view + (size_t)k * 2, 2 * sizeof(a3_pose));
                     } else {
                         overflow = true;
                     }
