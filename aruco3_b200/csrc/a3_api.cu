@@ -204,6 +204,7 @@ struct a3_detector {
     std::vector<std::vector<uint32_t>> frame_quads;  // per-frame quads of the batch in flight (capacity reused across calls)
     // one-shot route (pack_quads): K3's quads go to K2 on the device; launch and copy sizes come from the previous call
     a3::DevBuf<uint32_t> d_qoff;
+    a3::DevBuf<uint32_t> d_k2queue;  // K2's work counter where the one-shot arena does not provide it
     // arena of the one-shot route, one device-to-host copy per call: [0] quads in total, [1] route unusable; K3's per-frame
     // counters; the gathered quads; K2's records; K4's poses
     a3::DevBuf<uint8_t> d_shot;
@@ -240,7 +241,7 @@ double now_ms() {
 // ---- K3 -> K2 on the device -----------------------------------------------------------------------------------------
 // K3 leaves each frame's quads in its own block of quad_cap slots.  These two kernels gather them into the dense list in
 // frame / candidate order that K2, K4 and the marker assembly use, so the quads need not visit the host between the
-// contour stage and the decode.  info[0] = quads in total, info[1] = 1 when that route cannot be used for this call (the
+// contour stage and the decode.  info[0] = quads in total, info[2] = 0 (K2's work counter), info[1] = 1 when that route cannot be used for this call (the
 // speculative K3 finish gave up, a frame is flagged for the host stage, or the list does not fit `cap`): the host then takes
 // the ordinary route.
 __global__ void __launch_bounds__(1024) pack_offsets_kernel(const uint32_t *counts, const uint32_t *flags, uint32_t n_frames, uint32_t quad_cap,
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(1024) pack_offsets_kernel(const uint32_t *coun
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t base_s, bad_s;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) info[2] = 0;  // K2's work counter
     if (k3_failed && *k3_failed) {
         if (threadIdx.x == 0) { info[0] = 0; info[1] = 1; }
         return;
@@ -395,7 +397,7 @@ void a3_detector_destroy(a3_detector *d) {
     d->d_planes.release(); d->d_k3quads.release(); d->d_k3counts.release(); d->d_k3before.release(); d->d_k3flags.release();
     d->d_k3contours.release(); d->d_k3points.release(); d->h_k3quads.release(); d->h_k3counts.release(); d->h_k3before.release();
     d->h_k3flags.release(); d->h_k3contours.release(); d->h_k3points.release(); d->h_plane.release();
-    d->d_qoff.release(); d->d_shot.release(); d->h_shot.release();
+    d->d_qoff.release(); d->d_k2queue.release(); d->d_shot.release(); d->h_shot.release();
     d->d_pose_in.release(); d->d_pose_out.release(); d->h_pose_out.release();
     d->events.release();
     for (auto &b : d->blocks) b->release();
@@ -551,6 +553,11 @@ a3_status a3_decode_candidates(a3_detector *d, const uint8_t *grey, uint32_t n_f
     K2Params p = k2_params(d, d->d_grey.p, w, h);
     p.quads = d->d_quads.p; p.quad_frame = quad_frame ? d->d_qframe.p : nullptr; p.n_quads = n_quads;
     p.decodes = d->d_dec.p; p.patches = patches ? d->d_patches.p : nullptr;
+    if (n_quads > 2048) {  // more quads than one wave of warps: let the warps share them out
+        A3_CUDA(d->d_k2queue.reserve(1));
+        A3_CUDA(cudaMemsetAsync(d->d_k2queue.p, 0, 4, s));
+        p.queue = d->d_k2queue.p;
+    }
     A3_CUDA(k2_decode(p, s));
     A3_CUDA(cudaMemcpyAsync(decodes, d->d_dec.p, (size_t)n_quads * sizeof(a3_decode), cudaMemcpyDeviceToHost, s));
     if (patches) A3_CUDA(cudaMemcpyAsync(patches, d->d_patches.p, n_quads * np, cudaMemcpyDeviceToHost, s));
@@ -745,7 +752,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             pack_quads_kernel<<<sn, 128, 0, d->s_pixel>>>(d->d_k3quads.p, d->d_qoff.p, quad_cap, cap, d_info, d_quads, b.d_qframe.p);
             A3_CUDA(cudaGetLastError());
             K2Params p = k2_params(d, d->d_grey.p, w, h);
-            p.quads = d_quads; p.quad_frame = b.d_qframe.p; p.n_quads = cap; p.n_quads_dev = d_info; p.decodes = d_dec;
+            p.quads = d_quads; p.quad_frame = b.d_qframe.p; p.n_quads = cap; p.n_quads_dev = d_info; p.queue = d_info + 2; p.decodes = d_dec;
             p.patches = want_patches ? b.d_patches.p : nullptr;
             A3_CUDA(cudaEventRecord(b.ev_a, d->s_pixel));
             A3_CUDA(k2_decode(p, d->s_pixel));
@@ -936,6 +943,11 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             K2Params p = k2_params(d, d->d_grey.p, w, h);
             p.quads = b.d_quads.p; p.quad_frame = b.d_qframe.p; p.n_quads = nq; p.decodes = b.d_dec.p;
             p.patches = want_patches ? b.d_patches.p : nullptr;
+            if (nq > 2048) {  // more quads than one wave of warps: let the warps share them out
+                A3_CUDA(d->d_k2queue.reserve(1));
+                A3_CUDA(cudaMemsetAsync(d->d_k2queue.p, 0, 4, d->s_decode));
+                p.queue = d->d_k2queue.p;
+            }
             A3_CUDA(cudaEventRecord(b.ev_a, d->s_decode));
             A3_CUDA(k2_decode(p, d->s_decode));
             A3_CUDA(cudaEventRecord(b.ev_b, d->s_decode));

@@ -204,7 +204,14 @@ __global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const
 
     // one warp per candidate; warps never wait for each other
     const uint32_t n_quads = p.n_quads_dev ? min(*p.n_quads_dev, p.n_quads) : p.n_quads;
-    for (uint32_t q = blockIdx.x * kWarps + warp; q < n_quads; q += gridDim.x * kWarps) {
+    const uint32_t first_q = blockIdx.x * kWarps + warp, stride_q = gridDim.x * kWarps;
+    auto next_quad = [&](uint32_t q) -> uint32_t {  // the warp's next quad: fixed stride, or the shared counter behind the first round
+        if (!p.queue) return q + stride_q;
+        uint32_t t = 0;
+        if (lane == 0) t = stride_q + atomicAdd(p.queue, 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    for (uint32_t q = first_q; q < n_quads; q = next_quad(q)) {
         const uint32_t frame = p.quad_frame ? p.quad_frame[q] : 0;
         const uint8_t *grey = p.grey + (size_t)frame * p.w * p.h;
         make_projection(p.quads + (size_t)q * 8, (float)ps, ws->a, &ws->proj, lane);
@@ -402,7 +409,9 @@ cudaError_t k2_decode(const K2Params &p, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t want = (p.n_quads + kWarps - 1) / kWarps;
-    const uint32_t resident = (uint32_t)sms * (uint32_t)((227 * 1024) / (smem + 1024) ? (227 * 1024) / (smem + 1024) : 1);
+    int per_sm = 0;  // CTAs that are resident together (registers allow 3, shared memory depends on the dictionary)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_kernel, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const uint32_t resident = (uint32_t)sms * (uint32_t)per_sm;
     k2_kernel<<<want < resident ? want : resident, kThreads, smem, stream>>>(p, tp.max_taps);
     return cudaGetLastError();
 }

@@ -749,7 +749,8 @@ constexpr int kRdpStack = 64;
 // One warp per contour: approximate_polygon_dp(points, n * eps, closed) -> exactly 4 vertices? -> hull -> edge test
 // (src/aruco.rs:133-159).  Same span order and the same "first strict maximum" rule as host_quads.cpp:simplify_closed.
 __global__ void __launch_bounds__(128) k3_rdp(const Contour *contours, const uint32_t *points, uint32_t n_contours, double eps_factor,
-                                              uint32_t min_edge_length, uint32_t *quads, uint32_t *frame_flags, const uint32_t *dyn) {
+                                              uint32_t min_edge_length, uint32_t *quads, uint32_t *frame_flags, const uint32_t *dyn,
+                                              const bool small_coords) {
     __shared__ uint2 stacks[4][kRdpStack];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t ci = blockIdx.x * 4 + wid;
@@ -774,24 +775,50 @@ __global__ void __launch_bounds__(128) k3_rdp(const Contour *contours, const uin
         sp--;
         const Pt ps = unpack(pts[s.x]), pe = unpack(pts[s.y]);
         const long long a = (long long)ps.y - pe.y, b = (long long)pe.x - ps.x, cc = (long long)ps.x * pe.y - (long long)pe.x * ps.y;
-        const double den = sqrt((double)a * (double)a + (double)b * (double)b);
         // pass 1: largest numerator and the first index that reaches it (per lane in index order, then across lanes)
         long long best = 0;
         uint32_t best_i = 0xffffffffu;
-        for (uint32_t i = s.x + 1 + lane; i <= s.y; i += 32) {
-            const Pt p = unpack(pts[i]);
-            long long v = a * p.x + b * p.y + cc;
-            v = v < 0 ? -v : v;
-            if (v > best) { best = v; best_i = i; }
+        // a x + b y + cc == a (x - xs) + b (y - ys): with coordinates below 2^14 both products and their sum fit 32 bits
+        const int a32 = (int)a, b32 = (int)b, k32 = small_coords ? -(a32 * ps.x + b32 * ps.y) : 0;
+        if (small_coords) {
+            int best32 = 0;
+            for (uint32_t i = s.x + 1 + lane; i <= s.y; i += 32) {
+                const uint32_t pv = pts[i];
+                const int v = abs(b32 * (int)(pv >> 16) + (a32 * (int)(pv & 0xffffu) + k32));
+                if (v > best32) { best32 = v; best_i = i; }
+            }
+            const int wmax = __reduce_max_sync(0xffffffffu, best32);
+            best_i = __reduce_min_sync(0xffffffffu, best32 == wmax ? best_i : 0xffffffffu);
+            best = wmax;
+        } else {
+            for (uint32_t i = s.x + 1 + lane; i <= s.y; i += 32) {
+                const Pt p = unpack(pts[i]);
+                long long v = a * p.x + b * p.y + cc;
+                v = v < 0 ? -v : v;
+                if (v > best) { best = v; best_i = i; }
+            }
+            for (int off = 16; off; off >>= 1) {
+                const long long other = __shfl_xor_sync(0xffffffffu, best, off);
+                const uint32_t other_i = __shfl_xor_sync(0xffffffffu, best_i, off);
+                if (other > best || (other == best && other_i < best_i)) { best = other; best_i = other_i; }
+            }
         }
-        for (int off = 16; off; off >>= 1) {
-            const long long other = __shfl_xor_sync(0xffffffffu, best, off);
-            const uint32_t other_i = __shfl_xor_sync(0xffffffffu, best_i, off);
-            if (other > best || (other == best && other_i < best_i)) { best = other; best_i = other_i; }
-        }
-        double dmax = 0.0;
+        // dmax > eps, where dmax = best / den in f64 as the reference computes it.  With small numerators the comparison of
+        // the squares decides it without the square root and the division unless the two sides agree to 2^-40 (the f64
+        // results carry relative errors below 2^-50, so outside that band the rounded quotient lies on the same side of
+        // eps); and numerators below 2^40 are too far apart, relatively, for two of them to round to the same quotient, so
+        // the first index of the largest numerator is the reference's index.
+        bool split = false, decided = false;
         uint32_t index = 0;
-        if (best > 0) {
+        if (small_coords && best > 0) {
+            const double d2 = (double)(a32 * a32 + b32 * b32);
+            const double lhs = (double)best * (double)best, rhs = (eps * eps) * d2;
+            if (lhs > rhs * 1.0000000000009095) { split = true; index = best_i; decided = true; }        // 1 + 2^-40
+            else if (lhs < rhs * 0.9999999999990905) { decided = true; }                                // 1 - 2^-40
+        }
+        if (!decided && best > 0) {
+            const double den = sqrt((double)a * (double)a + (double)b * (double)b);
+            double dmax = 0.0;
             const double q = (double)best / den;
             if (q > 0.0) {
                 long long t = best;  // smallest numerator whose quotient equals the maximum's
@@ -810,8 +837,9 @@ __global__ void __launch_bounds__(128) k3_rdp(const Contour *contours, const uin
                 }
                 index = first;
             }
+            split = dmax > eps;
         }
-        if (dmax > eps) {
+        if (split) {
             // every split adds one vertex to the final polygon (vertices = splits + 1): the fourth split settles "not a quad"
             if (++nsplit >= 4) { nout = 5; break; }
             if (sp + 2 > kRdpStack) { overflow = true; break; }
@@ -1241,7 +1269,7 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
                                                                    w.walker_slot, w.ckpts, n_ckpts, w.contours, w.points, nullptr);
         K3_CUDA(cudaGetLastError());
         timer.mark("emit");
-        k3_rdp<<<(n_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, n_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags, nullptr);
+        k3_rdp<<<(n_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, n_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags, nullptr, p.w <= 16384 && p.h <= 16384);
         K3_CUDA(cudaGetLastError());
     }
     timer.mark("rdp");
@@ -1307,7 +1335,7 @@ cudaError_t k3_finish_speculative(K3Workspace &ws, const K3Params &p, cudaStream
                                                                    w.walker_slot, w.ckpts, cap_ckpts, w.contours, w.points, w.counters);
     K3_CUDA(cudaGetLastError());
     timer.mark("emit");
-    k3_rdp<<<(cap_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, cap_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags, w.counters);
+    k3_rdp<<<(cap_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, cap_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags, w.counters, p.w <= 16384 && p.h <= 16384);
     K3_CUDA(cudaGetLastError());
     timer.mark("rdp");
     K3_CUDA(cudaFuncSetAttribute(k3_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));

@@ -139,3 +139,30 @@ def test_many_small_masks_in_one_batch(a3, oracle):
             continue
         want, nc, npnt = _oracle_frame(oracle, masks[f], ocfg)
         assert quads[f].tolist() == want.tolist() and (int(contours[f]), int(points[f])) == (nc, npnt), f"frame {f}"
+
+
+def test_wide_frames_take_the_64_bit_distance_path(a3, oracle):
+    """Coordinates of 2^14 and more: k3_rdp's point-to-chord numerators no longer fit 32 bits (the fast loop is only taken
+    below that), and long thin quads make the products large."""
+    rng = np.random.default_rng(77)
+    h, w = 40, 40000
+    cfg = a3.DetectorConfig(min_side_length_factor=0.1, min_corner_separation_factor=0.05)
+    ocfg = oracle.default_config(min_side_length_factor=0.1, min_corner_separation_factor=0.05)
+    masks = []
+    for k in range(4):
+        m = np.zeros((h, w), np.uint8)
+        for _ in range(12):  # long thin rectangles and slanted bars far from the origin
+            x0, y0 = int(rng.integers(1, w - 9000)), int(rng.integers(1, h - 12))
+            ln, th = int(rng.integers(50, 8000)), int(rng.integers(2, 10))
+            m[y0:y0 + th, x0:x0 + ln] = 255
+            if k % 2:
+                for r in range(th):  # shear: one pixel per row
+                    m[y0 + r, x0:x0 + r] = 0
+        m[:, 0] = m[:, -1] = 0
+        m[0] = m[-1] = 0
+        noise = (rng.random((h, 2000)) < 0.5) * 255
+        m[:, 30000:32000] = noise.astype(np.uint8)
+        m[0, 30000:32000] = m[-1, 30000:32000] = 0
+        masks.append(m)
+    nflag = _check(a3, oracle, np.stack(masks), cfg, ocfg)
+    assert nflag == 0

@@ -118,3 +118,34 @@ def test_batches_of_changing_size(a3):
             assert _summary(d.detect_batch(frames[:n], full=True)) == want[:n]
             routes.append(d.last_stats["one_shot"])
     assert routes == [0, 1, 0, 1, 0, 1]
+
+
+def _markers_only(dets):
+    return [[(m.candidate, m.id, m.rotation, m.hamming_distance, m.code, m.corners) for m in x.markers] for x in dets]
+
+
+def test_markers_only_calls_assemble_on_the_device(a3):
+    """Without per-candidate outputs the one-shot route also builds the a3_marker records (and their poses) on the device;
+    they must equal the host-assembled ones of a call that asks for everything, in order, frame offsets included."""
+    from aruco3_b200 import synth
+    frames, _ = synth.render_batch("C1", 7)
+    frames[3] = 200  # a frame without markers in the middle: its offset range is empty
+    with a3.Detector() as d:
+        d.set_pose(40.0)
+        full = d.detect_batch(frames, full=True)
+    want = _markers_only(full)
+    want_poses = [[(p.error, p.rotation.tobytes(), p.translation.tobytes()) for m in x.markers for p in m.poses] for x in full]
+    assert want[3] == [] and sum(len(x) for x in want) > 20
+    with a3.Detector() as d:
+        d.set_pose(40.0)
+        for call in range(3):
+            got = d.detect_batch(frames)
+            assert d.last_stats["one_shot"] == (1 if call else 0)
+            assert _markers_only(got) == want
+            assert [[(p.error, p.rotation.tobytes(), p.translation.tobytes()) for m in x.markers for p in m.poses] for x in got] == want_poses
+        # a marker buffer that is too small: the count comes back, the second attempt of the wrapper succeeds
+        got = d.detect_batch(frames, marker_capacity=5)
+        assert _markers_only(got) == want
+    with a3.Detector() as d:  # and without the pose step
+        for call in range(2):
+            assert _markers_only(d.detect_batch(frames)) == want
