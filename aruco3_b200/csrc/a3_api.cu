@@ -245,7 +245,9 @@ double now_ms() {
 // speculative K3 finish gave up, a frame is flagged for the host stage, or the list does not fit `cap`): the host then takes
 // the ordinary route.
 __global__ void __launch_bounds__(1024) pack_offsets_kernel(const uint32_t *counts, const uint32_t *flags, uint32_t n_frames, uint32_t quad_cap,
-                                                            uint32_t cap, const uint32_t *k3_failed, uint32_t *offsets, uint32_t *info) {
+                                                            uint32_t cap, const uint32_t *k3_failed, uint32_t *offsets, uint32_t *info,
+                                                            uint32_t *chunk_end, uint32_t n_chunks) {
+    for (uint32_t i = threadIdx.x; i < n_chunks; i += blockDim.x) chunk_end[i] = 0xffffffffu;  // assemble_markers_kernel's chain
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t base_s, bad_s;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -302,6 +304,62 @@ __global__ void __launch_bounds__(128) pack_quads_kernel(const uint32_t *quads, 
         if (o0 + (i >> 3) < cap) out_quads[(size_t)o0 * 8 + i] = src[i];
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
         if (o0 + i < cap) out_frame[o0 + i] = f;
+}
+
+// Marker assembly on the device (src/aruco.rs:96-111) for callers that want markers only: the accepted candidates, in
+// frame / candidate order, as finished a3_marker records (corners.rotate_left(rotation), the observed code of the winning
+// rotation) with their poses beside them, so the host copies one block instead of walking every candidate.
+// info[3] = number of markers.
+__global__ void __launch_bounds__(1024) assemble_markers_kernel(const a3_decode *dec, const uint32_t *quads, const uint32_t *qframe,
+                                                                const uint32_t *qoff, const a3_pose *poses, uint32_t cap, uint32_t *info,
+                                                                volatile uint32_t *chunk_end, a3_marker *markers, a3_pose *mposes) {
+    // One CTA per 1024 quads; the number of markers before a chunk comes down a chain: chunk c waits for chunk_end[c - 1]
+    // (0xffffffff until written; pack_offsets_kernel resets the chain) and publishes its own.  All chunks are resident at
+    // once (a few dozen CTAs at most), so the chain cannot stall on an unscheduled block.
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t base_s;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x;
+    const bool bad = info[1] != 0;
+    const uint32_t nq = bad ? 0u : (info[0] < cap ? info[0] : cap);
+    const uint32_t k = c * 1024 + threadIdx.x;
+    const uint32_t acc = (k < nq && dec[k].accepted) ? 1u : 0u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, acc);
+    if (lane == 0) warp_sums[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (uint32_t i = 0; i < 32; i++) total += warp_sums[i];
+        uint32_t before = 0;
+        if (c > 0) {
+            while ((before = chunk_end[c - 1]) == 0xffffffffu) { }
+        }
+        base_s = before;
+        __threadfence();
+        chunk_end[c] = before + total;
+        if (c == gridDim.x - 1) info[3] = before + total;
+    }
+    __syncthreads();
+    if (!acc) return;
+    uint32_t idx = base_s + __popc(bal & ((1u << lane) - 1u));
+    for (uint32_t i = 0; i < warp; i++) idx += warp_sums[i];
+    const a3_decode dc = dec[k];
+    const uint32_t frame = qframe[k], rot = dc.rotation & 3u;
+    const uint32_t *q = quads + (size_t)k * 8;
+    a3_marker m;
+    m.id = dc.id;
+    m.code = dc.codes[rot];
+    for (uint32_t cc = 0; cc < 4; cc++) {  // corners.rotate_left(min_rotation)
+        const uint32_t sidx = (cc + rot) & 3u;
+        m.corners[2 * cc] = q[2 * sidx];
+        m.corners[2 * cc + 1] = q[2 * sidx + 1];
+    }
+    m.frame = frame;
+    m.candidate = k - qoff[frame];
+    m.hamming_distance = dc.hamming_distance;
+    m.rotation = dc.rotation;
+    for (int i = 0; i < 6; i++) m.reserved[i] = 0;
+    markers[idx] = m;
+    if (poses) { mposes[2 * (size_t)idx] = poses[2 * (size_t)k]; mposes[2 * (size_t)idx + 1] = poses[2 * (size_t)k + 1]; }
 }
 
 K2Params k2_params(const a3_detector *d, const uint8_t *grey, uint32_t w, uint32_t h) {
@@ -667,9 +725,15 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         const bool shot_hist = shot && d->hist_nq && d->hist_nq_n == n && d->hist_nq_w == w && d->hist_nq_h == h;
         const uint32_t shot_cap = shot_hist ? d->hist_nq + d->hist_nq / 8 + 256 : 0;  // quads the arena holds
         const size_t shot_c = ((size_t)sn + 1) & ~(size_t)1;
-        const size_t off_stats = 16, off_quads = (off_stats + 24 * shot_c + 15) & ~(size_t)15, off_dec = off_quads + (size_t)shot_cap * 32;
+        // markers only (no per-candidate outputs requested): the device also assembles the markers, and the copy stops after them
+        const bool lean = shot && markers && !(outs && (outs->candidates || outs->candidate_frame || outs->decodes || outs->homographies));
+        const size_t off_stats = 16, off_markers = (off_stats + 24 * shot_c + 15) & ~(size_t)15;
+        const size_t off_mposes = off_markers + (lean ? (size_t)shot_cap * sizeof(a3_marker) : 0);
+        const size_t off_quads = (off_mposes + ((lean && want_poses) ? (size_t)shot_cap * 2 * sizeof(a3_pose) : 0) + 15) & ~(size_t)15;
+        const size_t off_dec = off_quads + (size_t)shot_cap * 32;
         const size_t off_pose = off_dec + (size_t)shot_cap * sizeof(a3_decode);
         const size_t shot_bytes = off_pose + (want_poses ? (size_t)shot_cap * 2 * sizeof(a3_pose) : 0);
+        const size_t shot_copy_bytes = lean ? off_quads : shot_bytes;  // what goes back to the host
         if (shot) {
             A3_CUDA(d->d_shot.reserve(shot_bytes)); A3_CUDA(d->h_shot.reserve(shot_bytes));
             auto carve = [&](uint8_t *base, uint32_t *&c, uint32_t *&b, uint32_t *&f, uint32_t *&k, unsigned long long *&pt) {
@@ -715,7 +779,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         };
         // ---- device contour stage: copies of K3's results, and the one-shot route behind a speculative K3 finish ----
         K3Params k3_last{};
-        bool k3_spec_inflight = false, one_shot_enqueued = false, one_shot_done = false;
+        bool k3_spec_inflight = false, one_shot_enqueued = false, one_shot_done = false, lean_done = false;
         uint32_t one_shot_cap = 0;
         auto k3_stats_d2h = [&](uint32_t f0, uint32_t kn) -> a3_status {
             if (shot) {  // the counters are one block of the arena
@@ -743,11 +807,14 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             uint32_t *d_quads = reinterpret_cast<uint32_t *>(d->d_shot.p + off_quads);
             a3_decode *d_dec = reinterpret_cast<a3_decode *>(d->d_shot.p + off_dec);
             a3_pose *d_pose = reinterpret_cast<a3_pose *>(d->d_shot.p + off_pose);
-            A3_CUDA(d->d_qoff.reserve((size_t)sn + 1));
+            const uint32_t n_chunks = (cap + 1023) / 1024;
+            A3_CUDA(d->d_qoff.reserve((size_t)sn + 1 + n_chunks));  // frame offsets of the quads, then the marker-count chain
+            uint32_t *d_chain = d->d_qoff.p + sn + 1;
             A3_CUDA(b.d_qframe.reserve(cap));
             if (want_patches) A3_CUDA(b.d_patches.reserve(cap * np));
             if (!b.ev_a) { A3_CUDA(cudaEventCreate(&b.ev_a)); A3_CUDA(cudaEventCreate(&b.ev_b)); }
-            pack_offsets_kernel<<<1, 1024, 0, d->s_pixel>>>(ds_counts, ds_flags, sn, quad_cap, cap, k3_speculation_failed_flag(d->k3), d->d_qoff.p, d_info);
+            pack_offsets_kernel<<<1, 1024, 0, d->s_pixel>>>(ds_counts, ds_flags, sn, quad_cap, cap, k3_speculation_failed_flag(d->k3), d->d_qoff.p, d_info,
+                                                            d_chain, n_chunks);
             A3_CUDA(cudaGetLastError());
             pack_quads_kernel<<<sn, 128, 0, d->s_pixel>>>(d->d_k3quads.p, d->d_qoff.p, quad_cap, cap, d_info, d_quads, b.d_qframe.p);
             A3_CUDA(cudaGetLastError());
@@ -763,8 +830,15 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                 kp.marker_size = d->pose_marker_size; kp.image_w = w; kp.image_h = h; kp.k = d->pose_k; kp.poses = d_pose;
                 A3_CUDA(k4_pose(kp, d->s_pixel));
             }
-            // everything the host needs in one copy: route info, K3's counters, the quads, K2's records, K4's poses
-            A3_CUDA(cudaMemcpyAsync(d->h_shot.p, d->d_shot.p, shot_bytes, cudaMemcpyDeviceToHost, d->s_pixel));
+            if (lean) {
+                assemble_markers_kernel<<<n_chunks, 1024, 0, d->s_pixel>>>(d_dec, d_quads, b.d_qframe.p, d->d_qoff.p, want_poses ? d_pose : nullptr, cap, d_info,
+                                                                    d_chain, reinterpret_cast<a3_marker *>(d->d_shot.p + off_markers),
+                                                                    reinterpret_cast<a3_pose *>(d->d_shot.p + off_mposes));
+                A3_CUDA(cudaGetLastError());
+            }
+            // everything the host needs in one copy: route info, K3's counters, then either the finished markers (+ poses) or the
+            // quads, K2's records and K4's poses
+            A3_CUDA(cudaMemcpyAsync(d->h_shot.p, d->d_shot.p, shot_copy_bytes, cudaMemcpyDeviceToHost, d->s_pixel));
             one_shot_enqueued = true; one_shot_cap = cap;
             return A3_OK;
         };
@@ -782,7 +856,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                 uint32_t k = 0;
                 for (uint32_t i = 0; i < sn; i++) {
                     const uint32_t m = hs_counts[i] < quad_cap ? hs_counts[i] : quad_cap;
-                    frame_quads[i].assign(h_quads + (size_t)k * 8, h_quads + (size_t)(k + m) * 8);
+                    if (!lean) frame_quads[i].assign(h_quads + (size_t)k * 8, h_quads + (size_t)(k + m) * 8);
                     frame_stats[i].n_contours = hs_contours[i];
                     frame_stats[i].n_contour_points = hs_points[i];
                     frame_stats[i].n_before_discard = hs_before[i];
@@ -794,6 +868,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                 if (want_poses) st.pose_kernel_launches++;
                 st.one_shot = 1;
                 one_shot_done = true;
+                lean_done = lean;
                 return A3_OK;
             }
             if (!held || one_shot_enqueued) st.one_shot_retry = 1;
@@ -1028,6 +1103,24 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             st.n_contour_points += frame_stats[i].n_contour_points;
             st.n_candidates_before_discard += frame_stats[i].n_before_discard;
             st.ms_host_cpu += frame_ms[i];
+        }
+        if (lean_done) {  // the markers were assembled on the device: one block copy (lean implies a single super-batch and group)
+            DecodeBlock &b = *d->blocks[0];
+            if (b.n_quads) { cudaEventElapsedTime(&ms, b.ev_a, b.ev_b); st.ms_decode_kernel += ms; }
+            const uint32_t nm = h_info[3], take = nm < marker_capacity ? nm : marker_capacity;
+            memcpy(markers, d->h_shot.p + off_markers, (size_t)take * sizeof(a3_marker));
+            if (want_poses) memcpy(outs->marker_poses, d->h_shot.p + off_mposes, (size_t)take * 2 * sizeof(a3_pose));
+            if (nm > marker_capacity) overflow = true;
+            if (outs && outs->frame_marker_offsets) {
+                uint32_t i = 0;
+                for (uint32_t f = 0; f <= sn; f++) {
+                    while (i < take && markers[i].frame < f) i++;
+                    outs->frame_marker_offsets[f] = f < sn ? i : nm;
+                }
+            }
+            total_markers = nm;
+            total_cands = b.n_quads;
+            continue;
         }
         for (uint32_t g = 0; g < ngroups; g++) {
             DecodeBlock &b = *d->blocks[g];

@@ -322,9 +322,10 @@ def main():
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n * h * w * 3, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         # ours per step: K1, K2, K3's eight kernels (candidates, walk_short, walkers, flag_all, order, emit, rdp, finalize) and, on
-        # the one-shot route, the size check of the speculative K3 finish and the two kernels that gather its quads for K2
+        # the one-shot route, the size check of the speculative K3 finish, the two kernels that gather its quads for K2 and the
+        # marker assembly
         "gpu_launches": int(acc_dev["pixel_kernel_launches"] + acc_dev["decode_kernel_launches"] + acc_dev["pose_kernel_launches"]
-                            + 8 * acc_dev["contour_kernel_launches"] + 3 * acc_dev["one_shot"]),
+                            + 8 * acc_dev["contour_kernel_launches"] + 4 * acc_dev["one_shot"]),
         "one_shot_route_steps": int(acc_dev["one_shot"]),
         "contour_stage": args.contours, "host_fallback_frames_per_step": acc_dev["host_fallback_frames"] / args.steps,
         "roofline": {"bound": "hbm", "kernel": "k1_strips_kernel<RGB8> (fused into_luma8 + adaptive_threshold, TMA tensor tiles)",
