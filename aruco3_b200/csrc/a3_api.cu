@@ -134,7 +134,7 @@ private:
 struct DecodeBlock {
     PinBuf<uint32_t> h_quads, h_qframe;
     PinBuf<a3_decode> h_dec;
-    DevBuf<uint32_t> d_quads, d_qframe;
+    DevBuf<uint32_t> d_quads, d_qframe, d_info, d_qoff;  // d_info / d_qoff: the device-side gather of K3's quads for this group
     DevBuf<a3_decode> d_dec;
     DevBuf<uint8_t> d_patches;
     DevBuf<a3_pose> d_pose;   // K4: two poses per quad (written for accepted candidates only)
@@ -146,6 +146,7 @@ struct DecodeBlock {
     const a3_pose *pose_view = nullptr;
     void release() {
         h_quads.release(); h_qframe.release(); h_dec.release(); d_quads.release(); d_qframe.release(); d_dec.release(); d_patches.release();
+        d_info.release(); d_qoff.release();
         d_pose.release(); h_pose.release();
         for (cudaEvent_t *e : {&ev_a, &ev_b}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
     }
@@ -296,14 +297,14 @@ __global__ void __launch_bounds__(1024) pack_offsets_kernel(const uint32_t *coun
     }
 }
 __global__ void __launch_bounds__(128) pack_quads_kernel(const uint32_t *quads, const uint32_t *offsets, uint32_t quad_cap, uint32_t cap,
-                                                         const uint32_t *info, uint32_t *out_quads, uint32_t *out_frame) {
+                                                         const uint32_t *info, uint32_t *out_quads, uint32_t *out_frame, uint32_t frame_base) {
     if (info[1]) return;
     const uint32_t f = blockIdx.x, o0 = offsets[f], m = offsets[f + 1] - o0;
     const uint32_t *src = quads + (size_t)f * quad_cap * 8;
     for (uint32_t i = threadIdx.x; i < m * 8; i += blockDim.x)
         if (o0 + (i >> 3) < cap) out_quads[(size_t)o0 * 8 + i] = src[i];
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
-        if (o0 + i < cap) out_frame[o0 + i] = f;
+        if (o0 + i < cap) out_frame[o0 + i] = frame_base + f;
 }
 
 // Marker assembly on the device (src/aruco.rs:96-111) for callers that want markers only: the accepted candidates, in
@@ -816,7 +817,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             pack_offsets_kernel<<<1, 1024, 0, d->s_pixel>>>(ds_counts, ds_flags, sn, quad_cap, cap, k3_speculation_failed_flag(d->k3), d->d_qoff.p, d_info,
                                                             d_chain, n_chunks);
             A3_CUDA(cudaGetLastError());
-            pack_quads_kernel<<<sn, 128, 0, d->s_pixel>>>(d->d_k3quads.p, d->d_qoff.p, quad_cap, cap, d_info, d_quads, b.d_qframe.p);
+            pack_quads_kernel<<<sn, 128, 0, d->s_pixel>>>(d->d_k3quads.p, d->d_qoff.p, quad_cap, cap, d_info, d_quads, b.d_qframe.p, 0u);
             A3_CUDA(cudaGetLastError());
             K2Params p = k2_params(d, d->d_grey.p, w, h);
             p.quads = d_quads; p.quad_frame = b.d_qframe.p; p.n_quads = cap; p.n_quads_dev = d_info; p.queue = d_info + 2; p.decodes = d_dec;
@@ -1007,21 +1008,42 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             A3_CUDA(b.d_quads.reserve((size_t)nq * 8)); A3_CUDA(b.d_qframe.reserve(nq)); A3_CUDA(b.d_dec.reserve(nq));
             if (want_patches) A3_CUDA(b.d_patches.reserve(nq * np));
             uint32_t k = 0;
-            for (uint32_t i = f0; i < f1; i++) {
-                const uint32_t m = (uint32_t)(frame_quads[i].size() / 8);
-                if (m) memcpy(b.h_quads.p + (size_t)k * 8, frame_quads[i].data(), (size_t)m * 32);
-                for (uint32_t q = 0; q < m; q++) b.h_qframe.p[k + q] = i;
-                k += m;
-            }
-            A3_CUDA(cudaMemcpyAsync(b.d_quads.p, b.h_quads.p, (size_t)nq * 32, cudaMemcpyHostToDevice, d->s_decode));
-            A3_CUDA(cudaMemcpyAsync(b.d_qframe.p, b.h_qframe.p, (size_t)nq * 4, cudaMemcpyHostToDevice, d->s_decode));
+            // Device contour stage: K3's quads of these frames are still in device memory, so they are gathered there (the same two
+            // kernels as on the one-shot route) — a small host-to-device copy would queue behind the frame chunks in flight on
+            // the copy engine and hold the decode back by whole chunks.  Groups with a frame the host stage redid take the copy.
+            bool on_device = gpu_contours;
+            for (uint32_t i = f0; i < f1 && on_device; i++) on_device = hs_flags[i] == 0 && frame_quads[i].size() / 8 == (hs_counts[i] < quad_cap ? hs_counts[i] : quad_cap);
             K2Params p = k2_params(d, d->d_grey.p, w, h);
+            if (on_device) {
+                const uint32_t gn = f1 - f0, n_chunks = (nq + 1023) / 1024;
+                A3_CUDA(b.d_info.reserve(4)); A3_CUDA(b.d_qoff.reserve((size_t)gn + 1 + n_chunks));
+                pack_offsets_kernel<<<1, 1024, 0, d->s_decode>>>(ds_counts + f0, ds_flags + f0, gn, quad_cap, nq, nullptr, b.d_qoff.p, b.d_info.p,
+                                                                b.d_qoff.p + gn + 1, n_chunks);
+                A3_CUDA(cudaGetLastError());
+                pack_quads_kernel<<<gn, 128, 0, d->s_decode>>>(d->d_k3quads.p + (size_t)f0 * quad_cap * 8, b.d_qoff.p, quad_cap, nq, b.d_info.p,
+                                                              b.d_quads.p, b.d_qframe.p, f0);
+                A3_CUDA(cudaGetLastError());
+                p.n_quads_dev = b.d_info.p;
+            } else {
+                for (uint32_t i = f0; i < f1; i++) {
+                    const uint32_t m = (uint32_t)(frame_quads[i].size() / 8);
+                    if (m) memcpy(b.h_quads.p + (size_t)k * 8, frame_quads[i].data(), (size_t)m * 32);
+                    for (uint32_t q = 0; q < m; q++) b.h_qframe.p[k + q] = i;
+                    k += m;
+                }
+                A3_CUDA(cudaMemcpyAsync(b.d_quads.p, b.h_quads.p, (size_t)nq * 32, cudaMemcpyHostToDevice, d->s_decode));
+                A3_CUDA(cudaMemcpyAsync(b.d_qframe.p, b.h_qframe.p, (size_t)nq * 4, cudaMemcpyHostToDevice, d->s_decode));
+            }
             p.quads = b.d_quads.p; p.quad_frame = b.d_qframe.p; p.n_quads = nq; p.decodes = b.d_dec.p;
             p.patches = want_patches ? b.d_patches.p : nullptr;
             if (nq > 2048) {  // more quads than one wave of warps: let the warps share them out
-                A3_CUDA(d->d_k2queue.reserve(1));
-                A3_CUDA(cudaMemsetAsync(d->d_k2queue.p, 0, 4, d->s_decode));
-                p.queue = d->d_k2queue.p;
+                if (on_device) {
+                    p.queue = b.d_info.p + 2;  // zeroed by pack_offsets_kernel
+                } else {
+                    A3_CUDA(d->d_k2queue.reserve(1));
+                    A3_CUDA(cudaMemsetAsync(d->d_k2queue.p, 0, 4, d->s_decode));
+                    p.queue = d->d_k2queue.p;
+                }
             }
             A3_CUDA(cudaEventRecord(b.ev_a, d->s_decode));
             A3_CUDA(k2_decode(p, d->s_decode));
@@ -1052,6 +1074,8 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
 
         // ---- drive: front end `kStaging` chunks ahead, feed the pool, launch decode groups as they complete ----
         const double t_host0 = now_ms();
+        static const bool trace = getenv("A3_TRACE") != nullptr;  // debug aid: host timestamps of the phases of a call, on stderr
+        double t_first_sync = 0, t_loop_end = 0, t_synced = 0, t_events = 0;
         a3_status err = A3_OK;
         uint32_t next_group = 0;
         for (uint32_t j = 0; j < nfe && !err; j++) {
@@ -1059,6 +1083,8 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             if (err) break;
             const cudaError_t e = cudaEventSynchronize(ev_fe[j]);
             if (e != cudaSuccess) { err = cuda_fail(e, "cudaEventSynchronize(front end)"); break; }
+            if (trace && j == 0) t_first_sync = now_ms();
+            if (trace && j + 1 == nfe) t_loop_end = now_ms();
             const uint32_t upto = (j + 1) * (uint32_t)fe < sn ? (j + 1) * (uint32_t)fe : sn;
             if (gpu_contours) {
                 if (k3_spec_inflight && (err = settle_one_shot())) break;
@@ -1081,8 +1107,9 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         // ---- gather: stage timings, then markers in frame / candidate order (src/aruco.rs:75-113) ----
         A3_CUDA(cudaStreamSynchronize(d->s_decode));
         A3_CUDA(cudaStreamSynchronize(d->s_pixel));
+        if (trace) t_synced = now_ms();
         float ms = 0;
-        for (uint32_t j = 0; j < nfe; j++) {
+        for (uint32_t j = 0; j < nfe && stats; j++) {  // stage times only when the caller asked for statistics (about 2 us per query)
             if (mem == A3_MEM_HOST) { cudaEventElapsedTime(&ms, ev_h2da[j], ev_h2db[j]); st.ms_h2d += ms; }
             if (mem == A3_MEM_HOST || j == 0) { cudaEventElapsedTime(&ms, ev_k1a[j], ev_k1b[j]); st.ms_pixel_kernel += ms; }
             if (gpu_contours) {
@@ -1104,9 +1131,21 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             st.n_candidates_before_discard += frame_stats[i].n_before_discard;
             st.ms_host_cpu += frame_ms[i];
         }
+        if (trace) {
+            t_events = now_ms();
+            float h2d_span = 0, gpu_tail = 0;
+            if (mem == A3_MEM_HOST) {
+                cudaEventElapsedTime(&h2d_span, ev_h2da[0], ev_h2db[nfe - 1]);
+                cudaEventElapsedTime(&gpu_tail, ev_h2db[nfe - 1], ev_fe[nfe - 1]);
+            }
+            fprintf(stderr, "a3 trace: entry->loop %.3f | first front-end sync +%.3f, last +%.3f, loop end +%.3f, streams idle +%.3f, event queries +%.3f ms"
+                            " | H2D first byte -> last byte %.3f, last byte -> last front end %.3f ms\n",
+                    t_host0 - t_begin, t_first_sync - t_host0, t_loop_end - t_host0, st.ms_host_quads, t_synced - t_host0, t_events - t_host0,
+                    h2d_span, gpu_tail);
+        }
         if (lean_done) {  // the markers were assembled on the device: one block copy (lean implies a single super-batch and group)
             DecodeBlock &b = *d->blocks[0];
-            if (b.n_quads) { cudaEventElapsedTime(&ms, b.ev_a, b.ev_b); st.ms_decode_kernel += ms; }
+            if (b.n_quads && stats) { cudaEventElapsedTime(&ms, b.ev_a, b.ev_b); st.ms_decode_kernel += ms; }
             const uint32_t nm = h_info[3], take = nm < marker_capacity ? nm : marker_capacity;
             memcpy(markers, d->h_shot.p + off_markers, (size_t)take * sizeof(a3_marker));
             if (want_poses) memcpy(outs->marker_poses, d->h_shot.p + off_mposes, (size_t)take * 2 * sizeof(a3_pose));
@@ -1124,7 +1163,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         }
         for (uint32_t g = 0; g < ngroups; g++) {
             DecodeBlock &b = *d->blocks[g];
-            if (b.n_quads) { cudaEventElapsedTime(&ms, b.ev_a, b.ev_b); st.ms_decode_kernel += ms; }
+            if (b.n_quads && stats) { cudaEventElapsedTime(&ms, b.ev_a, b.ev_b); st.ms_decode_kernel += ms; }
             const uint32_t f0 = g * group, f1 = f0 + group_size(g);
             if (want_patches && b.n_quads && total_cands < outs->cand_capacity) {
                 const uint32_t room = outs->cand_capacity - total_cands, m = b.n_quads < room ? b.n_quads : room;
