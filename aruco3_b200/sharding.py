@@ -19,3 +19,48 @@ def merge_counts(per_rank: list) -> list:
     for part in per_rank:
         out.extend(part)
     return out
+
+
+class ShardedDetector:
+    """One `Detector` per listed device (a device may be listed more than once), each on its own host thread over its
+    contiguous block of frames; the per-frame results come back in frame order.  ctypes releases the GIL during
+    `a3_detect_batch`, so the shards really run side by side.  The in-process counterpart of `bench.py --gpus N`'s one
+    process per GPU, and the Python twin of `aruco3::ShardedDetector` (include/aruco3_b200.hpp)."""
+
+    def __init__(self, config=None, dictionary="ARUCO", devices=(0,), **kw):
+        from .detector import Detector
+        if not devices:
+            raise ValueError("ShardedDetector: no devices")
+        self.shards = [Detector(config, dictionary, device=dev, **kw) for dev in devices]
+
+    def detect_batch(self, frames, **kw) -> list:
+        import threading
+        world = len(self.shards)
+        parts, errors = [None] * world, [None] * world
+
+        def run(rank):
+            lo, hi = shard_range(len(frames), rank, world)
+            try:
+                parts[rank] = self.shards[rank].detect_batch(frames[lo:hi], **kw) if hi > lo else []
+            except BaseException as e:  # re-raised in the caller's thread
+                errors[rank] = e
+
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in errors:
+            if e is not None:
+                raise e
+        return merge_counts(parts)
+
+    def close(self):
+        for s in self.shards:
+            s.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

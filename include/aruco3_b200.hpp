@@ -13,8 +13,11 @@
 
 #include <array>
 #include <cstdint>
+#include <exception>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -208,6 +211,54 @@ public:
 private:
     int device_ = 0;
     a3_detector *h_ = nullptr;
+};
+
+// Frame-batch sharding over several GPUs: frames are independent, so a batch is cut into contiguous blocks,
+// one per device (block sizes differ by at most one frame, earlier devices take the extras — the rule of
+// aruco3_b200/sharding.py), each block goes through its own Detector on its own host thread, and the per-frame results
+// are concatenated in frame order.  No collective, no peer traffic.  The same device may be listed more than once.
+class ShardedDetector {
+public:
+    ShardedDetector(const DetectorConfig &cfg, const ARDictionary &dict, const std::vector<int> &devices) {
+        if (devices.empty()) throw Error(A3_ERR_INVALID_ARGUMENT, "ShardedDetector: no devices");
+        for (int dev : devices) shards_.emplace_back(new Detector(cfg, dict, dev));
+    }
+    size_t size() const { return shards_.size(); }
+    static std::pair<uint32_t, uint32_t> shard_range(uint32_t n_frames, uint32_t rank, uint32_t world) {
+        const uint32_t base = n_frames / world, extra = n_frames % world;
+        const uint32_t lo = rank * base + (rank < extra ? rank : extra);
+        return {lo, lo + base + (rank < extra ? 1u : 0u)};
+    }
+    std::vector<Detection> detect_batch(const uint8_t *frames, uint32_t n, uint32_t width, uint32_t height,
+                                        PixelFormat fmt = PixelFormat::Rgb8, bool full = false) const {
+        const uint32_t bpp = (fmt == PixelFormat::Rgb8 || fmt == PixelFormat::Bgr8) ? 3 : (fmt == PixelFormat::Luma8 ? 1 : 4);
+        const size_t stride = (size_t)width * bpp * height;
+        const uint32_t world = (uint32_t)shards_.size();
+        std::vector<std::vector<Detection>> parts(world);
+        std::vector<std::exception_ptr> errors(world);
+        std::vector<std::thread> threads;
+        for (uint32_t r = 0; r < world; r++)
+            threads.emplace_back([&, r] {
+                try {
+                    const auto range = shard_range(n, r, world);
+                    if (range.second > range.first)
+                        parts[r] = shards_[r]->detect_batch(frames + (size_t)range.first * stride, range.second - range.first, width, height, fmt, full);
+                } catch (...) {
+                    errors[r] = std::current_exception();
+                }
+            });
+        for (auto &t : threads) t.join();
+        for (auto &e : errors)
+            if (e) std::rethrow_exception(e);
+        std::vector<Detection> out;
+        out.reserve(n);
+        for (auto &part : parts)
+            for (auto &d : part) out.push_back(std::move(d));
+        return out;
+    }
+
+private:
+    std::vector<std::unique_ptr<Detector>> shards_;
 };
 
 // src/pinhole.rs:11-18

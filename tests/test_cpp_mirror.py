@@ -80,3 +80,55 @@ def test_cpp_detector_matches_oracle(oracle, tmp_path):
     for got, m in zip(poses, ref.markers):
         best, alt = oracle.solve_with_undistorted_points(m["corners"], 40.0, (640, 480))
         assert got == [np.float32(best.error)] + [np.float32(v) for v in best.translation] + [np.float32(alt.translation[2])]
+
+
+SHARDED = r'''
+#include <cstdio>
+#include <vector>
+#include "aruco3_b200.hpp"
+int main(int argc, char **argv) {
+    const uint32_t w = 640, h = 480, n = 7;
+    std::vector<uint8_t> rgb((size_t)n * w * h * 3);
+    FILE *f = fopen(argv[1], "rb");
+    if (!f || fread(rgb.data(), 1, rgb.size(), f) != rgb.size()) return 2;
+    fclose(f);
+    if (aruco3::ShardedDetector::shard_range(7, 0, 3) != std::make_pair(0u, 3u) || aruco3::ShardedDetector::shard_range(7, 2, 3) != std::make_pair(5u, 7u)) return 3;
+    const aruco3::ARDictionary dict = aruco3::ARDictionary::new_from_named_dict("ARUCO");
+    aruco3::Detector one(aruco3::DetectorConfig(), dict);
+    aruco3::ShardedDetector many(aruco3::DetectorConfig(), dict, {0, 0, 0});  // three shards (on the one device a test box has)
+    for (int round = 0; round < 2; round++) {
+        const auto a = one.detect_batch(rgb.data(), n, w, h), b = many.detect_batch(rgb.data(), n, w, h);
+        if (a.size() != n || b.size() != n) return 4;
+        for (uint32_t i = 0; i < n; i++) {
+            if (a[i].markers.size() != b[i].markers.size()) return 5;
+            for (size_t k = 0; k < a[i].markers.size(); k++)
+                if (a[i].markers[k].id != b[i].markers[k].id || a[i].markers[k].corners != b[i].markers[k].corners || a[i].markers[k].code != b[i].markers[k].code) return 6;
+            printf("frame %u markers %zu\n", i, b[i].markers.size());
+        }
+    }
+    return 0;
+}
+'''
+
+
+@pytest.mark.gpu
+def test_cpp_sharded_detector_equals_single(tmp_path):
+    """aruco3::ShardedDetector (contiguous frame blocks, one Detector and host thread per shard, no collective) returns what
+    one Detector returns for the whole batch, frame for frame."""
+    from aruco3_b200 import _ffi, synth
+    _ffi.lib()
+    frames, _ = synth.render_batch("C1", 7)
+    (tmp_path / "frames.rgb").write_bytes(frames.tobytes())
+    src, exe = tmp_path / "sharded.cpp", tmp_path / "sharded"
+    src.write_text(SHARDED)
+    lib_dir = ROOT / "aruco3_b200"
+    subprocess.run(["g++", "-std=c++17", "-pthread", "-I", str(ROOT / "include"), str(src), "-o", str(exe), f"-L{lib_dir}", "-laruco3_b200",
+                    f"-Wl,-rpath,{lib_dir}"], check=True)
+    out = subprocess.run([str(exe), str(tmp_path / "frames.rgb")], check=True, capture_output=True, text=True).stdout.splitlines()
+    assert len(out) == 14 and sum(int(ln.split()[-1]) for ln in out[:7]) > 20
+
+
+def test_sharded_header_compiles_without_gpu(tmp_path):
+    src = tmp_path / "sharded.cpp"
+    src.write_text(SHARDED)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-pthread", "-I", str(ROOT / "include"), "-c", str(src), "-o", str(tmp_path / "sharded.o")], check=True)

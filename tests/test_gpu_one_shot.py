@@ -149,3 +149,17 @@ def test_markers_only_calls_assemble_on_the_device(a3):
     with a3.Detector() as d:  # and without the pose step
         for call in range(2):
             assert _markers_only(d.detect_batch(frames)) == want
+
+
+def test_sharded_detector_in_one_process(a3):
+    """aruco3_b200.sharding.ShardedDetector: three shards (all on device 0 here), one host thread each, results in frame
+    order equal to a single detector's — first call and repeat calls (each shard then runs its own one-shot route)."""
+    from aruco3_b200 import synth
+    from aruco3_b200.sharding import ShardedDetector
+    frames, _ = synth.render_batch("C1", 8)
+    with a3.Detector() as d:
+        want = _markers_only(d.detect_batch(frames))
+    with ShardedDetector(devices=(0, 0, 0)) as sd:
+        for _ in range(3):
+            assert _markers_only(sd.detect_batch(frames)) == want
+        assert _summary(sd.detect_batch(frames[:2], full=True)) == _fresh(a3, frames[:2])  # fewer frames than shards
