@@ -1,8 +1,19 @@
-import ctypes as C, os, sys, time
-sys.path.insert(0, "/root/repo")
+#!/usr/bin/env python3
+"""Host timestamps and device spans of the phases of a host-input a3_detect_batch call over 256 x 1080p frames (A3_TRACE=1:
+the library prints them on stderr): where the time after the last byte of the H2D stream goes.
+usage: python tools/trace_e2e.py"""
+import ctypes as C
+import os
+import sys
+import time
+from pathlib import Path
+
 os.environ["A3_TRACE"] = "1"
-import numpy as np, torch
-from aruco3_b200 import Detector, _ffi, synth
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch  # noqa: E402
+
+from aruco3_b200 import Detector, _ffi, synth  # noqa: E402
+
 n, h, w = 256, 1080, 1920
 pinned = torch.empty((n, h, w, 3), dtype=torch.uint8, pin_memory=True)
 synth.render_batch("C3", n, 0, out=pinned.numpy())
