@@ -464,7 +464,9 @@ __global__ void __launch_bounds__(128) k3_walk_short(const Geo g, const StepTabl
 // current visit the border has 2s + 1 points, when it stands on the backward lane's previous visit it has 2s.  Every visit
 // is examined by one of the two for raster-earlier candidate cracks (either finding one kills the candidate).
 // (Measured before the pairing: fewer walkers per warp, software prefetch of the sector ahead and a register window all
-// made this kernel slower: its time is the dependent chain of the longest border, about 750 cycles per step.)
+// made this kernel slower: its time is the dependent chain of the longest border, about 750 cycles per step — which is
+// why the per-step exchange and tests were moved off that chain, see the blocks of kBlk steps below.)
+template <int kBlk>
 __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
     __shared__ uint16_t fwd[8][512];
     __shared__ uint16_t bwd[8][512];
@@ -505,34 +507,63 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
         if (back) { x = sx + ddx(pred); y = sy + ddy(pred); state = (uint32_t)((pred + 4) & 7); }  // backwards: the visit before it
         uint32_t min_pix = start_pix, n = 0, prev_back_id = 0xffffffffu, my_prev_id = 0xffffffffu;
         bool dead = false;
-        for (uint32_t s = 0;; s++) {
-            const uint32_t e = lut[state][hood9(plane, g.Hp, x, y)];
-            const uint32_t pix = (uint32_t)(y * (int)g.w + x);
-            const uint32_t fstate = back ? (e & 7u) : state;                  // direction of the previous border pixel at this visit
-            const uint32_t id = (pix << 3) | fstate;
-            // candidate cracks of this visit that come before me in raster order
-            const bool mine_dead = ((e & 8u) && x > 0 && (pix << 1) < me) || ((e & 16u) && x + 1 < (int)g.w && ((pix << 1) | 1u) < me);
-            const uint32_t other_id = __shfl_xor_sync(pair_mask, id, 1);
+        // Blocks of kBlk steps: inside a block a lane only walks (load, table, move: the dependent chain), remembering its
+        // visits; the exchange with the partner lane, the test for raster-earlier cracks and the meeting test follow once
+        // per block, off that chain.  A lane may so walk up to kBlk - 1 visits past the meeting point; those are visits its
+        // partner has examined already (same cracks, same verdict), checkpoints dropped there are valid positions of the
+        // same border (a checkpoint needs 64 walked points, so n >= 122 and n / 2 + kBlk < n), and the meeting point itself
+        // is taken from the remembered visit.
+        uint32_t meet_xy = 0, meet_state = 0;
+        for (uint32_t s0 = 0;; s0 += kBlk) {
+            uint32_t ids[kBlk], xys[kBlk], fsts[kBlk];
+            bool mine_dead = false;
+#pragma unroll
+            for (int k = 0; k < kBlk; k++) {
+                const uint32_t e = lut[state][hood9(plane, g.Hp, x, y)];
+                const uint32_t pix = (uint32_t)(y * (int)g.w + x);
+                const uint32_t fstate = back ? (e & 7u) : state;                  // direction of the previous border pixel at this visit
+                ids[k] = (pix << 3) | fstate;
+                xys[k] = (uint32_t)x | ((uint32_t)y << 16);
+                fsts[k] = fstate;
+                // candidate cracks of this visit that come before me in raster order
+                mine_dead |= ((e & 8u) && x > 0 && (pix << 1) < me) || ((e & 16u) && x + 1 < (int)g.w && ((pix << 1) | 1u) < me);
+                min_pix = min(min_pix, pix);
+                // checkpoints for k3_emit: forwards at index kSeg, 2 kSeg, ...; backwards kSeg, 2 kSeg, ... points before the end
+                const uint32_t walked = back ? s0 + k + 1 : s0 + k;
+                if (walked && walked % kSeg == 0) {
+                    const uint32_t c = atomicAdd(&l.counters[4], 1u);
+                    if (c < l.ckpt_cap) l.ckpts[c] = Ckpt{i, walked, xys[k], fstate | (back ? kCkptBackward : 0u)};
+                    else atomicOr(&l.counters[2], 1u);
+                }
+                x += (int)((e >> 5) & 3u) - 1;
+                y += (int)((e >> 7) & 3u) - 1;
+                state = e >> 9;
+            }
+            uint32_t oid[kBlk];
+#pragma unroll
+            for (int k = 0; k < kBlk; k++) oid[k] = __shfl_xor_sync(pair_mask, ids[k], 1);
             dead = __shfl_xor_sync(pair_mask, (int)mine_dead, 1) || mine_dead;
             if (dead) break;
-            // the forward lane compares with the backward lane's current and previous visit; the backward lane mirrors it
-            const uint32_t fwd_id = back ? other_id : id, back_id = back ? id : other_id;
-            const uint32_t back_prev = back ? my_prev_id : prev_back_id;
-            min_pix = min(min_pix, pix);
-            if (fwd_id == back_id) { n = 2 * s + 1; break; }
-            if (s > 0 && fwd_id == back_prev) { n = 2 * s; break; }
-            // checkpoints for k3_emit: forwards at index kSeg, 2 kSeg, ...; backwards kSeg, 2 kSeg, ... points before the end
-            const uint32_t walked = back ? s + 1 : s;
-            if (walked && walked % kSeg == 0) {
-                const uint32_t c = atomicAdd(&l.counters[4], 1u);
-                if (c < l.ckpt_cap) l.ckpts[c] = Ckpt{i, walked, (uint32_t)x | ((uint32_t)y << 16), fstate | (back ? kCkptBackward : 0u)};
-                else atomicOr(&l.counters[2], 1u);
+            // the forward lane compares with the backward lane's visit of the same step and of the step before; the backward
+            // lane mirrors it.  s is the step: forward visit index s, backward visit index n - 1 - s.
+            int met = -1;
+#pragma unroll
+            for (int k = 0; k < kBlk; k++) {
+                if (met >= 0) continue;
+                const uint32_t s = s0 + k;
+                const uint32_t fwd_id = back ? oid[k] : ids[k], back_id = back ? ids[k] : oid[k];
+                const uint32_t back_prev = k == 0 ? (back ? my_prev_id : prev_back_id) : (back ? ids[k > 0 ? k - 1 : 0] : oid[k > 0 ? k - 1 : 0]);
+                if (fwd_id == back_id) { n = 2 * s + 1; met = k; }
+                else if (s > 0 && fwd_id == back_prev) { n = 2 * s; met = k; }
             }
-            my_prev_id = id;
-            prev_back_id = other_id;
-            x += (int)((e >> 5) & 3u) - 1;
-            y += (int)((e >> 7) & 3u) - 1;
-            state = e >> 9;
+            if (met >= 0) {
+#pragma unroll
+                for (int k = 0; k < kBlk; k++)
+                    if (k == met) { meet_xy = xys[k]; meet_state = fsts[k]; }
+                break;
+            }
+            my_prev_id = ids[kBlk - 1];
+            prev_back_id = oid[kBlk - 1];
         }
         min_pix = min(min_pix, __shfl_xor_sync(pair_mask, min_pix, 1));
         if (back) continue;
@@ -542,7 +573,7 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
             // forward and the first backward segment (they may overlap: every segment writes the same values)
             if (n > kSeg) {
                 const uint32_t c = atomicAdd(&l.counters[4], 1u);
-                if (c < l.ckpt_cap) l.ckpts[c] = Ckpt{i, n / 2, (uint32_t)x | ((uint32_t)y << 16), state};
+                if (c < l.ckpt_cap) l.ckpts[c] = Ckpt{i, n / 2, meet_xy, meet_state};
                 else atomicOr(&l.counters[2], 1u);
             }
             slot = record_survivor(l, frame, key, kind, n, min_pix == start_pix, min_points);
@@ -1210,7 +1241,7 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     k3_walk_short<<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
     K3_CUDA(cudaGetLastError());
     timer.mark("walk_short");
-    k3_walkers<<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
+    k3_walkers<8><<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);  // blocks of 2 / 4 / 6 / 8 steps measured: 0.207 / 0.188 / 0.186 / 0.184 ms
     K3_CUDA(cudaGetLastError());
     timer.mark("walkers");
     k3_flag_all<<<(p.n + 127) / 128, 128, 0, stream>>>(p.frame_flags, p.n, w.counters, 0);
