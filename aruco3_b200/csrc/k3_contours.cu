@@ -1190,8 +1190,9 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         K3_CUDA(alloc_exact(w.frame_long_count, (size_t)p.n));
         w.frames_cap = p.n;
     }
-    // per-frame lists of the long borders for k3_order: kOrderCap entries per frame while that stays below 256 MB
-    const bool frame_lists = (size_t)p.n * kOrderCap * 12 <= ((size_t)256 << 20) && !getenv("A3_K3_RADIX_SORT");
+    // per-frame lists of the long borders for k3_order: kOrderCap entries per frame, for calls of up to 4096 frames (48 MB of
+    // lists; every CTA of k3_order also sums the counts of the frames before its own, which is quadratic in the frame count)
+    const bool frame_lists = p.n <= 4096 && !getenv("A3_K3_RADIX_SORT");
     if (frame_lists && p.n > w.frame_lists_cap) {
         K3_CUDA(alloc_exact(w.frame_keys, (size_t)p.n * kOrderCap));
         K3_CUDA(alloc_exact(w.frame_slots, (size_t)p.n * kOrderCap));
