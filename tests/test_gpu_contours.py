@@ -166,3 +166,21 @@ def test_wide_frames_take_the_64_bit_distance_path(a3, oracle):
         masks.append(m)
     nflag = _check(a3, oracle, np.stack(masks), cfg, ocfg)
     assert nflag == 0
+
+
+def test_more_than_4096_frames_take_the_radix_sort(a3, oracle):
+    """k3_order ranks the long borders frame by frame for calls of up to 4096 frames; larger calls (and frames with more than
+    1024 long borders) order them with the radix sort.  4500 small masks in one call, every unflagged one equal to the oracle."""
+    rng = np.random.default_rng(4500)
+    n, h, w = 4500, 24, 32
+    dens = rng.choice([0.2, 0.5, 0.8], size=n)
+    masks = ((rng.random((n, h, w)) < dens[:, None, None]) * 255).astype(np.uint8)
+    masks[:, :, 0] = 0  # no foreground in column 0: nothing can be flagged
+    cfg = a3.DetectorConfig(min_side_length_factor=0.05, min_corner_separation_factor=0.02)
+    ocfg = oracle.default_config(min_side_length_factor=0.05, min_corner_separation_factor=0.02)
+    with a3.Detector(cfg) as d:
+        quads, flags, contours, points = d.quads_from_masks_device(masks, quad_capacity=64)
+    assert not flags.any()
+    for f in range(0, n, 3):
+        want, nc, npnt = _oracle_frame(oracle, masks[f], ocfg)
+        assert quads[f].tolist() == want.tolist() and (int(contours[f]), int(points[f])) == (nc, npnt), f"frame {f}"
