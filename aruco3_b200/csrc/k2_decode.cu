@@ -131,12 +131,11 @@ __device__ void make_projection(const uint32_t *quad, float hs, double (*a)[9], 
     out->ok = 1;
 }
 
-__device__ __forceinline__ uint8_t clamp_u8_trunc(float x) {  // <u8 as Clamp<f32>>::clamp
-    if (x < 255.0f) {
-        if (x > 0.0f) return (uint8_t)x;
-        return 0;
-    }
-    return 255;
+// <u8 as Clamp<f32>>::clamp followed by `as u8`: x < 255 ? (x > 0 ? trunc(x) : 0) : 255, so NaN gives 255.  The
+// float-to-unsigned conversion (cvt.rzi.u32.f32) already saturates: negatives and NaN give 0, large values 2^32 - 1.
+__device__ __forceinline__ uint8_t clamp_u8_trunc(float x) {
+    const uint32_t v = min(__float2uint_rz(x), 255u);
+    return (uint8_t)(x != x ? 255u : v);
 }
 
 // warp_into's per-pixel body: projective map + interpolate_bilinear with default 0.
@@ -157,9 +156,9 @@ __device__ __forceinline__ uint8_t sample(const uint8_t *grey, uint32_t w, uint3
     float left = floorf(px), right = left + 1.0f, top = floorf(py), bottom = top + 1.0f;
     float rw = px - left, bw = py - top;
     if (left < 0.0f || right >= (float)w || top < 0.0f || bottom >= (float)h) return 0;
-    // NaN coordinates fall through every comparison (as in Rust) and `NaN as u32` is 0 there and here.
-    uint32_t l = isnan(left) ? 0u : (uint32_t)left, r = isnan(right) ? 0u : (uint32_t)right;
-    uint32_t tp = isnan(top) ? 0u : (uint32_t)top, b = isnan(bottom) ? 0u : (uint32_t)bottom;
+    // NaN coordinates fall through every comparison (as in Rust) and `NaN as u32` is 0 there and here (cvt.rzi.u32.f32 gives 0
+    // for NaN; everything else is inside the frame after the test above).
+    const uint32_t l = __float2uint_rz(left), r = __float2uint_rz(right), tp = __float2uint_rz(top), b = __float2uint_rz(bottom);
     float tl = (float)grey[(size_t)tp * w + l], tr = (float)grey[(size_t)tp * w + r];
     float bl = (float)grey[(size_t)b * w + l], br = (float)grey[(size_t)b * w + r];
     uint8_t topv = clamp_u8_trunc((1.0f - rw) * tl + rw * tr);
