@@ -132,3 +132,32 @@ def test_sharded_header_compiles_without_gpu(tmp_path):
     src = tmp_path / "sharded.cpp"
     src.write_text(SHARDED)
     subprocess.run(["g++", "-std=c++17", "-Wall", "-pthread", "-I", str(ROOT / "include"), "-c", str(src), "-o", str(tmp_path / "sharded.o")], check=True)
+
+
+def test_cpp_shard_range_equals_python(tmp_path):
+    """aruco3::ShardedDetector::shard_range is the rule of aruco3_b200.sharding.shard_range (no GPU needed: the function is
+    static and the program never creates a detector)."""
+    from aruco3_b200.sharding import shard_range
+    src, exe = tmp_path / "ranges.cpp", tmp_path / "ranges"
+    src.write_text(r'''
+#include <cstdio>
+#include "aruco3_b200.hpp"
+int main() {
+    for (unsigned n = 0; n <= 40; n++)
+        for (unsigned w = 1; w <= 9; w++)
+            for (unsigned r = 0; r < w; r++) {
+                auto p = aruco3::ShardedDetector::shard_range(n, r, w);
+                printf("%u %u %u %u %u\n", n, w, r, p.first, p.second);
+            }
+    return 0;
+}
+''')
+    lib_dir = ROOT / "aruco3_b200"
+    subprocess.run(["g++", "-std=c++17", "-pthread", "-I", str(ROOT / "include"), str(src), "-o", str(exe), f"-L{lib_dir}", "-laruco3_b200",
+                    f"-Wl,-rpath,{lib_dir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    vals = list(map(int, out))
+    assert len(vals) == 5 * 41 * 45
+    for i in range(0, len(vals), 5):
+        n, w, r, lo, hi = vals[i:i + 5]
+        assert (lo, hi) == shard_range(n, r, w), (n, w, r)
