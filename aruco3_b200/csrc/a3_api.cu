@@ -248,7 +248,7 @@ double now_ms() {
 __global__ void __launch_bounds__(1024) pack_offsets_kernel(const uint32_t *counts, const uint32_t *flags, uint32_t n_frames, uint32_t quad_cap,
                                                             uint32_t cap, const uint32_t *k3_failed, uint32_t *offsets, uint32_t *info,
                                                             uint32_t *chunk_end, uint32_t n_chunks) {
-    for (uint32_t i = threadIdx.x; i < n_chunks; i += blockDim.x) chunk_end[i] = 0xffffffffu;  // assemble_markers_kernel's chain
+    for (uint32_t i = threadIdx.x; i < n_chunks; i += blockDim.x) chunk_end[i] = 0;  // K2's accepted counts per 1024 quads (assemble_markers_kernel)
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t base_s, bad_s;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -313,36 +313,35 @@ __global__ void __launch_bounds__(128) pack_quads_kernel(const uint32_t *quads, 
 // info[3] = number of markers.
 __global__ void __launch_bounds__(1024) assemble_markers_kernel(const a3_decode *dec, const uint32_t *quads, const uint32_t *qframe,
                                                                 const uint32_t *qoff, const a3_pose *poses, uint32_t cap, uint32_t *info,
-                                                                volatile uint32_t *chunk_end, a3_marker *markers, a3_pose *mposes) {
-    // One CTA per 1024 quads; the number of markers before a chunk comes down a chain: chunk c waits for chunk_end[c - 1]
-    // (0xffffffff until written; pack_offsets_kernel resets the chain) and publishes its own.  All chunks are resident at
-    // once (a few dozen CTAs at most), so the chain cannot stall on an unscheduled block.
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t base_s;
+                                                                const uint32_t *chunk_accepted, a3_marker *markers, a3_pose *mposes) {
+    // One CTA per 1024 quads.  The number of markers before a chunk is the sum of the accepted counts of the chunks before
+    // it, which K2 accumulated while it decoded (K2Params::accept_counts; zeroed by pack_offsets_kernel): no CTA waits for
+    // another, so the kernel needs no co-residency and any number of chunks is fine.
+    __shared__ uint32_t warp_sums[32], warp_before[32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x;
     const bool bad = info[1] != 0;
     const uint32_t nq = bad ? 0u : (info[0] < cap ? info[0] : cap);
     const uint32_t k = c * 1024 + threadIdx.x;
     const uint32_t acc = (k < nq && dec[k].accepted) ? 1u : 0u;
     const uint32_t bal = __ballot_sync(0xffffffffu, acc);
-    if (lane == 0) warp_sums[warp] = __popc(bal);
+    uint32_t before = 0;
+    if (!bad)
+        for (uint32_t i = threadIdx.x; i < c; i += 1024) before += chunk_accepted[i];
+    for (uint32_t o = 16; o; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) { warp_sums[warp] = __popc(bal); warp_before[warp] = before; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t total = 0;
-        for (uint32_t i = 0; i < 32; i++) total += warp_sums[i];
-        uint32_t before = 0;
-        if (c > 0) {
-            while ((before = chunk_end[c - 1]) == 0xffffffffu) { }
-        }
-        base_s = before;
-        __threadfence();
-        chunk_end[c] = before + total;
-        if (c == gridDim.x - 1) info[3] = before + total;
+    uint32_t base = 0, idx = 0;
+    for (uint32_t i = 0; i < 32; i++) {
+        base += warp_before[i];
+        if (i < warp) idx += warp_sums[i];
     }
-    __syncthreads();
+    if (c == gridDim.x - 1 && threadIdx.x == 0) {
+        uint32_t total = base;
+        for (uint32_t i = 0; i < 32; i++) total += warp_sums[i];
+        info[3] = total;
+    }
     if (!acc) return;
-    uint32_t idx = base_s + __popc(bal & ((1u << lane) - 1u));
-    for (uint32_t i = 0; i < warp; i++) idx += warp_sums[i];
+    idx += base + __popc(bal & ((1u << lane) - 1u));
     const a3_decode dc = dec[k];
     const uint32_t frame = qframe[k], rot = dc.rotation & 3u;
     const uint32_t *q = quads + (size_t)k * 8;
@@ -809,7 +808,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             a3_decode *d_dec = reinterpret_cast<a3_decode *>(d->d_shot.p + off_dec);
             a3_pose *d_pose = reinterpret_cast<a3_pose *>(d->d_shot.p + off_pose);
             const uint32_t n_chunks = (cap + 1023) / 1024;
-            A3_CUDA(d->d_qoff.reserve((size_t)sn + 1 + n_chunks));  // frame offsets of the quads, then the marker-count chain
+            A3_CUDA(d->d_qoff.reserve((size_t)sn + 1 + n_chunks));  // frame offsets of the quads, then the accepted count of every 1024 quads
             uint32_t *d_chain = d->d_qoff.p + sn + 1;
             A3_CUDA(b.d_qframe.reserve(cap));
             if (want_patches) A3_CUDA(b.d_patches.reserve(cap * np));
@@ -821,6 +820,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             A3_CUDA(cudaGetLastError());
             K2Params p = k2_params(d, d->d_grey.p, w, h);
             p.quads = d_quads; p.quad_frame = b.d_qframe.p; p.n_quads = cap; p.n_quads_dev = d_info; p.queue = d_info + 2; p.decodes = d_dec;
+            p.accept_counts = lean ? d_chain : nullptr;
             p.patches = want_patches ? b.d_patches.p : nullptr;
             A3_CUDA(cudaEventRecord(b.ev_a, d->s_pixel));
             A3_CUDA(k2_decode(p, d->s_pixel));

@@ -67,6 +67,7 @@ struct K2Params {
     const uint32_t *n_quads_dev = nullptr;  // device, optional: the real number of quads (<= n_quads, which then only sizes the launch)
     uint32_t *queue = nullptr;  // device, optional, zero at launch: warps take quads from this counter instead of a fixed stride, so
                                 // the last, partial wave of quads spreads over all resident warps
+    uint32_t *accept_counts = nullptr;  // device, optional, zero at launch: [q >> 10] += 1 for every accepted quad q (marker assembly)
     uint32_t patch_size;        // homography_sample_size
     uint32_t mark_size;         // get_mark_size()
     const uint64_t *codes;      // device dictionary

@@ -234,7 +234,7 @@ size_t simplify_closed(const int32_t *xs, const int32_t *ys, size_t n, double ep
 }
 
 inline int orient(Pt p, Pt q, Pt r) {
-    const int32_t v = (q.y - p.y) * (r.x - q.x) - (q.x - p.x) * (r.y - q.y);
+    const int64_t v = (int64_t)(q.y - p.y) * (r.x - q.x) - (int64_t)(q.x - p.x) * (r.y - q.y);  // 64-bit: coordinates go up to 65535
     return v == 0 ? 0 : (v > 0 ? 1 : -1);  // 1 clockwise, -1 counter-clockwise (imageproc's naming)
 }
 inline double dist(Pt p, Pt q) {

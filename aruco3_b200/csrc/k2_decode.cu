@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const
             out.hamming_distance = (uint8_t)dist;
             out.accepted = (uint8_t)(good && (!p.filter_high_bit_errors || dist < p.tau));
             p.decodes[q] = out;
+            if (p.accept_counts && out.accepted) atomicAdd(&p.accept_counts[q >> 10], 1u);
         }
         __syncwarp();
     }

@@ -728,7 +728,7 @@ struct Pt { int x, y; };
 __device__ __forceinline__ Pt unpack(uint32_t v) { return Pt{(int)(v & 0xffffu), (int)(v >> 16)}; }
 
 __device__ __forceinline__ int orient(Pt p, Pt q, Pt r) {
-    const int v = (q.y - p.y) * (r.x - q.x) - (q.x - p.x) * (r.y - q.y);
+    const long long v = (long long)(q.y - p.y) * (r.x - q.x) - (long long)(q.x - p.x) * (r.y - q.y);  // 64-bit: coordinates go up to 65535
     return v == 0 ? 0 : (v > 0 ? 1 : -1);
 }
 __device__ __forceinline__ double pdist(Pt p, Pt q) {

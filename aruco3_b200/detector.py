@@ -76,11 +76,11 @@ class ARDictionary:
         return (idx.value, dist.value) if ok else None
 
     def make_binary_image(self, marker_id: int):
-        """src/dictionaries.rs:212-232 -> (bool list, width)"""
+        """src/dictionaries.rs:212-232 -> (width, bool list), the reference's order"""
         buf = np.zeros(256, np.uint8)
         n = C.c_uint32()
         w = lib().a3_make_binary_image(C.byref(self._c), marker_id, buf.ctypes.data, buf.size, C.byref(n))
-        return [bool(v) for v in buf[:n.value]], int(w)
+        return int(w), [bool(v) for v in buf[:n.value]]
 
 
 def hamming_distance(a: int, b: int) -> int:

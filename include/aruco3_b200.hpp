@@ -70,10 +70,10 @@ public:
         if (dist) *dist = dd;
         return ok;
     }
-    std::pair<std::vector<bool>, uint8_t> make_binary_image(size_t marker_id) const {  // :212-232
+    std::pair<uint8_t, std::vector<bool>> make_binary_image(size_t marker_id) const {  // :212-232, (width, bits) as there
         uint8_t buf[256]; uint32_t n = 0;
         const uint8_t w = a3_make_binary_image(&c_, marker_id, buf, sizeof(buf), &n);
-        return {std::vector<bool>(buf, buf + (n < sizeof(buf) ? n : sizeof(buf))), w};
+        return {w, std::vector<bool>(buf, buf + (n < sizeof(buf) ? n : sizeof(buf)))};
     }
     const a3_dictionary &c() const { return c_; }
 

@@ -340,7 +340,8 @@ size_t a3ref_approximate_polygon_dp(const a3ref_point *curve, size_t n, double e
 
 /* A.5  imageproc::geometry::convex_hull (call site src/aruco.rs:143) */
 static int orientation(int32_t px, int32_t py, int32_t qx, int32_t qy, int32_t rx, int32_t ry) {
-    int32_t val = (qy - py) * (rx - qx) - (qx - px) * (ry - qy);
+    /* 64-bit so that frames beyond 46340 px a side are not signed-overflow UB here; identical to i32 below that */
+    int64_t val = (int64_t)(qy - py) * (rx - qx) - (int64_t)(qx - px) * (ry - qy);
     return val == 0 ? 0 : (val > 0 ? 1 /* Clockwise */ : -1 /* CounterClockwise */);
 }
 static double pdist(a3ref_point p, a3ref_point q) {

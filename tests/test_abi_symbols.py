@@ -76,5 +76,5 @@ def test_dictionary_functions_match_reference_kats():
     assert set(a3.ARDictionary.get_dictionary_names()) >= {"ARUCO", "APRILTAG_36H11", "CHILITAGS", "ARTAG"}
     with pytest.raises(a3.A3Error):
         a3.ARDictionary.new_from_named_dict("nope")
-    bits, width = d.make_binary_image(5)
+    width, bits = d.make_binary_image(5)  # (width, bits) as src/dictionaries.rs:212
     assert width == 7 and len(bits) == 49 and not any(bits[:7])

@@ -163,3 +163,46 @@ def test_sharded_detector_in_one_process(a3):
         for _ in range(3):
             assert _markers_only(sd.detect_batch(frames)) == want
         assert _summary(sd.detect_batch(frames[:2], full=True)) == _fresh(a3, frames[:2])  # fewer frames than shards
+
+
+def test_more_than_400k_candidates_in_one_call(a3, oracle):
+    """Marker assembly on the device must not depend on how many of its CTAs are resident at once (it used to chain them
+    with a busy-wait): 3400 frames x 121 dark squares = 411 400 candidates in ONE call, 402 chunks of 1024 candidates against
+    296 resident CTAs.  With APRILTAG_36H11 an all-black interior is accepted as id 191, so every candidate
+    becomes a marker; the device-assembled records of the second call must equal the host-assembled ones of the first and
+    the oracle's for the (repeated) frame."""
+    import ctypes as C
+    from aruco3_b200 import _ffi
+    n, side, per = 3400, 256, 121
+    one = np.full((side, side), 200, np.uint8)
+    for cy in range(11):
+        for cx in range(11):
+            one[10 + 21 * cy: 22 + 21 * cy, 10 + 21 * cx: 22 + 21 * cx] = 20
+    ocfg = oracle.default_config()
+    ocfg.min_corner_separation_factor = 0.03
+    ref = oracle.detect(one, "APRILTAG_36H11", ocfg)
+    assert len(ref.markers) == per and all(m["id"] == 191 for m in ref.markers)
+    frames = np.ascontiguousarray(np.broadcast_to(one, (n, side, side)))
+    cfg = a3.DetectorConfig(min_corner_separation_factor=0.03)
+    L = _ffi.lib()
+    cap = (per + 7) * n
+    with a3.Detector(cfg, "APRILTAG_36H11") as d:
+        results = []
+        for call in range(3):
+            markers = (_ffi.A3Marker * cap)()
+            n_markers = C.c_uint32()
+            stats = _ffi.A3Stats()
+            _ffi.check(L.a3_detect_batch(d._h, frames.ctypes.data, _ffi.FMT_LUMA8, _ffi.MEM_HOST, n, side, side, side, side * side,
+                                         C.cast(markers, C.c_void_p), cap, C.byref(n_markers), None, C.byref(stats)))
+            assert n_markers.value == per * n and stats.n_candidates == per * n
+            assert stats.one_shot == (1 if call else 0), (call, stats.one_shot, stats.one_shot_retry)
+            results.append(np.frombuffer(markers, dtype=np.uint8, count=n_markers.value * C.sizeof(_ffi.A3Marker)).copy())
+        assert np.array_equal(results[0], results[1]) and np.array_equal(results[0], results[2])
+        rec = np.frombuffer(results[1], dtype=np.dtype([("id", "<u8"), ("code", "<u8"), ("corners", "<u4", 8), ("frame", "<u4"),
+                                                         ("candidate", "<u4"), ("hd", "u1"), ("rot", "u1"), ("pad", "u1", 6)]))
+        assert np.array_equal(rec["frame"], np.repeat(np.arange(n, dtype=np.uint32), per))
+        want_corners = np.array([m["corners"] for m in ref.markers], np.uint32)
+        for f in (0, 1, n // 2, n - 1):
+            assert np.array_equal(rec["corners"][per * f: per * (f + 1)], want_corners)
+            assert rec["id"][per * f: per * (f + 1)].tolist() == [191] * per
+            assert rec["rot"][per * f: per * (f + 1)].tolist() == [m["rotation"] for m in ref.markers]
