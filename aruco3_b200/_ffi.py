@@ -12,6 +12,7 @@ LIB_PATH = PKG / "libaruco3_b200.so"
 A3_OK, A3_ERR_INVALID_ARGUMENT, A3_ERR_UNKNOWN_DICTIONARY, A3_ERR_CUDA, A3_ERR_CAPACITY, A3_ERR_UNSUPPORTED, \
     A3_ERR_OUT_OF_MEMORY = range(7)
 FMT_RGB8, FMT_RGBA8, FMT_LUMA8, FMT_BGR8, FMT_BGRA8 = 0, 1, 2, 3, 4
+FMT_LUMAA8, FMT_LUMA16, FMT_LUMAA16, FMT_RGB16, FMT_RGBA16 = 5, 6, 7, 8, 9
 MEM_HOST, MEM_DEVICE = 0, 1
 CONTOURS_HOST, CONTOURS_DEVICE = 0, 1
 POSE_OFF, POSE_UNDISTORTED, POSE_INTRINSICS, POSE_NORMALIZED = 0, 1, 2, 3
@@ -46,7 +47,7 @@ class A3Stats(C.Structure):
                [(n, C.c_double) for n in ("ms_h2d", "ms_pixel_kernel", "ms_contour_kernels", "ms_mask_d2h", "ms_host_quads",
                                           "ms_decode_kernel", "ms_host_cpu", "ms_total")] + \
                [(n, C.c_uint32) for n in ("pixel_kernel_launches", "decode_kernel_launches", "host_threads", "contour_kernel_launches",
-                                          "host_fallback_frames", "pose_kernel_launches", "one_shot", "one_shot_retry")]
+                                          "host_fallback_frames", "pose_kernel_launches", "one_shot", "one_shot_retry", "input_staged", "output_staged")]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -124,6 +125,11 @@ def lib():
     L.a3_detector_create.argtypes = [C.POINTER(A3Config), C.POINTER(A3Dictionary), C.c_int32, C.POINTER(vp)]
     L.a3_detector_destroy.restype = None
     L.a3_detector_destroy.argtypes = [vp]
+    L.a3_detector_acquire.argtypes = [C.POINTER(A3Config), C.POINTER(A3Dictionary), C.c_int32, C.POINTER(vp)]
+    L.a3_detector_release.restype = None
+    L.a3_detector_release.argtypes = [vp]
+    L.a3_detector_cache_clear.restype = None
+    L.a3_detector_create_count.restype = C.c_uint64
     L.a3_detector_set_host_threads.argtypes = [vp, u32]
     L.a3_detector_set_contour_mode.argtypes = [vp, u32]
     L.a3_detector_set_k1_tuning.argtypes = [vp, C.POINTER(A3K1Tuning)]

@@ -19,6 +19,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -130,6 +131,75 @@ private:
     bool quit_ = false;
 };
 
+// Host threads that move bytes between the caller's pageable memory and the pinned staging rings (a3_detect_batch with
+// A3_MEM_HOST frames that are not page-locked, and `Detection.grey` into a pageable buffer): a FIFO of small tasks.  Callers
+// keep their own completion counters (atomics) and sleep on them with wait(); a task calls notify() when a counter reaches
+// its goal.
+class CopyPool {
+public:
+    ~CopyPool() { stop(); }
+    void start(uint32_t threads, int device) {
+        if (!workers_.empty()) return;
+        quit_ = false;
+        for (uint32_t t = 0; t < threads; t++)
+            workers_.emplace_back([this, device] {
+                cudaSetDevice(device);  // tasks wait on CUDA events of the detector's device
+                loop();
+            });
+    }
+    void submit(std::function<void()> fn) {
+        { std::lock_guard<std::mutex> lk(mu_); q_.push_back(std::move(fn)); }
+        cv_.notify_one();
+    }
+    void notify() { { std::lock_guard<std::mutex> lk(mu_); } cv_done_.notify_all(); }
+    template <typename Pred>
+    void wait(Pred pred) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, pred);
+    }
+    void drain() {  // until the queue is empty and no task is running
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [this] { return q_.empty() && running_ == 0; });
+    }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(mu_); quit_ = true; }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+        workers_.clear();
+    }
+
+private:
+    void loop() {
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_.wait(lk, [this] { return quit_ || !q_.empty(); });
+            if (quit_) return;
+            std::function<void()> fn = std::move(q_.front());
+            q_.pop_front();
+            running_++;
+            lk.unlock();
+            fn();
+            lk.lock();
+            running_--;
+            if (q_.empty() && running_ == 0) cv_done_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, cv_done_;
+    std::deque<std::function<void()>> q_;
+    uint32_t running_ = 0;
+    bool quit_ = false;
+};
+
+// Shared between a call and the copy tasks it has in flight (kept alive by the tasks, so an early error return cannot
+// leave a task with a dangling reference).
+struct StageState {
+    std::unique_ptr<std::atomic<uint32_t>[]> in_left;   // per front-end chunk: pieces of its stage-in copy still to do
+    struct Out { cudaEvent_t ev; std::atomic<uint32_t> left; };
+    std::deque<Out> out;                                // per grey sub-chunk, in issue order (deque: stable addresses)
+};
+
 // Buffers of one decode group (the quads of a few frames); kept for reuse across calls.
 struct DecodeBlock {
     PinBuf<uint32_t> h_quads, h_qframe;
@@ -183,7 +253,7 @@ struct a3_detector {
     bool has_tuning = false;
     uint32_t chunk_override = 0;
     cudaStream_t s_copy = nullptr, s_pixel = nullptr, s_decode = nullptr;
-    a3::DevBuf<uint8_t> d_src, d_grey, d_mask, d_patches;
+    a3::DevBuf<uint8_t> d_src, d_grey, d_mask, d_patches, d_luma;  // d_luma: K0's Luma8 copy of LumaA8 / 16-bit frames
     a3::DevBuf<uint32_t> d_bits, d_quads, d_qframe;
     a3::DevBuf<a3_decode> d_dec;
     a3::PinBuf<uint32_t> h_bits;
@@ -193,6 +263,9 @@ struct a3_detector {
     a3::EventPool events;
     std::vector<std::unique_ptr<a3::DecodeBlock>> blocks;
     a3::WorkerPool pool;
+    // pageable host memory at the boundary: pinned rings + copy threads (created on first use)
+    a3::CopyPool copy_pool;
+    a3::PinBuf<uint8_t> h_stage_in, h_stage_out;
     // GPU contour stage (K3)
     uint32_t contour_mode = A3_CONTOURS_DEVICE;
     a3::K3Workspace k3;
@@ -362,6 +435,19 @@ __global__ void __launch_bounds__(1024) assemble_markers_kernel(const a3_decode 
     if (poses) { mposes[2 * (size_t)idx] = poses[2 * (size_t)k]; mposes[2 * (size_t)idx + 1] = poses[2 * (size_t)k + 1]; }
 }
 
+// K1 over `p`.  LumaA8 / 16-bit frames first go through K0 (image's into_luma8 for those variants) into the detector's Luma8
+// scratch, rows padded to 16 bytes so that the warp-strip kernel stays eligible, and K1 then takes its Luma8 pass-through.
+cudaError_t run_k1(a3_detector *d, K1Params p, const K1Tuning *tune, cudaStream_t s) {
+    if (fmt_wide(p.format)) {
+        const size_t lp = ((size_t)p.w + 15) & ~(size_t)15, lf = lp * p.h;
+        cudaError_t e = d->d_luma.reserve(lf * p.n);
+        if (e == cudaSuccess) e = k0_to_luma8(p.src, p.format, p.n, p.w, p.h, p.pitch, p.frame_stride, d->d_luma.p, lp, lf, s);
+        if (e != cudaSuccess) return e;
+        p.src = d->d_luma.p; p.format = A3_FMT_LUMA8; p.pitch = lp; p.frame_stride = lf;
+    }
+    return k1_gray_threshold(p, tune, s, nullptr);
+}
+
 K2Params k2_params(const a3_detector *d, const uint8_t *grey, uint32_t w, uint32_t h) {
     K2Params p;
     p.grey = grey; p.w = w; p.h = h; p.quads = nullptr; p.quad_frame = nullptr; p.n_quads = 0;
@@ -375,6 +461,11 @@ K2Params k2_params(const a3_detector *d, const uint8_t *grey, uint32_t w, uint32
 }  // namespace a3
 
 using namespace a3;
+
+static std::atomic<uint64_t> g_created{0};        // successful a3_detector_create calls (a3_detector_create_count)
+static std::mutex g_cache_mu;                     // idle handles of a3_detector_acquire / a3_detector_release, oldest first
+static std::vector<a3_detector *> g_cache;
+static constexpr size_t kCacheMax = 16;
 
 extern "C" {
 
@@ -440,8 +531,61 @@ a3_status a3_detector_create(const a3_config *cfg, const a3_dictionary *dict, in
         a3_detector_destroy(d);
         return cuda_fail(e, "a3_detector_create");
     }
+    g_created.fetch_add(1);
     *out = d;
     return A3_OK;
+}
+
+uint64_t a3_detector_create_count(void) { return g_created.load(); }
+
+// ---- handle cache -------------------------------------------------------------------------------------------------
+// The reference's `Detector` is plain data built with a struct literal (src/aruco.rs:46-49, benches/detect_markers.rs:17-20),
+// so a binding that keeps that shape has nowhere to store a handle.  It brackets every call with acquire / release instead:
+// an idle handle with exactly this config, dictionary and device comes out of the cache warm (streams, device and pinned
+// buffers, K3 workspace and the one-shot history all survive), and a new one is created only when none is idle.
+a3_status a3_detector_acquire(const a3_config *cfg, const a3_dictionary *dict, int32_t device, a3_detector **out) {
+    if (!cfg || !dict || !out) return fail(A3_ERR_INVALID_ARGUMENT, "a3_detector_acquire: null argument");
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (size_t i = g_cache.size(); i-- > 0;) {  // most recently released first
+            a3_detector *d = g_cache[i];
+            const a3_config &c = d->cfg;
+            if (d->device == device && c.threshold_window == cfg->threshold_window &&
+                c.contour_simplification_epsilon == cfg->contour_simplification_epsilon &&
+                c.min_side_length_factor == cfg->min_side_length_factor && c.min_corner_separation_factor == cfg->min_corner_separation_factor &&
+                c.homography_sample_size == cfg->homography_sample_size && (c.filter_high_bit_errors != 0) == (cfg->filter_high_bit_errors != 0) &&
+                d->dict.codes == dict->codes && d->dict.n_codes == dict->n_codes && d->dict.num_bits == dict->num_bits && d->dict.tau == dict->tau) {
+                g_cache.erase(g_cache.begin() + (long)i);
+                *out = d;
+                return A3_OK;
+            }
+        }
+    }
+    return a3_detector_create(cfg, dict, device, out);
+}
+
+void a3_detector_release(a3_detector *d) {
+    if (!d) return;
+    // back to the state a3_detector_create leaves a handle in (the buffers stay)
+    d->contour_mode = A3_CONTOURS_DEVICE;
+    d->pose_mode = A3_POSE_OFF;
+    d->has_tuning = false; d->k1_tuning = K1Tuning{}; d->chunk_override = 0;
+    a3_detector *evict = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_cache.push_back(d);
+        if (g_cache.size() > kCacheMax) { evict = g_cache.front(); g_cache.erase(g_cache.begin()); }
+    }
+    if (evict) a3_detector_destroy(evict);
+}
+
+void a3_detector_cache_clear(void) {
+    std::vector<a3_detector *> all;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        all.swap(g_cache);
+    }
+    for (a3_detector *d : all) a3_detector_destroy(d);
 }
 
 void a3_detector_destroy(a3_detector *d) {
@@ -449,7 +593,7 @@ void a3_detector_destroy(a3_detector *d) {
     cudaSetDevice(d->device);
     for (cudaStream_t s : {d->s_copy, d->s_pixel, d->s_decode})
         if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
-    d->d_src.release(); d->d_grey.release(); d->d_mask.release(); d->d_patches.release();
+    d->d_src.release(); d->d_grey.release(); d->d_mask.release(); d->d_patches.release(); d->d_luma.release();
     d->d_bits.release(); d->d_quads.release(); d->d_qframe.release(); d->d_dec.release(); d->h_bits.release();
     d->d_codes.release(); d->d_taps.release(); d->d_meta.release();
     d->d_planes.release(); d->d_k3quads.release(); d->d_k3counts.release(); d->d_k3before.release(); d->d_k3flags.release();
@@ -457,6 +601,8 @@ void a3_detector_destroy(a3_detector *d) {
     d->h_k3flags.release(); d->h_k3contours.release(); d->h_k3points.release(); d->h_plane.release();
     d->d_qoff.release(); d->d_k2queue.release(); d->d_shot.release(); d->h_shot.release();
     d->d_pose_in.release(); d->d_pose_out.release(); d->h_pose_out.release();
+    d->copy_pool.stop();
+    d->h_stage_in.release(); d->h_stage_out.release();
     d->events.release();
     for (auto &b : d->blocks) b->release();
     delete d;
@@ -501,7 +647,7 @@ a3_status a3_gray_threshold_batch(a3_detector *d, const void *frames, a3_format 
     p.format = format; p.n = n; p.w = w; p.h = h; p.pitch = pitch; p.frame_stride = frame_stride; p.radius = d->cfg.threshold_window;
     if (mem == A3_MEM_DEVICE) {
         p.src = static_cast<const uint8_t *>(frames); p.grey = grey; p.mask = mask; p.bits = mask_bits;
-        A3_CUDA(k1_gray_threshold(p, tune, static_cast<cudaStream_t>(cuda_stream), nullptr));
+        A3_CUDA(run_k1(d, p, tune, static_cast<cudaStream_t>(cuda_stream)));
         return A3_OK;
     }
     // host pointers: stage chunk by chunk, synchronously
@@ -520,7 +666,7 @@ a3_status a3_gray_threshold_batch(a3_detector *d, const void *frames, a3_format 
         if (mask_bits) A3_CUDA(d->d_bits.reserve(c * wpr * h));
         p.src = d->d_src.p; p.n = c;
         p.grey = grey ? d->d_grey.p : nullptr; p.mask = mask ? d->d_mask.p : nullptr; p.bits = mask_bits ? d->d_bits.p : nullptr;
-        A3_CUDA(k1_gray_threshold(p, tune, s, nullptr));
+        A3_CUDA(run_k1(d, p, tune, s));
         if (grey) A3_CUDA(cudaMemcpyAsync(grey + f0 * px, d->d_grey.p, c * px, cudaMemcpyDeviceToHost, s));
         if (mask) A3_CUDA(cudaMemcpyAsync(mask + f0 * px, d->d_mask.p, c * px, cudaMemcpyDeviceToHost, s));
         if (mask_bits) A3_CUDA(cudaMemcpyAsync(mask_bits + f0 * wpr * h, d->d_bits.p, c * wpr * h * 4, cudaMemcpyDeviceToHost, s));
@@ -650,6 +796,20 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
     st.n_frames = n;
     st.host_threads = d->host_threads;
     if (d->pool.size() != d->host_threads) d->pool.resize(d->host_threads);
+    // Pageable host memory at the boundary (the Vec<u8> of a `DynamicImage`, a `Detection.grey` the caller got from malloc): a
+    // cudaMemcpyAsync on it is neither asynchronous nor fast, so such buffers go through pinned rings that the copy threads
+    // fill (input) or empty (grey) one front-end chunk ahead of / behind the DMA.
+    auto is_pageable = [](const void *ptr) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return true; }
+        return at.type == cudaMemoryTypeUnregistered;
+    };
+    static const bool no_staging = getenv("A3_NO_HOST_STAGING") != nullptr;
+    const bool stage_in = mem == A3_MEM_HOST && !no_staging && (size_t)n * frame_stride >= ((size_t)1 << 20) && is_pageable(frames);
+    const bool stage_out = want_grey && !no_staging && (size_t)n * px >= ((size_t)1 << 20) && is_pageable(outs->grey);
+    if (stage_in || stage_out) d->copy_pool.start(d->host_threads < 16u ? d->host_threads : 16u, d->device);
+    st.input_staged = stage_in ? 1u : 0u;
+    st.output_staged = stage_out ? 1u : 0u;
 
     // ---- sizes: super-batch (device footprint), front-end chunk (copy / event granularity), decode group ----
     size_t sb = ((size_t)3 << 30) / (px + bits_words * 4 + (want_mask ? px : 0));  // grey + bits (+ mask) stay resident per frame
@@ -716,6 +876,19 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         if (want_mask) A3_CUDA(d->d_mask.reserve(sn * px));
         if (mem == A3_MEM_HOST) A3_CUDA(d->d_src.reserve((size_t)kStaging * fe * frame_stride));
         while (d->blocks.size() < ngroups) d->blocks.emplace_back(new DecodeBlock());
+        // pinned rings for pageable memory: kHostRing front-end chunks of input, kOutRing sub-chunks (<= 32 MB) of grey
+        constexpr uint32_t kHostRing = 6, kOutRing = 4;
+        const size_t kPiece = (size_t)1 << 20;  // bytes per copy task
+        const size_t in_slot_bytes = fe * frame_stride;
+        const size_t out_slot_frames = ((size_t)32 << 20) / px ? ((size_t)32 << 20) / px : 1, out_slot_bytes = out_slot_frames * px;
+        if (stage_in) A3_CUDA(d->h_stage_in.reserve((nfe < kHostRing ? nfe : kHostRing) * in_slot_bytes));
+        if (stage_out) A3_CUDA(d->h_stage_out.reserve(kOutRing * out_slot_bytes));
+        auto stg = std::make_shared<StageState>();
+        if (stage_in) {
+            stg->in_left.reset(new std::atomic<uint32_t>[nfe]);
+            for (uint32_t j = 0; j < nfe; j++) stg->in_left[j].store(0);
+        }
+        uint32_t stage_submitted = 0;  // front-end chunks whose stage-in tasks are in the copy pool
         // K3's per-frame counters: separate buffers, or (one-shot route) sections of the arena that goes back in one copy
         uint32_t *ds_counts = d->d_k3counts.p, *ds_before = d->d_k3before.p, *ds_flags = d->d_k3flags.p, *ds_contours = d->d_k3contours.p;
         unsigned long long *ds_points = d->d_k3points.p;
@@ -772,7 +945,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                 p.bits = d->d_bits.p + (size_t)f0 * bits_words;
             }
             A3_CUDA(cudaEventRecord(ev_k1a[j], d->s_pixel));
-            A3_CUDA(k1_gray_threshold(p, tune, d->s_pixel, nullptr));
+            A3_CUDA(run_k1(d, p, tune, d->s_pixel));
             A3_CUDA(cudaEventRecord(ev_k1b[j], d->s_pixel));
             st.pixel_kernel_launches++;
             return A3_OK;
@@ -882,6 +1055,42 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             A3_CUDA(cudaStreamSynchronize(d->s_pixel));
             return A3_OK;
         };
+        // Detection.grey of frames [f0, f0 + cn): straight into page-locked memory, or through the pinned ring (the copy tasks
+        // wait for the sub-chunk's event and move it on to the caller's buffer)
+        auto grey_d2h = [&](uint32_t f0, uint32_t cn) -> a3_status {
+            if (!stage_out) {
+                A3_CUDA(cudaMemcpyAsync(outs->grey + (size_t)(s0 + f0) * px, d->d_grey.p + (size_t)f0 * px, (size_t)cn * px, cudaMemcpyDeviceToHost, d->s_pixel));
+                return A3_OK;
+            }
+            CopyPool *cp = &d->copy_pool;
+            for (uint32_t sub = 0; sub < cn; sub += (uint32_t)out_slot_frames) {
+                const uint32_t m = cn - sub < out_slot_frames ? cn - sub : (uint32_t)out_slot_frames;
+                const size_t q = stg->out.size(), bytes = (size_t)m * px;
+                if (q >= kOutRing) {  // the slot's previous tenant must have left for the caller's buffer
+                    StageState::Out *prev = &stg->out[q - kOutRing];
+                    cp->wait([prev] { return prev->left.load() == 0; });
+                }
+                uint8_t *slot = d->h_stage_out.p + (q % kOutRing) * out_slot_bytes;
+                A3_CUDA(cudaMemcpyAsync(slot, d->d_grey.p + (size_t)(f0 + sub) * px, bytes, cudaMemcpyDeviceToHost, d->s_pixel));
+                cudaEvent_t ev;
+                A3_CUDA(d->events.get(&ev));
+                A3_CUDA(cudaEventRecord(ev, d->s_pixel));
+                const uint32_t pieces = (uint32_t)((bytes + kPiece - 1) / kPiece);
+                stg->out.emplace_back();
+                StageState::Out *o = &stg->out.back();
+                o->ev = ev; o->left.store(pieces);
+                uint8_t *dst = outs->grey + (size_t)(s0 + f0 + sub) * px;
+                for (uint32_t k = 0; k < pieces; k++) {
+                    const size_t off = (size_t)k * kPiece, len = bytes - off < kPiece ? bytes - off : kPiece;
+                    cp->submit([stg, o, cp, dst, slot, off, len] {
+                        cudaEventSynchronize(o->ev);
+                        memcpy(dst + off, slot + off, len);
+                        if (o->left.fetch_sub(1) == 1) cp->notify();
+                    });
+                }
+            }
+            return A3_OK;
+        };
         auto bits_d2h = [&](uint32_t f0, uint32_t cn, uint32_t j) -> a3_status {
             if (gpu_contours) {
                 if (mem == A3_MEM_HOST || j == 0) {  // K3 over the frames K1 just produced (everything for resident input)
@@ -915,7 +1124,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
             }
             A3_CUDA(cudaEventRecord(ev_fe[j], d->s_pixel));
             if (want_grey)
-                A3_CUDA(cudaMemcpyAsync(outs->grey + (size_t)(s0 + f0) * px, d->d_grey.p + (size_t)f0 * px, (size_t)cn * px, cudaMemcpyDeviceToHost, d->s_pixel));
+                if (a3_status s = grey_d2h(f0, cn)) return s;
             if (want_mask)
                 A3_CUDA(cudaMemcpyAsync(outs->mask + (size_t)(s0 + f0) * px, d->d_mask.p + (size_t)f0 * px, (size_t)cn * px, cudaMemcpyDeviceToHost, d->s_pixel));
             return A3_OK;
@@ -924,12 +1133,53 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         // even though K3 synchronises the pixel stream once per chunk
         uint32_t copies_issued = 0, issued = 0;
         const uint32_t lookahead = gpu_contours ? 1 : kStaging;  // chunks whose compute is queued ahead of the one being consumed
+        // Pageable input: the copy threads move chunk c into pinned slot c % kHostRing; the slot is free once the H2D of chunk
+        // c - kHostRing has completed.  Chunks are handed to the threads as early as that allows (without blocking), and the
+        // caller only ever blocks for the chunk it is about to send (`must`).
+        auto advance_stage_in = [&](uint32_t must) -> a3_status {
+            CopyPool *cp = &d->copy_pool;
+            while (stage_submitted < nfe) {
+                const uint32_t c = stage_submitted;
+                if (c >= kHostRing) {
+                    const uint32_t prev = c - kHostRing;
+                    if (prev >= copies_issued) break;  // its H2D is not even queued yet
+                    if (c <= must) {
+                        A3_CUDA(cudaEventSynchronize(ev_h2db[prev]));
+                    } else if (cudaEventQuery(ev_h2db[prev]) != cudaSuccess) {
+                        cudaGetLastError();  // cudaErrorNotReady is not an error
+                        break;
+                    }
+                }
+                const uint32_t f0 = c * (uint32_t)fe, cn = sn - f0 < fe ? sn - f0 : (uint32_t)fe;
+                const size_t bytes = (size_t)cn * frame_stride;
+                const uint32_t pieces = (uint32_t)((bytes + kPiece - 1) / kPiece);
+                const uint8_t *src = src_all + (size_t)(s0 + f0) * frame_stride;
+                uint8_t *dst = d->h_stage_in.p + (size_t)(c % kHostRing) * in_slot_bytes;
+                stg->in_left[c].store(pieces);
+                for (uint32_t k = 0; k < pieces; k++) {
+                    const size_t off = (size_t)k * kPiece, len = bytes - off < kPiece ? bytes - off : kPiece;
+                    cp->submit([stg, cp, c, dst, src, off, len] {
+                        memcpy(dst + off, src + off, len);
+                        if (stg->in_left[c].fetch_sub(1) == 1) cp->notify();
+                    });
+                }
+                stage_submitted++;
+            }
+            return A3_OK;
+        };
         auto issue_copy = [&](uint32_t j) -> a3_status {
             const uint32_t f0 = j * (uint32_t)fe, cn = sn - f0 < fe ? sn - f0 : (uint32_t)fe;
             uint8_t *slot = d->d_src.p + (size_t)(j % kStaging) * fe * frame_stride;
+            const uint8_t *from = src_all + (size_t)(s0 + f0) * frame_stride;
+            if (stage_in) {
+                if (a3_status s = advance_stage_in(j)) return s;
+                StageState *sp = stg.get();
+                d->copy_pool.wait([sp, j] { return sp->in_left[j].load() == 0; });
+                from = d->h_stage_in.p + (size_t)(j % kHostRing) * in_slot_bytes;
+            }
             if (j >= kStaging) A3_CUDA(cudaStreamWaitEvent(d->s_copy, ev_k1b[j - kStaging], 0));  // the slot's previous K1 is done
             A3_CUDA(cudaEventRecord(ev_h2da[j], d->s_copy));
-            A3_CUDA(cudaMemcpyAsync(slot, src_all + (size_t)(s0 + f0) * frame_stride, (size_t)cn * frame_stride, cudaMemcpyHostToDevice, d->s_copy));
+            A3_CUDA(cudaMemcpyAsync(slot, from, (size_t)cn * frame_stride, cudaMemcpyHostToDevice, d->s_copy));
             A3_CUDA(cudaEventRecord(ev_h2db[j], d->s_copy));
             return A3_OK;
         };
@@ -1069,6 +1319,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                 d->pool.finish();
             }
             cudaStreamSynchronize(d->s_copy); cudaStreamSynchronize(d->s_pixel); cudaStreamSynchronize(d->s_decode);
+            if (stage_in || stage_out) d->copy_pool.drain();
             return s;
         };
 
@@ -1107,6 +1358,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
         // ---- gather: stage timings, then markers in frame / candidate order (src/aruco.rs:75-113) ----
         A3_CUDA(cudaStreamSynchronize(d->s_decode));
         A3_CUDA(cudaStreamSynchronize(d->s_pixel));
+        if (stage_in || stage_out) d->copy_pool.drain();  // the last grey sub-chunks reach the caller's buffer
         if (trace) t_synced = now_ms();
         float ms = 0;
         for (uint32_t j = 0; j < nfe && stats; j++) {  // stage times only when the caller asked for statistics (about 2 us per query)

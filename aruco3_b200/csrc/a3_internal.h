@@ -13,9 +13,17 @@
 namespace a3 {
 
 // ---- pixel formats (a3_format) ----------------------------------------------------------------------------
-__host__ __device__ constexpr int fmt_bpp(int f) { return (f == A3_FMT_RGB8 || f == A3_FMT_BGR8) ? 3 : ((f == A3_FMT_RGBA8 || f == A3_FMT_BGRA8) ? 4 : 1); }
+__host__ __device__ constexpr int fmt_bpp(int f) {
+    return (f == A3_FMT_RGB8 || f == A3_FMT_BGR8) ? 3
+           : (f == A3_FMT_RGBA8 || f == A3_FMT_BGRA8 || f == A3_FMT_LUMAA16) ? 4
+           : (f == A3_FMT_LUMAA8 || f == A3_FMT_LUMA16) ? 2
+           : f == A3_FMT_RGB16 ? 6
+           : f == A3_FMT_RGBA16 ? 8 : 1;
+}
 __host__ __device__ constexpr bool fmt_bgr(int f) { return f == A3_FMT_BGR8 || f == A3_FMT_BGRA8; }  // byte 0 is blue
-__host__ __device__ constexpr bool fmt_valid(int f) { return f >= 0 && f <= A3_FMT_BGRA8; }
+__host__ __device__ constexpr bool fmt_valid(int f) { return f >= 0 && f <= A3_FMT_RGBA16; }
+// LumaA8 and the 16-bit variants: brought to Luma8 by k0_to_luma8 first, K1 then takes the Luma8 pass-through
+__host__ __device__ constexpr bool fmt_wide(int f) { return f >= A3_FMT_LUMAA8 && f <= A3_FMT_RGBA16; }
 
 // ---- error plumbing -------------------------------------------------------------------------
 void set_error(const std::string &msg);
@@ -53,6 +61,9 @@ struct K1LaunchInfo {
     int tma, specialised_radius;
 };
 cudaError_t k1_gray_threshold(const K1Params &p, const K1Tuning *tuning, cudaStream_t stream, K1LaunchInfo *info);
+// K0: image 0.25's into_luma8 for LumaA8 / Luma16 / LumaA16 / Rgb16 / Rgba16 frames -> Luma8 frames (dst_pitch bytes per row)
+cudaError_t k0_to_luma8(const uint8_t *src, int format, uint32_t n, uint32_t w, uint32_t h, size_t pitch, size_t frame_stride, uint8_t *dst,
+                        size_t dst_pitch, size_t dst_frame_stride, cudaStream_t stream);
 // warp-strip fast path (k1_strips.cu): radius 7, 16-byte aligned rows, width % 4 == 0
 bool k1_strips_eligible(const K1Params &p);
 cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t stream, K1LaunchInfo *info);

@@ -320,11 +320,51 @@ cudaError_t dispatch(const K1Args &a, bool r7, bool tma, dim3 grid, dim3 block, 
 
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
+// K0 — into_luma8 of the DynamicImage variants K1 does not read directly (semantics [RECALLED] from image
+// 0.25: `FromColor<LumaA<S>> for Luma<T>` keeps the luma channel, `FromColor<Rgb<S>> for Luma<T>` is
+// T::from_primitive(rgb_to_luma(rgb)) with rgb_to_luma in the subpixel's `Larger` type — u32 for u16 — and
+// `FromPrimitive<u16> for u8` is (c + 128) / 257).  One thread per pixel; a streaming pass, nothing to tile.
+template <int FMT>
+__global__ void __launch_bounds__(256) k0_kernel(const uint8_t *src, uint32_t w, uint32_t h, size_t pitch, size_t frame_stride, uint8_t *dst,
+                                                 size_t dst_pitch, size_t dst_frame_stride) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= w) return;
+    const uint8_t *p = src + (size_t)f * frame_stride + (size_t)y * pitch + (size_t)x * fmt_bpp(FMT);
+    uint32_t g;
+    if constexpr (FMT == A3_FMT_LUMAA8) {
+        g = p[0];
+    } else {
+        auto u16at = [&](int i) { return (uint32_t)p[2 * i] | ((uint32_t)p[2 * i + 1] << 8); };  // native (little-endian) u16, any alignment
+        uint32_t l;
+        if constexpr (FMT == A3_FMT_LUMA16 || FMT == A3_FMT_LUMAA16) l = u16at(0);
+        else l = (2126u * u16at(0) + 7152u * u16at(1) + 722u * u16at(2)) / 10000u;
+        g = (l + 128u) / 257u;
+    }
+    dst[(size_t)f * dst_frame_stride + (size_t)y * dst_pitch + x] = (uint8_t)g;
+}
+
 }  // namespace
+
+cudaError_t k0_to_luma8(const uint8_t *src, int format, uint32_t n, uint32_t w, uint32_t h, size_t pitch, size_t frame_stride, uint8_t *dst,
+                        size_t dst_pitch, size_t dst_frame_stride, cudaStream_t stream) {
+    if (n == 0 || w == 0 || h == 0) return cudaSuccess;
+    if (h > 65535 || n > 65535) return cudaErrorInvalidConfiguration;
+    const dim3 grid((w + 255) / 256, h, n), block(256);
+    switch (format) {
+        case A3_FMT_LUMAA8: k0_kernel<A3_FMT_LUMAA8><<<grid, block, 0, stream>>>(src, w, h, pitch, frame_stride, dst, dst_pitch, dst_frame_stride); break;
+        case A3_FMT_LUMA16: k0_kernel<A3_FMT_LUMA16><<<grid, block, 0, stream>>>(src, w, h, pitch, frame_stride, dst, dst_pitch, dst_frame_stride); break;
+        case A3_FMT_LUMAA16: k0_kernel<A3_FMT_LUMAA16><<<grid, block, 0, stream>>>(src, w, h, pitch, frame_stride, dst, dst_pitch, dst_frame_stride); break;
+        case A3_FMT_RGB16: k0_kernel<A3_FMT_RGB16><<<grid, block, 0, stream>>>(src, w, h, pitch, frame_stride, dst, dst_pitch, dst_frame_stride); break;
+        case A3_FMT_RGBA16: k0_kernel<A3_FMT_RGBA16><<<grid, block, 0, stream>>>(src, w, h, pitch, frame_stride, dst, dst_pitch, dst_frame_stride); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t k1_gray_threshold(const K1Params &p, const K1Tuning *tuning, cudaStream_t stream, K1LaunchInfo *info) {
     if (p.n == 0 || p.w == 0 || p.h == 0) return cudaSuccess;
     if (p.radius == 0 || p.radius > (uint32_t)kMaxRadius) return cudaErrorInvalidValue;
+    if (fmt_wide(p.format)) return cudaErrorInvalidValue;  // callers convert those with k0_to_luma8 first
     if (!(tuning && tuning->force_generic) && k1_strips_eligible(p)) return k1_strips(p, tuning, stream, info);
     const uint32_t r = p.radius;
     const uint32_t bpp = fmt_bpp(p.format);

@@ -119,17 +119,22 @@ def _frames_view(frames: np.ndarray, order: str = "rgb"):
     """-> (contiguous uint8 array, format, n, h, w, pitch, frame_stride) for [n,H,W,3|4] or [n,H,W]; `order` "bgr" =
     camera byte order B,G,R[,A] (A3_FMT_BGR8 / A3_FMT_BGRA8)."""
     a = np.asarray(frames)
-    if a.dtype != np.uint8:
-        raise A3Error(_ffi.A3_ERR_UNSUPPORTED, "only 8-bit images are supported (Rgb8 / Rgba8 / Luma8)")
-    if a.ndim == 3:
+    if a.dtype == np.uint16 and order == "rgb" and (a.ndim == 3 or (a.ndim == 4 and a.shape[3] in (2, 3, 4))):
+        # Luma16 [n,H,W], LumaA16 [n,H,W,2], Rgb16 [n,H,W,3], Rgba16 [n,H,W,4]: native-endian u16 subpixels
+        fmt = _ffi.FMT_LUMA16 if a.ndim == 3 else {2: _ffi.FMT_LUMAA16, 3: _ffi.FMT_RGB16, 4: _ffi.FMT_RGBA16}[a.shape[3]]
+    elif a.dtype != np.uint8:
+        raise A3Error(_ffi.A3_ERR_UNSUPPORTED, "only 8- and 16-bit integer images are supported (convert float images with into_luma8 on the host)")
+    elif a.ndim == 3:
         fmt = _ffi.FMT_LUMA8
+    elif a.ndim == 4 and a.shape[3] == 2 and order == "rgb":
+        fmt = _ffi.FMT_LUMAA8
     elif a.ndim == 4 and (order, a.shape[3]) in _FMT:
         fmt = _FMT[(order, a.shape[3])]
     else:
         raise A3Error(_ffi.A3_ERR_INVALID_ARGUMENT, f"bad frame array shape {a.shape}")
     a = np.ascontiguousarray(a)
     n, h, w = a.shape[:3]
-    pitch = w * (a.shape[3] if a.ndim == 4 else 1)  # not a.strides: a size-1 axis of a C-contiguous view may report any stride
+    pitch = w * (a.shape[3] if a.ndim == 4 else 1) * a.itemsize  # not a.strides: a size-1 axis of a C-contiguous view may report any stride
     return a, fmt, n, h, w, pitch, pitch * h
 
 

@@ -15,8 +15,8 @@
  *     epsilon <= 0 inside imageproc).
  *   - there is NO CPU fallback: the pixel and decode stages run on the CUDA device or fail with
  *     A3_ERR_CUDA.
- *   - frames are tightly interleaved 8-bit pixels, row-major (`image::RgbImage` / `RgbaImage` /
- *     `GrayImage` buffers); `pitch` = bytes per row, `frame_stride` = bytes between frames.
+ *   - frames are interleaved pixels, row-major (`image::RgbImage` / `RgbaImage` / `GrayImage` buffers and
+ *     their 16-bit / LumaA siblings); `pitch` = bytes per row, `frame_stride` = bytes between frames.
  *   - a detector handle is thread-compatible, not thread-safe: one per (host thread, device).
  */
 #ifndef ARUCO3_B200_H
@@ -50,7 +50,16 @@ typedef enum {
      * pixel for pixel the host swizzle into an RgbImage / RgbaImage that examples/webcam_kamera.rs:38-52 does before
      * detect.  `Detection.grey` etc. are those of the swizzled image. */
     A3_FMT_BGR8 = 3,
-    A3_FMT_BGRA8 = 4
+    A3_FMT_BGRA8 = 4,
+    /* the other integer DynamicImage variants, converted on the device the way image 0.25's into_luma8
+     * converts them (src/aruco.rs:60): LumaA drops alpha; 16-bit subpixels (native-endian u16, as in the crate's Vec<u16>)
+     * go luma16 = (2126 R + 7152 G + 722 B) / 10000 in u32, then u8 = (luma16 + 128) / 257 (`FromPrimitive<u16> for u8`).
+     * [RECALLED from the crate, not pinned by anything in the reference.]  Float variants: convert on the host. */
+    A3_FMT_LUMAA8 = 5,
+    A3_FMT_LUMA16 = 6,
+    A3_FMT_LUMAA16 = 7,
+    A3_FMT_RGB16 = 8,
+    A3_FMT_RGBA16 = 9
 } a3_format;
 typedef enum { A3_MEM_HOST = 0, A3_MEM_DEVICE = 1 } a3_mem_kind;
 
@@ -113,6 +122,9 @@ typedef struct a3_stats {
      * synchronisation, sized from the previous call of the same geometry.  one_shot = 1 when this call's results came
      * from it; one_shot_retry = 1 when its sizes did not hold and the ordinary route finished the call instead. */
     uint32_t one_shot, one_shot_retry;
+    /* pageable memory at the boundary: 1 when this call's host frames (input) / Detection.grey (output) were not page-locked and
+     * went through the library's pinned staging rings (copy threads), 0 when the DMA used the caller's memory directly */
+    uint32_t input_staged, output_staged;
 } a3_stats;
 
 /* MarkerPose (src/pose.rs:8-12): scene-from-marker transform in OpenCV chirality (+Z forward, +Y down, +X right).
@@ -175,6 +187,19 @@ uint8_t a3_make_binary_image(const a3_dictionary *d, uint64_t marker_id, uint8_t
 void a3_config_default(a3_config *cfg);                                            /* Default, src/aruco.rs:32-43   */
 a3_status a3_detector_create(const a3_config *cfg, const a3_dictionary *dict, int32_t device, a3_detector **out);
 void a3_detector_destroy(a3_detector *det);
+/* Handle cache for bindings whose `Detector` is plain data built with a struct literal, as in the reference
+ * (src/aruco.rs:46-49, benches/detect_markers.rs:17-20, README.md:14-17), and so cannot own a handle: bracket each
+ * detect with acquire / release.  acquire returns an idle cached handle created with exactly this config, dictionary
+ * (same `codes` pointer, sizes and tau) and device — warm: streams, device / pinned buffers and the one-shot history
+ * survive — and creates one only when none is idle; release puts it back (pose / contour mode / tuning reset to the
+ * defaults) and never blocks on the GPU.  A handle is held by one caller at a time; the cache itself is thread-safe and
+ * keeps at most 16 idle handles (oldest destroyed).  a3_detector_cache_clear destroys the idle ones (call before unloading).
+ * a3_detector_create_count: successful a3_detector_create calls of this process so far (diagnostic: a per-frame loop over
+ * one Detector must not make it grow). */
+a3_status a3_detector_acquire(const a3_config *cfg, const a3_dictionary *dict, int32_t device, a3_detector **out);
+void a3_detector_release(a3_detector *det);
+void a3_detector_cache_clear(void);
+uint64_t a3_detector_create_count(void);
 /* number of host threads used for the contour / quad stage (default: all cores, capped at 64) */
 a3_status a3_detector_set_host_threads(a3_detector *det, uint32_t threads);
 

@@ -114,6 +114,80 @@ struct Detection {
 
 enum class PixelFormat { Rgb8 = A3_FMT_RGB8, Rgba8 = A3_FMT_RGBA8, Luma8 = A3_FMT_LUMA8, Bgr8 = A3_FMT_BGR8, Bgra8 = A3_FMT_BGRA8 };
 
+inline a3_config to_c(const DetectorConfig &config) {
+    a3_config c;
+    c.threshold_window = config.threshold_window;
+    c.contour_simplification_epsilon = config.contour_simplification_epsilon;
+    c.min_side_length_factor = config.min_side_length_factor;
+    c.min_corner_separation_factor = config.min_corner_separation_factor;
+    c.homography_sample_size = (uint32_t)config.homography_sample_size;
+    c.filter_high_bit_errors = config.filter_high_bit_errors ? 1 : 0;
+    return c;
+}
+
+// a3_detect_batch on handle `h` (host frames) unpacked into Detections; `full` fills grey / candidates / homographies,
+// otherwise only markers.
+inline std::vector<Detection> detect_batch_on(a3_detector *h_, const DetectorConfig &config, const uint8_t *frames, uint32_t n, uint32_t width,
+                                              uint32_t height, PixelFormat fmt, bool full, a3_stats *stats) {
+    const uint32_t bpp = (fmt == PixelFormat::Rgb8 || fmt == PixelFormat::Bgr8) ? 3 : (fmt == PixelFormat::Luma8 ? 1 : 4);
+    const size_t pitch = (size_t)width * bpp, stride = pitch * height, px = (size_t)width * height;
+    const size_t hs = config.homography_sample_size, np = hs * hs;
+    std::vector<Detection> out(n);
+    uint32_t cap_m = 64 * n + 1024, cap_c = 128 * n + 2048;
+    for (;;) {
+        std::vector<a3_marker> markers(cap_m);
+        std::vector<uint8_t> grey, patches;
+        std::vector<uint32_t> cands, cframe, offsets(n + 1);
+        std::vector<a3_decode> decs;
+        a3_outputs o{};
+        o.frame_marker_offsets = offsets.data();
+        if (full) {
+            grey.resize(n * px); cands.resize((size_t)cap_c * 8); cframe.resize(cap_c); patches.resize((size_t)cap_c * np); decs.resize(cap_c);
+            o.grey = grey.data(); o.candidates = cands.data(); o.candidate_frame = cframe.data();
+            o.homographies = patches.data(); o.decodes = decs.data(); o.cand_capacity = cap_c;
+        }
+        uint32_t nm = 0;
+        const a3_status s = a3_detect_batch(h_, frames, (a3_format)fmt, A3_MEM_HOST, n, width, height, pitch, stride, markers.data(),
+                                            cap_m, &nm, &o, stats);
+        if (s == A3_ERR_CAPACITY) {  // counts are valid: size once more
+            cap_m = nm > cap_m ? nm : cap_m;
+            cap_c = o.n_candidates > cap_c ? o.n_candidates : cap_c;
+            continue;
+        }
+        check(s);
+        for (uint32_t i = 0; i < nm; i++) {
+            const a3_marker &m = markers[i];
+            Marker mk;
+            mk.id = (size_t)m.id; mk.code = m.code; mk.hamming_distance = m.hamming_distance;
+            for (int k = 0; k < 4; k++) mk.corners.emplace_back(m.corners[2 * k], m.corners[2 * k + 1]);
+            out[m.frame].markers.push_back(std::move(mk));
+        }
+        if (full) {
+            for (uint32_t f = 0; f < n; f++) {
+                out[f].grey.width = width; out[f].grey.height = height;
+                out[f].grey.data.assign(grey.begin() + f * px, grey.begin() + (f + 1) * px);
+            }
+            for (uint32_t k = 0; k < o.n_candidates; k++) {
+                Detection &d = out[cframe[k]];
+                std::vector<std::pair<uint32_t, uint32_t>> poly;
+                for (int j = 0; j < 4; j++) poly.emplace_back(cands[(size_t)k * 8 + 2 * j], cands[(size_t)k * 8 + 2 * j + 1]);
+                d.candidates.push_back(std::move(poly));
+                GrayImage g;
+                if (decs[k].homography_ok) {
+                    g.width = g.height = (uint32_t)hs;
+                    g.data.assign(patches.begin() + (size_t)k * np, patches.begin() + (size_t)(k + 1) * np);
+                } else {
+                    g.width = g.height = 1;
+                    g.data.assign(1, 0);
+                }
+                d.homographies.push_back(std::move(g));
+            }
+        }
+        return out;
+    }
+}
+
+
 // `Detector { config, dictionary }` (src/aruco.rs:46-49) bound to one CUDA device.  Thread-compatible: one per
 // (host thread, device).  Public fields are read at construction; call rebuild() after changing them.
 class Detector {
@@ -129,13 +203,7 @@ public:
     void rebuild() {
         a3_detector_destroy(h_);
         h_ = nullptr;
-        a3_config c;
-        c.threshold_window = config.threshold_window;
-        c.contour_simplification_epsilon = config.contour_simplification_epsilon;
-        c.min_side_length_factor = config.min_side_length_factor;
-        c.min_corner_separation_factor = config.min_corner_separation_factor;
-        c.homography_sample_size = (uint32_t)config.homography_sample_size;
-        c.filter_high_bit_errors = config.filter_high_bit_errors ? 1 : 0;
+        const a3_config c = to_c(config);
         check(a3_detector_create(&c, &dictionary.c(), device_, &h_));
     }
 
@@ -148,62 +216,7 @@ public:
     // The same over n equally sized frames; `full` fills grey / candidates / homographies, otherwise only markers.
     std::vector<Detection> detect_batch(const uint8_t *frames, uint32_t n, uint32_t width, uint32_t height,
                                         PixelFormat fmt = PixelFormat::Rgb8, bool full = false, a3_stats *stats = nullptr) const {
-        const uint32_t bpp = (fmt == PixelFormat::Rgb8 || fmt == PixelFormat::Bgr8) ? 3 : (fmt == PixelFormat::Luma8 ? 1 : 4);
-        const size_t pitch = (size_t)width * bpp, stride = pitch * height, px = (size_t)width * height;
-        const size_t hs = config.homography_sample_size, np = hs * hs;
-        std::vector<Detection> out(n);
-        uint32_t cap_m = 64 * n + 1024, cap_c = 128 * n + 2048;
-        for (;;) {
-            std::vector<a3_marker> markers(cap_m);
-            std::vector<uint8_t> grey, patches;
-            std::vector<uint32_t> cands, cframe, offsets(n + 1);
-            std::vector<a3_decode> decs;
-            a3_outputs o{};
-            o.frame_marker_offsets = offsets.data();
-            if (full) {
-                grey.resize(n * px); cands.resize((size_t)cap_c * 8); cframe.resize(cap_c); patches.resize((size_t)cap_c * np); decs.resize(cap_c);
-                o.grey = grey.data(); o.candidates = cands.data(); o.candidate_frame = cframe.data();
-                o.homographies = patches.data(); o.decodes = decs.data(); o.cand_capacity = cap_c;
-            }
-            uint32_t nm = 0;
-            const a3_status s = a3_detect_batch(h_, frames, (a3_format)fmt, A3_MEM_HOST, n, width, height, pitch, stride, markers.data(),
-                                                cap_m, &nm, &o, stats);
-            if (s == A3_ERR_CAPACITY) {  // counts are valid: size once more
-                cap_m = nm > cap_m ? nm : cap_m;
-                cap_c = o.n_candidates > cap_c ? o.n_candidates : cap_c;
-                continue;
-            }
-            check(s);
-            for (uint32_t i = 0; i < nm; i++) {
-                const a3_marker &m = markers[i];
-                Marker mk;
-                mk.id = (size_t)m.id; mk.code = m.code; mk.hamming_distance = m.hamming_distance;
-                for (int k = 0; k < 4; k++) mk.corners.emplace_back(m.corners[2 * k], m.corners[2 * k + 1]);
-                out[m.frame].markers.push_back(std::move(mk));
-            }
-            if (full) {
-                for (uint32_t f = 0; f < n; f++) {
-                    out[f].grey.width = width; out[f].grey.height = height;
-                    out[f].grey.data.assign(grey.begin() + f * px, grey.begin() + (f + 1) * px);
-                }
-                for (uint32_t k = 0; k < o.n_candidates; k++) {
-                    Detection &d = out[cframe[k]];
-                    std::vector<std::pair<uint32_t, uint32_t>> poly;
-                    for (int j = 0; j < 4; j++) poly.emplace_back(cands[(size_t)k * 8 + 2 * j], cands[(size_t)k * 8 + 2 * j + 1]);
-                    d.candidates.push_back(std::move(poly));
-                    GrayImage g;
-                    if (decs[k].homography_ok) {
-                        g.width = g.height = (uint32_t)hs;
-                        g.data.assign(patches.begin() + (size_t)k * np, patches.begin() + (size_t)(k + 1) * np);
-                    } else {
-                        g.width = g.height = 1;
-                        g.data.assign(1, 0);
-                    }
-                    d.homographies.push_back(std::move(g));
-                }
-            }
-            return out;
-        }
+        return detect_batch_on(h_, config, frames, n, width, height, fmt, full, stats);
     }
 
     a3_detector *handle() const { return h_; }
@@ -211,6 +224,32 @@ public:
 private:
     int device_ = 0;
     a3_detector *h_ = nullptr;
+};
+
+// The reference's own shape: `Detector { config, dictionary }` is plain data built with a literal (src/aruco.rs:46-49,
+// benches/detect_markers.rs:17-20) and `detect` takes `&self`, so there is nowhere to keep a handle.  Every call leases
+// one from the library's cache (a3_detector_acquire / a3_detector_release): the first call creates it, later calls —
+// from any PlainDetector with the same config, dictionary and device — get it back warm.  This is what the Rust wrapper
+// in rust/aruco3-b200 does.
+struct PlainDetector {
+    DetectorConfig config;
+    ARDictionary dictionary;
+    int device = 0;
+
+    Detection detect(const uint8_t *pixels, uint32_t width, uint32_t height, PixelFormat fmt = PixelFormat::Rgb8) const {
+        std::vector<Detection> v = detect_batch(pixels, 1, width, height, fmt, /*full=*/true);
+        return std::move(v[0]);
+    }
+    std::vector<Detection> detect_batch(const uint8_t *frames, uint32_t n, uint32_t width, uint32_t height,
+                                        PixelFormat fmt = PixelFormat::Rgb8, bool full = false, a3_stats *stats = nullptr) const {
+        struct Lease {
+            a3_detector *h = nullptr;
+            ~Lease() { a3_detector_release(h); }
+        } lease;
+        const a3_config c = to_c(config);
+        check(a3_detector_acquire(&c, &dictionary.c(), device, &lease.h));
+        return detect_batch_on(lease.h, config, frames, n, width, height, fmt, full, stats);
+    }
 };
 
 // Frame-batch sharding over several GPUs: frames are independent, so a batch is cut into contiguous blocks,

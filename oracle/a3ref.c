@@ -142,6 +142,24 @@ void a3ref_to_luma8(const uint8_t *src, int format, uint32_t w, uint32_t h, size
             memcpy(o, row, w);
             continue;
         }
+        if (format >= A3REF_FMT_LUMAA8) {
+            /* [RECALLED, image 0.25 color.rs / traits.rs; nothing in the reference pins it] `to_luma8` = ImageBuffer::convert:
+             *   Luma<u8> from LumaA<u8>: the luma channel, alpha dropped;
+             *   Luma<u8> from Luma<u16> / LumaA<u16>: u8::from_primitive(l) = ((l as u32 + 128) / 257) as u8;
+             *   Luma<u8> from Rgb<u16> / Rgba<u16>: u8::from_primitive(rgb_to_luma(rgb)), rgb_to_luma in u32 (u16's Larger):
+             *     (2126 R + 7152 G + 722 B) / 10000, alpha ignored. */
+            const uint32_t ch = format == A3REF_FMT_LUMAA8 ? 2 : format == A3REF_FMT_LUMA16 ? 1 : format == A3REF_FMT_LUMAA16 ? 2
+                                : format == A3REF_FMT_RGB16 ? 3 : 4;
+            for (uint32_t x = 0; x < w; x++) {
+                if (format == A3REF_FMT_LUMAA8) { o[x] = row[x * 2]; continue; }
+                uint16_t s[4] = {0, 0, 0, 0};
+                memcpy(s, row + (size_t)x * ch * 2, (size_t)ch * 2);
+                uint32_t l = (format == A3REF_FMT_LUMA16 || format == A3REF_FMT_LUMAA16)
+                                 ? s[0] : (2126u * s[0] + 7152u * s[1] + 722u * s[2]) / 10000u;
+                o[x] = (uint8_t)((l + 128u) / 257u);
+            }
+            continue;
+        }
         uint32_t bpp = (format == A3REF_FMT_RGBA8 || format == A3REF_FMT_BGRA8) ? 4 : 3;
         int bgr = format == A3REF_FMT_BGR8 || format == A3REF_FMT_BGRA8; /* examples/webcam_kamera.rs:38-52: r = buffer[idx+2], b = buffer[idx+0] */
         for (uint32_t x = 0; x < w; x++) {

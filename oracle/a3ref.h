@@ -29,7 +29,9 @@ extern "C" {
 #endif
 
 /* BGR8 / BGRA8: the host swizzle of examples/webcam_kamera.rs:38-52 followed by into_luma8 */
-enum { A3REF_FMT_RGB8 = 0, A3REF_FMT_RGBA8 = 1, A3REF_FMT_LUMA8 = 2, A3REF_FMT_BGR8 = 3, A3REF_FMT_BGRA8 = 4 };
+enum { A3REF_FMT_RGB8 = 0, A3REF_FMT_RGBA8 = 1, A3REF_FMT_LUMA8 = 2, A3REF_FMT_BGR8 = 3, A3REF_FMT_BGRA8 = 4,
+       /* the other integer DynamicImage variants; 16-bit subpixels are native-endian u16 */
+       A3REF_FMT_LUMAA8 = 5, A3REF_FMT_LUMA16 = 6, A3REF_FMT_LUMAA16 = 7, A3REF_FMT_RGB16 = 8, A3REF_FMT_RGBA16 = 9 };
 
 /* src/aruco.rs:23-30 (DetectorConfig), same field order. */
 typedef struct a3ref_config {

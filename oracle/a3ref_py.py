@@ -12,6 +12,7 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 FMT_RGB8, FMT_RGBA8, FMT_LUMA8, FMT_BGR8, FMT_BGRA8 = 0, 1, 2, 3, 4
+FMT_LUMAA8, FMT_LUMA16, FMT_LUMAA16, FMT_RGB16, FMT_RGBA16 = 5, 6, 7, 8, 9
 
 
 class Config(C.Structure):
@@ -141,6 +142,10 @@ def try_find_nearest(d: Dictionary, bits: int):
 
 
 def _fmt_of(img: np.ndarray, order: str = "rgb") -> int:
+    if img.dtype == np.uint16:  # Luma16 [H,W], LumaA16 [H,W,2], Rgb16 [H,W,3], Rgba16 [H,W,4]
+        return FMT_LUMA16 if img.ndim == 2 else {2: FMT_LUMAA16, 3: FMT_RGB16, 4: FMT_RGBA16}[img.shape[2]]
+    if img.ndim == 3 and img.shape[2] == 2:
+        return FMT_LUMAA8
     if img.ndim == 2:
         return FMT_LUMA8
     return {("rgb", 3): FMT_RGB8, ("rgb", 4): FMT_RGBA8, ("bgr", 3): FMT_BGR8, ("bgr", 4): FMT_BGRA8}[(order, img.shape[2])]

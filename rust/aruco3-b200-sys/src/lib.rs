@@ -16,6 +16,11 @@ pub const A3_FMT_RGBA8: i32 = 1;
 pub const A3_FMT_LUMA8: i32 = 2;
 pub const A3_FMT_BGR8: i32 = 3; // camera byte order: what examples/webcam_kamera.rs:38-52 swizzles on the host
 pub const A3_FMT_BGRA8: i32 = 4;
+pub const A3_FMT_LUMAA8: i32 = 5; // the other integer DynamicImage variants: into_luma8 runs on the device (kernel K0)
+pub const A3_FMT_LUMA16: i32 = 6;
+pub const A3_FMT_LUMAA16: i32 = 7;
+pub const A3_FMT_RGB16: i32 = 8;
+pub const A3_FMT_RGBA16: i32 = 9;
 pub const A3_MEM_HOST: i32 = 0;
 pub const A3_MEM_DEVICE: i32 = 1;
 
@@ -94,6 +99,8 @@ pub struct a3_stats {
     pub pose_kernel_launches: u32,
     pub one_shot: u32,
     pub one_shot_retry: u32,
+    pub input_staged: u32,
+    pub output_staged: u32,
 }
 
 /// MarkerPose, reference `src/pose.rs:8-12`; rotation row-major
@@ -159,6 +166,11 @@ extern "C" {
     pub fn a3_config_default(cfg: *mut a3_config);
     pub fn a3_detector_create(cfg: *const a3_config, dict: *const a3_dictionary, device: i32, out: *mut *mut a3_detector) -> a3_status;
     pub fn a3_detector_destroy(det: *mut a3_detector);
+    // handle cache for plain-data `Detector` literals (reference src/aruco.rs:46-49): bracket each call
+    pub fn a3_detector_acquire(cfg: *const a3_config, dict: *const a3_dictionary, device: i32, out: *mut *mut a3_detector) -> a3_status;
+    pub fn a3_detector_release(det: *mut a3_detector);
+    pub fn a3_detector_cache_clear();
+    pub fn a3_detector_create_count() -> u64;
     pub fn a3_detector_set_host_threads(det: *mut a3_detector, threads: u32) -> a3_status;
     pub fn a3_detector_set_contour_mode(det: *mut a3_detector, mode: u32) -> a3_status;
     pub fn a3_detect_batch(

@@ -161,3 +161,89 @@ int main() {
     for i in range(0, len(vals), 5):
         n, w, r, lo, hi = vals[i:i + 5]
         assert (lo, hi) == shard_range(n, r, w), (n, w, r)
+
+
+PLAIN = r'''
+#include <cstdio>
+#include <vector>
+#include "aruco3_b200.hpp"
+// The reference's usage pattern (benches/detect_markers.rs:17-25, examples/webcam_kamera.rs:14-17, 56): a Detector built
+// with a struct literal, `detect` once per frame.  100 frames through one PlainDetector, a second literal with the same
+// fields in between, pageable std::vector input: exactly one a3_detector_create, and from the second call on the one-shot
+// route (the handle that comes back from the cache is warm).
+int main(int argc, char **argv) {
+    const uint32_t w = 640, h = 480;
+    std::vector<uint8_t> rgb((size_t)w * h * 3);
+    FILE *f = fopen(argv[1], "rb");
+    if (!f || fread(rgb.data(), 1, rgb.size(), f) != rgb.size()) return 2;
+    fclose(f);
+    const unsigned long long before = a3_detector_create_count();
+    const aruco3::PlainDetector detector{aruco3::DetectorConfig(), aruco3::ARDictionary::new_from_named_dict("ARUCO")};
+    size_t markers0 = 0;
+    unsigned warm = 0;
+    for (int i = 0; i < 100; i++) {
+        a3_stats st{};
+        const aruco3::PlainDetector again{aruco3::DetectorConfig(), aruco3::ARDictionary::new_from_named_dict("aruco")};
+        const auto dets = (i % 10 == 9 ? again : detector).detect_batch(rgb.data(), 1, w, h, aruco3::PixelFormat::Rgb8, /*full=*/i % 2 == 0, &st);
+        if (i == 0) markers0 = dets[0].markers.size();
+        if (dets[0].markers.size() != markers0) return 3;
+        warm += st.one_shot;
+    }
+    aruco3::DetectorConfig other;
+    other.min_corner_separation_factor = 0.05f;  // a different config is a different handle
+    const aruco3::PlainDetector third{other, aruco3::ARDictionary::new_from_named_dict("ARUCO")};
+    third.detect(rgb.data(), w, h);
+    printf("created %llu warm %u markers %zu\n", a3_detector_create_count() - before, warm, markers0);
+    a3_detector_cache_clear();
+    return 0;
+}
+'''
+
+
+def test_plain_header_compiles_without_gpu(tmp_path):
+    src = tmp_path / "plain.cpp"
+    src.write_text(PLAIN)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-I", str(ROOT / "include"), "-c", str(src), "-o", str(tmp_path / "plain.o")], check=True)
+
+
+@pytest.mark.gpu
+def test_cpp_plain_detector_creates_one_handle_for_100_detects(oracle, tmp_path):
+    from aruco3_b200 import _ffi, synth
+    _ffi.lib()
+    img, _ = synth.render_frame(synth.CONFIGS["C1"], 3)
+    (tmp_path / "frame.rgb").write_bytes(img.tobytes())
+    src, exe = tmp_path / "plain.cpp", tmp_path / "plain"
+    src.write_text(PLAIN)
+    lib_dir = ROOT / "aruco3_b200"
+    subprocess.run(["g++", "-std=c++17", "-I", str(ROOT / "include"), str(src), "-o", str(exe), f"-L{lib_dir}", "-laruco3_b200",
+                    f"-Wl,-rpath,{lib_dir}"], check=True)
+    out = subprocess.run([str(exe), str(tmp_path / "frame.rgb")], check=True, capture_output=True, text=True).stdout.split()
+    ref = oracle.detect(img, "ARUCO")
+    assert out == ["created", "2", "warm", "99", "markers", str(len(ref.markers))], out
+
+
+@pytest.mark.gpu
+def test_handle_cache_through_ctypes():
+    """a3_detector_acquire / a3_detector_release: same key -> same handle back, different key or a handle still leased -> a new one."""
+    import ctypes as C
+    from aruco3_b200 import _ffi
+    L = _ffi.lib()
+    L.a3_detector_cache_clear()
+    cfg, d = _ffi.A3Config(), _ffi.A3Dictionary()
+    L.a3_config_default(C.byref(cfg))
+    _ffi.check(L.a3_dictionary_by_name(b"ARUCO", C.byref(d)))
+    n0 = L.a3_detector_create_count()
+    h1, h2, h3 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _ffi.check(L.a3_detector_acquire(C.byref(cfg), C.byref(d), 0, C.byref(h1)))
+    _ffi.check(L.a3_detector_acquire(C.byref(cfg), C.byref(d), 0, C.byref(h2)))  # h1 is leased: a second handle
+    assert h1.value != h2.value and L.a3_detector_create_count() == n0 + 2
+    L.a3_detector_release(h1)
+    _ffi.check(L.a3_detector_acquire(C.byref(cfg), C.byref(d), 0, C.byref(h3)))
+    assert h3.value == h1.value and L.a3_detector_create_count() == n0 + 2
+    cfg.threshold_window = 5
+    h4 = C.c_void_p()
+    _ffi.check(L.a3_detector_acquire(C.byref(cfg), C.byref(d), 0, C.byref(h4)))
+    assert h4.value not in (h1.value, h2.value) and L.a3_detector_create_count() == n0 + 3
+    for h in (h2, h3, h4):
+        L.a3_detector_release(h)
+    L.a3_detector_cache_clear()

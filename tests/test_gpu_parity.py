@@ -363,6 +363,45 @@ def test_detect_other_pixel_formats(a3, oracle, channels):
         _check_detection(got[f], oracle.detect(imgs[f], "ARUCO"), f"{channels}ch[{f}]")
 
 
+def _widen(rgb8, kind, seed):
+    """An Rgb8 batch as one of the other integer DynamicImage variants; 16-bit subpixels = v * 257 + noise in the low byte
+    region, so the 16 -> 8 bit rounding is exercised on both sides of every step."""
+    rng = np.random.default_rng(seed)
+    n, h, w, _ = rgb8.shape
+    wide = rgb8.astype(np.int32) * 257 + rng.integers(-128, 129, size=rgb8.shape)
+    rgb16 = np.clip(wide, 0, 65535).astype(np.uint16)
+    if kind == "rgb16":
+        return rgb16
+    if kind == "rgba16":
+        return np.concatenate([rgb16, rng.integers(0, 65536, size=(n, h, w, 1), dtype=np.uint16)], axis=3)
+    if kind == "luma16":
+        return np.ascontiguousarray(rgb16[..., 1])
+    if kind == "lumaa16":
+        return np.stack([rgb16[..., 1], rng.integers(0, 65536, size=(n, h, w), dtype=np.uint16)], axis=3)
+    if kind == "lumaa8":
+        return np.stack([rgb8[..., 1], rng.integers(0, 256, size=(n, h, w), dtype=np.uint8)], axis=3)
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind", ["lumaa8", "luma16", "lumaa16", "rgb16", "rgba16"])
+def test_detect_wide_pixel_formats(a3, oracle, kind):
+    """the other integer DynamicImage variants (kernel K0 = image 0.25's into_luma8 for them, recalled
+    semantics — upstream parity unpinned — then the usual path): grey, mask, candidates, patches and markers equal the
+    oracle's, for a 640x480 batch (warp-strip K1 behind K0) and an odd-sized one (generic K1 behind K0)."""
+    from aruco3_b200 import synth
+    rgb, _ = synth.render_batch("C1", 3)
+    for imgs in (_widen(rgb, kind, 11), _widen(np.ascontiguousarray(rgb[:2, :277, :401]), kind, 12)):
+        with a3.Detector() as d:
+            got = d.detect_batch(imgs, full=True, want_mask=True)
+            g, m = d.gray_threshold(imgs)
+        for f in range(len(imgs)):
+            ref = oracle.detect(imgs[f], "ARUCO")
+            _check_detection(got[f], ref, f"{kind}[{f}] {imgs.shape}")
+            assert np.array_equal(g[f], ref.grey) and np.array_equal(m[f], ref.mask)
+        if imgs.shape[2] == 640:
+            assert sum(len(x.markers) for x in got) >= 10
+
+
 def test_detect_4k_frame(a3, oracle):
     """BASELINE.json configs[3] frame size (3840 x 2160), one frame, every intermediate against the oracle."""
     from aruco3_b200 import synth

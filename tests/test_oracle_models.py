@@ -152,3 +152,31 @@ def test_ground_truth_on_clean_frames(oracle):
         found += sum((have & want).values())
         wanted += sum(want.values())
     assert found >= 0.85 * wanted
+
+
+def test_wide_formats_into_luma8_model(oracle):
+    """oracle/a3ref.c's into_luma8 for LumaA8 / Luma16 / LumaA16 / Rgb16 / Rgba16 against an independent numpy model of the
+    image-crate rules it restates (recalled, unpinned upstream), and the crate's own claim about its
+    u16 -> u8 rule: (c + 128) / 257 == round(c * 255 / 65535) for every c."""
+    c = np.arange(65536, dtype=np.int64)
+    assert np.array_equal((c + 128) // 257, np.floor(c * 255 / 65535 + 0.5).astype(np.int64))
+    rng = np.random.default_rng(3)
+    h, w = 37, 53
+    rgba16 = rng.integers(0, 65536, size=(h, w, 4), dtype=np.uint16)
+    rgba16[0, :8] = [[0, 0, 0, 0], [65535] * 4, [65535, 0, 0, 9], [0, 65535, 0, 9], [0, 0, 65535, 9], [127, 128, 129, 0], [385, 386, 384, 0], [32767, 32768, 32769, 1]]
+    x = rgba16.astype(np.uint64)
+    l16 = (2126 * x[..., 0] + 7152 * x[..., 1] + 722 * x[..., 2]) // 10000
+    want_rgb = ((l16 + 128) // 257).astype(np.uint8)
+    assert np.array_equal(oracle.to_luma8(rgba16), want_rgb)
+    assert np.array_equal(oracle.to_luma8(np.ascontiguousarray(rgba16[..., :3])), want_rgb)
+    want_l = ((x[..., 0] + 128) // 257).astype(np.uint8)
+    assert np.array_equal(oracle.to_luma8(np.ascontiguousarray(rgba16[..., 0])), want_l)
+    assert np.array_equal(oracle.to_luma8(np.ascontiguousarray(rgba16[..., :2])), want_l)
+    la8 = rng.integers(0, 256, size=(h, w, 2), dtype=np.uint8)
+    assert np.array_equal(oracle.to_luma8(la8), la8[..., 0])
+    # a detect() on a 16-bit image equals detect() on its Luma8 conversion
+    from aruco3_b200 import synth
+    rgb, _ = synth.render_frame(synth.CONFIGS["C1"], 1)
+    rgb16 = rgb.astype(np.uint16) * 257
+    a, b = oracle.detect(rgb16, "ARUCO"), oracle.detect(oracle.to_luma8(rgb16), "ARUCO")
+    assert np.array_equal(a.grey, b.grey) and a.markers == b.markers and len(a.markers) >= 3
