@@ -13,6 +13,7 @@
 // Device input runs K1 once over the whole (super-)batch; host input runs it per front-end chunk right behind the
 // copy, so the PCIe transfer, the host stage and the decode kernel all overlap.
 // There is no CPU fallback: without a CUDA device every compute entry point returns A3_ERR_CUDA.
+#include <immintrin.h>
 #include <math.h>
 #include <string.h>
 
@@ -191,6 +192,27 @@ private:
     uint32_t running_ = 0;
     bool quit_ = false;
 };
+
+// memcpy for the staging rings: the destination is written once and read next by the DMA engine (input ring) or by nobody
+// soon (the caller's grey buffer), so streaming stores keep it out of the caches and spare the read-for-ownership of every
+// destination line — a third of the DRAM traffic of a plain copy, and the copy threads share the memory bus with the DMA.
+__attribute__((target("avx2"))) void copy_stream_avx2(uint8_t *dst, const uint8_t *src, size_t len) {
+    while (len && ((uintptr_t)dst & 31)) { *dst++ = *src++; len--; }
+    size_t i = 0;
+    for (; i + 128 <= len; i += 128) {
+        const __m256i a = _mm256_loadu_si256((const __m256i *)(src + i)), b = _mm256_loadu_si256((const __m256i *)(src + i + 32));
+        const __m256i c = _mm256_loadu_si256((const __m256i *)(src + i + 64)), d = _mm256_loadu_si256((const __m256i *)(src + i + 96));
+        _mm256_stream_si256((__m256i *)(dst + i), a); _mm256_stream_si256((__m256i *)(dst + i + 32), b);
+        _mm256_stream_si256((__m256i *)(dst + i + 64), c); _mm256_stream_si256((__m256i *)(dst + i + 96), d);
+    }
+    _mm_sfence();
+    if (i < len) memcpy(dst + i, src + i, len - i);
+}
+void copy_stream(uint8_t *dst, const uint8_t *src, size_t len) {
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("A3_PLAIN_MEMCPY");
+    if (avx2 && len >= 4096) copy_stream_avx2(dst, src, len);
+    else memcpy(dst, src, len);
+}
 
 // Shared between a call and the copy tasks it has in flight (kept alive by the tasks, so an early error return cannot
 // leave a task with a dangling reference).
@@ -1084,7 +1106,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                     const size_t off = (size_t)k * kPiece, len = bytes - off < kPiece ? bytes - off : kPiece;
                     cp->submit([stg, o, cp, dst, slot, off, len] {
                         cudaEventSynchronize(o->ev);
-                        memcpy(dst + off, slot + off, len);
+                        copy_stream(dst + off, slot + off, len);
                         if (o->left.fetch_sub(1) == 1) cp->notify();
                     });
                 }
@@ -1159,7 +1181,7 @@ a3_status a3_detect_batch(a3_detector *d, const void *frames, a3_format format, 
                 for (uint32_t k = 0; k < pieces; k++) {
                     const size_t off = (size_t)k * kPiece, len = bytes - off < kPiece ? bytes - off : kPiece;
                     cp->submit([stg, cp, c, dst, src, off, len] {
-                        memcpy(dst + off, src + off, len);
+                        copy_stream(dst + off, src + off, len);
                         if (stg->in_left[c].fetch_sub(1) == 1) cp->notify();
                     });
                 }

@@ -27,6 +27,8 @@
 // moves 3 + 1 + 1/8 B / pixel (+ the row / column halos, served mostly by L2).
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "a3_internal.h"
 
 namespace a3 {
@@ -95,12 +97,22 @@ struct Fmt {
     static constexpr int box_x = row_bytes / 4;                           // box width in u32 elements (<= 256)
 };
 
-// grey of one [R,G,B,x] word ([B,G,R,x] when BGR), left in byte 1 of the result (bytes 2 and 3 are zero)
+// Luma by two dp2a (u16 weights x pixel bytes): v = 2126 R + 7152 G + 722 B needs no byte-split weights, no shift between
+// the two dot products and, for 3-byte pixels, no byte permutes either: a pixel that straddles two words takes one dp2a from
+// each.  A weight pair names the bytes (lo: bytes 0,1; hi: bytes 2,3 of the word) it multiplies.
+//   floor(v / 10000) << 8 | fraction byte = umulhi(v, ceil(2^40 / 10^4))   (exact for every v <= 2 550 000)
+template <bool BGR>
+struct W {
+    static constexpr uint32_t r = BGR ? 722u : 2126u, g = 7152u, b = BGR ? 2126u : 722u;  // weights of pixel bytes 0, 1, 2
+    static constexpr uint32_t w01 = r | (g << 16);   // bytes (0,1) or (2,3) of a word = pixel bytes 0,1
+    static constexpr uint32_t w2_ = b;               // ... = pixel byte 2, then a byte of another pixel (weight 0)
+    static constexpr uint32_t w_0 = r << 16;         // ... = a byte of another pixel, then pixel byte 0
+    static constexpr uint32_t w12 = g | (b << 16);   // ... = pixel bytes 1,2
+};
+// grey of the pixel in bytes 0..2 of `px` (byte 3 ignored), left in byte 1 of the result (bytes 2 and 3 are zero)
 template <bool BGR>
 __device__ __forceinline__ uint32_t luma_h(uint32_t px) {
-    const uint32_t hi = __dp4a(px, BGR ? 0x00081b02u : 0x00021b08u, 0u);      // 8 R + 27 G + 2 B
-    const uint32_t v = __dp4a(px, BGR ? 0x004ef0d2u : 0x00d2f04eu, hi << 8);  // + 78 R + 240 G + 210 B  = 2126 R + 7152 G + 722 B
-    return __umulhi(v, kMagic);                                                // floor(v / 10000) << 8 | fraction byte
+    return __umulhi(__dp2a_hi(W<BGR>::w2_, px, __dp2a_lo(W<BGR>::w01, px, 0u)), kMagic);
 }
 
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
@@ -130,15 +142,16 @@ __device__ __forceinline__ void load_grey8(uint32_t row, uint32_t &p01, uint32_t
         constexpr bool BGR = fmt_bgr(FMT);
         if constexpr (fmt_bpp(FMT) == 3) {
             const uint2 a = lds64(row), b = lds64(row + 8), c = lds64(row + 16);
-            // 12 bytes -> 4 pixel words; the 4th byte of each word has weight 0
-            h[0] = luma_h<BGR>(a.x);
-            h[1] = luma_h<BGR>(__byte_perm(a.x, a.y, 0x6543));
-            h[2] = luma_h<BGR>(__byte_perm(a.y, b.x, 0x5432));
-            h[3] = luma_h<BGR>(b.x >> 8);
-            h[4] = luma_h<BGR>(b.y);
-            h[5] = luma_h<BGR>(__byte_perm(b.y, c.x, 0x6543));
-            h[6] = luma_h<BGR>(__byte_perm(c.x, c.y, 0x5432));
-            h[7] = luma_h<BGR>(c.y >> 8);
+            // 12 bytes = 4 pixels: [p0 p0 p0 p1] [p1 p1 p2 p2] [p2 p3 p3 p3]
+            using K = W<BGR>;
+            auto quad = [](uint32_t x, uint32_t y, uint32_t z, uint32_t *h) {
+                h[0] = __umulhi(__dp2a_hi(K::w2_, x, __dp2a_lo(K::w01, x, 0u)), kMagic);
+                h[1] = __umulhi(__dp2a_lo(K::w12, y, __dp2a_hi(K::w_0, x, 0u)), kMagic);
+                h[2] = __umulhi(__dp2a_lo(K::w2_, z, __dp2a_hi(K::w01, y, 0u)), kMagic);
+                h[3] = __umulhi(__dp2a_hi(K::w12, z, __dp2a_lo(K::w_0, z, 0u)), kMagic);
+            };
+            quad(a.x, a.y, b.x, h);
+            quad(b.y, c.x, c.y, h + 4);
         } else {
             const uint4 a = lds128(row), b = lds128(row + 16);
             h[0] = luma_h<BGR>(a.x); h[1] = luma_h<BGR>(a.y); h[2] = luma_h<BGR>(a.z); h[3] = luma_h<BGR>(a.w);
@@ -224,7 +237,10 @@ __device__ __forceinline__ void wait_box(uint32_t bar, uint32_t parity) {
 // Consume one staged input row: update the column sums and, when OUT, emit the output row 7 rows behind it.
 // src: the lane's pixels of the row; ring_new / ring_old / ring_pix: the lane's ring slots of this row, of the row
 // 15 behind (leaving the window) and of the row 7 behind (the output row).
-template <int FMT, bool MASK, bool BITS, bool OUT>
+// INT (only with OUT, in the fast bodies of x-interior warps): every pixel of the warp has the full 15 x 15 window, so cnt = 225
+// is a compile-time constant: -256 cnt rides in on the accumulator of one pair sum and cnt << 8 (j & 3) is an immediate,
+// which drops one add per pixel and the 16 registers of L.cvec / L.tbase from the hot loop.
+template <int FMT, bool MASK, bool BITS, bool OUT, bool INT = false>
 __device__ __forceinline__ void row_step(Lane &L, uint32_t src, uint32_t ring_new, uint32_t ring_old, uint32_t ring_pix) {
     uint32_t p01, p23, p45, p67;
     uint2 g;
@@ -246,7 +262,7 @@ __device__ __forceinline__ void row_step(Lane &L, uint32_t src, uint32_t ring_ne
         w[10] = __shfl_down_sync(0xffffffffu, L.cs2, 1); w[11] = __shfl_down_sync(0xffffffffu, L.cs3, 1);
         uint32_t f[12];
 #pragma unroll
-        for (int i = 1; i <= 10; i++) f[i] = __dp2a_lo(w[i], 0x0101u, 0u);  // lo + hi
+        for (int i = 1; i <= 10; i++) f[i] = __dp2a_lo(w[i], 0x0101u, (INT && i == 7) ? 0u - 256u * 225u : 0u);  // lo + hi (f[7] is in every T and never leaves)
         uint32_t T[4];
         T[0] = (f[1] + f[2] + f[3]) + (f[4] + f[5] + f[6]) + f[7];
         T[1] = T[0] + f[8] - f[1];
@@ -257,12 +273,12 @@ __device__ __forceinline__ void row_step(Lane &L, uint32_t src, uint32_t ring_ne
 #pragma unroll
         for (int j = 7; j >= 0; j--) {
             // S - 256 cnt:  even column j: T[j/2] + hi(w[j/2]);  odd: T[j/2] + lo(w[(j+15)/2])
-            const uint32_t acc = (j & 1) ? __dp2a_lo(w[(j + 15) / 2], 0x0001u, T[j / 2] + L.tbase[j])
-                                         : __dp2a_lo(w[j / 2], 0x0100u, T[j / 2] + L.tbase[j]);
-            const uint32_t u = __dp4a(j < 4 ? pc0 : pc1, L.cvec[j], acc);  // + (255 - pix) * cnt
+            const uint32_t t = INT ? T[j / 2] : T[j / 2] + L.tbase[j];
+            const uint32_t acc = (j & 1) ? __dp2a_lo(w[(j + 15) / 2], 0x0001u, t) : __dp2a_lo(w[j / 2], 0x0100u, t);
+            const uint32_t u = __dp4a(j < 4 ? pc0 : pc1, INT ? 225u << (8 * (j & 3)) : L.cvec[j], acc);  // + (255 - pix) * cnt
             bits8 = __funnelshift_l(u, bits8, 1);                          // sign bit: S < (pix + 1) * cnt
         }
-        bits8 &= L.valid8;
+        if constexpr (!INT) bits8 &= L.valid8;  // an interior warp's core lanes have all 8 pixels, its halo lanes store nothing
         if (L.store_mode == 1) {
             *reinterpret_cast<uint2 *>(L.grey) = pix;
             if constexpr (MASK) *reinterpret_cast<uint2 *>(L.mask) = make_uint2(expand4(bits8 & 15u), expand4(bits8 >> 4));
@@ -287,7 +303,7 @@ __device__ __forceinline__ void row_step(Lane &L, uint32_t src, uint32_t ring_ne
 // Rows R .. 7 of the body that starts at input row k0 (k0 % 8 == 0).  FAST: all 8 rows exist, all emit output and all
 // output rows have ny == 15 (already in L.cvec / L.tbase); otherwise every row is guarded.
 // ring_lo: the lane's slot (k0 & 8); ring_hi: slot (k0 & 8) ^ 8.
-template <int FMT, bool MASK, bool BITS, bool FAST, int R>
+template <int FMT, bool MASK, bool BITS, bool FAST, bool INT, int R>
 __device__ __forceinline__ void body_rows(Lane &L, const March &m, int k0, uint32_t ring_lo, uint32_t ring_hi) {
     if constexpr (R < kBody) {
         constexpr int box_in_body = R / kBoxRows;
@@ -302,12 +318,14 @@ __device__ __forceinline__ void body_rows(Lane &L, const March &m, int k0, uint3
             const uint32_t ro = R < 7 ? ring_lo + 256 * (R + 1) : ring_hi;           // row k - 15
             const uint32_t rp = R < 7 ? ring_hi + 256 * (R + 1) : ring_lo;           // row k - 7
             if constexpr (FAST) {
-                row_step<FMT, MASK, BITS, true>(L, src, rn, ro, rp);
+                row_step<FMT, MASK, BITS, true, INT>(L, src, rn, ro, rp);
             } else {
                 if (k0 + R >= 14) {
                     const int yo = m.ys + k0 + R - 14;
                     const uint32_t ny = (uint32_t)(min(m.h - 1, yo + 7) - max(0, yo - 7) + 1);
-                    if (ny != L.ny_cur) set_ny(L, m, ny);  // only in the top / bottom 7 rows of the frame
+                    // only in the top / bottom 7 rows of the frame; an interior warp recomputes every time, so that cvec / tbase
+                    // are dead across its fast bodies (which do not read them) and cost no registers there
+                    if (INT || ny != L.ny_cur) set_ny(L, m, ny);
                     row_step<FMT, MASK, BITS, true>(L, src, rn, ro, rp);
                 } else {
                     row_step<FMT, MASK, BITS, false>(L, src, rn, ro, rp);
@@ -320,7 +338,7 @@ __device__ __forceinline__ void body_rows(Lane &L, const March &m, int k0, uint3
             const int box = (k0 + R) / kBoxRows;
             if (m.lane == 0 && box + kStages < m.nboxes) arm_box<FMT>(m, box + kStages);
         }
-        body_rows<FMT, MASK, BITS, FAST, R + 1>(L, m, k0, ring_lo, ring_hi);
+        body_rows<FMT, MASK, BITS, FAST, INT, R + 1>(L, m, k0, ring_lo, ring_hi);
     }
 }
 
@@ -381,18 +399,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) k1_strips_ke
     L.row_px = a.w;
     L.row_bits = a.bits_row_bytes;
 
-    for (int k0 = 0; k0 < m.total_rows; k0 += kBody) {
-        const uint32_t ring_lo = m.ring + ((uint32_t)(k0 & 8) << 8);
-        const uint32_t ring_hi = m.ring + ((uint32_t)((k0 & 8) ^ 8) << 8);
-        const int yo_first = m.ys + k0 - 14;  // output row of the body's first input row
-        const bool fast = k0 >= 16 && k0 + kBody <= m.total_rows && yo_first >= 7 && yo_first + 7 <= m.h - 8;
-        if (fast) {
-            if (L.ny_cur != 15u) set_ny(L, m, 15);
-            body_rows<FMT, MASK, BITS, true, 0>(L, m, k0, ring_lo, ring_hi);
-        } else {
-            body_rows<FMT, MASK, BITS, false, 0>(L, m, k0, ring_lo, ring_hi);
+    // x-interior warp: none of its core columns is within 7 px of the left or right image edge (6 of the 8 strips of a 1080p
+    // row, 14 of 16 at 4K); warp-uniform
+    const bool interior = strip > 0 && (uint32_t)kCore * strip + kCore + 7 <= a.w;
+    auto march = [&](auto int_tag) {
+        constexpr bool INT = decltype(int_tag)::value;
+        for (int k0 = 0; k0 < m.total_rows; k0 += kBody) {
+            const uint32_t ring_lo = m.ring + ((uint32_t)(k0 & 8) << 8);
+            const uint32_t ring_hi = m.ring + ((uint32_t)((k0 & 8) ^ 8) << 8);
+            const int yo_first = m.ys + k0 - 14;  // output row of the body's first input row
+            const bool fast = k0 >= 16 && k0 + kBody <= m.total_rows && yo_first >= 7 && yo_first + 7 <= m.h - 8;
+            if (fast) {
+                if (!INT && L.ny_cur != 15u) set_ny(L, m, 15);
+                body_rows<FMT, MASK, BITS, true, INT, 0>(L, m, k0, ring_lo, ring_hi);
+            } else {
+                body_rows<FMT, MASK, BITS, false, INT, 0>(L, m, k0, ring_lo, ring_hi);
+            }
         }
-    }
+    };
+    if (interior) march(std::true_type{});
+    else march(std::false_type{});
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)

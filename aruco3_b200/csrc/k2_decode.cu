@@ -1,7 +1,11 @@
 // K2 — per-candidate decode (sm_100a). Compile this file with -fmad=false: the reference is Rust, which never
 // contracts a*b+c, and every float below is written in the reference's operation order.
 //
-// For each candidate quad this replaces, bit for bit (against oracle/a3ref.c):
+// Parity status: bit-exact against the in-repo oracle (oracle/a3ref.c); parity with the upstream crates is UNPINNED — the
+// reference holds no vector for this stage and imageproc solves the 8x8 system below through nalgebra's SVD, not by
+// elimination.  tests/test_oracle_risk.py measures what that can change: an independent f64 SVD moves an f32 coefficient
+// in about 2 % of quads, a patch byte (by one) in a tenth of those, and no code, id, rotation or distance in any.
+// For each candidate quad this replaces:
 //   extract_homographies            /root/reference/src/aruco.rs:234-261  (imageproc Projection::from_control_points,
 //                                                                          warp_into Bilinear, default 0)
 //   homography_to_code_permutations /root/reference/src/aruco.rs:263-313  (otsu_level, threshold Binary,

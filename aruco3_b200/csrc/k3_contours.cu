@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
     const uint32_t last_k = (g.w - 1) >> 5, last_bit = (g.w - 1) & 31;
     for (uint32_t frame = blockIdx.y; frame < g.n; frame += gridDim.y)
     for (uint32_t k = blockIdx.x; k < g.wpr; k += gridDim.x)
-    for (uint32_t base0 = 0; base0 < g.h; base0 += stride * kBatch) {  // warp-uniform trip count: rows beyond h read as empty words
+    for (uint32_t base0 = blockIdx.z * stride * kBatch; base0 < g.h; base0 += gridDim.z * stride * kBatch) {  // warp-uniform trip count: rows beyond h read as empty words
         const uint32_t base = base0 + threadIdx.x;
         const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
         const uint32_t *colk = plane + (size_t)(k + 1) * g.Hp + 1;  // row 0 of word column k
@@ -1154,7 +1154,14 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     const size_t pixels = (size_t)p.w * p.h;
     const size_t mp = p.min_points < 4 ? 4 : p.min_points;
     const size_t want_walkers = (size_t)p.n * (pixels / 32 + 4096), want_long = (size_t)p.n * (pixels / (4 * mp) + 1024);
-    const size_t want_cands = (size_t)p.n * (pixels / 8 + 4096);  // what does not fit is walked inside k3_candidates
+    // what does not fit is walked inside k3_candidates (slow: one thread per word).  A pure-noise frame leaves about 0.22
+    // candidates per pixel after the word filters, so calls of a few frames get room for a third of their pixels
+    size_t want_cands = (size_t)p.n * (pixels / 8 + 4096);
+    {
+        const size_t roomy = (size_t)p.n * (pixels / 3), cap = (size_t)16 << 20;
+        const size_t alt = roomy < cap ? roomy : cap;
+        if (alt > want_cands) want_cands = alt;
+    }
     if (want_cands > w.cands_cap) {
         K3_CUDA(alloc_exact(w.cands, want_cands));
         w.cands_cap = want_cands;
@@ -1235,7 +1242,17 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         uint32_t bd = ((p.h + 4 * passes - 1) / (4 * passes) + 31) & ~31u;
         if (bd < 64) bd = 64;
         if (bd > 256) bd = 256;
-        k3_candidates<<<dim3(gx, gy), bd, 0, stream>>>(g, w.d_tables, p.min_points, l);
+        // a call of a few frames (single-frame latency): columns x frames alone leave most SMs idle, so the rows of a column are
+        // cut into chunks of 256 as well (blockIdx.z)
+        uint32_t gz = 1;
+        if ((uint64_t)gx * gy * 2 <= resident) {
+            bd = 64;
+            gz = (p.h + 4 * bd - 1) / (4 * bd);
+            const uint32_t room = resident / (gx * gy);
+            if (gz > room) gz = room;
+            if (gz < 1) gz = 1;
+        }
+        k3_candidates<<<dim3(gx, gy, gz), bd, 0, stream>>>(g, w.d_tables, p.min_points, l);
     }
     K3_CUDA(cudaGetLastError());
     timer.mark("candidates");

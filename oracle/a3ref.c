@@ -594,17 +594,29 @@ static uint8_t clamp_u8_trunc(float x) { /* <u8 as Clamp<f32>>::clamp */
     return 255;
 }
 
-/* A.7  warp_into(grey, projection, Bilinear, Luma([0]), out) (call site src/aruco.rs:253)
- * Returns 1 when the projection exists, 0 when the reference pushes GrayImage::new(1,1) (Q5). */
-int a3ref_extract_homography(const uint8_t *grey, uint32_t w, uint32_t h, const uint32_t quad[8],
-                             uint32_t size, uint8_t *patch) {
-    float hs = (float)size;
-    float from[8], to[8] = {0.0f, 0.0f, hs, 0.0f, hs, hs, 0.0f, hs};
-    for (int i = 0; i < 8; i++) from[i] = (float)quad[i];
-    float fwd[9], inv[9];
-    int cls;
+/* The second half of from_control_points (f32 transform -> class + inverse) and warp_into, for a GIVEN forward transform:
+ * what a3ref_extract_homography does after its own solve.  Exposed so that tests/test_oracle_risk.py can feed it the
+ * coefficients of an independent solver and switch the bilinear variant (R4):
+ *   variant 0  the restated imageproc 0.25 blend_bilinear: the two horizontal blends are clamped and truncated to u8 before the
+ *              vertical blend (what the product implements)
+ *   variant 1  one stage: the three blends in f32, one clamp + truncation at the end
+ *   variant 2  one stage, rounded to nearest at the end
+ * Returns 1 when the projection exists. */
+int a3ref_warp_with_transform(const uint8_t *grey, uint32_t w, uint32_t h, const float transform[9], uint32_t size, int variant,
+                              uint8_t *patch) {
     memset(patch, 0, (size_t)size * size);
-    if (!a3ref_projection_from_control_points(from, to, fwd, inv, &cls)) return 0;
+    for (int i = 0; i < 8; i++)
+        if (!isfinite(transform[i])) return 0;
+    int cls = 2;
+    if (fabsf(transform[6]) < 1e-10f && fabsf(transform[7]) < 1e-10f && fabsf(transform[8] - 1.0f) < 1e-10f) {
+        if (fabsf(transform[0] - 1.0f) < 1e-10f && fabsf(transform[1]) < 1e-10f && fabsf(transform[3]) < 1e-10f &&
+            fabsf(transform[4] - 1.0f) < 1e-10f)
+            cls = 0;
+        else
+            cls = 1;
+    }
+    float inv[9];
+    if (!try_inverse(transform, inv)) return 0;
     const float *t = inv; /* projection.invert(): maps output pixels back into the image */
     for (uint32_t oy = 0; oy < size; oy++) {
         for (uint32_t ox = 0; ox < size; ox++) {
@@ -630,14 +642,34 @@ int a3ref_extract_homography(const uint8_t *grey, uint32_t w, uint32_t h, const 
                 uint32_t tp = isnan(top) ? 0 : (uint32_t)top, b = isnan(bottom) ? 0 : (uint32_t)bottom;
                 float tl = grey[(size_t)tp * w + l], tr = grey[(size_t)tp * w + r];
                 float bl = grey[(size_t)b * w + l], br = grey[(size_t)b * w + r];
-                uint8_t topv = clamp_u8_trunc((1.0f - rw) * tl + rw * tr);
-                uint8_t botv = clamp_u8_trunc((1.0f - rw) * bl + rw * br);
-                o = clamp_u8_trunc((1.0f - bw) * (float)topv + bw * (float)botv);
+                if (variant == 0) {
+                    uint8_t topv = clamp_u8_trunc((1.0f - rw) * tl + rw * tr);
+                    uint8_t botv = clamp_u8_trunc((1.0f - rw) * bl + rw * br);
+                    o = clamp_u8_trunc((1.0f - bw) * (float)topv + bw * (float)botv);
+                } else {
+                    float topf = (1.0f - rw) * tl + rw * tr, botf = (1.0f - rw) * bl + rw * br;
+                    float v = (1.0f - bw) * topf + bw * botf;
+                    o = variant == 1 ? clamp_u8_trunc(v) : clamp_u8_trunc(v + 0.5f);
+                }
             }
             patch[(size_t)oy * size + ox] = o;
         }
     }
     return 1;
+}
+
+/* A.7  warp_into(grey, projection, Bilinear, Luma([0]), out) (call site src/aruco.rs:253)
+ * Returns 1 when the projection exists, 0 when the reference pushes GrayImage::new(1,1) (Q5). */
+int a3ref_extract_homography(const uint8_t *grey, uint32_t w, uint32_t h, const uint32_t quad[8],
+                             uint32_t size, uint8_t *patch) {
+    float hs = (float)size;
+    float from[8], to[8] = {0.0f, 0.0f, hs, 0.0f, hs, hs, 0.0f, hs};
+    for (int i = 0; i < 8; i++) from[i] = (float)quad[i];
+    float fwd[9], inv[9];
+    int cls;
+    memset(patch, 0, (size_t)size * size);
+    if (!a3ref_projection_from_control_points(from, to, fwd, inv, &cls)) return 0;
+    return a3ref_warp_with_transform(grey, w, h, fwd, size, 0, patch);
 }
 
 /* A.8  imageproc::contrast::otsu_level (call site src/aruco.rs:264) */

@@ -130,6 +130,9 @@ int a3ref_projection_from_control_points(const float from[8], const float to[8],
                                          float inverse[9], int *cls);
 int a3ref_extract_homography(const uint8_t *grey, uint32_t w, uint32_t h, const uint32_t quad[8],
                              uint32_t size, uint8_t *patch);
+/* the warp for a given forward transform (f32[9]) and bilinear variant (0 = the restated two-stage blend): risk probes */
+int a3ref_warp_with_transform(const uint8_t *grey, uint32_t w, uint32_t h, const float transform[9], uint32_t size, int variant,
+                              uint8_t *patch);
 uint8_t a3ref_otsu_level(const uint8_t *img, uint32_t w, uint32_t h);
 void a3ref_resize_triangle(const uint8_t *src, uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh, uint8_t *dst);
 int a3ref_homography_to_code_permutations(const uint8_t *patch, uint32_t pw, uint32_t ph, uint8_t mark_size,
