@@ -7,7 +7,8 @@ import subprocess
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libaruco3_b200.so"
+# A3_LIB_PATH: load another build of the same library (A/B timing of kernel variants, tools/k1_variants.sh); never a fallback
+LIB_PATH = Path(os.environ["A3_LIB_PATH"]).resolve() if os.environ.get("A3_LIB_PATH") else PKG / "libaruco3_b200.so"
 
 A3_OK, A3_ERR_INVALID_ARGUMENT, A3_ERR_UNKNOWN_DICTIONARY, A3_ERR_CUDA, A3_ERR_CAPACITY, A3_ERR_UNSUPPORTED, \
     A3_ERR_OUT_OF_MEMORY = range(7)

@@ -95,22 +95,12 @@ struct Fmt {
     static constexpr int box_x = row_bytes / 4;                           // box width in u32 elements (<= 256)
 };
 
-// Luma by two dp2a (u16 weights x pixel bytes): v = 2126 R + 7152 G + 722 B needs no byte-split weights, no shift between
-// the two dot products and, for 3-byte pixels, no byte permutes either: a pixel that straddles two words takes one dp2a from
-// each.  A weight pair names the bytes (lo: bytes 0,1; hi: bytes 2,3 of the word) it multiplies.
-//   floor(v / 10000) << 8 | fraction byte = umulhi(v, ceil(2^40 / 10^4))   (exact for every v <= 2 550 000)
-template <bool BGR>
-struct W {
-    static constexpr uint32_t r = BGR ? 722u : 2126u, g = 7152u, b = BGR ? 2126u : 722u;  // weights of pixel bytes 0, 1, 2
-    static constexpr uint32_t w01 = r | (g << 16);   // bytes (0,1) or (2,3) of a word = pixel bytes 0,1
-    static constexpr uint32_t w2_ = b;               // ... = pixel byte 2, then a byte of another pixel (weight 0)
-    static constexpr uint32_t w_0 = r << 16;         // ... = a byte of another pixel, then pixel byte 0
-    static constexpr uint32_t w12 = g | (b << 16);   // ... = pixel bytes 1,2
-};
-// grey of the pixel in bytes 0..2 of `px` (byte 3 ignored), left in byte 1 of the result (bytes 2 and 3 are zero)
+// grey of one [R,G,B,x] word ([B,G,R,x] when BGR), left in byte 1 of the result (bytes 2 and 3 are zero)
 template <bool BGR>
 __device__ __forceinline__ uint32_t luma_h(uint32_t px) {
-    return __umulhi(__dp2a_hi(W<BGR>::w2_, px, __dp2a_lo(W<BGR>::w01, px, 0u)), kMagic);
+    const uint32_t hi = __dp4a(px, BGR ? 0x00081b02u : 0x00021b08u, 0u);      // 8 R + 27 G + 2 B
+    const uint32_t v = __dp4a(px, BGR ? 0x004ef0d2u : 0x00d2f04eu, hi << 8);  // + 78 R + 240 G + 210 B  = 2126 R + 7152 G + 722 B
+    return __umulhi(v, kMagic);                                                // floor(v / 10000) << 8 | fraction byte
 }
 
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
@@ -140,16 +130,15 @@ __device__ __forceinline__ void load_grey8(uint32_t row, uint32_t &p01, uint32_t
         constexpr bool BGR = fmt_bgr(FMT);
         if constexpr (fmt_bpp(FMT) == 3) {
             const uint2 a = lds64(row), b = lds64(row + 8), c = lds64(row + 16);
-            // 12 bytes = 4 pixels: [p0 p0 p0 p1] [p1 p1 p2 p2] [p2 p3 p3 p3]
-            using K = W<BGR>;
-            auto quad = [](uint32_t x, uint32_t y, uint32_t z, uint32_t *h) {
-                h[0] = __umulhi(__dp2a_hi(K::w2_, x, __dp2a_lo(K::w01, x, 0u)), kMagic);
-                h[1] = __umulhi(__dp2a_lo(K::w12, y, __dp2a_hi(K::w_0, x, 0u)), kMagic);
-                h[2] = __umulhi(__dp2a_lo(K::w2_, z, __dp2a_hi(K::w01, y, 0u)), kMagic);
-                h[3] = __umulhi(__dp2a_hi(K::w12, z, __dp2a_lo(K::w_0, z, 0u)), kMagic);
-            };
-            quad(a.x, a.y, b.x, h);
-            quad(b.y, c.x, c.y, h + 4);
+            // 12 bytes -> 4 pixel words; the 4th byte of each word has weight 0
+            h[0] = luma_h<BGR>(a.x);
+            h[1] = luma_h<BGR>(__byte_perm(a.x, a.y, 0x6543));
+            h[2] = luma_h<BGR>(__byte_perm(a.y, b.x, 0x5432));
+            h[3] = luma_h<BGR>(b.x >> 8);
+            h[4] = luma_h<BGR>(b.y);
+            h[5] = luma_h<BGR>(__byte_perm(b.y, c.x, 0x6543));
+            h[6] = luma_h<BGR>(__byte_perm(c.x, c.y, 0x5432));
+            h[7] = luma_h<BGR>(c.y >> 8);
         } else {
             const uint4 a = lds128(row), b = lds128(row + 16);
             h[0] = luma_h<BGR>(a.x); h[1] = luma_h<BGR>(a.y); h[2] = luma_h<BGR>(a.z); h[3] = luma_h<BGR>(a.w);
@@ -167,11 +156,10 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nib) { return ((nib * 0x002
 // Per-lane marching state (registers).
 struct Lane {
     uint32_t cs0, cs1, cs2, cs3;   // running 15-row column sums of the lane's 8 columns, u16 pairs
-    uint32_t tab;                  // shared address of the window-area constants of the lane's class (see set_ny)
-    uint32_t ny_cur;               // window rows the table is currently written for (warp-uniform)
+    uint32_t cvec[8], tbase[8];    // cnt << 8 (j & 3)  and  -256 cnt,  cnt = nx * ny of the current output row
+    uint32_t ny_cur;
     uint32_t valid8;               // which of the lane's 8 pixels are output pixels
     int store_mode;                // 0 nothing, 1 one 8-byte store per array, 2 4-byte stores
-    int tab_writer;                // 0 no, 1 writes its own class (a lane clipped by an image edge), 2 writes class 0 (nx = 15)
     uint8_t *grey, *mask, *bits;   // output addresses of the lane's pixels in the next output row
     uint32_t row_px, row_bits;     // bytes per output row
 };
@@ -179,48 +167,35 @@ struct Lane {
 // Warp-uniform marching context.
 struct March {
     const CUtensorMap *tmap;
-    uint32_t base;       // shared address of the warp's carve: stages, then the grey ring, then the constants table, then the mbarriers
+    uint32_t base;       // shared address of the warp's carve: stages, then the grey ring, then the mbarriers
     uint32_t ring;       // this lane's slot 0 of the grey ring (slot s at ring + 256 s)
     uint32_t full;       // mbarrier of stage s at full + 8 s
     uint32_t lane_src;   // shared address of the lane's pixels in row 0 of stage 0
     int x, w, h, ys, total_rows, nboxes, cx, cy0, frame, lane;
 };
 
-// The march consumes one TMA box of 2 input rows per iteration of a ROLLED loop over a 2-stage ring (the loop body is a few
-// hundred instructions: an earlier version unrolled 8 rows with compile-time ring slots, 8600 instructions per kernel, and
-// ncu showed it waiting for the instruction cache - stall_no_instruction 2.4 cycles per issue, icc hit rate 77 %).
-constexpr int kBoxRows = 2, kStages = 2;
-// Window areas cnt = nx * ny (clipped window width x height).  ny is warp-uniform and changes only in the top / bottom 7 rows
-// of the frame; nx differs from 15 only for the few lanes within 7 columns of the left / right image edge.  The per-pixel
-// constants (-256 cnt, cnt << 8 (j & 3)) therefore live in a small per-warp shared table of kClasses lane classes - class 0:
-// nx = 15 everywhere, classes 1..3: one clipped lane each - instead of 16 registers per lane (which spilled at the 72-register
-// cap).  x-interior warps do not read it at all in the steady state (template INT: cnt = 225 is an immediate).
-constexpr int kClasses = 4;
-constexpr int kTabBytes = kClasses * 64;
+// cnt = nx * ny of the lane's 8 columns for an output row with ny window rows (nx: clipped window width, 0 outside)
+__device__ __forceinline__ void set_ny(Lane &L, const March &m, uint32_t ny) {
+    L.ny_cur = ny;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int xx = m.x + j;
+        const uint32_t nx = (xx >= 0 && xx < m.w) ? (uint32_t)(min(m.w - 1, xx + 7) - max(0, xx - 7) + 1) : 0u;
+        const uint32_t c = nx * ny;
+        L.cvec[j] = c << (8 * (j & 3));
+        L.tbase[j] = 0u - 256u * c;
+    }
+}
+
+// The march is organised in bodies of 8 input rows = 4 TMA boxes of 2 rows over a 2-stage ring, so that inside a
+// body every ring slot, stage and mbarrier phase is a compile-time constant.
+constexpr int kBody = 8, kBoxRows = 2, kStages = 2;
 template <int FMT>
 struct Stage {
     static constexpr int tx_bytes = kBoxRows * Fmt<FMT>::row_bytes;  // bytes one box delivers
     static constexpr int bytes = (tx_bytes + 127) & ~127;            // stage stride: TMA destinations are 128-byte aligned
-    static constexpr int per_warp = (kStages * bytes + kRing * 256 + kTabBytes + 8 * kStages + 127) & ~127;
+    static constexpr int per_warp = (kStages * bytes + kRing * 256 + 8 * kStages + 127) & ~127;
 };
-
-__device__ __forceinline__ uint32_t clipped_nx(const March &m, int xx) {
-    return (xx >= 0 && xx < m.w) ? (uint32_t)(min(m.w - 1, xx + 7) - max(0, xx - 7) + 1) : 0u;
-}
-// (re)write the constants table for output rows with ny window rows: entry j of a class = {-256 cnt_j, cnt_j << 8 (j & 3)}
-__device__ __forceinline__ void set_ny(Lane &L, const March &m, uint32_t ny) {
-    L.ny_cur = ny;
-    __syncwarp();  // every lane has finished reading the previous values
-    if (L.tab_writer) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint32_t nx = L.tab_writer == 2 ? 15u : clipped_nx(m, m.x + j);
-            const uint32_t c = nx * ny;
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(L.tab + 8 * j), "r"(0u - 256u * c), "r"(c << (8 * (j & 3))) : "memory");
-        }
-    }
-    __syncwarp();
-}
 
 template <int FMT>
 __device__ __forceinline__ void arm_box(const March &m, int box) {  // lane 0: request rows cy0 + 2 box .. into stage box & 1
@@ -249,9 +224,7 @@ __device__ __forceinline__ void wait_box(uint32_t bar, uint32_t parity) {
 // Consume one staged input row: update the column sums and, when OUT, emit the output row 7 rows behind it.
 // src: the lane's pixels of the row; ring_new / ring_old / ring_pix: the lane's ring slots of this row, of the row
 // 15 behind (leaving the window) and of the row 7 behind (the output row).
-// INT (only with OUT, steady-state rows of x-interior warps): every pixel of the warp has the full 15 x 15 window, so cnt = 225
-// is a compile-time constant: -256 cnt rides in on the accumulator of the pair sums and cnt << 8 (j & 3) is an immediate.
-template <int FMT, bool MASK, bool BITS, bool OUT, bool INT = false>
+template <int FMT, bool MASK, bool BITS, bool OUT>
 __device__ __forceinline__ void row_step(Lane &L, uint32_t src, uint32_t ring_new, uint32_t ring_old, uint32_t ring_pix) {
     uint32_t p01, p23, p45, p67;
     uint2 g;
@@ -271,58 +244,83 @@ __device__ __forceinline__ void row_step(Lane &L, uint32_t src, uint32_t ring_ne
         w[4] = L.cs0; w[5] = L.cs1; w[6] = L.cs2; w[7] = L.cs3;
         w[8] = __shfl_down_sync(0xffffffffu, L.cs0, 1); w[9] = __shfl_down_sync(0xffffffffu, L.cs1, 1);
         w[10] = __shfl_down_sync(0xffffffffu, L.cs2, 1); w[11] = __shfl_down_sync(0xffffffffu, L.cs3, 1);
-        // sliding sums of 7 pair words, still packed (even columns | odd columns << 16; a half is at most 7 * 15 * 255 < 2^16),
-        // then T[i] = both halves of window i: the 14 columns that all of pixel 2i's and pixel 2i+1's windows share
-        uint32_t A[4], T[4];
-        A[0] = (w[1] + w[2] + w[3]) + (w[4] + w[5] + w[6]) + w[7];
-        A[1] = A[0] + w[8] - w[1];
-        A[2] = A[1] + w[9] - w[2];
-        A[3] = A[2] + w[10] - w[3];
+        uint32_t f[12];
 #pragma unroll
-        for (int i = 0; i < 4; i++) T[i] = __dp2a_lo(A[i], 0x0101u, INT ? 0u - 256u * 225u : 0u);
+        for (int i = 1; i <= 10; i++) f[i] = __dp2a_lo(w[i], 0x0101u, 0u);  // lo + hi
+        uint32_t T[4];
+        T[0] = (f[1] + f[2] + f[3]) + (f[4] + f[5] + f[6]) + f[7];
+        T[1] = T[0] + f[8] - f[1];
+        T[2] = T[1] + f[9] - f[2];
+        T[3] = T[2] + f[10] - f[3];
         const uint32_t pc0 = ~pix.x, pc1 = ~pix.y;
         uint32_t bits8 = 0;
 #pragma unroll
-        for (int jj = 3; jj >= 0; jj--) {
-            uint4 c = make_uint4(0u, 0u, 0u, 0u);   // {-256 cnt, cnt << 8 (j & 3)} of pixels 2 jj and 2 jj + 1
-            if constexpr (!INT) c = lds128(L.tab + 16 * jj);
-#pragma unroll
-            for (int j = 2 * jj + 1; j >= 2 * jj; j--) {
-                // S - 256 cnt:  even column j: T[j/2] + hi(w[j/2]);  odd: T[j/2] + lo(w[(j+15)/2])
-                const uint32_t t = INT ? T[jj] : T[jj] + ((j & 1) ? c.z : c.x);
-                const uint32_t acc = (j & 1) ? __dp2a_lo(w[(j + 15) / 2], 0x0001u, t) : __dp2a_lo(w[j / 2], 0x0100u, t);
-                const uint32_t u = __dp4a(j < 4 ? pc0 : pc1, INT ? 225u << (8 * (j & 3)) : ((j & 1) ? c.w : c.y), acc);  // + (255 - pix) * cnt
-                bits8 = __funnelshift_l(u, bits8, 1);                          // sign bit: S < (pix + 1) * cnt
-            }
+        for (int j = 7; j >= 0; j--) {
+            // S - 256 cnt:  even column j: T[j/2] + hi(w[j/2]);  odd: T[j/2] + lo(w[(j+15)/2])
+            const uint32_t acc = (j & 1) ? __dp2a_lo(w[(j + 15) / 2], 0x0001u, T[j / 2] + L.tbase[j])
+                                         : __dp2a_lo(w[j / 2], 0x0100u, T[j / 2] + L.tbase[j]);
+            const uint32_t u = __dp4a(j < 4 ? pc0 : pc1, L.cvec[j], acc);  // + (255 - pix) * cnt
+            bits8 = __funnelshift_l(u, bits8, 1);                          // sign bit: S < (pix + 1) * cnt
         }
-        if constexpr (INT) {
-            // an x-interior warp: its core lanes have all 8 pixels and take the wide stores, its halo lanes store nothing
-            if (L.store_mode) {
-                *reinterpret_cast<uint2 *>(L.grey) = pix;
-                if constexpr (MASK) *reinterpret_cast<uint2 *>(L.mask) = make_uint2(expand4(bits8 & 15u), expand4(bits8 >> 4));
-                if constexpr (BITS) *L.bits = (uint8_t)bits8;
+        bits8 &= L.valid8;
+        if (L.store_mode == 1) {
+            *reinterpret_cast<uint2 *>(L.grey) = pix;
+            if constexpr (MASK) *reinterpret_cast<uint2 *>(L.mask) = make_uint2(expand4(bits8 & 15u), expand4(bits8 >> 4));
+            if constexpr (BITS) *L.bits = (uint8_t)bits8;
+        } else if (L.store_mode == 2) {
+            if (L.valid8 & 0x0fu) {
+                *reinterpret_cast<uint32_t *>(L.grey) = pix.x;
+                if constexpr (MASK) *reinterpret_cast<uint32_t *>(L.mask) = expand4(bits8 & 15u);
             }
-        } else {
-            bits8 &= L.valid8;
-            if (L.store_mode == 1) {
-                *reinterpret_cast<uint2 *>(L.grey) = pix;
-                if constexpr (MASK) *reinterpret_cast<uint2 *>(L.mask) = make_uint2(expand4(bits8 & 15u), expand4(bits8 >> 4));
-                if constexpr (BITS) *L.bits = (uint8_t)bits8;
-            } else if (L.store_mode == 2) {
-                if (L.valid8 & 0x0fu) {
-                    *reinterpret_cast<uint32_t *>(L.grey) = pix.x;
-                    if constexpr (MASK) *reinterpret_cast<uint32_t *>(L.mask) = expand4(bits8 & 15u);
-                }
-                if (L.valid8 & 0xf0u) {
-                    *reinterpret_cast<uint32_t *>(L.grey + 4) = pix.y;
-                    if constexpr (MASK) *reinterpret_cast<uint32_t *>(L.mask + 4) = expand4(bits8 >> 4);
-                }
-                if constexpr (BITS) *L.bits = (uint8_t)bits8;
+            if (L.valid8 & 0xf0u) {
+                *reinterpret_cast<uint32_t *>(L.grey + 4) = pix.y;
+                if constexpr (MASK) *reinterpret_cast<uint32_t *>(L.mask + 4) = expand4(bits8 >> 4);
             }
+            if constexpr (BITS) *L.bits = (uint8_t)bits8;
         }
         L.grey += L.row_px;
         if constexpr (MASK) L.mask += L.row_px;
         if constexpr (BITS) L.bits += L.row_bits;
+    }
+}
+
+// Rows R .. 7 of the body that starts at input row k0 (k0 % 8 == 0).  FAST: all 8 rows exist, all emit output and all
+// output rows have ny == 15 (already in L.cvec / L.tbase); otherwise every row is guarded.
+// ring_lo: the lane's slot (k0 & 8); ring_hi: slot (k0 & 8) ^ 8.
+template <int FMT, bool MASK, bool BITS, bool FAST, int R>
+__device__ __forceinline__ void body_rows(Lane &L, const March &m, int k0, uint32_t ring_lo, uint32_t ring_hi) {
+    if constexpr (R < kBody) {
+        constexpr int box_in_body = R / kBoxRows;
+        constexpr uint32_t st = box_in_body & 1;
+        const bool row_ok = FAST || (k0 + R < m.total_rows);  // warp-uniform
+        if constexpr (R % kBoxRows == 0) {
+            if (row_ok) wait_box(m.full + 8 * st, (uint32_t)(box_in_body >> 1) & 1u);  // each stage completes twice per body
+        }
+        if (row_ok) {
+            const uint32_t src = m.lane_src + st * Stage<FMT>::bytes + (R % kBoxRows) * Fmt<FMT>::row_bytes;
+            const uint32_t rn = ring_lo + 256 * R;                                   // row k        -> slot (k0 & 8) + R
+            const uint32_t ro = R < 7 ? ring_lo + 256 * (R + 1) : ring_hi;           // row k - 15
+            const uint32_t rp = R < 7 ? ring_hi + 256 * (R + 1) : ring_lo;           // row k - 7
+            if constexpr (FAST) {
+                row_step<FMT, MASK, BITS, true>(L, src, rn, ro, rp);
+            } else {
+                if (k0 + R >= 14) {
+                    const int yo = m.ys + k0 + R - 14;
+                    const uint32_t ny = (uint32_t)(min(m.h - 1, yo + 7) - max(0, yo - 7) + 1);
+                    if (ny != L.ny_cur) set_ny(L, m, ny);  // only in the top / bottom 7 rows of the frame
+                    row_step<FMT, MASK, BITS, true>(L, src, rn, ro, rp);
+                } else {
+                    row_step<FMT, MASK, BITS, false>(L, src, rn, ro, rp);
+                }
+            }
+        }
+        if constexpr (R % kBoxRows == kBoxRows - 1) {
+            // every lane has consumed the box (its values are in registers): refill the stage with the box 2 ahead
+            __syncwarp();
+            const int box = (k0 + R) / kBoxRows;
+            if (m.lane == 0 && box + kStages < m.nboxes) arm_box<FMT>(m, box + kStages);
+        }
+        body_rows<FMT, MASK, BITS, FAST, R + 1>(L, m, k0, ring_lo, ring_hi);
     }
 }
 
@@ -341,8 +339,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) k1_strips_ke
     m.tmap = &tmap;
     m.base = smem_u32(smem) + (uint32_t)warp * Stage<FMT>::per_warp;
     m.ring = m.base + kStages * Stage<FMT>::bytes + 8 * lane;
-    const uint32_t tab = m.base + kStages * Stage<FMT>::bytes + kRing * 256;
-    m.full = tab + kTabBytes;
+    m.full = m.base + kStages * Stage<FMT>::bytes + kRing * 256;
     m.lane_src = m.base + Fmt<FMT>::lead_bytes + lane * 8 * Fmt<FMT>::bpp;
     m.x = x0 + 8 * lane;                              // first of this lane's 8 columns
     m.w = (int)a.w; m.h = (int)a.h;
@@ -370,21 +367,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) k1_strips_ke
 
     Lane L;
     L.cs0 = L.cs1 = L.cs2 = L.cs3 = 0;
+    set_ny(L, m, 15);
     const bool lane_core = lane >= 1 && lane <= 30 && m.x < m.w;
     L.valid8 = 0;
-    bool clipped = false;  // an output pixel of this lane has a window narrower than 15 columns
 #pragma unroll
     for (int j = 0; j < 8; j++)
-        if (lane_core && m.x + j < m.w) {
-            L.valid8 |= 1u << j;
-            clipped |= clipped_nx(m, m.x + j) != 15u;
-        }
-    // lane classes of the constants table: the (at most kClasses - 1, k1_strips_eligible) clipped lanes get one each
-    const uint32_t clipped_lanes = __ballot_sync(0xffffffffu, clipped);
-    const uint32_t cls = clipped ? 1u + (uint32_t)__popc(clipped_lanes & ((1u << lane) - 1u)) : 0u;
-    L.tab = tab + 64u * cls;
-    L.tab_writer = clipped ? 1 : (lane == __ffs(~clipped_lanes) - 1 ? 2 : 0);
-    L.ny_cur = 0;
+        if (lane_core && m.x + j < m.w) L.valid8 |= 1u << j;
     L.store_mode = !lane_core ? 0 : ((a.wide_stores && L.valid8 == 0xffu) ? 1 : 2);
     const size_t o_px = ((size_t)frame * a.h + m.ys) * a.w + m.x;
     L.grey = a.grey + o_px;
@@ -393,47 +381,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) k1_strips_ke
     L.row_px = a.w;
     L.row_bits = a.bits_row_bytes;
 
-    // x-interior warp: none of its core columns is within 7 px of the left or right image edge (6 of the 8 strips of a 1080p
-    // row, 14 of 16 at 4K) and its core lanes take the 8-byte stores; warp-uniform
-    const bool interior = strip > 0 && (uint32_t)kCore * strip + kCore + 7 <= a.w && a.wide_stores;
-#pragma unroll 1
-    for (int box = 0; box < m.nboxes; box++) {
-        const uint32_t st = (uint32_t)box & 1u;
-        wait_box(m.full + 8 * st, ((uint32_t)box >> 1) & 1u);  // each stage completes once per two boxes
-        const int k = box * kBoxRows;                           // first input row of the box
-        // ring slots: row r lives in slot r & 15 (256 bytes apart).  With k even:
-        //   row k -> o0, row k + 1 -> o0 + 256; rows k - 15, k - 14 (leaving) -> o0 + 256, o1; rows k - 7, k - 6 (output) -> o4 + 256, o5
-        const uint32_t a9 = (uint32_t)box << 9;
-        const uint32_t o0 = a9 & 0xe00u, o1 = (a9 + 0x200u) & 0xe00u;
-        const uint32_t r0 = m.ring + o0, r1 = m.ring + o1, r4 = m.ring + (o0 ^ 0x800u), r5 = m.ring + (o1 ^ 0x800u);
-        const uint32_t src = m.lane_src + st * Stage<FMT>::bytes;
-        const int yo = m.ys + k - 14;                           // output row of the box's first input row
-        const bool fast = k >= 14 && k + 1 < m.total_rows && yo >= 7 && yo + 1 <= m.h - 8;  // both rows exist, emit, and have ny == 15
-        if (fast && interior) {
-            row_step<FMT, MASK, BITS, true, true>(L, src, r0, r0 + 256, r4 + 256);
-            row_step<FMT, MASK, BITS, true, true>(L, src + Fmt<FMT>::row_bytes, r0 + 256, r1, r5);
-        } else if (fast) {
+    for (int k0 = 0; k0 < m.total_rows; k0 += kBody) {
+        const uint32_t ring_lo = m.ring + ((uint32_t)(k0 & 8) << 8);
+        const uint32_t ring_hi = m.ring + ((uint32_t)((k0 & 8) ^ 8) << 8);
+        const int yo_first = m.ys + k0 - 14;  // output row of the body's first input row
+        const bool fast = k0 >= 16 && k0 + kBody <= m.total_rows && yo_first >= 7 && yo_first + 7 <= m.h - 8;
+        if (fast) {
             if (L.ny_cur != 15u) set_ny(L, m, 15);
-            row_step<FMT, MASK, BITS, true>(L, src, r0, r0 + 256, r4 + 256);
-            row_step<FMT, MASK, BITS, true>(L, src + Fmt<FMT>::row_bytes, r0 + 256, r1, r5);
+            body_rows<FMT, MASK, BITS, true, 0>(L, m, k0, ring_lo, ring_hi);
         } else {
-#pragma unroll 1
-            for (int r = 0; r < kBoxRows; r++) {
-                if (k + r >= m.total_rows) break;
-                const uint32_t rn = r ? r0 + 256 : r0, ro = r ? r1 : r0 + 256, rp = r ? r5 : r4 + 256;
-                if (k + r >= 14) {
-                    const int y = yo + r;
-                    const uint32_t ny = (uint32_t)(min(m.h - 1, y + 7) - max(0, y - 7) + 1);
-                    if (ny != L.ny_cur) set_ny(L, m, ny);  // only in the top / bottom 7 rows of the frame
-                    row_step<FMT, MASK, BITS, true>(L, src + r * Fmt<FMT>::row_bytes, rn, ro, rp);
-                } else {
-                    row_step<FMT, MASK, BITS, false>(L, src + r * Fmt<FMT>::row_bytes, rn, ro, rp);
-                }
-            }
+            body_rows<FMT, MASK, BITS, false, 0>(L, m, k0, ring_lo, ring_hi);
         }
-        // every lane has consumed the box (its values are in registers or in the ring): refill the stage with the box 2 ahead
-        __syncwarp();
-        if (lane == 0 && box + kStages < m.nboxes) arm_box<FMT>(m, box + kStages);
     }
 }
 
