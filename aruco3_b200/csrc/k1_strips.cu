@@ -27,6 +27,8 @@
 // moves 3 + 1 + 1/8 B / pixel (+ the row / column halos, served mostly by L2).
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "a3_internal.h"
 
 namespace a3 {
@@ -164,31 +166,28 @@ __device__ __forceinline__ void load_grey8(uint32_t row, uint32_t &p01, uint32_t
 // 4 mask bits -> 4 bytes of 0 / 255
 __device__ __forceinline__ uint32_t expand4(uint32_t nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xffu; }
 
-// Per-lane marching state (registers).
+// Per-lane marching state (registers).  Everything the steady-state rows do not need lives elsewhere: the kernel runs at the
+// 72-register cap of 7 CTAs per SM, and every value kept live across the loop was a value rematerialised inside it.
 struct Lane {
     uint32_t cs0, cs1, cs2, cs3;   // running 15-row column sums of the lane's 8 columns, u16 pairs
     uint32_t tab;                  // shared address of the window-area constants of the lane's class (see set_ny)
-    uint32_t ny_cur;               // window rows the table is currently written for (warp-uniform)
     uint32_t valid8;               // which of the lane's 8 pixels are output pixels
     int store_mode;                // 0 nothing, 1 one 8-byte store per array, 2 4-byte stores
-    int tab_writer;                // 0 no, 1 writes its own class (a lane clipped by an image edge), 2 writes class 0 (nx = 15)
     uint8_t *grey, *mask, *bits;   // output addresses of the lane's pixels in the next output row
-    uint32_t row_px, row_bits;     // bytes per output row
 };
 
-// Warp-uniform marching context.
+// Warp-uniform marching context (registers): shared addresses and the loop bounds.
 struct March {
-    const CUtensorMap *tmap;
-    uint32_t base;       // shared address of the warp's carve: stages, then the grey ring, then the constants table, then the mbarriers
+    uint32_t base;       // shared address of the warp's carve: stages, then the grey ring, then the constants table, the mbarriers, the scratch
     uint32_t ring;       // this lane's slot 0 of the grey ring (slot s at ring + 256 s)
-    uint32_t full;       // mbarrier of stage s at full + 8 s
     uint32_t lane_src;   // shared address of the lane's pixels in row 0 of stage 0
-    int x, w, h, ys, total_rows, nboxes, cx, cy0, frame, lane;
+    int nboxes;          // boxes of 2 input rows
+    int fast_lo, fast_hi;  // boxes fast_lo .. fast_hi: both rows exist, emit output and have the full 15 window rows
 };
 
-// The march consumes one TMA box of 2 input rows per iteration of a ROLLED loop over a 2-stage ring (the loop body is a few
-// hundred instructions: an earlier version unrolled 8 rows with compile-time ring slots, 8600 instructions per kernel, and
-// ncu showed it waiting for the instruction cache - stall_no_instruction 2.4 cycles per issue, icc hit rate 77 %).
+// The march consumes TMA boxes of 2 input rows in a ROLLED loop over a 2-stage ring (an earlier version unrolled 8 rows with
+// compile-time ring slots, 8600 instructions per kernel, and ncu showed it waiting for the instruction cache:
+// stall_no_instruction 2.4 cycles per issue, icc hit rate 77 %).
 constexpr int kBoxRows = 2, kStages = 2;
 // Window areas cnt = nx * ny (clipped window width x height).  ny is warp-uniform and changes only in the top / bottom 7 rows
 // of the frame; nx differs from 15 only for the few lanes within 7 columns of the left / right image edge.  The per-pixel
@@ -197,39 +196,60 @@ constexpr int kBoxRows = 2, kStages = 2;
 // cap).  x-interior warps do not read it at all in the steady state (template INT: cnt = 225 is an immediate).
 constexpr int kClasses = 4;
 constexpr int kTabBytes = kClasses * 64;
+// per-warp scratch behind the mbarriers: what only lane 0's TMA requests and the few border rows need
+constexpr int kScrX0 = 0, kScrYs = 4, kScrCx = 8, kScrFrame = 12, kScrNy = 16, kScrRows = 20, kScrBytes = 32;
 template <int FMT>
 struct Stage {
     static constexpr int tx_bytes = kBoxRows * Fmt<FMT>::row_bytes;  // bytes one box delivers
     static constexpr int bytes = (tx_bytes + 127) & ~127;            // stage stride: TMA destinations are 128-byte aligned
-    static constexpr int per_warp = (kStages * bytes + kRing * 256 + kTabBytes + 8 * kStages + 127) & ~127;
+    static constexpr int ring_off = kStages * bytes;
+    static constexpr int tab_off = ring_off + kRing * 256;
+    static constexpr int bar_off = tab_off + kTabBytes;              // mbarrier of stage s at bar_off + 8 s
+    static constexpr int scr_off = bar_off + 8 * kStages;
+    static constexpr int per_warp = (scr_off + kScrBytes + 127) & ~127;
 };
 
-__device__ __forceinline__ uint32_t clipped_nx(const March &m, int xx) {
-    return (xx >= 0 && xx < m.w) ? (uint32_t)(min(m.w - 1, xx + 7) - max(0, xx - 7) + 1) : 0u;
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
-// (re)write the constants table for output rows with ny window rows: entry j of a class = {-256 cnt_j, cnt_j << 8 (j & 3)}
-__device__ __forceinline__ void set_ny(Lane &L, const March &m, uint32_t ny) {
-    L.ny_cur = ny;
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+__device__ __forceinline__ uint32_t clipped_nx(int w, int xx) {
+    return (xx >= 0 && xx < w) ? (uint32_t)(min(w - 1, xx + 7) - max(0, xx - 7) + 1) : 0u;
+}
+// (re)write the constants table for output rows with ny window rows: entry j of a class = {-256 cnt_j, cnt_j << 8 (j & 3)}.
+// Lanes clipped by an image edge write their own class, the first unclipped lane writes class 0 (nx = 15).
+template <int FMT>
+__device__ __noinline__ void set_ny(uint32_t base, uint32_t tab, uint32_t ny, int w) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t scr = base + Stage<FMT>::scr_off;
     __syncwarp();  // every lane has finished reading the previous values
-    if (L.tab_writer) {
+    const int x = (int)lds32(scr + kScrX0) + 8 * lane;
+    const uint32_t cls = (tab - (base + Stage<FMT>::tab_off)) >> 6;
+    const uint32_t first0 = (uint32_t)__ffs(__ballot_sync(0xffffffffu, cls == 0u)) - 1u;
+    if (cls != 0u || (uint32_t)lane == first0) {
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const uint32_t nx = L.tab_writer == 2 ? 15u : clipped_nx(m, m.x + j);
+            const uint32_t nx = cls == 0u ? 15u : clipped_nx(w, x + j);
             const uint32_t c = nx * ny;
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(L.tab + 8 * j), "r"(0u - 256u * c), "r"(c << (8 * (j & 3))) : "memory");
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(tab + 8 * j), "r"(0u - 256u * c), "r"(c << (8 * (j & 3))) : "memory");
         }
     }
+    if (lane == 0) sts32(scr + kScrNy, ny);
     __syncwarp();
 }
 
 template <int FMT>
-__device__ __forceinline__ void arm_box(const March &m, int box) {  // lane 0: request rows cy0 + 2 box .. into stage box & 1
-    const uint32_t st = (uint32_t)box & 1u;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m.full + 8 * st), "r"(Stage<FMT>::tx_bytes) : "memory");
+__device__ __forceinline__ void arm_box(const CUtensorMap *tmap, uint32_t base, int box) {  // lane 0: request rows ys - 7 + 2 box .. into stage box & 1
+    const uint32_t st = (uint32_t)box & 1u, bar = base + Stage<FMT>::bar_off + 8 * st, scr = base + Stage<FMT>::scr_off;
+    const int cx = (int)lds32(scr + kScrCx), cy = (int)lds32(scr + kScrYs) - 7 + box * kBoxRows, cz = (int)lds32(scr + kScrFrame);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(Stage<FMT>::tx_bytes) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-            m.base + st * Stage<FMT>::bytes),
-        "l"(m.tmap), "r"(m.cx), "r"(m.cy0 + box * kBoxRows), "r"(m.frame), "r"(m.full + 8 * st)
+            base + st * Stage<FMT>::bytes),
+        "l"(tmap), "r"(cx), "r"(cy), "r"(cz), "r"(bar)
         : "memory");
 }
 __device__ __forceinline__ void wait_box(uint32_t bar, uint32_t parity) {
@@ -252,7 +272,7 @@ __device__ __forceinline__ void wait_box(uint32_t bar, uint32_t parity) {
 // INT (only with OUT, steady-state rows of x-interior warps): every pixel of the warp has the full 15 x 15 window, so cnt = 225
 // is a compile-time constant: -256 cnt rides in on the accumulator of the pair sums and cnt << 8 (j & 3) is an immediate.
 template <int FMT, bool MASK, bool BITS, bool OUT, bool INT = false>
-__device__ __forceinline__ void row_step(Lane &L, uint32_t src, uint32_t ring_new, uint32_t ring_old, uint32_t ring_pix) {
+__device__ __forceinline__ void row_step(Lane &L, const StripArgs &a, uint32_t src, uint32_t ring_new, uint32_t ring_old, uint32_t ring_pix) {
     uint32_t p01, p23, p45, p67;
     uint2 g;
     load_grey8<FMT>(src, p01, p23, p45, p67, g);
@@ -320,14 +340,14 @@ __device__ __forceinline__ void row_step(Lane &L, uint32_t src, uint32_t ring_ne
                 if constexpr (BITS) *L.bits = (uint8_t)bits8;
             }
         }
-        L.grey += L.row_px;
-        if constexpr (MASK) L.mask += L.row_px;
-        if constexpr (BITS) L.bits += L.row_bits;
+        L.grey += a.w;
+        if constexpr (MASK) L.mask += a.w;
+        if constexpr (BITS) L.bits += a.bits_row_bytes;
     }
 }
 
 template <int FMT, bool MASK, bool BITS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) k1_strips_kernel(const __grid_constant__ CUtensorMap tmap, const StripArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) k1_strips_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StripArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t job = blockIdx.x * kWarpsPerCta + warp;
@@ -336,104 +356,114 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) k1_strips_ke
     const uint32_t seg = (job / a.nstrips) % a.nsegs;
     const uint32_t frame = job / (a.nstrips * a.nsegs);
     const int x0 = (int)strip * kCore - kHalo;        // first column of the warp's 256
+    const int x = x0 + 8 * lane;                      // first of this lane's 8 columns
+    const int ys = (int)(seg * a.seg_rows);
+    const int ye = min((int)a.h, ys + (int)a.seg_rows);
+    const int total_rows = (ye - ys) + 14;            // input rows ys-7 .. ye+6
 
     March m;
-    m.tmap = &tmap;
     m.base = smem_u32(smem) + (uint32_t)warp * Stage<FMT>::per_warp;
-    m.ring = m.base + kStages * Stage<FMT>::bytes + 8 * lane;
-    const uint32_t tab = m.base + kStages * Stage<FMT>::bytes + kRing * 256;
-    m.full = tab + kTabBytes;
+    m.ring = m.base + Stage<FMT>::ring_off + 8 * lane;
     m.lane_src = m.base + Fmt<FMT>::lead_bytes + lane * 8 * Fmt<FMT>::bpp;
-    m.x = x0 + 8 * lane;                              // first of this lane's 8 columns
-    m.w = (int)a.w; m.h = (int)a.h;
-    m.ys = (int)(seg * a.seg_rows);
-    const int ye = min(m.h, m.ys + (int)a.seg_rows);
-    m.total_rows = (ye - m.ys) + 14;                  // input rows ys-7 .. ye+6
-    m.nboxes = (m.total_rows + kBoxRows - 1) / kBoxRows;
-    m.cx = (x0 - Fmt<FMT>::lead_px) * Fmt<FMT>::bpp / 4;  // u32 element coordinate of the box, a multiple of 4
-    m.cy0 = m.ys - 7;
-    m.frame = (int)frame;
-    m.lane = lane;
-
+    m.nboxes = (total_rows + kBoxRows - 1) / kBoxRows;
+    // box b holds input rows k = 2b, 2b + 1, whose output rows are yo = ys + k - 14 and yo + 1.  Fast: k >= 14, k + 1 < total_rows,
+    // yo >= 7 and yo + 1 <= h - 8 (window rows all inside the frame)
+    {
+        const int k_lo = max(14, 21 - ys), k_hi = min(total_rows - 2, (int)a.h - 9 - ys + 14);
+        m.fast_lo = (k_lo + 1) >> 1;
+        m.fast_hi = k_hi >= 0 ? k_hi >> 1 : -1;
+    }
+    const uint32_t scr = m.base + Stage<FMT>::scr_off, bar = m.base + Stage<FMT>::bar_off;
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(m.full));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(m.full + 8));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sts32(scr + kScrX0, (uint32_t)x0);
+        sts32(scr + kScrYs, (uint32_t)ys);
+        sts32(scr + kScrCx, (uint32_t)((x0 - Fmt<FMT>::lead_px) * Fmt<FMT>::bpp / 4));  // u32 element coordinate of the box, a multiple of 4
+        sts32(scr + kScrFrame, frame);
+        sts32(scr + kScrNy, 0u);                      // window rows the constants table is written for
+        sts32(scr + kScrRows, (uint32_t)total_rows);
     }
 #pragma unroll
     for (int s = 0; s < kRing; s++) sts64(m.ring + 256 * s, make_uint2(0u, 0u));
     __syncwarp();
     if (lane == 0) {
-        arm_box<FMT>(m, 0);
-        if (m.nboxes > 1) arm_box<FMT>(m, 1);
+        arm_box<FMT>(&tmap, m.base, 0);
+        if (m.nboxes > 1) arm_box<FMT>(&tmap, m.base, 1);
     }
 
     Lane L;
     L.cs0 = L.cs1 = L.cs2 = L.cs3 = 0;
-    const bool lane_core = lane >= 1 && lane <= 30 && m.x < m.w;
+    const bool lane_core = lane >= 1 && lane <= 30 && x < (int)a.w;
     L.valid8 = 0;
     bool clipped = false;  // an output pixel of this lane has a window narrower than 15 columns
 #pragma unroll
     for (int j = 0; j < 8; j++)
-        if (lane_core && m.x + j < m.w) {
+        if (lane_core && x + j < (int)a.w) {
             L.valid8 |= 1u << j;
-            clipped |= clipped_nx(m, m.x + j) != 15u;
+            clipped |= clipped_nx((int)a.w, x + j) != 15u;
         }
-    // lane classes of the constants table: the (at most kClasses - 1, k1_strips_eligible) clipped lanes get one each
+    // lane classes of the constants table: a warp has at most kClasses - 1 clipped lanes (the lane at x = 0 and the one or two
+    // lanes that hold the columns w - 7 .. w - 1), each gets its own class
     const uint32_t clipped_lanes = __ballot_sync(0xffffffffu, clipped);
     const uint32_t cls = clipped ? 1u + (uint32_t)__popc(clipped_lanes & ((1u << lane) - 1u)) : 0u;
-    L.tab = tab + 64u * cls;
-    L.tab_writer = clipped ? 1 : (lane == __ffs(~clipped_lanes) - 1 ? 2 : 0);
-    L.ny_cur = 0;
+    L.tab = m.base + Stage<FMT>::tab_off + 64u * cls;
     L.store_mode = !lane_core ? 0 : ((a.wide_stores && L.valid8 == 0xffu) ? 1 : 2);
-    const size_t o_px = ((size_t)frame * a.h + m.ys) * a.w + m.x;
+    const size_t o_px = ((size_t)frame * a.h + ys) * a.w + x;
     L.grey = a.grey + o_px;
     L.mask = a.mask + o_px;
-    L.bits = a.bits + (size_t)frame * a.bits_frame_bytes + (size_t)m.ys * a.bits_row_bytes + (size_t)(m.x >> 5) * a.bits_col_bytes + ((m.x >> 3) & 3);
-    L.row_px = a.w;
-    L.row_bits = a.bits_row_bytes;
+    L.bits = a.bits + (size_t)frame * a.bits_frame_bytes + (size_t)ys * a.bits_row_bytes + (size_t)(x >> 5) * a.bits_col_bytes + ((x >> 3) & 3);
 
     // x-interior warp: none of its core columns is within 7 px of the left or right image edge (6 of the 8 strips of a 1080p
     // row, 14 of 16 at 4K) and its core lanes take the 8-byte stores; warp-uniform
     const bool interior = strip > 0 && (uint32_t)kCore * strip + kCore + 7 <= a.w && a.wide_stores;
-#pragma unroll 1
-    for (int box = 0; box < m.nboxes; box++) {
-        const uint32_t st = (uint32_t)box & 1u;
-        wait_box(m.full + 8 * st, ((uint32_t)box >> 1) & 1u);  // each stage completes once per two boxes
-        const int k = box * kBoxRows;                           // first input row of the box
-        // ring slots: row r lives in slot r & 15 (256 bytes apart).  With k even:
-        //   row k -> o0, row k + 1 -> o0 + 256; rows k - 15, k - 14 (leaving) -> o0 + 256, o1; rows k - 7, k - 6 (output) -> o4 + 256, o5
-        const uint32_t a9 = (uint32_t)box << 9;
-        const uint32_t o0 = a9 & 0xe00u, o1 = (a9 + 0x200u) & 0xe00u;
-        const uint32_t r0 = m.ring + o0, r1 = m.ring + o1, r4 = m.ring + (o0 ^ 0x800u), r5 = m.ring + (o1 ^ 0x800u);
-        const uint32_t src = m.lane_src + st * Stage<FMT>::bytes;
-        const int yo = m.ys + k - 14;                           // output row of the box's first input row
-        const bool fast = k >= 14 && k + 1 < m.total_rows && yo >= 7 && yo + 1 <= m.h - 8;  // both rows exist, emit, and have ny == 15
+    // One box (2 input rows, first row k = 2 box, stage ST) with the ring slots of its rows: new rows at n0 / n1, the rows
+    // leaving the window at o0 / o1, the output rows at p0 / p1.
+    auto do_box = [&](auto st_tag, int box, uint32_t parity, uint32_t n0, uint32_t n1, uint32_t o0, uint32_t o1, uint32_t p0, uint32_t p1) {
+        constexpr uint32_t ST = decltype(st_tag)::value;
+        wait_box(m.base + Stage<FMT>::bar_off + 8 * ST, parity);
+        const uint32_t src = m.lane_src + ST * Stage<FMT>::bytes;
+        const bool fast = box >= m.fast_lo && box <= m.fast_hi;
         if (fast && interior) {
-            row_step<FMT, MASK, BITS, true, true>(L, src, r0, r0 + 256, r4 + 256);
-            row_step<FMT, MASK, BITS, true, true>(L, src + Fmt<FMT>::row_bytes, r0 + 256, r1, r5);
+            row_step<FMT, MASK, BITS, true, true>(L, a, src, n0, o0, p0);
+            row_step<FMT, MASK, BITS, true, true>(L, a, src + Fmt<FMT>::row_bytes, n1, o1, p1);
         } else if (fast) {
-            if (L.ny_cur != 15u) set_ny(L, m, 15);
-            row_step<FMT, MASK, BITS, true>(L, src, r0, r0 + 256, r4 + 256);
-            row_step<FMT, MASK, BITS, true>(L, src + Fmt<FMT>::row_bytes, r0 + 256, r1, r5);
+            if (lds32(m.base + Stage<FMT>::scr_off + kScrNy) != 15u) set_ny<FMT>(m.base, L.tab, 15u, (int)a.w);
+            row_step<FMT, MASK, BITS, true>(L, a, src, n0, o0, p0);
+            row_step<FMT, MASK, BITS, true>(L, a, src + Fmt<FMT>::row_bytes, n1, o1, p1);
         } else {
+            const uint32_t scr = m.base + Stage<FMT>::scr_off;
+            const int k = box * kBoxRows, rows = (int)lds32(scr + kScrRows), yo = (int)lds32(scr + kScrYs) + k - 14;
 #pragma unroll 1
             for (int r = 0; r < kBoxRows; r++) {
-                if (k + r >= m.total_rows) break;
-                const uint32_t rn = r ? r0 + 256 : r0, ro = r ? r1 : r0 + 256, rp = r ? r5 : r4 + 256;
+                if (k + r >= rows) break;
+                const uint32_t rn = r ? n1 : n0, ro = r ? o1 : o0, rp = r ? p1 : p0;
                 if (k + r >= 14) {
                     const int y = yo + r;
-                    const uint32_t ny = (uint32_t)(min(m.h - 1, y + 7) - max(0, y - 7) + 1);
-                    if (ny != L.ny_cur) set_ny(L, m, ny);  // only in the top / bottom 7 rows of the frame
-                    row_step<FMT, MASK, BITS, true>(L, src + r * Fmt<FMT>::row_bytes, rn, ro, rp);
+                    const uint32_t ny = (uint32_t)(min((int)a.h - 1, y + 7) - max(0, y - 7) + 1);
+                    if (ny != lds32(scr + kScrNy)) set_ny<FMT>(m.base, L.tab, ny, (int)a.w);  // only in the top / bottom 7 rows of the frame
+                    row_step<FMT, MASK, BITS, true>(L, a, src + r * Fmt<FMT>::row_bytes, rn, ro, rp);
                 } else {
-                    row_step<FMT, MASK, BITS, false>(L, src + r * Fmt<FMT>::row_bytes, rn, ro, rp);
+                    row_step<FMT, MASK, BITS, false>(L, a, src + r * Fmt<FMT>::row_bytes, rn, ro, rp);
                 }
             }
         }
         // every lane has consumed the box (its values are in registers or in the ring): refill the stage with the box 2 ahead
         __syncwarp();
-        if (lane == 0 && box + kStages < m.nboxes) arm_box<FMT>(m, box + kStages);
+        if (lane == 0 && box + kStages < m.nboxes) arm_box<FMT>(&tmap, m.base, box + kStages);
+    };
+    // Two boxes (4 input rows) per iteration, so the stage of a box and its mbarrier are compile-time constants.  Ring slots:
+    // row r lives in slot r & 15, 256 bytes apart; with k = 4 it the rows k .. k + 3 are at A .. A + 768, the rows leaving the
+    // window (k - 15 .. k - 12) at A + 256 .. A + 768 and B, the output rows (k - 7 .. k - 4) at C + 256 .. C + 768 and D.
+#pragma unroll 1
+    for (int it = 0; 2 * it < m.nboxes; it++) {
+        const uint32_t oa = ((uint32_t)it & 3u) << 10, ob = ((uint32_t)(it + 1) & 3u) << 10;
+        const uint32_t A = m.ring + oa, B = m.ring + ob, C = m.ring + (oa ^ 0x800u), D = m.ring + (ob ^ 0x800u);
+        const uint32_t parity = (uint32_t)it & 1u;              // each stage completes once per iteration
+        do_box(std::integral_constant<uint32_t, 0>{}, 2 * it, parity, A, A + 256, A + 256, A + 512, C + 256, C + 512);
+        if (2 * it + 1 < m.nboxes)
+            do_box(std::integral_constant<uint32_t, 1>{}, 2 * it + 1, parity, A + 512, A + 768, A + 768, B, C + 768, D);
     }
 }
 
