@@ -534,12 +534,16 @@ cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t st
     a.grey = p.grey; a.mask = p.mask; a.bits = reinterpret_cast<uint8_t *>(p.bits);
     a.n = p.n; a.w = p.w; a.h = p.h;
     a.nstrips = (p.w + kCore - 1) / kCore;
-    // row segments: as many as still fit in ONE wave of resident warps (measured best on B200: 64 x 1080p -> 8
-    // segments, 256 x 1080p -> 2); every segment re-reads a 14-row halo, so they stay >= 128 rows
+    // row segments: at least as many as fill the resident warp slots once, and short enough (about 180 rows) that the grid
+    // is several waves of CTAs: the block scheduler then evens out the slower edge strips and the warps drift out of phase.
+    // Measured on B200, 256 x 1080p: one wave of 540-row segments 0.465 ms, 360 rows 0.454, 270 rows 0.426, 180 rows 0.420,
+    // 135 rows 0.422, 108 rows 0.438 (every segment re-reads a 14-row halo, so they stay >= 128 rows)
     uint32_t nsegs = tuning && tuning->seg_rows ? (p.h + tuning->seg_rows - 1) / tuning->seg_rows : 0;
     if (nsegs == 0) {
         const uint64_t per_seg = (uint64_t)p.n * a.nstrips;
         nsegs = per_seg >= slots ? 1 : (uint32_t)(slots / per_seg);
+        const uint32_t pref = (p.h + 90) / 180;
+        if (nsegs < pref) nsegs = pref;
         const uint32_t max_segs = p.h / 128 ? p.h / 128 : 1;
         if (nsegs > max_segs) nsegs = max_segs;
     }
