@@ -44,7 +44,8 @@ constexpr int kDx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};  // ring order w nw n ne e s
 constexpr int kDy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
 
 // step table entry: bits 0-2 direction of the next pixel, bit 3 west side examined, bit 4 east side examined,
-// bits 5-6 dx + 1, bits 7-8 dy + 1, bits 9-11 state at the next pixel (direction back to this one)
+// bits 5-6 dx + 1, bits 7-8 dy + 1, bits 10-12 state at the next pixel (direction back to this one): e & 0x1c00 is the byte
+// offset of that state's row of 512 entries
 struct StepTables {
     uint16_t fwd[8][512];  // [ring direction of the previous border pixel][3x3 neighbourhood]
     uint16_t bwd[8][512];  // [ring direction of the next border pixel][3x3 neighbourhood]
@@ -68,7 +69,7 @@ void build_tables(StepTables &t) {
                     examined |= 1u << c;
                 }
                 const uint16_t e = (uint16_t)(d | (((examined >> 0) & 1u) << 3) | (((examined >> 4) & 1u) << 4) | ((kDx[d] + 1) << 5) |
-                                              ((kDy[d] + 1) << 7) | (((d + 4) & 7) << 9));
+                                              ((kDy[d] + 1) << 7) | (((d + 4) & 7) << 10));
                 (back ? t.bwd : t.fwd)[state][hood] = e;
             }
         }
@@ -244,7 +245,7 @@ __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (
         n++;
         x += (int)((e >> 5) & 3u) - 1;
         y += (int)((e >> 7) & 3u) - 1;
-        state = e >> 9;
+        state = e >> 10;
     }
     first_pixel = min_pix == start_pix;
     return kSurvivor;
@@ -466,6 +467,20 @@ __global__ void __launch_bounds__(128) k3_walk_short(const Geo g, const StepTabl
 // (Measured before the pairing: fewer walkers per warp, software prefetch of the sector ahead and a register window all
 // made this kernel slower: its time is the dependent chain of the longest border, about 750 cycles per step — which is
 // why the per-step exchange and tests were moved off that chain, see the blocks of kBlk steps below.)
+// 3x3 neighbourhood of the pixel at guarded column o = x + 31, row y, times two (the byte offset of its entry in a row of the
+// step tables): three loads from one word column, the second column only when the three pixel columns straddle two words
+__device__ __forceinline__ uint32_t hood2(const uint32_t *plane, uint32_t Hp, int o, int y) {
+    const uint32_t *p = plane + ((uint32_t)(o >> 5) * Hp + (uint32_t)y);
+    const int sh = o & 31;
+    uint32_t t = __ldg(p), m = __ldg(p + 1), b = __ldg(p + 2), t2 = 0, m2 = 0, b2 = 0;
+    if (sh > 29) {
+        const uint32_t *q = p + Hp;
+        t2 = __ldg(q); m2 = __ldg(q + 1); b2 = __ldg(q + 2);
+    }
+    t = __funnelshift_r(t, t2, sh); m = __funnelshift_r(m, m2, sh); b = __funnelshift_r(b, b2, sh);
+    return ((t << 1) & 0x00eu) | ((m << 4) & 0x070u) | ((b << 7) & 0x380u);
+}
+
 template <int kBlk>
 __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
     __shared__ uint16_t fwd[8][512];
@@ -478,15 +493,17 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
     const uint32_t total = min(l.counters[0], l.walkers_cap);
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, back = tid & 1u;
     const uint32_t pair_mask = 3u << (threadIdx.x & 30u);   // the two lanes of this pair: they never diverge from each other
-    const uint16_t (*lut)[512] = back ? bwd : fwd;
+    const unsigned char *lut = reinterpret_cast<const unsigned char *>(back ? &bwd[0][0] : &fwd[0][0]);
+    const int w = (int)g.w, o_max = w + 30;
     for (uint32_t i = tid >> 1; i < total; i += (gridDim.x * blockDim.x) >> 1) {
         const unsigned long long key = l.walkers[i];
         uint32_t frame;
         int sx, sy, kind;
         decode_key(g, key, frame, sx, sy, kind);
         const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
-        const uint32_t me = ((uint32_t)(sy * (int)g.w + sx) << 1) | (uint32_t)kind;
-        const uint32_t start_pix = (uint32_t)(sy * (int)g.w + sx);
+        asm volatile("" : "+l"(plane));  // keep the frame's base in registers: otherwise it is recomputed (64-bit) in every step
+        const uint32_t start_pix = (uint32_t)(sy * w + sx);
+        const uint32_t me = (start_pix << 1) | (uint32_t)kind;
         const uint32_t nb0 = ring_of(hood9(plane, g.Hp, sx, sy));
         const int adj = kind ? 4 : 0;
         int pred = -1;
@@ -502,9 +519,16 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
             }
             continue;
         }
-        int x = sx, y = sy;
-        uint32_t state = (uint32_t)pred;  // forwards: the start visit
-        if (back) { x = sx + ddx(pred); y = sy + ddy(pred); state = (uint32_t)((pred + 4) & 7); }  // backwards: the visit before it
+        // The position is kept as (o = x + 31, y, pix = y w + x) and the state as the byte offset of its table row: a step is
+        // three loads of one word column, three funnel shifts, the table entry, and four adds.
+        int o = sx + 31, y = sy;
+        uint32_t pix = start_pix, state_off = (uint32_t)pred << 10;  // forwards: the start visit
+        if (back) {  // backwards: the visit before it
+            o += ddx(pred); y += ddy(pred); pix = (uint32_t)(y * w + o - 31); state_off = (uint32_t)((pred + 4) & 7) << 10;
+        }
+        // a candidate crack of a visit comes before me in raster order:  west crack  2 pix < me  <=>  pix < tw;  east crack
+        // 2 pix + 1 < me  <=>  pix < te
+        const uint32_t tw = (me + 1u) >> 1, te = me >> 1;
         uint32_t min_pix = start_pix, n = 0, prev_back_id = 0xffffffffu, my_prev_id = 0xffffffffu;
         bool dead = false;
         // Blocks of kBlk steps: inside a block a lane only walks (load, table, move: the dependent chain), remembering its
@@ -513,31 +537,30 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
         // partner has examined already (same cracks, same verdict), checkpoints dropped there are valid positions of the
         // same border (a checkpoint needs 64 walked points, so n >= 122 and n / 2 + kBlk < n), and the meeting point itself
         // is taken from the remembered visit.
-        uint32_t meet_xy = 0, meet_state = 0;
+        uint32_t meet_id = 0;
         for (uint32_t s0 = 0;; s0 += kBlk) {
-            uint32_t ids[kBlk], xys[kBlk], fsts[kBlk];
+            uint32_t ids[kBlk];
             bool mine_dead = false;
 #pragma unroll
             for (int k = 0; k < kBlk; k++) {
-                const uint32_t e = lut[state][hood9(plane, g.Hp, x, y)];
-                const uint32_t pix = (uint32_t)(y * (int)g.w + x);
-                const uint32_t fstate = back ? (e & 7u) : state;                  // direction of the previous border pixel at this visit
+                const uint32_t h2 = hood2(plane, g.Hp, o, y);
+                const uint32_t e = *reinterpret_cast<const uint16_t *>(lut + state_off + h2);
+                const uint32_t fstate = back ? (e & 7u) : (state_off >> 10);      // direction of the previous border pixel at this visit
                 ids[k] = (pix << 3) | fstate;
-                xys[k] = (uint32_t)x | ((uint32_t)y << 16);
-                fsts[k] = fstate;
-                // candidate cracks of this visit that come before me in raster order
-                mine_dead |= ((e & 8u) && x > 0 && (pix << 1) < me) || ((e & 16u) && x + 1 < (int)g.w && ((pix << 1) | 1u) < me);
+                // candidate cracks of this visit that come before me in raster order (west needs x > 0, east x + 1 < w)
+                mine_dead |= ((e & 8u) && o > 31 && pix < tw) || ((e & 16u) && o < o_max && pix < te);
                 min_pix = min(min_pix, pix);
                 // checkpoints for k3_emit: forwards at index kSeg, 2 kSeg, ...; backwards kSeg, 2 kSeg, ... points before the end
                 const uint32_t walked = back ? s0 + k + 1 : s0 + k;
                 if (walked && walked % kSeg == 0) {
                     const uint32_t c = atomicAdd(&l.counters[4], 1u);
-                    if (c < l.ckpt_cap) l.ckpts[c] = Ckpt{i, walked, xys[k], fstate | (back ? kCkptBackward : 0u)};
+                    if (c < l.ckpt_cap) l.ckpts[c] = Ckpt{i, walked, (uint32_t)(o - 31) | ((uint32_t)y << 16), fstate | (back ? kCkptBackward : 0u)};
                     else atomicOr(&l.counters[2], 1u);
                 }
-                x += (int)((e >> 5) & 3u) - 1;
-                y += (int)((e >> 7) & 3u) - 1;
-                state = e >> 9;
+                const int dx = (int)((e >> 5) & 3u) - 1, dy = (int)((e >> 7) & 3u) - 1;
+                o += dx; y += dy;
+                pix += (uint32_t)(dy * w + dx);
+                state_off = e & 0x1c00u;
             }
             uint32_t oid[kBlk];
 #pragma unroll
@@ -546,22 +569,17 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
             if (dead) break;
             // the forward lane compares with the backward lane's visit of the same step and of the step before; the backward
             // lane mirrors it.  s is the step: forward visit index s, backward visit index n - 1 - s.
-            int met = -1;
+            bool met = false;
 #pragma unroll
             for (int k = 0; k < kBlk; k++) {
-                if (met >= 0) continue;
+                if (met) continue;
                 const uint32_t s = s0 + k;
                 const uint32_t fwd_id = back ? oid[k] : ids[k], back_id = back ? ids[k] : oid[k];
                 const uint32_t back_prev = k == 0 ? (back ? my_prev_id : prev_back_id) : (back ? ids[k > 0 ? k - 1 : 0] : oid[k > 0 ? k - 1 : 0]);
-                if (fwd_id == back_id) { n = 2 * s + 1; met = k; }
-                else if (s > 0 && fwd_id == back_prev) { n = 2 * s; met = k; }
+                if (fwd_id == back_id) { n = 2 * s + 1; met = true; meet_id = ids[k]; }
+                else if (s > 0 && fwd_id == back_prev) { n = 2 * s; met = true; meet_id = ids[k]; }
             }
-            if (met >= 0) {
-#pragma unroll
-                for (int k = 0; k < kBlk; k++)
-                    if (k == met) { meet_xy = xys[k]; meet_state = fsts[k]; }
-                break;
-            }
+            if (met) break;
             my_prev_id = ids[kBlk - 1];
             prev_back_id = oid[kBlk - 1];
         }
@@ -573,7 +591,8 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
             // forward and the first backward segment (they may overlap: every segment writes the same values)
             if (n > kSeg) {
                 const uint32_t c = atomicAdd(&l.counters[4], 1u);
-                if (c < l.ckpt_cap) l.ckpts[c] = Ckpt{i, n / 2, meet_xy, meet_state};
+                const uint32_t mp = meet_id >> 3, my = mp / (uint32_t)w, mx = mp - my * (uint32_t)w;
+                if (c < l.ckpt_cap) l.ckpts[c] = Ckpt{i, n / 2, mx | (my << 16), meet_id & 7u};
                 else atomicOr(&l.counters[2], 1u);
             }
             slot = record_survivor(l, frame, key, kind, n, min_pix == start_pix, min_points);
@@ -711,7 +730,7 @@ __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *ta
         const uint32_t e = fwd[state][win_hood(win, x)];
         x += (int)((e >> 5) & 3u) - 1;
         y += (int)((e >> 7) & 3u) - 1;
-        state = e >> 9;
+        state = e >> 10;
         win_move(win, x, y);
         return v;
     };
@@ -1259,7 +1278,8 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     k3_walk_short<<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
     K3_CUDA(cudaGetLastError());
     timer.mark("walk_short");
-    k3_walkers<8><<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);  // blocks of 2 / 4 / 6 / 8 steps measured: 0.207 / 0.188 / 0.186 / 0.184 ms
+    // blocks of 2 / 4 / 6 / 8 steps measured: 0.207 / 0.188 / 0.186 / 0.184 ms (before the lighter step: 0.152 ms with 8)
+    k3_walkers<8><<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
     K3_CUDA(cudaGetLastError());
     timer.mark("walkers");
     k3_flag_all<<<(p.n + 127) / 128, 128, 0, stream>>>(p.frame_flags, p.n, w.counters, 0);
