@@ -320,11 +320,11 @@ namespace {
 
 a3_status check_config(const a3_config &c) {
     if (c.threshold_window == 0) return fail(A3_ERR_INVALID_ARGUMENT, "threshold_window must be > 0 (imageproc asserts block_radius > 0)");
-    if (c.threshold_window > 16) return fail(A3_ERR_UNSUPPORTED, "threshold_window > 16 is not supported by the CUDA path");
+    if (c.threshold_window > 127) return fail(A3_ERR_UNSUPPORTED, "threshold_window > 127 is not supported by the CUDA path (16-bit column sums)");
     if (!(c.contour_simplification_epsilon > 0.0))
         return fail(A3_ERR_INVALID_ARGUMENT, "contour_simplification_epsilon must be > 0 (approximate_polygon_dp panics otherwise)");
-    if (c.homography_sample_size == 0 || c.homography_sample_size > 256)
-        return fail(A3_ERR_UNSUPPORTED, "homography_sample_size must be in 1..256");
+    if (c.homography_sample_size == 0) return fail(A3_ERR_INVALID_ARGUMENT, "homography_sample_size must be > 0");
+    if (c.homography_sample_size > 4096) return fail(A3_ERR_UNSUPPORTED, "homography_sample_size > 4096 is not supported by the CUDA path");
     return A3_OK;
 }
 
@@ -538,6 +538,11 @@ a3_status a3_detector_create(const a3_config *cfg, const a3_dictionary *dict, in
     d->mark_size = mark_size_of(dict->num_bits);
     uint32_t hc = std::thread::hardware_concurrency();
     d->host_threads = hc ? (hc > 64 ? 64 : hc) : 1;
+    if (!k2_supported(cfg->homography_sample_size, d->mark_size, dict->n_codes)) {
+        a3_detector_destroy(d);
+        return fail(A3_ERR_UNSUPPORTED, "homography_sample_size is too large for the CUDA path: one sampled patch (size^2 bytes) and the dictionary "
+                                        "must fit the 220 KB of shared memory of an SM (about 400 with the shipped dictionaries)");
+    }
     ResizeTaps tp = make_resize_taps(cfg->homography_sample_size, d->mark_size);
     d->max_taps = tp.max_taps;
     cudaError_t e = cudaSuccess;

@@ -92,6 +92,8 @@ struct K2Params {
 };
 cudaError_t k2_decode(const K2Params &p, cudaStream_t stream);
 size_t k2_smem_bytes(uint32_t patch_size, uint32_t mark_size, uint32_t n_codes);
+// whether K2 can decode with this homography_sample_size / dictionary at all (at least one patch + the dictionary in shared memory)
+bool k2_supported(uint32_t patch_size, uint32_t mark_size, uint32_t n_codes);
 
 // image::imageops::resize(Triangle) tap table for n_in -> n_out, computed on the host in f32 with the
 // reference's expression order.  weights[o*max_taps + i], meta[2*o] = left, meta[2*o+1] = count.

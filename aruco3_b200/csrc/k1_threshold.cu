@@ -25,7 +25,7 @@ namespace {
 
 constexpr int kStages = 4;        // TMA ring depth (rows in flight)
 constexpr int kMaxThreads = 512;  // 4 columns per thread -> at most 2048 columns per strip
-constexpr int kMaxRadius = 16;
+constexpr int kMaxRadius = 127;   // column sums of 2 r + 1 rows are exchanged as u16: 255 * 255 < 2^16
 
 // Exact fixed-point form of (2126 R + 7152 G + 722 B) / 10000 for all 2^24 (R,G,B):
 //   grey = (kWr*R + kWg*G + kWb*B + kBias) >> 24        (weights sum to 2^24; the maximum is < 2^32)
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kMaxThreads) k1_kernel(const K1Args a) {
     const uint32_t frame = bid / a.segs;
     const int cx0 = strip * a.strip_cols;
     const int cx1 = min((int)a.w, cx0 + (int)a.strip_cols);
-    const int lx0 = cx0 == 0 ? 0 : ((cx0 - r) & ~31);
+    const int lx0 = max(0, cx0 - r) & ~31;
     const int lx1 = min((int)a.w, cx1 + r);
     const int y0 = seg * a.seg_rows;
     const int y1 = min((int)a.h, y0 + (int)a.seg_rows);
@@ -368,7 +368,13 @@ cudaError_t k1_gray_threshold(const K1Params &p, const K1Tuning *tuning, cudaStr
     if (!(tuning && tuning->force_generic) && k1_strips_eligible(p)) return k1_strips(p, tuning, stream, info);
     const uint32_t r = p.radius;
     const uint32_t bpp = fmt_bpp(p.format);
-    const uint32_t max_core = 4 * kMaxThreads - 64;  // leave room for the 32-aligned left halo and the right halo
+    // threads per CTA: bounded by kMaxThreads and by shared memory (a ring of 2 r + 1 grey rows, 4 bytes per thread and row, the
+    // TMA stages and the exchange rows); a strip's loaded span is its core plus r columns on either side, its start rounded down to 32
+    const uint32_t per_thread = 4 * (2 * r + 1) + 4 * bpp * (uint32_t)kStages + 16;
+    uint32_t nt_max = ((200u * 1024u) / per_thread) & ~31u;
+    if (nt_max > (uint32_t)kMaxThreads) nt_max = kMaxThreads;
+    if (4 * nt_max < 2 * r + 32 + 32) return cudaErrorInvalidConfiguration;
+    const uint32_t max_core = (4 * nt_max - (2 * r + 32)) & ~31u;
 
     // ---- tiling ----
     uint32_t strip_cols = tuning && tuning->strip_cols ? round_up(tuning->strip_cols, 32) : 0;
@@ -407,7 +413,7 @@ cudaError_t k1_gray_threshold(const K1Params &p, const K1Tuning *tuning, cudaStr
                ((uintptr_t)p.src % 16 == 0);
     for (uint32_t s = 0; s < strips; s++) {
         uint32_t cx0 = s * strip_cols, cx1 = cx0 + strip_cols < p.w ? cx0 + strip_cols : p.w;
-        uint32_t lx0 = cx0 == 0 ? 0 : ((cx0 - r) & ~31u);
+        uint32_t lx0 = (cx0 > r ? cx0 - r : 0u) & ~31u;
         uint32_t lx1 = cx1 + r < p.w ? cx1 + r : p.w;
         if (lx1 - lx0 > max_cols) max_cols = lx1 - lx0;
         if (((lx1 - lx0) * bpp) % 16 != 0 || (lx0 * bpp) % 16 != 0) tma = false;

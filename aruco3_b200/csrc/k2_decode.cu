@@ -200,14 +200,16 @@ __global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const
     uint8_t *reduced = reinterpret_cast<uint8_t *>(tmp + ms * ps);            // ms * ms (padded to x4)
     uint8_t *patch = reduced + ((ms * ms + 3) & ~3u);                         // ps * ps
 
-    for (uint32_t i = threadIdx.x; i < p.n_codes; i += kThreads) dict[i] = p.codes[i];
-    for (uint32_t i = threadIdx.x; i < ms * max_taps; i += kThreads) taps[i] = p.resize_w[i];
-    for (uint32_t i = threadIdx.x; i < 2 * ms; i += kThreads) meta[i] = p.resize_meta[i];
+    // (the block has 8 warps, fewer when homography_sample_size is so large that 8 patches do not fit shared memory)
+    for (uint32_t i = threadIdx.x; i < p.n_codes; i += blockDim.x) dict[i] = p.codes[i];
+    for (uint32_t i = threadIdx.x; i < ms * max_taps; i += blockDim.x) taps[i] = p.resize_w[i];
+    for (uint32_t i = threadIdx.x; i < 2 * ms; i += blockDim.x) meta[i] = p.resize_meta[i];
     __syncthreads();
 
     // one warp per candidate; warps never wait for each other
     const uint32_t n_quads = p.n_quads_dev ? min(*p.n_quads_dev, p.n_quads) : p.n_quads;
-    const uint32_t first_q = blockIdx.x * kWarps + warp, stride_q = gridDim.x * kWarps;
+    const uint32_t nwarps = blockDim.x >> 5;
+    const uint32_t first_q = blockIdx.x * nwarps + warp, stride_q = gridDim.x * nwarps;
     auto next_quad = [&](uint32_t q) -> uint32_t {  // the warp's next quad: fixed stride, or the shared counter behind the first round
         if (!p.queue) return q + stride_q;
         uint32_t t = 0;
@@ -395,28 +397,40 @@ __global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const
 
 }  // namespace
 
-size_t k2_smem_bytes(uint32_t ps, uint32_t ms, uint32_t n_codes) {
+static size_t k2_smem_for(uint32_t ps, uint32_t ms, uint32_t n_codes, uint32_t warps) {
     ResizeTaps tp = make_resize_taps(ps, ms);
     size_t b = (size_t)n_codes * 8 + (size_t)ms * tp.max_taps * 4 + (size_t)2 * ms * 4 + 16;
-    return b + (size_t)kWarps * k2_warp_bytes(ps, ms);
+    return b + (size_t)warps * k2_warp_bytes(ps, ms);
 }
+// warps per CTA: 8, fewer when the patches of 8 candidates (homography_sample_size^2 bytes each) do not fit shared memory; 0 = not even one
+static uint32_t k2_warps(uint32_t ps, uint32_t ms, uint32_t n_codes) {
+    for (uint32_t w = kWarps; w >= 1; w >>= 1)
+        if (k2_smem_for(ps, ms, n_codes, w) <= 220 * 1024) return w;
+    return 0;
+}
+size_t k2_smem_bytes(uint32_t ps, uint32_t ms, uint32_t n_codes) {
+    const uint32_t w = k2_warps(ps, ms, n_codes);
+    return k2_smem_for(ps, ms, n_codes, w ? w : 1);
+}
+bool k2_supported(uint32_t ps, uint32_t ms, uint32_t n_codes) { return ps > 0 && ms >= 3 && ms <= 16 && k2_warps(ps, ms, n_codes) != 0; }
 
 cudaError_t k2_decode(const K2Params &p, cudaStream_t stream) {
     if (p.n_quads == 0) return cudaSuccess;
     if (p.mark_size > 16 || p.mark_size < 3 || p.patch_size == 0 || p.n_codes >= (1u << 22)) return cudaErrorInvalidValue;
     ResizeTaps tp = make_resize_taps(p.patch_size, p.mark_size);
-    size_t smem = k2_smem_bytes(p.patch_size, p.mark_size, p.n_codes);
-    if (smem > 220 * 1024) return cudaErrorInvalidValue;
+    const uint32_t warps = k2_warps(p.patch_size, p.mark_size, p.n_codes);
+    if (warps == 0) return cudaErrorInvalidValue;
+    const size_t smem = k2_smem_for(p.patch_size, p.mark_size, p.n_codes, warps);
     cudaError_t e = cudaFuncSetAttribute(k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t want = (p.n_quads + kWarps - 1) / kWarps;
+    const uint32_t want = (p.n_quads + warps - 1) / warps;
     int per_sm = 0;  // CTAs that are resident together (registers allow 3, shared memory depends on the dictionary)
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_kernel, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_kernel, (int)warps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const uint32_t resident = (uint32_t)sms * (uint32_t)per_sm;
-    k2_kernel<<<want < resident ? want : resident, kThreads, smem, stream>>>(p, tp.max_taps);
+    k2_kernel<<<want < resident ? want : resident, warps * 32, smem, stream>>>(p, tp.max_taps);
     return cudaGetLastError();
 }
 

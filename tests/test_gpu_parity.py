@@ -103,12 +103,22 @@ def test_detect_bgra_equals_swizzled_rgba(a3):
     assert sum(len(x.markers) for x in got) > 5
 
 
-@pytest.mark.parametrize("radius", [1, 2, 3, 5, 7, 8, 12, 16])
+@pytest.mark.parametrize("radius", [1, 2, 3, 5, 7, 8, 12, 16, 17, 33, 64, 127])
 def test_k1_radius(a3, oracle, radius):
-    """threshold_window is a public config field (src/aruco.rs:24)."""
+    """threshold_window is a public config field (src/aruco.rs:24); the reference accepts any block radius, the CUDA path 1..127
+    (its column sums of 2 r + 1 rows travel as 16-bit values), windows wider or taller than the frame included."""
     with a3.Detector(a3.DetectorConfig(threshold_window=radius)) as d:
         _check_k1(d, oracle, _noise(radius, (2, 120, 212, 3)), radius)
         _check_k1(d, oracle, _smooth(radius, 1, 61, 1000, 3), radius)
+        if radius > 16:
+            _check_k1(d, oracle, _noise(radius + 1, (1, 300, 2300, 3)), radius)  # several strips, a halo wider than a 32-column word
+
+
+def test_k1_radius_beyond_the_cuda_path(a3):
+    """threshold_window > 127: A3_ERR_UNSUPPORTED, stated, not a wrong answer (the reference itself has no limit)."""
+    with pytest.raises(a3.A3Error) as e:
+        a3.Detector(a3.DetectorConfig(threshold_window=128))
+    assert e.value.status == a3._ffi.A3_ERR_UNSUPPORTED
 
 
 def test_k1_extremes(det, oracle):
@@ -446,7 +456,8 @@ def test_decode_stress_batch(a3, oracle):
         assert gm == rm and len(gm) >= 150, f"C5[{f}]: {len(gm)} markers"
 
 
-@pytest.mark.parametrize("dict_name,hs", [("ARUCO", 49), ("APRILTAG_16H5", 49), ("CHILITAGS", 49), ("APRILTAG_36H11", 32), ("ARUCO_MIP_36H12", 77)])
+@pytest.mark.parametrize("dict_name,hs", [("ARUCO", 49), ("APRILTAG_16H5", 49), ("CHILITAGS", 49), ("APRILTAG_36H11", 32), ("ARUCO_MIP_36H12", 77),
+                                          ("ARUCO", 200), ("APRILTAG_36H9", 300)])
 def test_decode_fuzz(a3, oracle, dict_name, hs):
     """K2 against the oracle on 1500 arbitrary quads (any four points: rotated, concave, tiny, huge, partly outside) over a
     smooth and a noisy frame, for mark sizes 6 / 7 / 8 / 10 and other homography_sample_size values: projection class and
@@ -454,7 +465,7 @@ def test_decode_fuzz(a3, oracle, dict_name, hs):
     rng = np.random.default_rng(hash((dict_name, hs)) & 0xffff)
     w, h = 352, 288
     grey = np.stack([_smooth(5, 1, h, w, 1)[0, :, :, 0], _noise(6, (h, w))])
-    n = 1500
+    n = 1500 if hs <= 100 else 160  # large homography_sample_size: fewer warps per CTA share the shared memory (k2_decode.cu)
     kind = rng.integers(0, 4, n)
     quads = np.zeros((n, 8), np.int64)
     for k in range(n):
