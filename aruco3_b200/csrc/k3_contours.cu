@@ -203,11 +203,27 @@ struct Lists {
 };
 
 
+// 3x3 neighbourhood of the pixel at guarded column o = x + 31, row y, times two (the byte offset of its entry in a row of the
+// step tables): three loads from one word column, the second column only when the three pixel columns straddle two words
+__device__ __forceinline__ uint32_t hood2(const uint32_t *plane, uint32_t Hp, int o, int y) {
+    const uint32_t *p = plane + ((uint32_t)(o >> 5) * Hp + (uint32_t)y);
+    const int sh = o & 31;
+    uint32_t t = __ldg(p), m = __ldg(p + 1), b = __ldg(p + 2), t2 = 0, m2 = 0, b2 = 0;
+    if (sh > 29) {
+        const uint32_t *q = p + Hp;
+        t2 = __ldg(q); m2 = __ldg(q + 1); b2 = __ldg(q + 2);
+    }
+    t = __funnelshift_r(t, t2, sh); m = __funnelshift_r(m, m2, sh); b = __funnelshift_r(b, b2, sh);
+    return ((t << 1) & 0x00eu) | ((m << 4) & 0x070u) | ((b << 7) & 0x380u);
+}
+
 // The candidate (x, y, kind) walks its border for at most `budget` steps.  kSurvivor: it is the raster-first candidate
 // crack of the border (n = number of points of the border, first_pixel = it is also the border's raster-first pixel).
 __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (*fwd)[512], const uint16_t (*bwd)[512], int sx, int sy, int kind,
                            uint32_t budget, uint32_t &n, bool &first_pixel) {
-    const uint32_t me = ((uint32_t)(sy * (int)g.w + sx) << 1) | (uint32_t)kind;
+    const int w = (int)g.w, o_max = w + 30;
+    const uint32_t start_pix = (uint32_t)(sy * w + sx);
+    const uint32_t me = (start_pix << 1) | (uint32_t)kind;
     const uint32_t nb0 = ring_of(hood9(plane, g.Hp, sx, sy));
     const int adj = kind ? 4 : 0;
     int pred = -1;
@@ -218,34 +234,35 @@ __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (
     n = 1;
     first_pixel = true;
     if (pred < 0) return (kind == 0 || sx == 0) ? kSurvivor : kDead;  // isolated pixel: its west crack (if a candidate) comes first
-    const uint32_t start_pix = (uint32_t)(sy * (int)g.w + sx);
-    uint32_t min_pix = start_pix;
-    int x, y;
-    uint32_t state;
+    // position as (o = x + 31, y, pix = y w + x), state as the byte offset of its table row (see k3_walkers)
+    uint32_t min_pix = start_pix, pix = start_pix, state_off;
+    int o = sx + 31, y = sy;
     if (kind) {  // forwards from the start pixel, previous pixel in direction `pred` (this is the reference's own trace)
-        x = sx; y = sy; state = (uint32_t)pred;
+        state_off = (uint32_t)pred << 10;
         n = 0;
     } else {     // backwards: the start pixel's own visit owns the west crack and nothing raster-earlier
-        x = sx + ddx(pred); y = sy + ddy(pred); state = (uint32_t)((pred + 4) & 7);
+        o += ddx(pred); y += ddy(pred); pix = (uint32_t)(y * w + o - 31); state_off = (uint32_t)((pred + 4) & 7) << 10;
     }
-    const uint16_t (*lut)[512] = kind ? fwd : bwd;
+    const unsigned char *lut = reinterpret_cast<const unsigned char *>(kind ? &fwd[0][0] : &bwd[0][0]);
+    // a candidate crack of a visit comes before me in raster order:  west  2 pix < me  <=>  pix < tw;  east  2 pix + 1 < me  <=>  pix < te
+    const uint32_t tw = (me + 1u) >> 1, te = me >> 1, pred_off = (uint32_t)pred << 10;
     for (uint32_t steps = 0;; steps++) {
-        const uint32_t e = lut[state][hood9(plane, g.Hp, x, y)];
-        const uint32_t pix = (uint32_t)(y * (int)g.w + x);
+        const uint32_t e = *reinterpret_cast<const uint16_t *>(lut + state_off + hood2(plane, g.Hp, o, y));
         if (kind) {
-            if (n && pix == start_pix && state == (uint32_t)pred) break;  // back in the starting state
+            if (n && pix == start_pix && state_off == pred_off) break;  // back in the starting state
         } else {
             if (pix == start_pix && (e & 8u)) break;                     // back at the visit that owns the west crack
         }
-        // candidate cracks of this visit that come before me in raster order
-        if ((e & 8u) && x > 0 && (pix << 1) < me) return kDead;
-        if ((e & 16u) && x + 1 < (int)g.w && ((pix << 1) | 1u) < me) return kDead;
+        // candidate cracks of this visit that come before me in raster order (west needs x > 0, east x + 1 < w)
+        if ((e & 8u) && o > 31 && pix < tw) return kDead;
+        if ((e & 16u) && o < o_max && pix < te) return kDead;
         if (steps >= budget) return kUndecided;
         min_pix = min(min_pix, pix);
         n++;
-        x += (int)((e >> 5) & 3u) - 1;
-        y += (int)((e >> 7) & 3u) - 1;
-        state = e >> 10;
+        const int dx = (int)((e >> 5) & 3u) - 1, dy = (int)((e >> 7) & 3u) - 1;
+        o += dx; y += dy;
+        pix += (uint32_t)(dy * w + dx);
+        state_off = e & 0x1c00u;
     }
     first_pixel = min_pix == start_pix;
     return kSurvivor;
@@ -467,20 +484,6 @@ __global__ void __launch_bounds__(128) k3_walk_short(const Geo g, const StepTabl
 // (Measured before the pairing: fewer walkers per warp, software prefetch of the sector ahead and a register window all
 // made this kernel slower: its time is the dependent chain of the longest border, about 750 cycles per step — which is
 // why the per-step exchange and tests were moved off that chain, see the blocks of kBlk steps below.)
-// 3x3 neighbourhood of the pixel at guarded column o = x + 31, row y, times two (the byte offset of its entry in a row of the
-// step tables): three loads from one word column, the second column only when the three pixel columns straddle two words
-__device__ __forceinline__ uint32_t hood2(const uint32_t *plane, uint32_t Hp, int o, int y) {
-    const uint32_t *p = plane + ((uint32_t)(o >> 5) * Hp + (uint32_t)y);
-    const int sh = o & 31;
-    uint32_t t = __ldg(p), m = __ldg(p + 1), b = __ldg(p + 2), t2 = 0, m2 = 0, b2 = 0;
-    if (sh > 29) {
-        const uint32_t *q = p + Hp;
-        t2 = __ldg(q); m2 = __ldg(q + 1); b2 = __ldg(q + 2);
-    }
-    t = __funnelshift_r(t, t2, sh); m = __funnelshift_r(m, m2, sh); b = __funnelshift_r(b, b2, sh);
-    return ((t << 1) & 0x00eu) | ((m << 4) & 0x070u) | ((b << 7) & 0x380u);
-}
-
 template <int kBlk>
 __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
     __shared__ uint16_t fwd[8][512];
@@ -676,6 +679,7 @@ struct Contour {
 // Writes the points (x | y << 16) of the long borders (sorted by raster position of the start) in the reference's order,
 // i.e. the forward trace from the start pixel, kSeg points per thread: thread ci < n_contours starts at the border's
 // start pixel, the others at a checkpoint dropped by the border's walker.
+template <bool LIGHT>
 __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *tables, const unsigned long long *keys, const uint32_t *lens,
                                                const uint32_t *offsets, uint32_t n_contours, const uint32_t *rank, const uint32_t *walker_slot,
                                                const Ckpt *ckpts, uint32_t n_ckpts, Contour *contours, uint32_t *points, const uint32_t *dyn) {
@@ -721,18 +725,32 @@ __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *ta
     }
     Window win;
     win.plane = g.planes + (size_t)frame * g.frame_words; win.Hp = g.Hp;
-    win_load(win, x, y);
+    if constexpr (!LIGHT) win_load(win, x, y);
     uint32_t *out = points + offsets[ci] + first;
     // four points per 16-byte store where the destination allows it (points + offset is only 4-byte aligned in general)
     uint32_t i = 0;
+    const uint32_t *plane = win.plane;
+    asm volatile("" : "+l"(plane));
+    const unsigned char *lut = reinterpret_cast<const unsigned char *>(&fwd[0][0]);
+    int o = x + 31;
+    uint32_t state_off = state << 10;
     auto step = [&]() {
-        const uint32_t v = (uint32_t)x | ((uint32_t)y << 16);
-        const uint32_t e = fwd[state][win_hood(win, x)];
-        x += (int)((e >> 5) & 3u) - 1;
-        y += (int)((e >> 7) & 3u) - 1;
-        state = e >> 10;
-        win_move(win, x, y);
-        return v;
+        if constexpr (LIGHT) {  // the walkers' step: three loads, three funnel shifts, the table entry, three adds
+            const uint32_t v = (uint32_t)(o - 31) | ((uint32_t)y << 16);
+            const uint32_t e = *reinterpret_cast<const uint16_t *>(lut + state_off + hood2(plane, g.Hp, o, y));
+            o += (int)((e >> 5) & 3u) - 1;
+            y += (int)((e >> 7) & 3u) - 1;
+            state_off = e & 0x1c00u;
+            return v;
+        } else {
+            const uint32_t v = (uint32_t)x | ((uint32_t)y << 16);
+            const uint32_t e = fwd[state][win_hood(win, x)];
+            x += (int)((e >> 5) & 3u) - 1;
+            y += (int)((e >> 7) & 3u) - 1;
+            state = e >> 10;
+            win_move(win, x, y);
+            return v;
+        }
     };
     while (i < count && ((uintptr_t)(out + i) & 15u)) out[i++] = step();
     for (; i + 4 <= count; i += 4) {
@@ -1142,6 +1160,13 @@ struct PhaseTimer {
     }
 };
 
+// k3_emit's step: the register window when many segments are in flight (256 x 1080p: 0.094 ms against 0.115 ms), the walkers'
+// lighter step for calls of a few frames, where the chain of one segment is what is waited for (noise frame: 0.025 against 0.040 ms)
+static bool emit_light(uint32_t n_frames) {
+    static const char *v = getenv("A3_K3_EMIT_LIGHT");  // experiment switch: 0 / 1 forces the variant
+    return v ? v[0] == '1' : n_frames <= 4;
+}
+
 cudaError_t k3_quads(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     cudaError_t e = k3_begin(ws, p, stream);
     return e == cudaSuccess ? k3_finish(ws, p, stream) : e;
@@ -1334,7 +1359,7 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
             K3_CUDA(cudaGetLastError());
         }
         timer.mark("order");
-        k3_emit<<<(n_long + n_ckpts + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, n_long, w.long_rank,
+        (emit_light(p.n) ? k3_emit<true> : k3_emit<false>)<<<(n_long + n_ckpts + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, n_long, w.long_rank,
                                                                    w.walker_slot, w.ckpts, n_ckpts, w.contours, w.points, nullptr);
         K3_CUDA(cudaGetLastError());
         timer.mark("emit");
@@ -1400,7 +1425,7 @@ cudaError_t k3_finish_speculative(K3Workspace &ws, const K3Params &p, cudaStream
         K3_CUDA(cudaGetLastError());
     }
     timer.mark("order");
-    k3_emit<<<(cap_long + cap_ckpts + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, cap_long, w.long_rank,
+    (emit_light(p.n) ? k3_emit<true> : k3_emit<false>)<<<(cap_long + cap_ckpts + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, cap_long, w.long_rank,
                                                                    w.walker_slot, w.ckpts, cap_ckpts, w.contours, w.points, w.counters);
     K3_CUDA(cudaGetLastError());
     timer.mark("emit");

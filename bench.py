@@ -125,7 +125,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self.stop_flag.wait(0.002)
+            self.stop_flag.wait(0.01)  # 100 Hz: NVML calls take a driver-wide lock, and at N = 8 eight processes poll at once
 
     def result(self):
         self.stop_flag.set()
@@ -311,19 +311,32 @@ def run_b200(args, wl_name, ctx):
             step(ptrs[k % len(ptrs)], mem, True, outs)
             k += 1
         acc = {}
-        barrier()
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(local_rank)  # NVML set up and polling before the barrier, not inside the timed region
         sampler.start()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per_step = []
         e0.record()
         for _ in range(steps):
+            t0 = time.perf_counter()
             s = step(ptrs[k % len(ptrs)], mem, stats_in_loop, outs)
+            per_step.append((time.perf_counter() - t0) * 1e3)
             k += 1
             for key, v in (s or {}).items():
                 acc[key] = acc.get(key, 0) + v
         e1.record()
         barrier()
         clocks = sampler.result()
+        clocks["samples"] = len(sampler.sm)
+        # per-rank view of the same timed region (diagnostic: which rank, which step): host wall time of every call
+        mine = {"rank": rank, "ms": e0.elapsed_time(e1), "step_ms_median": float(np.median(per_step)), "step_ms_max": float(max(per_step)),
+                "slowest_step": int(np.argmax(per_step)), "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")}
+        if world > 1:
+            allr = [None] * world
+            dist.all_gather_object(allr, mine)
+        else:
+            allr = [mine]
+        clocks["per_rank"] = allr
         if not stats_in_loop:
             for _ in range(steps):
                 for key, v in step(ptrs[k % len(ptrs)], mem, True, outs).items():

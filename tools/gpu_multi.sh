@@ -10,6 +10,11 @@ for WL in C3 C5 C4; do
       > $OUT/${TAG}_n${N}_bench_${WL}.json 2> $OUT/${TAG}_n${N}_bench_${WL}.err
   tail -c 400 $OUT/${TAG}_n${N}_bench_${WL}.json; echo
 done
+if [ $N -ge 8 ]; then  # the N = 4 headline figure on the same box (GPUs 0-3)
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 10 --warmup 3 --workload C3 \
+      > $OUT/${TAG}_n4on8_bench_C3.json 2> $OUT/${TAG}_n4on8_bench_C3.err
+  tail -c 300 $OUT/${TAG}_n4on8_bench_C3.json; echo
+fi
 SETS="0"; [ $N -ge 2 ] && SETS="$SETS 0,1"; [ $N -ge 4 ] && SETS="$SETS 0,1,2,3"; [ $N -ge 8 ] && SETS="$SETS 4,5,6,7 0,1,2,3,4,5,6,7 0,4 0,2,4,6"
 timeout 600 aruco3_b200/csrc/build/pcie_matrix --mb 1024 --passes 4 $SETS > $OUT/${TAG}_n${N}_pcie_matrix.jsonl 2> $OUT/${TAG}_n${N}_pcie_matrix.err
 tail -3 $OUT/${TAG}_n${N}_pcie_matrix.jsonl
