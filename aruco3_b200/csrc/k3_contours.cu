@@ -183,7 +183,7 @@ struct Lists {
     unsigned long long *long_keys;     // surviving borders with >= min_points points: the same key ...
     uint32_t *long_n;                  // ... and their number of points
     uint32_t *counters;                // [0] walkers, [1] long borders, [2] overflow of a list, [3] candidates, [4] checkpoints,
-                                       // [5] speculative finish gave up, [7] most long borders in one frame
+                                       // [5] speculative finish gave up, [6] relay cracks, [7] most long borders in one frame
     uint32_t *long_slot;               // value array of the sort: the border's slot in long_keys / long_n
     uint32_t *walker_slot;             // per entry of `walkers`: slot of the border it survived as, or 0xffffffff
     Ckpt *ckpts;                       // checkpoints dropped by k3_walkers
@@ -200,7 +200,26 @@ struct Lists {
     uint32_t *frame_long_count;
     unsigned long long *frame_keys;
     uint32_t *frame_slots;
+    // relays (tools/relay_proto.py is the spec): the west / east cracks on every (1 << relay_shift)-th row.  counters[6] = how many
+    uint2 *relays;                     // per relay crack: {x | y << 16, frame << 1 | side (0 west, 1 east)}
+    struct Seg *segs;                  // per relay crack: its segment of the border (k3_segments), then its place in it (k3_cycles)
+    uint32_t *relay_base;              // per (frame, relay row, word column): index of the word's first relay crack
+    uint32_t relay_cap;                // 0 = relays off
+    uint32_t relay_shift, nrr;         // log2 of the row spacing; relay rows per frame
 };
+// One relay's segment: the visits from its own up to (not including) the next relay visit of the border.
+struct __align__(16) Seg {
+    uint32_t next;       // index of the relay crack that names the next relay visit
+    uint32_t len;        // visits in the segment; 0 = not a relay (an isolated pixel, or an east crack whose visit owns a west crack too)
+    uint32_t cand;       // smallest candidate key (pixel << 1 | kind) among the segment's visits, 0xffffffff = none
+    uint32_t cand_pos;   // index of that visit within the segment
+    uint32_t min_pix;    // raster-first pixel of the segment
+    uint32_t slot;       // k3_cycles: slot of the border among the long borders, 0xffffffff = not recorded
+    uint32_t off;        // k3_cycles: index of the segment's first visit in the border's point list
+    uint32_t state;      // state of the relay's own visit
+};
+constexpr uint32_t kNone = 0xffffffffu;
+constexpr uint32_t kRelayFlag = 0x80000000u;  // in long_n: the border's points come from relay segments
 
 
 // 3x3 neighbourhood of the pixel at guarded column o = x + 31, row y, times two (the byte offset of its entry in a row of the
@@ -219,8 +238,11 @@ __device__ __forceinline__ uint32_t hood2(const uint32_t *plane, uint32_t Hp, in
 
 // The candidate (x, y, kind) walks its border for at most `budget` steps.  kSurvivor: it is the raster-first candidate
 // crack of the border (n = number of points of the border, first_pixel = it is also the border's raster-first pixel).
+// rmask: a visit that owns a west or east crack on a row y & rmask == 0 is a relay visit — its border belongs to k3_segments /
+// k3_cycles, so the candidate gives up (kDead) there (template relay_on: the batch route compiles none of it).
+template <bool relay_on>
 __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (*fwd)[512], const uint16_t (*bwd)[512], int sx, int sy, int kind,
-                           uint32_t budget, uint32_t &n, bool &first_pixel) {
+                           uint32_t budget, uint32_t &n, bool &first_pixel, uint32_t rmask) {
     const int w = (int)g.w, o_max = w + 30;
     const uint32_t start_pix = (uint32_t)(sy * w + sx);
     const uint32_t me = (start_pix << 1) | (uint32_t)kind;
@@ -234,6 +256,7 @@ __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (
     n = 1;
     first_pixel = true;
     if (pred < 0) return (kind == 0 || sx == 0) ? kSurvivor : kDead;  // isolated pixel: its west crack (if a candidate) comes first
+    if (relay_on && ((uint32_t)sy & rmask) == 0u) return kDead;       // my own crack is a relay crack: a relay border
     // position as (o = x + 31, y, pix = y w + x), state as the byte offset of its table row (see k3_walkers)
     uint32_t min_pix = start_pix, pix = start_pix, state_off;
     int o = sx + 31, y = sy;
@@ -253,6 +276,7 @@ __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (
         } else {
             if (pix == start_pix && (e & 8u)) break;                     // back at the visit that owns the west crack
         }
+        if (relay_on && ((uint32_t)y & rmask) == 0u && (((e & 8u) && o > 31) || ((e & 16u) && o < o_max))) return kDead;  // a relay border
         // candidate cracks of this visit that come before me in raster order (west needs x > 0, east x + 1 < w)
         if ((e & 8u) && o > 31 && pix < tw) return kDead;
         if ((e & 16u) && o < o_max && pix < te) return kDead;
@@ -269,7 +293,7 @@ __device__ int walk_border(const uint32_t *plane, const Geo &g, const uint16_t (
 }
 
 __device__ __forceinline__ uint32_t record_survivor(const Lists &l, uint32_t frame, unsigned long long key, int kind, uint32_t n, bool first_pixel,
-                                                    uint32_t min_points) {
+                                                    uint32_t min_points, bool relay = false) {
     atomicAdd(&l.frame_contours[frame], 1u);
     atomicAdd(&l.frame_points[frame], (unsigned long long)n);
     if (kind == 0 && !first_pixel) atomicOr(&l.frame_flags[frame], 1u);  // a west start below the top of its border: barred natural start
@@ -277,7 +301,7 @@ __device__ __forceinline__ uint32_t record_survivor(const Lists &l, uint32_t fra
         const uint32_t slot = atomicAdd(&l.counters[1], 1u);
         if (slot < l.long_cap) {
             l.long_keys[slot] = key;
-            l.long_n[slot] = n;
+            l.long_n[slot] = relay ? (n | kRelayFlag) : n;
             l.long_slot[slot] = slot;
             l.long_off_slot[slot] = (uint32_t)atomicAdd(l.long_points, (unsigned long long)n);  // totals beyond 32 bits flag the whole call
             if (l.frame_cap) {
@@ -295,6 +319,7 @@ __device__ __forceinline__ uint32_t record_survivor(const Lists &l, uint32_t fra
     return 0xffffffffu;
 }
 
+template <bool RELAY>
 __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
     __shared__ uint16_t fwd[8][512];  // only for candidates that do not fit the list (walked right here)
     __shared__ uint16_t bwd[8][512];
@@ -337,6 +362,23 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
                 hg[u] = f & ~((f >> 1) | (rv[u] << 31));
                 if (k == 0) og[u] &= ~1u;                        // `x > 0`
                 if (k == last_k) hg[u] &= ~(1u << last_bit);     // `x + 1 < w`
+                // relay rows: every candidate crack of the row (west with x > 0, east with x + 1 < w) is listed; the entries of a word are
+                // consecutive, in the order (bit, west before east), and the word's first index is kept for k3_segments' lookups
+                const uint32_t y = base + (uint32_t)u * stride;
+                if (RELAY && (og[u] | hg[u]) && (y & ((1u << l.relay_shift) - 1u)) == 0u) {
+                    const uint32_t cnt = (uint32_t)(__popc(og[u]) + __popc(hg[u]));
+                    uint32_t j = atomicAdd(&l.counters[6], cnt);
+                    l.relay_base[((size_t)frame * l.nrr + (y >> l.relay_shift)) * g.wpr + k] = j;
+                    if (j + cnt <= l.relay_cap) {
+                        for (uint32_t pending = og[u] | hg[u]; pending; pending &= pending - 1) {
+                            const uint32_t bit = (uint32_t)__ffs(pending) - 1u, xy = (k * 32 + bit) | (y << 16);
+                            if ((og[u] >> bit) & 1u) l.relays[j++] = make_uint2(xy, frame << 1);
+                            if ((hg[u] >> bit) & 1u) l.relays[j++] = make_uint2(xy, (frame << 1) | 1u);
+                        }
+                    } else {
+                        atomicOr(&l.counters[2], 1u);
+                    }
+                }
             }
         }
         // phase 2: the row above (three words) of the words that have such cracks, all loads first
@@ -414,7 +456,7 @@ __global__ void __launch_bounds__(256) k3_candidates(const Geo g, const StepTabl
                     } else {  // list full (very dense noise): walk it here, same rules as k3_walk_short
                         uint32_t n;
                         bool first_pixel;
-                        const int r = walk_border(plane, g, fwd, bwd, (int)(k * 32 + bit), (int)y, (int)kind, kBudget, n, first_pixel);
+                        const int r = walk_border<RELAY>(plane, g, fwd, bwd, (int)(k * 32 + bit), (int)y, (int)kind, kBudget, n, first_pixel, (1u << l.relay_shift) - 1u);
                         if (r == kSurvivor) {
                             record_survivor(l, frame, key, (int)kind, n, first_pixel, min_points);
                         } else if (r == kUndecided) {
@@ -448,6 +490,7 @@ __device__ __forceinline__ void decode_key(const Geo &g, unsigned long long key,
 }
 
 // One thread per listed candidate: walk at most kBudget steps.  Nearly all die within a few; short borders finish.
+template <bool RELAY>
 __global__ void __launch_bounds__(128) k3_walk_short(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
     __shared__ uint16_t fwd[8][512];
     __shared__ uint16_t bwd[8][512];
@@ -464,7 +507,7 @@ __global__ void __launch_bounds__(128) k3_walk_short(const Geo g, const StepTabl
         bool first_pixel;
         decode_key(g, key, frame, x, y, kind);
         const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
-        const int r = walk_border(plane, g, fwd, bwd, x, y, kind, kBudget, n, first_pixel);
+        const int r = walk_border<RELAY>(plane, g, fwd, bwd, x, y, kind, kBudget, n, first_pixel, (1u << l.relay_shift) - 1u);
         if (r == kSurvivor) {
             record_survivor(l, frame, key, kind, n, first_pixel, min_points);
         } else if (r == kUndecided) {
@@ -472,6 +515,117 @@ __global__ void __launch_bounds__(128) k3_walk_short(const Geo g, const StepTabl
             if (slot < l.walkers_cap) l.walkers[slot] = key;
             else atomicOr(&l.counters[2], 1u);
         }
+    }
+}
+
+// Index of the relay crack (x, y, side) of `frame`: the word's first index + the number of relay cracks before it in the word.
+__device__ __forceinline__ uint32_t relay_index(const Lists &l, const Geo &g, const uint32_t *plane, uint32_t frame, int x, int y, uint32_t side) {
+    const uint32_t k = (uint32_t)x >> 5, bit = (uint32_t)x & 31u;
+    const uint32_t *p = plane + ((size_t)(k + 1) * g.Hp + (uint32_t)y + 1u);
+    const uint32_t f = __ldg(p), lv = __ldg(p - g.Hp), rv = __ldg(p + g.Hp);
+    uint32_t rw = f & ~((f << 1) | (lv >> 31)), re = f & ~((f >> 1) | (rv << 31));
+    if (k == 0) rw &= ~1u;                                            // candidates only: west with x > 0,
+    if (k == ((g.w - 1) >> 5)) re &= ~(1u << ((g.w - 1) & 31u));      // east with x + 1 < w
+    const uint32_t below = (1u << bit) - 1u;
+    return l.relay_base[((size_t)frame * l.nrr + ((uint32_t)y >> l.relay_shift)) * g.wpr + k] + (uint32_t)__popc(rw & below) + (uint32_t)__popc(re & below) +
+           ((side && ((rw >> bit) & 1u)) ? 1u : 0u);
+}
+
+// Relay walks (spec and proof by test: tools/relay_proto.py).  A border's time used to be the chain of half its visits (a pair
+// of lanes per border); with a walker per relay crack it is the longest stretch between two relay rows.  One thread per listed
+// crack: find the visit that owns it (an east crack whose visit owns a west crack too is an alias and drops out), follow the
+// border to the next relay visit and record where that is, how many visits lie between, the raster-first candidate crack among
+// them and its position, and the raster-first pixel.
+__global__ void __launch_bounds__(128) k3_segments(const Geo g, const StepTables *tables, const Lists l) {
+    __shared__ uint16_t fwd[8][512];
+    for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) (&fwd[0][0])[i] = (&tables->fwd[0][0])[i];
+    __syncthreads();
+    if (l.counters[6] > l.relay_cap) return;  // the list overflowed: every frame of the call goes to the host stage
+    const uint32_t total = l.counters[6], rmask = (1u << l.relay_shift) - 1u;
+    const unsigned char *lut = reinterpret_cast<const unsigned char *>(&fwd[0][0]);
+    const int w = (int)g.w, o_max = w + 30;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint2 r = l.relays[i];
+        const int sx = (int)(r.x & 0xffffu), sy = (int)(r.x >> 16);
+        const uint32_t frame = r.y >> 1, side = r.y & 1u;
+        const uint32_t *plane = g.planes + (size_t)frame * g.frame_words;
+        asm volatile("" : "+l"(plane));
+        const uint32_t nb0 = ring_of(hood9(plane, g.Hp, sx, sy));
+        const int adj = side ? 4 : 0;
+        int pred = -1;
+        for (int k = 0; k < 8; k++) {  // clockwise from the crack's side: the state of the visit that owns it
+            const int d = (adj + k) & 7;
+            if ((nb0 >> d) & 1) { pred = d; break; }
+        }
+        Seg out;
+        out.next = i; out.len = 0; out.cand = kNone; out.cand_pos = 0; out.min_pix = kNone; out.slot = kNone; out.off = 0; out.state = 0;
+        int o = sx + 31, y = sy;
+        uint32_t pix = (uint32_t)(sy * w + sx), state_off = (uint32_t)(pred < 0 ? 0 : pred) << 10;
+        uint32_t e = *reinterpret_cast<const uint16_t *>(lut + state_off + hood2(plane, g.Hp, o, y));
+        if (pred < 0 || (side && (e & 8u) && o > 31)) {  // an isolated pixel has no visits; the west crack names a visit that owns both
+            l.segs[i] = out;
+            continue;
+        }
+        uint32_t t = 0, best = kNone, best_pos = 0, min_pix = kNone;
+        for (;;) {
+            if ((e & 8u) && o > 31 && (pix << 1) < best) { best = pix << 1; best_pos = t; }            // west candidate: x > 0
+            if ((e & 16u) && o < o_max && ((pix << 1) | 1u) < best) { best = (pix << 1) | 1u; best_pos = t; }  // east: x + 1 < w
+            min_pix = min(min_pix, pix);
+            const int dx = (int)((e >> 5) & 3u) - 1, dy = (int)((e >> 7) & 3u) - 1;
+            o += dx; y += dy;
+            pix += (uint32_t)(dy * w + dx);
+            state_off = e & 0x1c00u;
+            t++;
+            e = *reinterpret_cast<const uint16_t *>(lut + state_off + hood2(plane, g.Hp, o, y));
+            // the next relay visit (my own, if the border has no other): it owns a candidate crack on a relay row
+            if (((uint32_t)y & rmask) == 0u && (((e & 8u) && o > 31) || ((e & 16u) && o < o_max))) break;
+        }
+        out.next = relay_index(l, g, plane, frame, o - 31, y, ((e & 8u) && o > 31) ? 0u : 1u);
+        out.len = t; out.cand = best; out.cand_pos = best_pos; out.min_pix = min_pix; out.state = (uint32_t)pred;
+        l.segs[i] = out;
+    }
+}
+
+// The relays of a border form a cycle of segments.  Every relay walks its cycle until it meets a smaller index (then it is not
+// the leader) or comes back to itself; the leader — the smallest index of the cycle — knows the border: its length is the sum
+// of the segments, its start the smallest candidate key on the way (the reference's discovery point; none = the reference
+// never follows this border), and it records the border like a surviving candidate does, then tells every segment where its
+// points go.
+__global__ void __launch_bounds__(256) k3_cycles(const Geo g, const uint32_t min_points, const Lists l) {
+    if (l.counters[6] > l.relay_cap) return;
+    const uint32_t total = l.counters[6];
+    const size_t words_per_frame = (size_t)g.h * g.wpr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const Seg mine = l.segs[i];
+        if (mine.len == 0) continue;
+        uint32_t j = i, n = 0, best = kNone, best_off = 0, min_pix = kNone;
+        bool leader = true;
+        Seg q = mine;
+        for (;;) {
+            if (q.cand < best) { best = q.cand; best_off = n + q.cand_pos; }
+            min_pix = min(min_pix, q.min_pix);
+            n += q.len;
+            j = q.next;
+            if (j == i) break;
+            if (j < i) { leader = false; break; }
+            q = l.segs[j];
+        }
+        if (!leader || best == kNone) continue;
+        const uint32_t frame = l.relays[i].y >> 1, kind = best & 1u, spix = best >> 1;
+        const uint32_t sy = spix / g.w, sx = spix - sy * g.w;
+        const unsigned long long gid = (unsigned long long)frame * words_per_frame + (unsigned long long)sy * g.wpr + (sx >> 5);
+        const unsigned long long key = (((gid << 5) | (sx & 31u)) << 1) | kind;
+        const uint32_t slot = record_survivor(l, frame, key, (int)kind, n, min_pix == spix, min_points, true);
+        if (slot == kNone) continue;
+        uint32_t cum = 0;
+        j = i;
+        do {
+            const uint32_t len = l.segs[j].len, nx = l.segs[j].next;
+            l.segs[j].slot = slot;
+            l.segs[j].off = cum >= best_off ? cum - best_off : cum + n - best_off;
+            cum += len;
+            j = nx;
+        } while (j != i);
     }
 }
 
@@ -484,7 +638,7 @@ __global__ void __launch_bounds__(128) k3_walk_short(const Geo g, const StepTabl
 // (Measured before the pairing: fewer walkers per warp, software prefetch of the sector ahead and a register window all
 // made this kernel slower: its time is the dependent chain of the longest border, about 750 cycles per step — which is
 // why the per-step exchange and tests were moved off that chain, see the blocks of kBlk steps below.)
-template <int kBlk>
+template <int kBlk, bool relay_on>
 __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables *tables, const uint32_t min_points, const Lists l) {
     __shared__ uint16_t fwd[8][512];
     __shared__ uint16_t bwd[8][512];
@@ -498,6 +652,7 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
     const uint32_t pair_mask = 3u << (threadIdx.x & 30u);   // the two lanes of this pair: they never diverge from each other
     const unsigned char *lut = reinterpret_cast<const unsigned char *>(back ? &bwd[0][0] : &fwd[0][0]);
     const int w = (int)g.w, o_max = w + 30;
+    const uint32_t rmask = (1u << l.relay_shift) - 1u;
     for (uint32_t i = tid >> 1; i < total; i += (gridDim.x * blockDim.x) >> 1) {
         const unsigned long long key = l.walkers[i];
         uint32_t frame;
@@ -550,8 +705,10 @@ __global__ void __launch_bounds__(128) k3_walkers(const Geo g, const StepTables 
                 const uint32_t e = *reinterpret_cast<const uint16_t *>(lut + state_off + h2);
                 const uint32_t fstate = back ? (e & 7u) : (state_off >> 10);      // direction of the previous border pixel at this visit
                 ids[k] = (pix << 3) | fstate;
-                // candidate cracks of this visit that come before me in raster order (west needs x > 0, east x + 1 < w)
-                mine_dead |= ((e & 8u) && o > 31 && pix < tw) || ((e & 16u) && o < o_max && pix < te);
+                // candidate cracks of this visit that come before me in raster order (west needs x > 0, east x + 1 < w); a relay
+                // visit means the border belongs to k3_segments / k3_cycles
+                mine_dead |= ((e & 8u) && o > 31 && pix < tw) || ((e & 16u) && o < o_max && pix < te) ||
+                             (relay_on && ((uint32_t)y & rmask) == 0u && (((e & 8u) && o > 31) || ((e & 16u) && o < o_max)));
                 min_pix = min(min_pix, pix);
                 // checkpoints for k3_emit: forwards at index kSeg, 2 kSeg, ...; backwards kSeg, 2 kSeg, ... points before the end
                 const uint32_t walked = back ? s0 + k + 1 : s0 + k;
@@ -659,12 +816,12 @@ __global__ void __launch_bounds__(256) k3_order(const Lists l, uint32_t n_frames
 // exactly); the sort input is padded to its speculated size with keys that sort last.
 __global__ void __launch_bounds__(256) k3_spec_prepare(unsigned long long *long_keys, uint32_t *long_slot, uint32_t *counters,
                                                        const unsigned long long *long_points, uint32_t cap_long, uint32_t cap_ckpts,
-                                                       unsigned long long cap_points, uint32_t cap_frame_long) {
+                                                       unsigned long long cap_points, uint32_t cap_frame_long, uint32_t cap_relays) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_long = counters[1];
     if (i == 0)
         counters[kSpecFail] = (counters[2] || n_long > cap_long || counters[4] > cap_ckpts || *long_points > cap_points ||
-                               counters[7] > cap_frame_long) ? 1u : 0u;
+                               counters[7] > cap_frame_long || counters[6] > cap_relays) ? 1u : 0u;
     if (i >= n_long && i < cap_long) {
         long_keys[i] = ~0ull;
         long_slot[i] = 0xffffffffu;
@@ -682,19 +839,45 @@ struct Contour {
 template <bool LIGHT>
 __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *tables, const unsigned long long *keys, const uint32_t *lens,
                                                const uint32_t *offsets, uint32_t n_contours, const uint32_t *rank, const uint32_t *walker_slot,
-                                               const Ckpt *ckpts, uint32_t n_ckpts, Contour *contours, uint32_t *points, const uint32_t *dyn) {
+                                               const Ckpt *ckpts, uint32_t n_ckpts, Contour *contours, uint32_t *points, const uint32_t *dyn,
+                                               const uint2 *relays, const Seg *segs, uint32_t n_relays) {
     __shared__ uint16_t fwd[8][512];
     if (dyn) {  // speculative finish: the real sizes are on the device only
         if (dyn[kSpecFail]) return;
-        n_contours = dyn[1]; n_ckpts = dyn[4];
-        if (blockIdx.x * blockDim.x >= n_contours + n_ckpts) return;
+        n_contours = dyn[1]; n_ckpts = dyn[4]; n_relays = min(n_relays, dyn[6]);
+        if (blockIdx.x * blockDim.x >= n_contours + n_ckpts + n_relays) return;
     }
     for (int i = threadIdx.x; i < 8 * 512; i += blockDim.x) (&fwd[0][0])[i] = (&tables->fwd[0][0])[i];
     __syncthreads();
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_contours + n_ckpts) return;
+    if (t >= n_contours + n_ckpts + n_relays) return;
     uint32_t frame, ci, first, count, state;
     int x, y, sx, sy, kind;
+    if (t >= n_contours + n_ckpts) {
+        // a relay segment: its visits go to (off + i) mod n of the border's list; borders the reference never follows, or too
+        // short to matter, were not recorded
+        const uint32_t ri = t - n_contours - n_ckpts;
+        const Seg sg = segs[ri];
+        if (sg.len == 0 || sg.slot == kNone) return;
+        const uint2 r = relays[ri];
+        ci = rank[sg.slot];
+        const uint32_t n = lens[ci] & ~kRelayFlag;
+        uint32_t *out = points + offsets[ci];
+        const uint32_t *plane = g.planes + (size_t)(r.y >> 1) * g.frame_words;
+        asm volatile("" : "+l"(plane));
+        const unsigned char *lut = reinterpret_cast<const unsigned char *>(&fwd[0][0]);
+        int o = (int)(r.x & 0xffffu) + 31, yy = (int)(r.x >> 16);
+        uint32_t state_off = sg.state << 10, pos = sg.off;
+        for (uint32_t i = 0; i < sg.len; i++) {
+            out[pos] = (uint32_t)(o - 31) | ((uint32_t)yy << 16);
+            if (++pos == n) pos = 0;
+            const uint32_t e = *reinterpret_cast<const uint16_t *>(lut + state_off + hood2(plane, g.Hp, o, yy));
+            o += (int)((e >> 5) & 3u) - 1;
+            yy += (int)((e >> 7) & 3u) - 1;
+            state_off = e & 0x1c00u;
+        }
+        return;
+    }
     if (t < n_contours) {
         ci = t;
         decode_key(g, keys[ci], frame, sx, sy, kind);
@@ -706,8 +889,8 @@ __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *ta
             const int d = (adj + q) & 7;
             if ((nb0 >> d) & 1) { pred = d; break; }
         }
-        const uint32_t n = lens[ci];
-        first = 0; count = min(kSeg, n);  // the rest is covered from the checkpoints (none for borders of at most kSeg points)
+        const uint32_t n = lens[ci] & ~kRelayFlag;
+        first = 0; count = (lens[ci] & kRelayFlag) ? 0u : min(kSeg, n);  // the rest is covered from the checkpoints (none for borders of at most kSeg points); a relay border's points all come from its segments
         x = sx; y = sy; state = (uint32_t)pred;
         Contour c;
         c.frame = frame; c.start = (uint32_t)sx | ((uint32_t)sy << 16); c.n = n; c.kind = (uint32_t)kind; c.point_off = offsets[ci];
@@ -718,7 +901,7 @@ __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *ta
         if (slot == 0xffffffffu) return;  // that walker did not survive (or its border is too short to matter)
         ci = rank[slot];
         decode_key(g, keys[ci], frame, sx, sy, kind);
-        const uint32_t n = lens[ci];
+        const uint32_t n = lens[ci] & ~kRelayFlag;
         first = (c.state & kCkptBackward) ? n - c.pos : c.pos;
         count = min(kSeg, n - first);
         x = (int)(c.xy & 0xffffu); y = (int)(c.xy >> 16); state = c.state & 7u;
@@ -1069,6 +1252,11 @@ struct K3Workspace::Impl {
     unsigned long long *frame_keys = nullptr;
     size_t frame_lists_cap = 0;              // frames the per-frame lists are allocated for
     Ckpt *ckpts = nullptr;
+    uint2 *relays = nullptr;
+    Seg *segs = nullptr;
+    uint32_t *relay_base = nullptr;
+    size_t relay_cap = 0, relay_base_cap = 0;
+    uint32_t hist_relays = 0, spec_relays = 0;
     size_t cands_cap = 0, walkers_cap = 0, long_cap = 0, frames_cap = 0, ckpt_cap = 0;
     void *cub_tmp = nullptr;
     size_t cub_bytes = 0;
@@ -1100,7 +1288,8 @@ K3Workspace::~K3Workspace() {
                     (void *)impl->frame_points, (void *)impl->long_n, (void *)impl->long_n_sorted, (void *)impl->long_off, (void *)impl->counters,
                     (void *)impl->frame_contours, impl->cub_tmp, (void *)impl->contours, (void *)impl->contour_quads, (void *)impl->points,
                     (void *)impl->dead, (void *)impl->long_slot, (void *)impl->long_slot_sorted, (void *)impl->long_rank, (void *)impl->walker_slot,
-                    (void *)impl->ckpts, (void *)impl->long_off_slot, (void *)impl->frame_long_count, (void *)impl->frame_slots, (void *)impl->frame_keys})
+                    (void *)impl->ckpts, (void *)impl->long_off_slot, (void *)impl->frame_long_count, (void *)impl->frame_slots, (void *)impl->frame_keys,
+                    (void *)impl->relays, (void *)impl->segs, (void *)impl->relay_base})
         if (p) cudaFree(p);
     if (impl->h_counts) cudaFreeHost(impl->h_counts);
     delete impl;
@@ -1253,6 +1442,28 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         K3_CUDA(alloc_exact(w.dead, (size_t)p.n * p.quad_cap));
         w.dead_cap = (size_t)p.n * p.quad_cap;
     }
+    // relays: the candidate cracks of every 16th row (32nd above 1200 rows).  A pure-noise frame has about w / 2 of them per
+    // row; the lists are sized for that, capped at 48 M entries (an overflow sends the call to the host stage like any other list).
+    // Relay walks are for calls of a few frames, where the time of the stage is the chain of the longest border (the reference
+    // bench's noise frame: walks 1.48 -> 0.10 ms, the call 2.3 -> 1.2 ms).  A batch has enough borders to fill the machine, and there the
+    // lane pairs win: 256 x 1080p with relays 1.01 ms against 0.55 ms (segment lengths are very uneven - edges nearly parallel to the
+    // rows - so a warp waits for its longest, the list allocation and the survivors' records are same-address atomics in short kernels).
+    // A3_K3_RELAY_MAX_FRAMES overrides the threshold (0 = never, read at every call: tests drive both routes).
+    const char *relay_env = getenv("A3_K3_RELAY_MAX_FRAMES");
+    const bool relays_off = p.n > (relay_env ? (uint32_t)strtoul(relay_env, nullptr, 10) : 4u);
+    const uint32_t relay_shift = p.h > 1200 ? 5u : 4u, nrr = (p.h + (1u << relay_shift) - 1) >> relay_shift;
+    size_t want_relays = relays_off ? 0 : (size_t)p.n * nrr * (p.w / 2 + 64);
+    if (want_relays > ((size_t)48 << 20)) want_relays = (size_t)48 << 20;
+    if (want_relays > w.relay_cap) {
+        K3_CUDA(alloc_exact(w.relays, want_relays));
+        K3_CUDA(alloc_exact(w.segs, want_relays));
+        w.relay_cap = want_relays;
+    }
+    const size_t want_base = relays_off ? 0 : (size_t)p.n * nrr * ((p.w + 31) / 32);
+    if (want_base > w.relay_base_cap) {
+        K3_CUDA(alloc_exact(w.relay_base, want_base));
+        w.relay_base_cap = want_base;
+    }
     K3_CUDA(cudaMemsetAsync(w.frame_points, 0, (size_t)p.n * 8, stream));
     K3_CUDA(cudaMemsetAsync(w.frame_contours, 0, (size_t)p.n * 4, stream));
     K3_CUDA(cudaMemsetAsync(w.frame_long_count, 0, (size_t)p.n * 4, stream));
@@ -1271,6 +1482,8 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     l.long_off_slot = w.long_off_slot; l.frame_cap = frame_lists ? kOrderCap : 0u; l.frame_long_count = w.frame_long_count;
     l.frame_keys = w.frame_keys; l.frame_slots = w.frame_slots;
     l.ckpt_cap = (uint32_t)(w.ckpt_cap > 0x7fffffffull ? 0x7fffffffull : w.ckpt_cap);
+    l.relays = w.relays; l.segs = w.segs; l.relay_base = w.relay_base; l.relay_cap = (uint32_t)want_relays;
+    l.relay_shift = relay_shift; l.nrr = nrr;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1296,15 +1509,26 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
             if (gz > room) gz = room;
             if (gz < 1) gz = 1;
         }
-        k3_candidates<<<dim3(gx, gy, gz), bd, 0, stream>>>(g, w.d_tables, p.min_points, l);
+        if (l.relay_cap) k3_candidates<true><<<dim3(gx, gy, gz), bd, 0, stream>>>(g, w.d_tables, p.min_points, l);
+        else k3_candidates<false><<<dim3(gx, gy, gz), bd, 0, stream>>>(g, w.d_tables, p.min_points, l);
     }
     K3_CUDA(cudaGetLastError());
     timer.mark("candidates");
-    k3_walk_short<<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
+    if (l.relay_cap) {
+        k3_segments<<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, l);
+        K3_CUDA(cudaGetLastError());
+        timer.mark("segments");
+        k3_cycles<<<(uint32_t)sms * 4, 256, 0, stream>>>(g, p.min_points, l);
+        K3_CUDA(cudaGetLastError());
+        timer.mark("cycles");
+    }
+    if (l.relay_cap) k3_walk_short<true><<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
+    else k3_walk_short<false><<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
     K3_CUDA(cudaGetLastError());
     timer.mark("walk_short");
     // blocks of 2 / 4 / 6 / 8 steps measured: 0.207 / 0.188 / 0.186 / 0.184 ms (before the lighter step: 0.152 ms with 8)
-    k3_walkers<8><<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
+    if (l.relay_cap) k3_walkers<8, true><<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
+    else k3_walkers<8, false><<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, p.min_points, l);
     K3_CUDA(cudaGetLastError());
     timer.mark("walkers");
     k3_flag_all<<<(p.n + 127) / 128, 128, 0, stream>>>(p.frame_flags, p.n, w.counters, 0);
@@ -1331,11 +1555,13 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     uint32_t n_long = hc[1] < l.long_cap ? hc[1] : l.long_cap;
     const unsigned long long n_points = w.h_counts[4];
     const uint32_t n_ckpts = hc[4] < l.ckpt_cap ? hc[4] : l.ckpt_cap;
-    if (timer.on) fprintf(stderr, "k3 lists: %u candidates, %u walkers, %u long borders, %llu points, %u checkpoints\n", hc[3], hc[0], hc[1], n_points, hc[4]);
+    if (timer.on) fprintf(stderr, "k3 lists: %u candidates, %u walkers, %u long borders, %llu points, %u checkpoints, %u relay cracks\n", hc[3], hc[0], hc[1], n_points, hc[4], hc[6]);
     w.hist_valid = !hc[2] && n_points < 0xffffffffull;
     w.hist_n = p.n; w.hist_w = p.w; w.hist_h = p.h; w.hist_long = hc[1]; w.hist_ckpts = hc[4]; w.hist_points = n_points;
     w.hist_frame_long = hc[7];
+    w.hist_relays = hc[6];
     w.spec_long = 0;
+    const uint32_t n_relays = hc[6] < l.relay_cap ? hc[6] : l.relay_cap;
     if (n_points >= 0xffffffffull && !hc[2]) {  // point offsets are 32-bit: hand the whole call to the host stage
         k3_flag_all<<<(p.n + 127) / 128, 128, 0, stream>>>(p.frame_flags, p.n, w.counters, 1);
         K3_CUDA(cudaGetLastError());
@@ -1359,8 +1585,8 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
             K3_CUDA(cudaGetLastError());
         }
         timer.mark("order");
-        (emit_light(p.n) ? k3_emit<true> : k3_emit<false>)<<<(n_long + n_ckpts + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, n_long, w.long_rank,
-                                                                   w.walker_slot, w.ckpts, n_ckpts, w.contours, w.points, nullptr);
+        (emit_light(p.n) ? k3_emit<true> : k3_emit<false>)<<<(n_long + n_ckpts + n_relays + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, n_long, w.long_rank,
+                                                                   w.walker_slot, w.ckpts, n_ckpts, w.contours, w.points, nullptr, w.relays, w.segs, n_relays);
         K3_CUDA(cudaGetLastError());
         timer.mark("emit");
         k3_rdp<<<(n_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, n_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags, nullptr, p.w <= 16384 && p.h <= 16384);
@@ -1400,6 +1626,9 @@ cudaError_t k3_finish_speculative(K3Workspace &ws, const K3Params &p, cudaStream
     unsigned long long cap_points = w.hist_points + w.hist_points / 8 + 65536;
     if (cap_points > 0xfffffffeull) cap_points = 0xfffffffeull;
     const uint32_t cap_long = (uint32_t)cap_long64, cap_ckpts = (uint32_t)cap_ckpts64;
+    unsigned long long cap_relays64 = (unsigned long long)w.hist_relays + w.hist_relays / 8 + 1024;
+    if (cap_relays64 > l.relay_cap) cap_relays64 = l.relay_cap;
+    const uint32_t cap_relays = (uint32_t)cap_relays64;
     if ((size_t)cap_long > w.contours_cap) {
         K3_CUDA(alloc_exact(w.contours, (size_t)cap_long + cap_long / 4 + 1024));
         K3_CUDA(alloc_exact(w.contour_quads, ((size_t)cap_long + cap_long / 4 + 1024) * 8));
@@ -1412,7 +1641,7 @@ cudaError_t k3_finish_speculative(K3Workspace &ws, const K3Params &p, cudaStream
     const bool per_frame = l.frame_cap && w.hist_frame_long + w.hist_frame_long / 4 + 16 <= l.frame_cap;
     const uint32_t cap_frame_long = per_frame ? l.frame_cap : 0xffffffffu;
     k3_spec_prepare<<<(cap_long + 255) / 256, 256, 0, stream>>>(w.long_keys, w.long_slot, w.counters, w.long_points, cap_long, cap_ckpts, cap_points,
-                                                                cap_frame_long);
+                                                                cap_frame_long, cap_relays);
     K3_CUDA(cudaGetLastError());
     if (per_frame) {
         k3_order<<<p.n, 256, 0, stream>>>(l, p.n, w.long_keys_sorted, w.long_n_sorted, w.long_off, w.long_rank, w.counters);
@@ -1425,8 +1654,8 @@ cudaError_t k3_finish_speculative(K3Workspace &ws, const K3Params &p, cudaStream
         K3_CUDA(cudaGetLastError());
     }
     timer.mark("order");
-    (emit_light(p.n) ? k3_emit<true> : k3_emit<false>)<<<(cap_long + cap_ckpts + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, cap_long, w.long_rank,
-                                                                   w.walker_slot, w.ckpts, cap_ckpts, w.contours, w.points, w.counters);
+    (emit_light(p.n) ? k3_emit<true> : k3_emit<false>)<<<(cap_long + cap_ckpts + cap_relays + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, cap_long, w.long_rank,
+                                                                   w.walker_slot, w.ckpts, cap_ckpts, w.contours, w.points, w.counters, w.relays, w.segs, cap_relays);
     K3_CUDA(cudaGetLastError());
     timer.mark("emit");
     k3_rdp<<<(cap_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, cap_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags, w.counters, p.w <= 16384 && p.h <= 16384);
@@ -1440,6 +1669,7 @@ cudaError_t k3_finish_speculative(K3Workspace &ws, const K3Params &p, cudaStream
     if (p.frame_contours) K3_CUDA(cudaMemcpyAsync(p.frame_contours, w.frame_contours, (size_t)p.n * 4, cudaMemcpyDeviceToDevice, stream));
     if (p.frame_points) K3_CUDA(cudaMemcpyAsync(p.frame_points, w.frame_points, (size_t)p.n * 8, cudaMemcpyDeviceToDevice, stream));
     w.spec_long = cap_long ? cap_long : 1; w.spec_ckpts = cap_ckpts; w.spec_points = cap_points; w.spec_frame_long = cap_frame_long;
+    w.spec_relays = cap_relays;
     *speculated = true;
     return cudaSuccess;
 }
@@ -1454,10 +1684,12 @@ bool k3_speculation_held(K3Workspace &ws, const K3Params &p) {
     if (!w.spec_long) return false;
     const uint32_t *hc = reinterpret_cast<const uint32_t *>(&w.h_counts[0]);
     const unsigned long long n_points = w.h_counts[4];
-    const bool held = !hc[2] && hc[1] <= w.spec_long && hc[4] <= w.spec_ckpts && n_points <= w.spec_points && hc[7] <= w.spec_frame_long;
+    const bool held = !hc[2] && hc[1] <= w.spec_long && hc[4] <= w.spec_ckpts && n_points <= w.spec_points && hc[7] <= w.spec_frame_long &&
+                      hc[6] <= w.spec_relays;
     w.hist_valid = !hc[2] && n_points < 0xffffffffull;
     w.hist_n = p.n; w.hist_w = p.w; w.hist_h = p.h; w.hist_long = hc[1]; w.hist_ckpts = hc[4]; w.hist_points = n_points;
     w.hist_frame_long = hc[7];
+    w.hist_relays = hc[6];
     w.spec_long = 0;
     return held;
 }

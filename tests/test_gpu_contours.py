@@ -184,3 +184,52 @@ def test_more_than_4096_frames_take_the_radix_sort(a3, oracle):
     for f in range(0, n, 3):
         want, nc, npnt = _oracle_frame(oracle, masks[f], ocfg)
         assert quads[f].tolist() == want.tolist() and (int(contours[f]), int(points[f])) == (nc, npnt), f"frame {f}"
+
+
+@pytest.mark.parametrize("route", ["relays", "pairs"])
+def test_both_walk_routes(a3, oracle, route, monkeypatch):
+    """Long borders are walked from relay cracks (k3_segments / k3_cycles; calls of up to 4 frames by default) or by lane pairs from
+    their start candidate (k3_walkers; batches).  A3_K3_RELAY_MAX_FRAMES, read at every call, forces either route: both must give the
+    oracle's quads and contour statistics on random, blocky, striped and noise content, single frames and batches alike."""
+    monkeypatch.setenv("A3_K3_RELAY_MAX_FRAMES", "1000000" if route == "relays" else "0")
+    rng = np.random.default_rng(4242)
+    cfg = a3.DetectorConfig(min_side_length_factor=0.02, min_corner_separation_factor=0.01)
+    ocfg = oracle.default_config(min_side_length_factor=0.02, min_corner_separation_factor=0.01)
+    for (w, h) in [(33, 17), (97, 131), (200, 120), (640, 70)]:
+        masks = []
+        for density in (0.1, 0.5, 0.9):
+            m = ((rng.random((h, w)) < density) * 255).astype(np.uint8)
+            m[0] = m[-1] = 0
+            m[:, 0] = m[:, -1] = 0
+            masks.append(m)
+        for _ in range(6):  # blocks, holes, long horizontal and vertical bars: borders that cross many relay rows, or none
+            m = np.zeros((h, w), np.uint8)
+            for _ in range(6):
+                x0, y0 = rng.integers(1, w - 1), rng.integers(1, h - 1)
+                m[y0:min(h - 1, y0 + rng.integers(1, 60)), x0:min(w - 1, x0 + rng.integers(1, 90))] = 255
+            for _ in range(3):
+                x0, y0 = rng.integers(1, w - 1), rng.integers(1, h - 1)
+                m[y0:min(h - 1, y0 + rng.integers(1, 14)), x0:min(w - 1, x0 + rng.integers(1, 14))] = 0
+            m[h // 2, 1:w - 1] = 255          # a one-pixel line across the frame
+            m[1:h - 1, w // 3] = 255
+            masks.append(m)
+        masks = np.stack(masks)
+        assert _check(a3, oracle, masks, cfg, ocfg, allow_flags=False) == 0          # one call with all frames
+        for f in (0, 4, len(masks) - 1):                                              # and frame by frame
+            assert _check(a3, oracle, masks[f:f + 1], cfg, ocfg, allow_flags=False) == 0
+
+
+def test_relay_route_on_detection_frames(a3, oracle, monkeypatch):
+    """The whole path on rendered frames with relays forced on for a batch and off for single frames: same markers as the oracle."""
+    from aruco3_b200 import synth
+    frames, _ = synth.render_batch("C1", 6)
+    want = [[(m["id"], m["rotation"], m["hamming_distance"], m["code"], m["corners"]) for m in oracle.detect(f, "ARUCO").markers] for f in frames]
+    for env, batches in (("1000000", [frames]), ("0", [frames[i:i + 1] for i in range(3)])):
+        monkeypatch.setenv("A3_K3_RELAY_MAX_FRAMES", env)
+        with a3.Detector() as d:
+            k = 0
+            for b in batches:
+                for _ in range(2):  # second call: the one-shot route with speculated list sizes
+                    got = d.detect_batch(b)
+                assert [[(m.id, m.rotation, m.hamming_distance, m.code, [v for c in m.corners for v in c]) for m in x.markers] for x in got] == want[k:k + len(b)]
+                k += len(b)
