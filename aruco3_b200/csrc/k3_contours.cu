@@ -1454,6 +1454,10 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     const uint32_t relay_shift = p.h > 1200 ? 5u : 4u, nrr = (p.h + (1u << relay_shift) - 1) >> relay_shift;
     size_t want_relays = relays_off ? 0 : (size_t)p.n * nrr * (p.w / 2 + 64);
     if (want_relays > ((size_t)48 << 20)) want_relays = (size_t)48 << 20;
+    if (const char *cap_env = getenv("A3_K3_RELAY_CAP")) {  // test hook: a list too small for the call (overflow -> host stage)
+        const size_t c = strtoull(cap_env, nullptr, 10);
+        if (want_relays > c) want_relays = c ? c : 1;
+    }
     if (want_relays > w.relay_cap) {
         K3_CUDA(alloc_exact(w.relays, want_relays));
         K3_CUDA(alloc_exact(w.segs, want_relays));

@@ -233,3 +233,23 @@ def test_relay_route_on_detection_frames(a3, oracle, monkeypatch):
                     got = d.detect_batch(b)
                 assert [[(m.id, m.rotation, m.hamming_distance, m.code, [v for c in m.corners for v in c]) for m in x.markers] for x in got] == want[k:k + len(b)]
                 k += len(b)
+
+
+def test_relay_list_overflow_goes_to_the_host_stage(a3, oracle, monkeypatch):
+    """A relay list too small for the call (A3_K3_RELAY_CAP, a test hook) is an overflow like that of any other K3 list: every frame
+    of the call is flagged and redone by the host stage, and the answer stays the oracle's."""
+    from aruco3_b200 import synth
+    frames, _ = synth.render_batch("C1", 2)
+    want = [[(m["id"], m["rotation"], m["hamming_distance"], m["code"], m["corners"]) for m in oracle.detect(f, "ARUCO").markers] for f in frames]
+    monkeypatch.setenv("A3_K3_RELAY_CAP", "8")
+    with a3.Detector() as d:
+        for _ in range(2):
+            got = d.detect_batch(frames)
+            assert [[(m.id, m.rotation, m.hamming_distance, m.code, [v for c in m.corners for v in c]) for m in x.markers] for x in got] == want
+        masks = np.stack([d.gray_threshold(f[None])[1][0] for f in frames])
+        _, flags, _, _ = d.quads_from_masks_device(masks)
+        assert all(int(f) & 8 for f in flags)  # bit 3: a work list overflowed
+    monkeypatch.delenv("A3_K3_RELAY_CAP")
+    with a3.Detector() as d:
+        _, flags, _, _ = d.quads_from_masks_device(masks)
+        assert not any(int(f) for f in flags)
