@@ -204,6 +204,7 @@ struct Lists {
     uint2 *relays;                     // per relay crack: {x | y << 16, frame << 1 | side (0 west, 1 east)}
     struct Seg *segs;                  // per relay crack: its segment of the border (k3_segments), then its place in it (k3_cycles)
     uint32_t *relay_base;              // per (frame, relay row, word column): index of the word's first relay crack
+    unsigned long long *seg_owner;     // per relay crack: (leader of its cycle << 32) | visits of the cycle before its segment (k3_cycles)
     uint32_t relay_cap;                // 0 = relays off
     uint32_t relay_shift, nrr;         // log2 of the row spacing; relay rows per frame
 };
@@ -214,8 +215,8 @@ struct __align__(16) Seg {
     uint32_t cand;       // smallest candidate key (pixel << 1 | kind) among the segment's visits, 0xffffffff = none
     uint32_t cand_pos;   // index of that visit within the segment
     uint32_t min_pix;    // raster-first pixel of the segment
-    uint32_t slot;       // k3_cycles: slot of the border among the long borders, 0xffffffff = not recorded
-    uint32_t off;        // k3_cycles: index of the segment's first visit in the border's point list
+    uint32_t slot;       // k3_cycles, in the record of the cycle's leader: slot of the border among the long borders, 0xffffffff = not recorded
+    uint32_t off;        // k3_cycles, in the leader's record: index of the border's start visit, counted from the leader's own visit
     uint32_t state;      // state of the relay's own visit
 };
 constexpr uint32_t kNone = 0xffffffffu;
@@ -559,6 +560,7 @@ __global__ void __launch_bounds__(128) k3_segments(const Geo g, const StepTables
         }
         Seg out;
         out.next = i; out.len = 0; out.cand = kNone; out.cand_pos = 0; out.min_pix = kNone; out.slot = kNone; out.off = 0; out.state = 0;
+        l.seg_owner[i] = ~0ull;
         int o = sx + 31, y = sy;
         uint32_t pix = (uint32_t)(sy * w + sx), state_off = (uint32_t)(pred < 0 ? 0 : pred) << 10;
         uint32_t e = *reinterpret_cast<const uint16_t *>(lut + state_off + hood2(plane, g.Hp, o, y));
@@ -588,20 +590,23 @@ __global__ void __launch_bounds__(128) k3_segments(const Geo g, const StepTables
 
 // The relays of a border form a cycle of segments.  Every relay walks its cycle until it meets a smaller index (then it is not
 // the leader) or comes back to itself; the leader — the smallest index of the cycle — knows the border: its length is the sum
-// of the segments, its start the smallest candidate key on the way (the reference's discovery point; none = the reference
-// never follows this border), and it records the border like a surviving candidate does, then tells every segment where its
-// points go.
+// of the segments, its start the smallest candidate key on the way (the reference's discovery point), and it records the border
+// like a surviving candidate does.  Where a segment's points go is settled in the same pass: every walker leaves
+// (its index << 32 | visits before this segment, counted from itself) in the segments it passes with an atomic minimum, and
+// since the leader has the smallest index and passes them all, its values are what remains; the leader's own record then holds
+// the border's slot and the position of the start visit (one walk round the cycle instead of two: the cycle of the noise
+// frame's largest border has thousands of segments, and following them is a chain of dependent loads).
 __global__ void __launch_bounds__(256) k3_cycles(const Geo g, const uint32_t min_points, const Lists l) {
     if (l.counters[6] > l.relay_cap) return;
     const uint32_t total = l.counters[6];
     const size_t words_per_frame = (size_t)g.h * g.wpr;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const Seg mine = l.segs[i];
-        if (mine.len == 0) continue;
+        Seg q = l.segs[i];
+        if (q.len == 0) continue;
         uint32_t j = i, n = 0, best = kNone, best_off = 0, min_pix = kNone;
         bool leader = true;
-        Seg q = mine;
         for (;;) {
+            atomicMin(&l.seg_owner[j], ((unsigned long long)i << 32) | n);
             if (q.cand < best) { best = q.cand; best_off = n + q.cand_pos; }
             min_pix = min(min_pix, q.min_pix);
             n += q.len;
@@ -615,17 +620,8 @@ __global__ void __launch_bounds__(256) k3_cycles(const Geo g, const uint32_t min
         const uint32_t sy = spix / g.w, sx = spix - sy * g.w;
         const unsigned long long gid = (unsigned long long)frame * words_per_frame + (unsigned long long)sy * g.wpr + (sx >> 5);
         const unsigned long long key = (((gid << 5) | (sx & 31u)) << 1) | kind;
-        const uint32_t slot = record_survivor(l, frame, key, (int)kind, n, min_pix == spix, min_points, true);
-        if (slot == kNone) continue;
-        uint32_t cum = 0;
-        j = i;
-        do {
-            const uint32_t len = l.segs[j].len, nx = l.segs[j].next;
-            l.segs[j].slot = slot;
-            l.segs[j].off = cum >= best_off ? cum - best_off : cum + n - best_off;
-            cum += len;
-            j = nx;
-        } while (j != i);
+        l.segs[i].off = best_off;
+        l.segs[i].slot = record_survivor(l, frame, key, (int)kind, n, min_pix == spix, min_points, true);
     }
 }
 
@@ -840,7 +836,7 @@ template <bool LIGHT>
 __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *tables, const unsigned long long *keys, const uint32_t *lens,
                                                const uint32_t *offsets, uint32_t n_contours, const uint32_t *rank, const uint32_t *walker_slot,
                                                const Ckpt *ckpts, uint32_t n_ckpts, Contour *contours, uint32_t *points, const uint32_t *dyn,
-                                               const uint2 *relays, const Seg *segs, uint32_t n_relays) {
+                                               const uint2 *relays, const Seg *segs, const unsigned long long *seg_owner, uint32_t n_relays) {
     __shared__ uint16_t fwd[8][512];
     if (dyn) {  // speculative finish: the real sizes are on the device only
         if (dyn[kSpecFail]) return;
@@ -858,16 +854,20 @@ __global__ void __launch_bounds__(128) k3_emit(const Geo g, const StepTables *ta
         // short to matter, were not recorded
         const uint32_t ri = t - n_contours - n_ckpts;
         const Seg sg = segs[ri];
-        if (sg.len == 0 || sg.slot == kNone) return;
+        if (sg.len == 0) return;
+        const unsigned long long own = seg_owner[ri];
+        const uint32_t leader = (uint32_t)(own >> 32), cum = (uint32_t)own;
+        const uint32_t slot = segs[leader].slot, start = segs[leader].off;
+        if (slot == kNone) return;
         const uint2 r = relays[ri];
-        ci = rank[sg.slot];
+        ci = rank[slot];
         const uint32_t n = lens[ci] & ~kRelayFlag;
         uint32_t *out = points + offsets[ci];
         const uint32_t *plane = g.planes + (size_t)(r.y >> 1) * g.frame_words;
         asm volatile("" : "+l"(plane));
         const unsigned char *lut = reinterpret_cast<const unsigned char *>(&fwd[0][0]);
         int o = (int)(r.x & 0xffffu) + 31, yy = (int)(r.x >> 16);
-        uint32_t state_off = sg.state << 10, pos = sg.off;
+        uint32_t state_off = sg.state << 10, pos = cum >= start ? cum - start : cum + n - start;
         for (uint32_t i = 0; i < sg.len; i++) {
             out[pos] = (uint32_t)(o - 31) | ((uint32_t)yy << 16);
             if (++pos == n) pos = 0;
@@ -1163,22 +1163,34 @@ __global__ void __launch_bounds__(32) k3_finalize(const uint32_t *contour_quads,
     (void)n_frames; (void)dead_scratch;
     uint32_t nq = 0;
     bool over = false;
-    for (uint32_t base = c0; base < c1; base += 32) {
-        const uint32_t ci = base + lane;
-        const bool valid = ci < c1 && contour_quads[(size_t)ci * 8] != 0xffffffffu;
-        const uint32_t m = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const uint32_t slot = nq + __popc(m & ((1u << lane) - 1));
-            if (slot < quad_cap) {
-                const uint4 a = *reinterpret_cast<const uint4 *>(contour_quads + (size_t)ci * 8);
-                const uint4 b = *reinterpret_cast<const uint4 *>(contour_quads + (size_t)ci * 8 + 4);
-                uint32_t *p = sq + (size_t)slot * 8;
-                p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
-            } else {
-                over = true;
-            }
+    // eight groups of 32 contours per round, their loads issued together: a frame of the noise workload has 17 k long borders
+    // and one warp walks them all, so this loop was 525 dependent round trips to L2 (0.17 ms of a single-frame call)
+    constexpr int kGroups = 8;
+    for (uint32_t base = c0; base < c1; base += 32 * kGroups) {
+        uint32_t first[kGroups];
+#pragma unroll
+        for (int u = 0; u < kGroups; u++) {
+            const uint32_t ci = base + 32 * u + lane;
+            first[u] = ci < c1 ? contour_quads[(size_t)ci * 8] : 0xffffffffu;
         }
-        nq += __popc(m);
+#pragma unroll
+        for (int u = 0; u < kGroups; u++) {
+            const uint32_t ci = base + 32 * u + lane;
+            const bool valid = first[u] != 0xffffffffu;
+            const uint32_t m = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const uint32_t slot = nq + __popc(m & ((1u << lane) - 1));
+                if (slot < quad_cap) {
+                    const uint4 a = *reinterpret_cast<const uint4 *>(contour_quads + (size_t)ci * 8);
+                    const uint4 b = *reinterpret_cast<const uint4 *>(contour_quads + (size_t)ci * 8 + 4);
+                    uint32_t *p = sq + (size_t)slot * 8;
+                    p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+                } else {
+                    over = true;
+                }
+            }
+            nq += __popc(m);
+        }
     }
     over = __any_sync(0xffffffffu, over);
     if (over) nq = quad_cap;
@@ -1254,6 +1266,7 @@ struct K3Workspace::Impl {
     Ckpt *ckpts = nullptr;
     uint2 *relays = nullptr;
     Seg *segs = nullptr;
+    unsigned long long *seg_owner = nullptr;
     uint32_t *relay_base = nullptr;
     size_t relay_cap = 0, relay_base_cap = 0;
     uint32_t hist_relays = 0, spec_relays = 0;
@@ -1289,7 +1302,7 @@ K3Workspace::~K3Workspace() {
                     (void *)impl->frame_contours, impl->cub_tmp, (void *)impl->contours, (void *)impl->contour_quads, (void *)impl->points,
                     (void *)impl->dead, (void *)impl->long_slot, (void *)impl->long_slot_sorted, (void *)impl->long_rank, (void *)impl->walker_slot,
                     (void *)impl->ckpts, (void *)impl->long_off_slot, (void *)impl->frame_long_count, (void *)impl->frame_slots, (void *)impl->frame_keys,
-                    (void *)impl->relays, (void *)impl->segs, (void *)impl->relay_base})
+                    (void *)impl->relays, (void *)impl->segs, (void *)impl->relay_base, (void *)impl->seg_owner})
         if (p) cudaFree(p);
     if (impl->h_counts) cudaFreeHost(impl->h_counts);
     delete impl;
@@ -1461,6 +1474,7 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     if (want_relays > w.relay_cap) {
         K3_CUDA(alloc_exact(w.relays, want_relays));
         K3_CUDA(alloc_exact(w.segs, want_relays));
+        K3_CUDA(alloc_exact(w.seg_owner, want_relays));
         w.relay_cap = want_relays;
     }
     const size_t want_base = relays_off ? 0 : (size_t)p.n * nrr * ((p.w + 31) / 32);
@@ -1486,7 +1500,7 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     l.long_off_slot = w.long_off_slot; l.frame_cap = frame_lists ? kOrderCap : 0u; l.frame_long_count = w.frame_long_count;
     l.frame_keys = w.frame_keys; l.frame_slots = w.frame_slots;
     l.ckpt_cap = (uint32_t)(w.ckpt_cap > 0x7fffffffull ? 0x7fffffffull : w.ckpt_cap);
-    l.relays = w.relays; l.segs = w.segs; l.relay_base = w.relay_base; l.relay_cap = (uint32_t)want_relays;
+    l.relays = w.relays; l.segs = w.segs; l.seg_owner = w.seg_owner; l.relay_base = w.relay_base; l.relay_cap = (uint32_t)want_relays;
     l.relay_shift = relay_shift; l.nrr = nrr;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1590,7 +1604,7 @@ cudaError_t k3_finish(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         }
         timer.mark("order");
         (emit_light(p.n) ? k3_emit<true> : k3_emit<false>)<<<(n_long + n_ckpts + n_relays + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, n_long, w.long_rank,
-                                                                   w.walker_slot, w.ckpts, n_ckpts, w.contours, w.points, nullptr, w.relays, w.segs, n_relays);
+                                                                   w.walker_slot, w.ckpts, n_ckpts, w.contours, w.points, nullptr, w.relays, w.segs, w.seg_owner, n_relays);
         K3_CUDA(cudaGetLastError());
         timer.mark("emit");
         k3_rdp<<<(n_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, n_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags, nullptr, p.w <= 16384 && p.h <= 16384);
@@ -1659,7 +1673,7 @@ cudaError_t k3_finish_speculative(K3Workspace &ws, const K3Params &p, cudaStream
     }
     timer.mark("order");
     (emit_light(p.n) ? k3_emit<true> : k3_emit<false>)<<<(cap_long + cap_ckpts + cap_relays + 127) / 128, 128, 0, stream>>>(g, w.d_tables, w.long_keys_sorted, w.long_n_sorted, w.long_off, cap_long, w.long_rank,
-                                                                   w.walker_slot, w.ckpts, cap_ckpts, w.contours, w.points, w.counters, w.relays, w.segs, cap_relays);
+                                                                   w.walker_slot, w.ckpts, cap_ckpts, w.contours, w.points, w.counters, w.relays, w.segs, w.seg_owner, cap_relays);
     K3_CUDA(cudaGetLastError());
     timer.mark("emit");
     k3_rdp<<<(cap_long + 3) / 4, 128, 0, stream>>>(w.contours, w.points, cap_long, p.eps_factor, p.min_edge_length, w.contour_quads, p.frame_flags, w.counters, p.w <= 16384 && p.h <= 16384);

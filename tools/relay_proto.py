@@ -120,42 +120,42 @@ def relay_borders(mask, R):
             x, y, st = x + DX[d], y + DY[d], (d + 4) & 7
             t += 1
         seg[i] = (nxt, t, best, best_pos, min_pix)
-    # ---- cycles: the smallest relay index of a cycle is its leader ----
-    out = {}
+    # ---- cycles: the smallest relay index of a cycle is its leader; every walker leaves (its index, visits before this segment,
+    # counted from itself) in the segments it passes, the minimum stays: the leader's, since it passes them all ----
+    owner = [(NONE, 0)] * len(relays)
+    info = {}
     for i, s in enumerate(seg):
         if s is None:
             continue
-        j, total, best, leader = i, 0, (NONE, 0, 0), True
+        j, total, best, leader = i, 0, (NONE, 0), True
         while True:
             nxt, ln, cand, pos, mp = seg[j]
-            if j < i:
-                leader = False
-                break
+            owner[j] = min(owner[j], (i, total))
             if cand < best[0]:
-                best = (cand, total + pos, 0)
+                best = (cand, total + pos)
             total += ln
             j = nxt
             if j == i:
                 break
-        if not leader or best[0] == NONE:
-            continue
-        start_off = best[1]
-        pts = [None] * total
-        j, cum = i, 0
-        while True:
-            nxt, ln, _, _, _ = seg[j]
-            x, y, st = relays[j]
-            off = (cum - start_off) % total
-            for t in range(ln):
-                pts[(off + t) % total] = (x, y)
-                d, _ = step(img, x, y, st)
-                x, y, st = x + DX[d], y + DY[d], (d + 4) & 7
-            cum += ln
-            j = nxt
-            if j == i:
+            if j < i:
+                leader = False
                 break
+        if leader and best[0] != NONE:
+            info[i] = (best[0], best[1], total)
+    # ---- emission: one walker per relay again ----
+    out = {k: (n, [None] * n) for (k, _, n) in info.values()}
+    for j, s in enumerate(seg):
+        if s is None or owner[j][0] not in info:
+            continue
+        key, start, n = info[owner[j][0]]
+        x, y, st = relays[j]
+        off = (owner[j][1] - start) % n
+        for t in range(s[1]):
+            out[key][1][(off + t) % n] = (x, y)
+            d, _ = step(img, x, y, st)
+            x, y, st = x + DX[d], y + DY[d], (d + 4) & 7
+    for k, (n, pts) in out.items():
         assert all(p is not None for p in pts)
-        out[best[0]] = (total, pts)
     return out
 
 
