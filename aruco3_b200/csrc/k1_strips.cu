@@ -241,8 +241,16 @@ __device__ __noinline__ void set_ny(uint32_t base, uint32_t tab, uint32_t ny, in
     __syncwarp();
 }
 
+// Measured and left off: boxes further ahead than the two stages hold can be asked into L2 (cp.async.bulk.prefetch.tensor), so
+// that the stage's own request finds its rows there — ncu's samples have 24 % of the kernel's stalls on the two mbarrier waits, and a
+// third stage would cost the 7th CTA of an SM.  256 x 1080p: 0.421 ms without, 0.435 ms with a prefetch 2 boxes ahead, 0.442 ms 4
+// boxes ahead: lane 0's extra request per box costs more issue slots than the shorter waits give back.
+#ifndef A3_K1_PREFETCH
+#define A3_K1_PREFETCH 0
+#endif
+constexpr int kPrefetchAhead = A3_K1_PREFETCH;  // boxes beyond the one being requested; 0 = off
 template <int FMT>
-__device__ __forceinline__ void arm_box(const CUtensorMap *tmap, uint32_t base, int box) {  // lane 0: request rows ys - 7 + 2 box .. into stage box & 1
+__device__ __forceinline__ void arm_box(const CUtensorMap *tmap, uint32_t base, int box, int nboxes) {  // lane 0: request rows ys - 7 + 2 box .. into stage box & 1
     const uint32_t st = (uint32_t)box & 1u, bar = base + Stage<FMT>::bar_off + 8 * st, scr = base + Stage<FMT>::scr_off;
     const int cx = (int)lds32(scr + kScrCx), cy = (int)lds32(scr + kScrYs) - 7 + box * kBoxRows, cz = (int)lds32(scr + kScrFrame);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(Stage<FMT>::tx_bytes) : "memory");
@@ -251,6 +259,9 @@ __device__ __forceinline__ void arm_box(const CUtensorMap *tmap, uint32_t base, 
             base + st * Stage<FMT>::bytes),
         "l"(tmap), "r"(cx), "r"(cy), "r"(cz), "r"(bar)
         : "memory");
+    if (kPrefetchAhead > 0 && box + kPrefetchAhead < nboxes)
+        asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(cx), "r"(cy + kPrefetchAhead * kBoxRows), "r"(cz)
+                     : "memory");
 }
 __device__ __forceinline__ void wait_box(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -389,8 +400,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) k1_strips_ke
     for (int s = 0; s < kRing; s++) sts64(m.ring + 256 * s, make_uint2(0u, 0u));
     __syncwarp();
     if (lane == 0) {
-        arm_box<FMT>(&tmap, m.base, 0);
-        if (m.nboxes > 1) arm_box<FMT>(&tmap, m.base, 1);
+        arm_box<FMT>(&tmap, m.base, 0, m.nboxes);
+        if (m.nboxes > 1) arm_box<FMT>(&tmap, m.base, 1, m.nboxes);
     }
 
     Lane L;
@@ -451,7 +462,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtasPerSm) k1_strips_ke
         }
         // every lane has consumed the box (its values are in registers or in the ring): refill the stage with the box 2 ahead
         __syncwarp();
-        if (lane == 0 && box + kStages < m.nboxes) arm_box<FMT>(&tmap, m.base, box + kStages);
+        if (lane == 0 && box + kStages < m.nboxes) arm_box<FMT>(&tmap, m.base, box + kStages, m.nboxes);
     };
     // Two boxes (4 input rows) per iteration, so the stage of a box and its mbarrier are compile-time constants.  Ring slots:
     // row r lives in slot r & 15, 256 bytes apart; with k = 4 it the rows k .. k + 3 are at A .. A + 768, the rows leaving the
