@@ -1457,13 +1457,14 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     }
     // relays: the candidate cracks of every 16th row (32nd above 1200 rows).  A pure-noise frame has about w / 2 of them per
     // row; the lists are sized for that, capped at 48 M entries (an overflow sends the call to the host stage like any other list).
-    // Relay walks are for calls of a few frames, where the time of the stage is the chain of the longest border (the reference
+    // Relay walks are for calls of up to 16 frames (one front-end chunk of host input), where the time of the stage is the chain of the longest border (the reference
     // bench's noise frame: walks 1.48 -> 0.10 ms, the call 2.3 -> 1.2 ms).  A batch has enough borders to fill the machine, and there the
     // lane pairs win: 256 x 1080p with relays 1.01 ms against 0.55 ms (segment lengths are very uneven - edges nearly parallel to the
     // rows - so a warp waits for its longest, the list allocation and the survivors' records are same-address atomics in short kernels).
+    // On marker frames the two routes take the same time from 2 to 32 frames per call (0.28 ... 0.33 ms), at 64 the pairs win (0.36 against 0.41 ms).
     // A3_K3_RELAY_MAX_FRAMES overrides the threshold (0 = never, read at every call: tests drive both routes).
     const char *relay_env = getenv("A3_K3_RELAY_MAX_FRAMES");
-    const bool relays_off = p.n > (relay_env ? (uint32_t)strtoul(relay_env, nullptr, 10) : 4u);
+    const bool relays_off = p.n > (relay_env ? (uint32_t)strtoul(relay_env, nullptr, 10) : 16u);
     const uint32_t relay_shift = p.h > 1200 ? 5u : 4u, nrr = (p.h + (1u << relay_shift) - 1) >> relay_shift;
     size_t want_relays = relays_off ? 0 : (size_t)p.n * nrr * (p.w / 2 + 64);
     if (want_relays > ((size_t)48 << 20)) want_relays = (size_t)48 << 20;

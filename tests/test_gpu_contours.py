@@ -188,7 +188,7 @@ def test_more_than_4096_frames_take_the_radix_sort(a3, oracle):
 
 @pytest.mark.parametrize("route", ["relays", "pairs"])
 def test_both_walk_routes(a3, oracle, route, monkeypatch):
-    """Long borders are walked from relay cracks (k3_segments / k3_cycles; calls of up to 4 frames by default) or by lane pairs from
+    """Long borders are walked from relay cracks (k3_segments / k3_cycles; calls of up to 16 frames by default) or by lane pairs from
     their start candidate (k3_walkers; batches).  A3_K3_RELAY_MAX_FRAMES, read at every call, forces either route: both must give the
     oracle's quads and contour statistics on random, blocky, striped and noise content, single frames and batches alike."""
     monkeypatch.setenv("A3_K3_RELAY_MAX_FRAMES", "1000000" if route == "relays" else "0")
