@@ -26,6 +26,10 @@
 // ->  k3_emit (one thread per border writes its points)  ->  k3_rdp (one
 // warp per border: Ramer-Douglas-Peucker, hull, edge test)  ->  k3_finalize (one warp per frame: ordered compaction,
 // clockwise, discard_too_near).
+// Calls of up to 16 frames walk differently (their time is the chain of the longest border, not throughput): every border that
+// owns a candidate crack on a relay row (every 16th) is walked from ALL those cracks at once (k3_segments), the relays of a border
+// are linked into a cycle whose smallest candidate key is the border's start (k3_cycles), and the candidate walks above keep only
+// the borders between two relay rows.  tools/relay_proto.py is the specification, tests/test_relay_proto.py checks it.
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
 #include <cub/device/device_radix_sort.cuh>
