@@ -28,7 +28,7 @@
 // clockwise, discard_too_near).
 // Calls of up to 16 frames walk differently (their time is the chain of the longest border, not throughput): every border that
 // owns a candidate crack on a relay row (every 16th) is walked from ALL those cracks at once (k3_segments), the relays of a border
-// are linked into a cycle whose smallest candidate key is the border's start (k3_cycles), and the candidate walks above keep only
+// are linked into a cycle whose smallest candidate key is the border's start (k3_jumps, k3_cycles, k3_spread), and the candidate walks above keep only
 // the borders between two relay rows.  tools/relay_proto.py is the specification, tests/test_relay_proto.py checks it.
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
@@ -209,6 +209,9 @@ struct Lists {
     struct Seg *segs;                  // per relay crack: its segment of the border (k3_segments), then its place in it (k3_cycles)
     uint32_t *relay_base;              // per (frame, relay row, word column): index of the word's first relay crack
     unsigned long long *seg_owner;     // per relay crack: (leader of its cycle << 32) | visits of the cycle before its segment (k3_cycles)
+    struct Jump *jumps;                // per relay crack: the next `jump_hops` segments summed up (k3_jumps)
+    unsigned long long *anchor_owner;  // per relay crack a walker of k3_cycles jumped from: (walker << 32) | visits so far (k3_spread hands it on)
+    uint32_t jump_hops;
     uint32_t relay_cap;                // 0 = relays off
     uint32_t relay_shift, nrr;         // log2 of the row spacing; relay rows per frame
 };
@@ -222,6 +225,16 @@ struct __align__(16) Seg {
     uint32_t slot;       // k3_cycles, in the record of the cycle's leader: slot of the border among the long borders, 0xffffffff = not recorded
     uint32_t off;        // k3_cycles, in the leader's record: index of the border's start visit, counted from the leader's own visit
     uint32_t state;      // state of the relay's own visit
+};
+// The next `hops` segments after a relay, summed up: a cycle of k segments is then followed in k / hops dependent steps.
+struct __align__(16) Jump {
+    uint32_t dest;       // the relay after them
+    uint32_t len;        // their visits
+    uint32_t cand;       // smallest candidate key among them, 0xffffffff = none
+    uint32_t cand_off;   // index of that visit, counted from the first of them
+    uint32_t min_pix;    // raster-first pixel among them
+    uint32_t min_idx;    // smallest index among the relays landed on or passed (the start excluded, dest included)
+    uint32_t pad0, pad1;
 };
 constexpr uint32_t kNone = 0xffffffffu;
 constexpr uint32_t kRelayFlag = 0x80000000u;  // in long_n: the border's points come from relay segments
@@ -565,6 +578,7 @@ __global__ void __launch_bounds__(128) k3_segments(const Geo g, const StepTables
         Seg out;
         out.next = i; out.len = 0; out.cand = kNone; out.cand_pos = 0; out.min_pix = kNone; out.slot = kNone; out.off = 0; out.state = 0;
         l.seg_owner[i] = ~0ull;
+        l.anchor_owner[i] = ~0ull;
         int o = sx + 31, y = sy;
         uint32_t pix = (uint32_t)(sy * w + sx), state_off = (uint32_t)(pred < 0 ? 0 : pred) << 10;
         uint32_t e = *reinterpret_cast<const uint16_t *>(lut + state_off + hood2(plane, g.Hp, o, y));
@@ -592,32 +606,67 @@ __global__ void __launch_bounds__(128) k3_segments(const Geo g, const StepTables
     }
 }
 
-// The relays of a border form a cycle of segments.  Every relay walks its cycle until it meets a smaller index (then it is not
-// the leader) or comes back to itself; the leader — the smallest index of the cycle — knows the border: its length is the sum
-// of the segments, its start the smallest candidate key on the way (the reference's discovery point), and it records the border
-// like a surviving candidate does.  Where a segment's points go is settled in the same pass: every walker leaves
-// (its index << 32 | visits before this segment, counted from itself) in the segments it passes with an atomic minimum, and
-// since the leader has the smallest index and passes them all, its values are what remains; the leader's own record then holds
-// the border's slot and the position of the start visit (one walk round the cycle instead of two: the cycle of the noise
-// frame's largest border has thousands of segments, and following them is a chain of dependent loads).
+// The relays of a border form a cycle of segments, and following a cycle is a chain of dependent loads: the largest border of the
+// reference bench's noise frame has well over a thousand segments.  So first every relay sums up the `jump_hops` segments after it
+// (all relays at once, jump_hops dependent steps).
+__global__ void __launch_bounds__(256) k3_jumps(const Lists l) {
+    if (l.counters[6] > l.relay_cap) return;
+    const uint32_t total = l.counters[6];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        Seg q = l.segs[i];
+        if (q.len == 0) continue;
+        Jump out;
+        out.len = 0; out.cand = kNone; out.cand_off = 0; out.min_pix = kNone; out.min_idx = kNone; out.pad0 = out.pad1 = 0;
+        uint32_t j = i;
+        for (uint32_t h = 0;;) {
+            if (q.cand < out.cand) { out.cand = q.cand; out.cand_off = out.len + q.cand_pos; }
+            out.min_pix = min(out.min_pix, q.min_pix);
+            out.len += q.len;
+            j = q.next;
+            out.min_idx = min(out.min_idx, j);
+            if (++h == l.jump_hops || j == i) break;
+            q = l.segs[j];
+        }
+        out.dest = j;
+        l.jumps[i] = out;
+    }
+}
+
+// Every relay then follows its cycle: it jumps while every relay it would land on or pass has a larger index, leaving
+// (its index << 32 | visits so far) at the relays it jumps from; when its own index is among the next jump_hops it closes the
+// cycle segment by segment, leaving the same in each; when a smaller index is, it is not the leader and stops.  The leader — the
+// smallest index of the cycle — so learns the border: its length, its start (the smallest candidate key on the way = the
+// reference's discovery point) and its raster-first pixel, and records it like a surviving candidate does; its own record then
+// holds the border's slot and the position of the start visit.  Everything left on the way is merged with an atomic minimum:
+// the leader has the smallest index and passes everything, so its values are what remains.
 __global__ void __launch_bounds__(256) k3_cycles(const Geo g, const uint32_t min_points, const Lists l) {
     if (l.counters[6] > l.relay_cap) return;
     const uint32_t total = l.counters[6];
     const size_t words_per_frame = (size_t)g.h * g.wpr;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        Seg q = l.segs[i];
-        if (q.len == 0) continue;
+        if (l.segs[i].len == 0) continue;
         uint32_t j = i, n = 0, best = kNone, best_off = 0, min_pix = kNone;
         bool leader = true;
         for (;;) {
-            atomicMin(&l.seg_owner[j], ((unsigned long long)i << 32) | n);
-            if (q.cand < best) { best = q.cand; best_off = n + q.cand_pos; }
-            min_pix = min(min_pix, q.min_pix);
-            n += q.len;
-            j = q.next;
-            if (j == i) break;
-            if (j < i) { leader = false; break; }
-            q = l.segs[j];
+            const Jump jp = l.jumps[j];
+            if (jp.min_idx < i) { leader = false; break; }
+            if (jp.min_idx == i) {  // the segments after j lead back to me
+                for (;;) {
+                    const Seg q = l.segs[j];
+                    atomicMin(&l.seg_owner[j], ((unsigned long long)i << 32) | n);
+                    if (q.cand < best) { best = q.cand; best_off = n + q.cand_pos; }
+                    min_pix = min(min_pix, q.min_pix);
+                    n += q.len;
+                    j = q.next;
+                    if (j == i) break;
+                }
+                break;
+            }
+            atomicMin(&l.anchor_owner[j], ((unsigned long long)i << 32) | n);
+            if (jp.cand < best) { best = jp.cand; best_off = n + jp.cand_off; }
+            min_pix = min(min_pix, jp.min_pix);
+            n += jp.len;
+            j = jp.dest;
         }
         if (!leader || best == kNone) continue;
         const uint32_t frame = l.relays[i].y >> 1, kind = best & 1u, spix = best >> 1;
@@ -626,6 +675,24 @@ __global__ void __launch_bounds__(256) k3_cycles(const Geo g, const uint32_t min
         const unsigned long long key = (((gid << 5) | (sx & 31u)) << 1) | kind;
         l.segs[i].off = best_off;
         l.segs[i].slot = record_survivor(l, frame, key, (int)kind, n, min_pix == spix, min_points, true);
+    }
+}
+
+// A relay that was jumped from hands (walker, visits so far) on to the jump_hops segments after it.
+__global__ void __launch_bounds__(256) k3_spread(const Lists l) {
+    if (l.counters[6] > l.relay_cap) return;
+    const uint32_t total = l.counters[6];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned long long a = l.anchor_owner[i];
+        if (a == ~0ull) continue;
+        const unsigned long long owner = a & 0xffffffff00000000ull;
+        uint32_t cum = (uint32_t)a, j = i;
+        for (uint32_t h = 0; h < l.jump_hops; h++) {
+            const Seg q = l.segs[j];
+            atomicMin(&l.seg_owner[j], owner | cum);
+            cum += q.len;
+            j = q.next;
+        }
     }
 }
 
@@ -1270,7 +1337,8 @@ struct K3Workspace::Impl {
     Ckpt *ckpts = nullptr;
     uint2 *relays = nullptr;
     Seg *segs = nullptr;
-    unsigned long long *seg_owner = nullptr;
+    unsigned long long *seg_owner = nullptr, *anchor_owner = nullptr;
+    Jump *jumps = nullptr;
     uint32_t *relay_base = nullptr;
     size_t relay_cap = 0, relay_base_cap = 0;
     uint32_t hist_relays = 0, spec_relays = 0;
@@ -1306,7 +1374,7 @@ K3Workspace::~K3Workspace() {
                     (void *)impl->frame_contours, impl->cub_tmp, (void *)impl->contours, (void *)impl->contour_quads, (void *)impl->points,
                     (void *)impl->dead, (void *)impl->long_slot, (void *)impl->long_slot_sorted, (void *)impl->long_rank, (void *)impl->walker_slot,
                     (void *)impl->ckpts, (void *)impl->long_off_slot, (void *)impl->frame_long_count, (void *)impl->frame_slots, (void *)impl->frame_keys,
-                    (void *)impl->relays, (void *)impl->segs, (void *)impl->relay_base, (void *)impl->seg_owner})
+                    (void *)impl->relays, (void *)impl->segs, (void *)impl->relay_base, (void *)impl->seg_owner, (void *)impl->anchor_owner, (void *)impl->jumps})
         if (p) cudaFree(p);
     if (impl->h_counts) cudaFreeHost(impl->h_counts);
     delete impl;
@@ -1480,6 +1548,8 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         K3_CUDA(alloc_exact(w.relays, want_relays));
         K3_CUDA(alloc_exact(w.segs, want_relays));
         K3_CUDA(alloc_exact(w.seg_owner, want_relays));
+        K3_CUDA(alloc_exact(w.anchor_owner, want_relays));
+        K3_CUDA(alloc_exact(w.jumps, want_relays));
         w.relay_cap = want_relays;
     }
     const size_t want_base = relays_off ? 0 : (size_t)p.n * nrr * ((p.w + 31) / 32);
@@ -1507,6 +1577,12 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
     l.ckpt_cap = (uint32_t)(w.ckpt_cap > 0x7fffffffull ? 0x7fffffffull : w.ckpt_cap);
     l.relays = w.relays; l.segs = w.segs; l.seg_owner = w.seg_owner; l.relay_base = w.relay_base; l.relay_cap = (uint32_t)want_relays;
     l.relay_shift = relay_shift; l.nrr = nrr;
+    l.jumps = w.jumps; l.anchor_owner = w.anchor_owner;
+    {
+        const char *jump_env = getenv("A3_K3_JUMP");  // test hook: short jumps exercise the multi-jump paths on small masks
+        const unsigned long jh = jump_env ? strtoul(jump_env, nullptr, 10) : 32ul;
+        l.jump_hops = jh < 1 ? 1u : (jh > 1024 ? 1024u : (uint32_t)jh);
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1541,7 +1617,9 @@ cudaError_t k3_begin(K3Workspace &ws, const K3Params &p, cudaStream_t stream) {
         k3_segments<<<(uint32_t)sms * 8, 128, 0, stream>>>(g, w.d_tables, l);
         K3_CUDA(cudaGetLastError());
         timer.mark("segments");
+        k3_jumps<<<(uint32_t)sms * 4, 256, 0, stream>>>(l);
         k3_cycles<<<(uint32_t)sms * 4, 256, 0, stream>>>(g, p.min_points, l);
+        k3_spread<<<(uint32_t)sms * 4, 256, 0, stream>>>(l);
         K3_CUDA(cudaGetLastError());
         timer.mark("cycles");
     }

@@ -186,12 +186,14 @@ def test_more_than_4096_frames_take_the_radix_sort(a3, oracle):
         assert quads[f].tolist() == want.tolist() and (int(contours[f]), int(points[f])) == (nc, npnt), f"frame {f}"
 
 
-@pytest.mark.parametrize("route", ["relays", "pairs"])
+@pytest.mark.parametrize("route", ["relays", "relays-short-jumps", "pairs"])
 def test_both_walk_routes(a3, oracle, route, monkeypatch):
     """Long borders are walked from relay cracks (k3_segments / k3_cycles; calls of up to 16 frames by default) or by lane pairs from
     their start candidate (k3_walkers; batches).  A3_K3_RELAY_MAX_FRAMES, read at every call, forces either route: both must give the
     oracle's quads and contour statistics on random, blocky, striped and noise content, single frames and batches alike."""
-    monkeypatch.setenv("A3_K3_RELAY_MAX_FRAMES", "1000000" if route == "relays" else "0")
+    monkeypatch.setenv("A3_K3_RELAY_MAX_FRAMES", "0" if route == "pairs" else "1000000")
+    if route == "relays-short-jumps":  # k3_jumps sums 32 segments per jump; 2 makes the cycles of these small masks take many jumps
+        monkeypatch.setenv("A3_K3_JUMP", "2")
     rng = np.random.default_rng(4242)
     cfg = a3.DetectorConfig(min_side_length_factor=0.02, min_corner_separation_factor=0.01)
     ocfg = oracle.default_config(min_side_length_factor=0.02, min_corner_separation_factor=0.01)

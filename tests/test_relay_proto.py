@@ -22,8 +22,8 @@ def test_relay_borders_equal_plain_traces():
             for _ in range(4):
                 x0, y0 = int(rng.integers(0, w)), int(rng.integers(0, h))
                 m[y0:y0 + int(rng.integers(2, h)), x0:x0 + int(rng.integers(2, w))] ^= True
-        for R in (1, 4, 16):
-            a, _ = relay_proto.check(m, R)
+        for R, J in ((1, 2), (4, 1), (4, 3), (16, 32)):  # J: segments summed up per jump (k3_jumps)
+            a, _ = relay_proto.check(m, R, J)
             relay_borders += a
     assert relay_borders > 1000
 

@@ -77,7 +77,7 @@ def cand_keys(img, x, y, ex):
     return keys
 
 
-def relay_borders(mask, R):
+def relay_borders(mask, R, J=32):
     """The relay scheme: {start candidate key: (n, points)} for every border that owns a relay crack and a candidate."""
     img = Img(mask)
     w, h = img.w, img.h
@@ -120,28 +120,68 @@ def relay_borders(mask, R):
             x, y, st = x + DX[d], y + DY[d], (d + 4) & 7
             t += 1
         seg[i] = (nxt, t, best, best_pos, min_pix)
-    # ---- cycles: the smallest relay index of a cycle is its leader; every walker leaves (its index, visits before this segment,
-    # counted from itself) in the segments it passes, the minimum stays: the leader's, since it passes them all ----
+    # ---- jumps: every relay sums up the next J segments (J dependent steps, all relays at once), so that a cycle of k segments is
+    # followed in k / J steps: (relay after J hops, visits, best candidate and its offset, first pixel, smallest index landed on) ----
+    jump = [None] * len(relays)
+    for i, s in enumerate(seg):
+        if s is None:
+            continue
+        j, total, best, mp, mi, hops = i, 0, (NONE, 0), NONE, NONE, 0
+        while True:
+            nxt, ln, cand, pos, pix = seg[j]
+            if cand < best[0]:
+                best = (cand, total + pos)
+            mp = min(mp, pix)
+            total += ln
+            j = nxt
+            hops += 1
+            mi = min(mi, j)
+            if hops == J or j == i:
+                break
+        jump[i] = (j, total, best[0], best[1], mp, mi)
+    # ---- cycles: the smallest relay index of a cycle is its leader.  A walker jumps while every relay it would land on or pass
+    # has a larger index, leaving (its index, visits so far) at the relays it jumps from (anchors); when its own index is
+    # among the next J it closes the cycle step by step; when a smaller index is, it is not the leader.  Minimum wins everywhere:
+    # the leader has the smallest index and passes everything. ----
     owner = [(NONE, 0)] * len(relays)
+    anchor = [(NONE, 0)] * len(relays)
     info = {}
     for i, s in enumerate(seg):
         if s is None:
             continue
         j, total, best, leader = i, 0, (NONE, 0), True
         while True:
-            nxt, ln, cand, pos, mp = seg[j]
-            owner[j] = min(owner[j], (i, total))
-            if cand < best[0]:
-                best = (cand, total + pos)
-            total += ln
-            j = nxt
-            if j == i:
-                break
-            if j < i:
+            dest, jt, jc, jo, jmp, jmi = jump[j]
+            if jmi < i:
                 leader = False
                 break
+            if jmi == i:  # the span from j comes back to me: close step by step
+                while True:
+                    nxt, ln, cand, pos, mp = seg[j]
+                    owner[j] = min(owner[j], (i, total))
+                    if cand < best[0]:
+                        best = (cand, total + pos)
+                    total += ln
+                    j = nxt
+                    if j == i:
+                        break
+                break
+            anchor[j] = min(anchor[j], (i, total))
+            if jc < best[0]:
+                best = (jc, total + jo)
+            total += jt
+            j = dest
         if leader and best[0] != NONE:
             info[i] = (best[0], best[1], total)
+    # ---- spread: every anchor hands (owner, visits so far) to the J segments after it ----
+    for a_, (own, cum) in enumerate(anchor):
+        if own == NONE:
+            continue
+        j = a_
+        for _ in range(J):
+            owner[j] = min(owner[j], (own, cum))
+            cum += seg[j][1]
+            j = seg[j][0]
     # ---- emission: one walker per relay again ----
     out = {k: (n, [None] * n) for (k, _, n) in info.values()}
     for j, s in enumerate(seg):
@@ -188,9 +228,9 @@ def plain_borders(mask, R):
     return out
 
 
-def check(mask, R):
+def check(mask, R, J=32):
     want = plain_borders(mask, R)
-    got = relay_borders(mask, R)
+    got = relay_borders(mask, R, J)
     want_relay = {k: v[:2] for k, v in want.items() if v[2]}
     assert set(got) == set(want_relay), (sorted(set(got) ^ set(want_relay))[:5])
     for k, (n, pts) in got.items():
@@ -223,7 +263,7 @@ def main():
             m[:, 0] = rng.random(h) < 0.7  # pressure on the x == 0 / x == w - 1 rules
             m[:, -1] = rng.random(h) < 0.7
         for R in (int(rng.choice([1, 2, 3, 4, 8])), 32 if t % 16 else 5):
-            a, b = check(m, R)
+            a, b = check(m, R, int(rng.choice([1, 2, 3, 5, 32])))
             nb += a; nn += b
     print(f"relay_proto ok: {trials} masks, {nb} relay borders identical to the plain trace, {nn} borders without a relay left to the candidate walks")
 
