@@ -548,14 +548,15 @@ cudaError_t k1_strips(const K1Params &p, const K1Tuning *tuning, cudaStream_t st
     // row segments: at least as many as fill the resident warp slots once, and short enough (about 180 rows) that the grid
     // is several waves of CTAs: the block scheduler then evens out the slower edge strips and the warps drift out of phase.
     // Measured on B200, 256 x 1080p: one wave of 540-row segments 0.465 ms, 360 rows 0.454, 270 rows 0.426, 180 rows 0.420,
-    // 135 rows 0.422, 108 rows 0.438 (every segment re-reads a 14-row halo, so they stay >= 128 rows)
+    // 135 rows 0.422, 108 rows 0.438 (every segment re-reads a 14-row halo, so a batch keeps them long; a single frame, whose time is
+    // the march of one warp, is cut down to 64-row segments)
     uint32_t nsegs = tuning && tuning->seg_rows ? (p.h + tuning->seg_rows - 1) / tuning->seg_rows : 0;
     if (nsegs == 0) {
         const uint64_t per_seg = (uint64_t)p.n * a.nstrips;
         nsegs = per_seg >= slots ? 1 : (uint32_t)(slots / per_seg);
         const uint32_t pref = (p.h + 90) / 180;
         if (nsegs < pref) nsegs = pref;
-        const uint32_t max_segs = p.h / 128 ? p.h / 128 : 1;
+        const uint32_t max_segs = p.h / 64 ? p.h / 64 : 1;  // calls of a few frames: down to 64 rows, so that more warps share the frame
         if (nsegs > max_segs) nsegs = max_segs;
     }
     a.seg_rows = (p.h + nsegs - 1) / nsegs;
