@@ -21,6 +21,7 @@
 // warp min so that both strict-< tie rules of the reference hold (lowest rotation, then lowest index).
 // Latency-bound and tiny next to K1: what matters is how many candidates are in flight, hence a warp each.
 #include <math.h>
+#include <stdlib.h>
 
 #include "a3_internal.h"
 
@@ -184,6 +185,9 @@ __host__ __device__ inline uint32_t k2_warp_bytes(uint32_t ps, uint32_t ms) {
     return (b + 15) & ~15u;
 }
 
+// WIDE (a launch of few candidates, e.g. one frame per call): a CTA per candidate instead of a warp — all its warps take the
+// 2401 bilinear samples together (the longest stretch of a candidate's chain), warp 0 does everything else in its own slice.
+template <bool WIDE>
 __global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const uint32_t max_taps) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t ps = p.patch_size, ms = p.mark_size, np = ps * ps;
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const
     uintptr_t cur = (reinterpret_cast<uintptr_t>(meta + 2 * ms) + 15) & ~(uintptr_t)15;
     const uint32_t warp_bytes = k2_warp_bytes(ps, ms);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *mine = reinterpret_cast<uint8_t *>(cur) + (size_t)warp * warp_bytes;
+    uint8_t *mine = reinterpret_cast<uint8_t *>(cur) + (size_t)(WIDE ? 0 : warp) * warp_bytes;
     WarpScratch *ws = reinterpret_cast<WarpScratch *>(mine);
     float *tmp = reinterpret_cast<float *>(mine + sizeof(WarpScratch));       // ms * ps  (vertical pass, f32)
     uint8_t *reduced = reinterpret_cast<uint8_t *>(tmp + ms * ps);            // ms * ms (padded to x4)
@@ -208,10 +212,10 @@ __global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const
 
     // one warp per candidate; warps never wait for each other
     const uint32_t n_quads = p.n_quads_dev ? min(*p.n_quads_dev, p.n_quads) : p.n_quads;
-    const uint32_t nwarps = blockDim.x >> 5;
-    const uint32_t first_q = blockIdx.x * nwarps + warp, stride_q = gridDim.x * nwarps;
+    const uint32_t nwarps = WIDE ? 1u : blockDim.x >> 5;
+    const uint32_t first_q = WIDE ? blockIdx.x : blockIdx.x * nwarps + warp, stride_q = gridDim.x * nwarps;
     auto next_quad = [&](uint32_t q) -> uint32_t {  // the warp's next quad: fixed stride, or the shared counter behind the first round
-        if (!p.queue) return q + stride_q;
+        if (WIDE || !p.queue) return q + stride_q;
         uint32_t t = 0;
         if (lane == 0) t = stride_q + atomicAdd(p.queue, 1u);
         return __shfl_sync(0xffffffffu, t, 0);
@@ -219,12 +223,44 @@ __global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const
     for (uint32_t q = first_q; q < n_quads; q = next_quad(q)) {
         const uint32_t frame = p.quad_frame ? p.quad_frame[q] : 0;
         const uint8_t *grey = p.grey + (size_t)frame * p.w * p.h;
-        make_projection(p.quads + (size_t)q * 8, (float)ps, ws->a, &ws->proj, lane);
-        for (int i = lane; i < 256; i += 32) ws->hist[i] = 0;
-        __syncwarp();
+        if (!WIDE || warp == 0) {
+            make_projection(p.quads + (size_t)q * 8, (float)ps, ws->a, &ws->proj, lane);
+            for (int i = lane; i < 256; i += 32) ws->hist[i] = 0;
+        }
+        if constexpr (WIDE) __syncthreads(); else __syncwarp();
         const int ok = ws->proj.ok;
         uint32_t otsu_level = 0;
+        if constexpr (WIDE) {
+            if (ok) {  // every thread of the CTA: samples threadIdx.x, + blockDim.x, ...
+                float inv[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) inv[k] = ws->proj.inv[k];
+                const int cls = ws->proj.cls;
+                for (uint32_t base = threadIdx.x; base < np; base += blockDim.x * kInFlight) {
+                    uint8_t v[kInFlight];
+#pragma unroll
+                    for (int u = 0; u < kInFlight; u++) {
+                        const uint32_t i = base + blockDim.x * u;
+                        v[u] = i < np ? sample(grey, p.w, p.h, inv, cls, i % ps, i / ps) : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < kInFlight; u++) {
+                        const uint32_t i = base + blockDim.x * u;
+                        if (i < np) {
+                            patch[i] = v[u];
+                            atomicAdd(&ws->hist[v[u]], 1u);
+                        }
+                    }
+                }
+            }
+            __syncthreads();   // the patch and its histogram are complete
+            if (warp != 0) {   // the other warps wait for warp 0 at the end of the round
+                __syncthreads();
+                continue;
+            }
+        }
         if (ok) {
+            if constexpr (!WIDE) {
             // ---- warp: ps*ps bilinear samples, histogram on the fly ----
             // The inverse map goes into registers first: it lives in shared memory next to the histogram the loop updates
             // with atomics, so the compiler would otherwise reload all nine coefficients (generic loads) for every sample.
@@ -255,6 +291,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const
                         atomicAdd(&ws->hist[v[u]], 1u);
                     }
                 }
+            }
             }
             __syncwarp();
             // ---- otsu_level: integer prefix sums are exact; the f64 expression keeps the reference's order ----
@@ -392,6 +429,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_kernel(const K2Params p, const
             if (p.accept_counts && out.accepted) atomicAdd(&p.accept_counts[q >> 10], 1u);
         }
         __syncwarp();
+        if constexpr (WIDE) __syncthreads();  // warp 0 is done with the slice: the next candidate may overwrite it
     }
 }
 
@@ -421,16 +459,27 @@ cudaError_t k2_decode(const K2Params &p, cudaStream_t stream) {
     const uint32_t warps = k2_warps(p.patch_size, p.mark_size, p.n_codes);
     if (warps == 0) return cudaErrorInvalidValue;
     const size_t smem = k2_smem_for(p.patch_size, p.mark_size, p.n_codes, warps);
-    cudaError_t e = cudaFuncSetAttribute(k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // few candidates (a frame or two per call): a CTA each, one per SM and round — the time of the launch is one candidate's chain,
+    // and eight warps take its samples eight times sooner than one.  A3_K2_WIDE = 0 / 1 forces the choice (tests, timing).
+    static const char *wide_env = getenv("A3_K2_WIDE");
+    const bool wide = wide_env ? wide_env[0] == '1' : p.n_quads <= 3u * (uint32_t)sms;  // n_quads may be a capacity (history + headroom), the real count lives on the device
+    if (wide) {
+        const size_t wsmem = k2_smem_for(p.patch_size, p.mark_size, p.n_codes, 1);
+        cudaError_t e = cudaFuncSetAttribute(k2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+        if (e != cudaSuccess) return e;
+        k2_kernel<true><<<p.n_quads < (uint32_t)sms * 3 ? p.n_quads : (uint32_t)sms * 3, kThreads, wsmem, stream>>>(p, tp.max_taps);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaFuncSetAttribute(k2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     const uint32_t want = (p.n_quads + warps - 1) / warps;
     int per_sm = 0;  // CTAs that are resident together (registers allow 3, shared memory depends on the dictionary)
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_kernel, (int)warps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_kernel<false>, (int)warps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const uint32_t resident = (uint32_t)sms * (uint32_t)per_sm;
-    k2_kernel<<<want < resident ? want : resident, warps * 32, smem, stream>>>(p, tp.max_taps);
+    k2_kernel<false><<<want < resident ? want : resident, warps * 32, smem, stream>>>(p, tp.max_taps);
     return cudaGetLastError();
 }
 
